@@ -1,0 +1,132 @@
+"""ctypes binding of libavsync_b200.so (C-ABI declared in include/avsync.h).
+
+There is deliberately no fallback: if the shared library is missing, or the
+device is not sm_100, every entry point raises.  torch is used only for device
+memory, streams and (elsewhere) torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_longlong, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libavsync_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2}
+
+# every exported symbol of include/avsync.h: name -> (restype, argtypes)
+_P = c_void_p
+SIGNATURES = {
+    "avs_version": (c_int, []),
+    "avs_last_error_string": (c_char_p, []),
+    "avs_device_check": (c_int, [c_int]),
+    "avs_launch_count": (c_longlong, []),
+    "avs_mfcc_plan_create": (c_int, [c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(_P)]),
+    "avs_mfcc_plan_destroy": (None, [_P]),
+    "avs_mfcc_plan_unique_frames": (c_int, [_P]),
+    "avs_mfcc_plan_frames": (c_int, [_P]),
+    "avs_mfcc_workspace_bytes": (c_size_t, [_P, c_int]),
+    "avs_mfcc_stats_sweep": (c_int, [_P, _P, c_int, _P, _P, c_size_t, _P]),
+    "avs_mfcc_sweep_debug": (c_int, [_P, _P, c_int, _P, _P, _P, c_size_t, _P]),
+    "avs_stcnn_create": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P, POINTER(_P)]),
+    "avs_stcnn_destroy": (None, [_P]),
+    "avs_stcnn_workspace_bytes": (c_size_t, [_P, c_int]),
+    "avs_stcnn_forward": (c_int, [_P, _P, c_int, _P, _P, _P, c_size_t, _P]),
+    "avs_stcnn_forward_debug": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "avs_bigru_create": (c_int, [c_int, c_int, c_int] + [_P] * 10 + [c_int, _P, POINTER(_P)]),
+    "avs_bigru_destroy": (None, [_P]),
+    "avs_bigru_workspace_bytes": (c_size_t, [_P, c_int, c_int]),
+    "avs_bigru_forward": (c_int, [_P, _P, c_int, c_int, _P, _P, c_size_t, _P]),
+    "avs_sweep_score_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "avs_sweep_score": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
+    "avs_ctc_greedy": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "avs_sweep_create": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, POINTER(_P)]),
+    "avs_sweep_destroy": (None, [_P]),
+    "avs_sweep_run": (c_int, [_P, _P, _P, c_int, _P, _P, _P]),
+    "avs_sweep_run_host": (c_int, [_P, _P, _P, c_int, _P, _P]),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libavsync_b200.so (in-tree)."""
+    r = subprocess.run(["make", "-C", CSRC, "-j", str(os.cpu_count() or 4)], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:])
+        print(r.stderr[-4000:])
+    if r.returncode != 0:
+        raise RuntimeError("building libavsync_b200.so failed")
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library, with prototypes set.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU or eager fallback for this path)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().avs_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError(f"libavsync_b200 {what} failed (code {rc}): {msg}")
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the B200 path has no CPU fallback")
+
+
+def ptr(t) -> c_void_p:
+    return c_void_p(0) if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def device_check() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: the B200 path has no CPU fallback")
+    check(lib().avs_device_check(torch.cuda.current_device()), "device_check")
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+class Handle:
+    """Owns one native handle; frees it with the given destroy function."""
+
+    def __init__(self, h: c_void_p, destroy, keep=()):
+        self.h = h
+        self._destroy = destroy
+        self._keep = keep          # tensors the native handle points into
+
+    def __del__(self):
+        try:
+            if self.h:
+                self._destroy(self.h)
+                self.h = None
+        except Exception:
+            pass

@@ -1,0 +1,548 @@
+// K2 — STCNN layer on the 5th-gen tensor cores: implicit-GEMM Conv3d (3 x KH x KW, "same" padding)
+// with the bias + ReLU + MaxPool3d((1,2,2)) epilogue fused (model.py:67-76;
+// misalignment_detection_train.py:132-140).  bf16 operands, fp32 accumulation in TMEM; optional
+// hi/lo bf16 split (3 MMAs per product) for fp32-grade results.
+//
+// Data layout ("parity planes").  A layer's INPUT lives in HBM as
+//     act[clip][tp = t+1 in 0..T+1][chunk][parity][PP positions][8 channels]   (bf16, 16 B per position)
+// where a "position" is a pixel of the zero-padded plane, flattened with row pitch Wt = W + pw
+// (the pw-wide gap after each row is the right pad of that row AND the left pad of the next),
+// rows split by parity of the padded row index (even rows in one array, odd rows in the other),
+// and the T axis zero-padded by one plane each side.  With this layout
+//   * the A operand of tap (kd, kh, kw) for 128 consecutive output positions is the SAME shared-
+//     memory tile as for tap (0,0,0), shifted by (dr*Wt + kw) * 16 bytes: im2col is a descriptor
+//     offset, never a copy (K-major no-swizzle UMMA layout: rows 16 B apart, 8-channel chunks LBO apart);
+//   * conv rows 2r and 2r+1 are accumulated in two TMEM accumulators over the same lanes, so the
+//     2x2 max-pool is max(acc0, acc1) per thread plus one shuffle with the neighbouring lane;
+//   * a tile's halo'd input is one contiguous run per (chunk, parity): plain cp.async.bulk.
+//
+// Kernel structure: persistent CTAs (one per SM), 8 warps:
+//   warp 0  lane 0 : A producer   — bulk-copies A units (one time plane, or half its channels)
+//   warp 2  lane 0 : B producer   — bulk-copies weight stages (one filter tap each)
+//   warp 1  lane 0 : MMA issuer   — walks the per-layer K-step table, tcgen05.mma into TMEM
+//   warp 2         : TMEM allocator
+//   warps 4..7     : epilogue     — tcgen05.ld, pool, bias, ReLU, bf16 (hi/lo) pack, store
+// mbarrier rings: a_full/a_empty[RING], w_full/w_empty[WSTAGES], acc_full/acc_empty[NBUF].
+#include <vector>
+#include "stcnn.cuh"
+
+namespace avs {
+
+constexpr int kConvThreads = 256;
+constexpr int kMaxUnits = 6;
+constexpr int kMaxRing = 4;
+constexpr int kMaxWStages = 8;
+
+struct UnitDesc {
+  int kd, chunk0, nchunks, kstep_end;  // ksteps [prev.kstep_end, kstep_end) read this unit
+};
+
+struct ConvKernelParams {
+  const __nv_bfloat16* act;
+  const __nv_bfloat16* w;
+  const KStep* ksteps;
+  const float* bias;
+  EpiOut eo;
+  UnitDesc units[kMaxUnits];
+  int n_units;
+  int N, acc_stride, NT, NBUF, ring, wstages;
+  int n_ksteps, ksteps_per_stage, stage_bytes, n_stages;
+  int unit_slot_bytes, region_pos, region_full;
+  int n_chunks, PP, Wt, Ho, Wo, n_tiles, n_tilesets;
+  int T, n_items;
+  long long clip_stride, plane_stride;  // elements (bf16) between clips / time planes of `act`
+};
+
+__device__ __forceinline__ void decode_item(const ConvKernelParams& p, int item, int& b, int& t, int& ts) {
+  ts = item % p.n_tilesets;
+  const int r = item / p.n_tilesets;
+  t = r % p.T;
+  b = r / p.T;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // carve: [unit slots][weight stages][kstep table][barriers][tmem ptr]
+  uint8_t* s_units = smem;
+  uint8_t* s_w = s_units + static_cast<size_t>(p.ring) * p.unit_slot_bytes +
+                 static_cast<size_t>(p.region_full - p.region_pos) * 16;  // slack for garbage-lane over-reads
+  KStep* s_ks = reinterpret_cast<KStep*>(s_w + static_cast<size_t>(p.wstages) * p.stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(
+      reinterpret_cast<uint8_t*>(s_ks) + ((static_cast<size_t>(p.n_ksteps) * sizeof(KStep) + 15) / 16) * 16);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kMaxRing;
+  uint64_t* w_full = a_empty + kMaxRing;
+  uint64_t* w_empty = w_full + kMaxWStages;
+  uint64_t* acc_full = w_empty + kMaxWStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < p.n_ksteps * static_cast<int>(sizeof(KStep) / 4); i += kConvThreads)
+    reinterpret_cast<uint32_t*>(s_ks)[i] = reinterpret_cast<const uint32_t*>(p.ksteps)[i];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.ring; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 1);
+    for (int i = 0; i < p.wstages; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
+    for (int i = 0; i < p.NBUF; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 4);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<512>(s_tmem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0 && lane == 0) {
+    // ============================================================ A producer
+    uint32_t seq = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      int b, t, ts;
+      decode_item(p, item, b, t, ts);
+      const int q0 = ts * p.NT * 128;
+      const int len = min(p.region_pos, p.PP - q0);  // positions per (chunk, parity) run
+      for (int u = 0; u < p.n_units; ++u, ++seq) {
+        const int slot = seq % p.ring;
+        mbar_wait(&a_empty[slot], ((seq / p.ring) & 1) ^ 1);
+        const UnitDesc ud = p.units[u];
+        const uint32_t bytes = static_cast<uint32_t>(len) * 16u;
+        mbar_expect_tx(&a_full[slot], bytes * 2u * ud.nchunks);
+        const __nv_bfloat16* src = p.act + b * p.clip_stride + (t + ud.kd) * p.plane_stride +
+                                   (static_cast<long long>(ud.chunk0) * 2 * p.PP + q0) * 8;
+        uint8_t* dst = s_units + static_cast<size_t>(slot) * p.unit_slot_bytes;
+        for (int c = 0; c < ud.nchunks * 2; ++c)
+          bulk_g2s(dst + static_cast<size_t>(c) * p.region_pos * 16, src + static_cast<long long>(c) * p.PP * 8, bytes,
+                   &a_full[slot]);
+      }
+    }
+  } else if (warp == 2 && lane == 0) {
+    // ============================================================ B (weights) producer
+    uint32_t seq = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int s = 0; s < p.n_stages; ++s, ++seq) {
+        const int slot = seq % p.wstages;
+        mbar_wait(&w_empty[slot], ((seq / p.wstages) & 1) ^ 1);
+        mbar_expect_tx(&w_full[slot], p.stage_bytes);
+        bulk_g2s(s_w + static_cast<size_t>(slot) * p.stage_bytes,
+                 reinterpret_cast<const uint8_t*>(p.w) + static_cast<size_t>(s) * p.stage_bytes, p.stage_bytes,
+                 &w_full[slot]);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ============================================================ MMA issuer
+    const uint32_t idesc = umma_idesc_bf16(128, p.N);
+    const uint32_t units_addr = smem_u32(s_units), w_addr = smem_u32(s_w);
+    uint32_t useq = 0, wseq = 0, step = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++step) {
+      int b, t, ts;
+      decode_item(p, item, b, t, ts);
+      const int nt = min(p.NT, p.n_tiles - ts * p.NT);
+      const int buf = step % p.NBUF;
+      mbar_wait(&acc_empty[buf], ((step / p.NBUF) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + buf * (p.NT * 2 * p.acc_stride);
+      int u = 0;
+      uint32_t unit_base = 0, stage_base = 0;
+      for (int e = 0; e < p.n_ksteps; ++e) {
+        if (e == (u == 0 ? 0 : p.units[u - 1].kstep_end)) {  // first K-step of unit u
+          const int slot = useq % p.ring;
+          mbar_wait(&a_full[slot], (useq / p.ring) & 1);
+          tc_fence_after();
+          unit_base = units_addr + slot * p.unit_slot_bytes;
+        }
+        if (e % p.ksteps_per_stage == 0) {
+          const int slot = wseq % p.wstages;
+          mbar_wait(&w_full[slot], (wseq / p.wstages) & 1);
+          tc_fence_after();
+          stage_base = w_addr + slot * p.stage_bytes;
+        }
+        const KStep ks = s_ks[e];
+        const uint64_t bdesc = umma_desc_kmajor(stage_base + ks.b_off, p.N * 16, 128);
+        for (int i = 0; i < nt; ++i) {
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const uint64_t adesc = umma_desc_kmajor(unit_base + ks.a_off[a] + i * (128 * 16), ks.lbo, 128);
+            umma_f16(d_base + (i * 2 + a) * p.acc_stride, adesc, bdesc, idesc, e > 0 ? 1u : 0u);
+          }
+        }
+        if ((e + 1) % p.ksteps_per_stage == 0) {
+          tc_commit(&w_empty[wseq % p.wstages]);
+          ++wseq;
+        }
+        if (e + 1 == p.units[u].kstep_end) {
+          tc_commit(&a_empty[useq % p.ring]);
+          ++useq;
+          ++u;
+        }
+      }
+      tc_commit(&acc_full[buf]);
+    }
+  } else if (warp >= 4) {
+    // ============================================================ epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    uint32_t step = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++step) {
+      int b, t, ts;
+      decode_item(p, item, b, t, ts);
+      const int nt = min(p.NT, p.n_tiles - ts * p.NT);
+      const int buf = step % p.NBUF;
+      mbar_wait(&acc_full[buf], (step / p.NBUF) & 1);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + buf * (p.NT * 2 * p.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
+      for (int i = 0; i < nt; ++i) {
+        const int Q = (ts * p.NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
+        const int r = Q / p.Wt, wc = Q % p.Wt;                // pooled row, conv column
+        const int wo = wc >> 1;
+        const bool valid = (r < p.Ho) && (wo < p.Wo);
+        const int half = lane & 1;                            // even lane: channels 0..15 of the block, odd: 16..31
+        for (int cb = 0; cb < p.N; cb += 32) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(d_base + (i * 2 + 0) * p.acc_stride + cb, v0);
+          tmem_ld32(d_base + (i * 2 + 1) * p.acc_stride + cb, v1);
+          tmem_ld_wait();
+          float o[16];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float m = fmaxf(__uint_as_float(v0[c]), __uint_as_float(v1[c]));  // rows 2r, 2r+1
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));                 // columns 2wo, 2wo+1
+            if ((c >> 4) == half) o[c & 15] = fmaxf(m + __ldg(p.bias + cb + c), 0.f);
+          }
+          const int ch0 = cb + half * 16;
+          if (valid && p.eo.mode == 0) {
+            const int hp = r + p.eo.ph_next;
+            const long long pos = p.eo.pw_next + (hp >> 1) * p.eo.Wt_next + wo;
+            __nv_bfloat16* base = p.eo.act +
+                                  ((static_cast<long long>(b) * (p.T + 2) + t + 1) * p.eo.n_chunks_next) * 2 * p.eo.PP_next * 8;
+#pragma unroll
+            for (int c8 = 0; c8 < 2; ++c8) {
+              const int chunk = (ch0 >> 3) + c8;
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float x0 = o[c8 * 8 + 2 * e], x1 = o[c8 * 8 + 2 * e + 1];
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                hi[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+                lo[e] = pack_bf16x2(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+              }
+              const int idx = p.eo.split_next ? 2 * chunk : chunk;
+              uint4* dst = reinterpret_cast<uint4*>(base + ((static_cast<long long>(idx) * 2 + (hp & 1)) * p.eo.PP_next + pos) * 8);
+              *dst = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              if (p.eo.split_next) {
+                uint4* dl = reinterpret_cast<uint4*>(base + ((static_cast<long long>(idx + 1) * 2 + (hp & 1)) * p.eo.PP_next + pos) * 8);
+                *dl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
+            }
+          } else if (valid) {
+            const int plane = p.Ho * p.Wo;
+            float* dst = p.eo.emb + (static_cast<long long>(b) * p.T + t) * (static_cast<long long>(p.N) * plane) +
+                         static_cast<long long>(ch0) * plane + r * p.Wo + wo;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) dst[static_cast<long long>(c) * plane] = o[c];
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ layout kernels
+// frames f32 [B,1,T,H,W] -> layer-1 input: X8 layout, position p holds the 8 consecutive padded-row values
+// val(p) .. val(p+7) (so the kw taps are the K index of the MMA).  One thread per (clip, tp, parity, position).
+__global__ void __launch_bounds__(256)
+pack_frames_kernel(const float* __restrict__ frames, __nv_bfloat16* __restrict__ act, LayerGeom g, int split, int T,
+                   long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int pos = static_cast<int>(idx % g.PP);
+  long long r = idx / g.PP;
+  const int par = static_cast<int>(r % 2);
+  r /= 2;
+  const int tp = static_cast<int>(r % (T + 2));
+  const long long b = r / (T + 2);
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int pe = pos + e - g.pw;
+    float x = 0.f;
+    if (pe >= 0 && tp >= 1 && tp <= T) {
+      const int row = pe / g.Wt, wq = pe % g.Wt;
+      const int h = 2 * row + par - g.ph;
+      if (h >= 0 && h < g.H && wq < g.W) x = frames[((b * T + (tp - 1)) * g.H + h) * g.W + wq];
+    }
+    v[e] = x;
+  }
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
+    hi[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+    lo[e] = pack_bf16x2(v[2 * e] - __bfloat162float(h0), v[2 * e + 1] - __bfloat162float(h1));
+  }
+  const int nch = split ? 2 : 1;
+  __nv_bfloat16* base = act + ((b * (T + 2) + tp) * nch) * 2 * static_cast<long long>(g.PP) * 8;
+  *reinterpret_cast<uint4*>(base + (static_cast<long long>(par) * g.PP + pos) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (split)
+    *reinterpret_cast<uint4*>(base + ((2LL + par) * g.PP + pos) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// debug: parity-plane input of a layer (C channels, geometry g) -> f32 NCDHW [B, C, T, H, W]
+__global__ void __launch_bounds__(256)
+unpack_act_kernel(const __nv_bfloat16* __restrict__ act, float* __restrict__ out, LayerGeom g, int split, int C, int T,
+                  long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int w = static_cast<int>(idx % g.W);
+  long long r = idx / g.W;
+  const int h = static_cast<int>(r % g.H);
+  r /= g.H;
+  const int t = static_cast<int>(r % T);
+  r /= T;
+  const int c = static_cast<int>(r % C);
+  const long long b = r / C;
+  const int hp = h + g.ph;
+  const long long pos = g.pw + (hp >> 1) * g.Wt + w;
+  const int chunk = c >> 3, nch = g.n_chunks;
+  const __nv_bfloat16* base = act + ((b * (T + 2) + t + 1) * nch) * 2 * static_cast<long long>(g.PP) * 8;
+  const int i0 = split ? 2 * chunk : chunk;
+  float v = __bfloat162float(base[((static_cast<long long>(i0) * 2 + (hp & 1)) * g.PP + pos) * 8 + (c & 7)]);
+  if (split) v += __bfloat162float(base[((static_cast<long long>(i0 + 1) * 2 + (hp & 1)) * g.PP + pos) * 8 + (c & 7)]);
+  out[idx] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static uint16_t f2bf(float x) {  // round-to-nearest-even, like __float2bfloat16_rn (finite inputs)
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+static float bf2f(uint16_t h) {
+  uint32_t u = static_cast<uint32_t>(h) << 16;
+  float x;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+struct LayerCfg { int NT, NBUF, ring, wstages; };
+
+static LayerCfg pick_cfg(const LayerGeom& g, int split) {
+  if (g.Cin == 1) return {4, 2, 3, 4};
+  if (g.Cout == 64) return split ? LayerCfg{1, 2, 3, 3} : LayerCfg{2, 2, 3, 4};
+  return {2, 1, 3, 4};  // Cout = 96 (TMEM: 2 tiles x 2 accs x 128 columns)
+}
+
+void geom_finalize(LayerGeom& g, int split) {
+  g.ph = g.KH / 2;
+  g.pw = g.KW / 2;
+  g.Ho = g.H / 2;
+  g.Wo = g.W / 2;
+  g.Wt = g.W + g.pw;
+  g.Hh = g.Ho + g.KH / 2;
+  g.n_q = g.Ho * g.Wt;
+  g.n_tiles = cdiv(g.n_q, 128);
+  g.n_chunks = (g.Cin == 1 ? 1 : g.Cin / 8) * (split ? 2 : 1);
+  const LayerCfg c = pick_cfg(g, split);
+  const int halo = (g.Cin == 1) ? (g.KH / 2 + 1) * g.Wt + 8 : (g.KH / 2) * g.Wt + g.KW - 1;
+  const int region_full = c.NT * 128 + halo;
+  const int n_tilesets = cdiv(g.n_tiles, c.NT);
+  const int extent = static_cast<int>(align_up(static_cast<size_t>(g.pw + g.Hh * g.Wt + (g.Cin == 1 ? 8 : 0)), 8));
+  g.PP = (n_tilesets == 1) ? std::min(region_full, extent) : (n_tilesets - 1) * c.NT * 128 + region_full;
+}
+
+size_t umma_act_bytes(const LayerGeom& g, int split, int B) {
+  (void)split;
+  return static_cast<size_t>(B) * (AVS_T + 2) * g.n_chunks * 2 * g.PP * 16;
+}
+
+int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w, const float* bias) {
+  L->g = g;
+  L->split = split;
+  const LayerCfg c = pick_cfg(g, split);
+  L->NT = c.NT; L->NBUF = c.NBUF; L->ring = c.ring; L->wstages = c.wstages;
+  L->acc_stride = (g.Cout == 96) ? 128 : g.Cout;
+  const int halo = (g.Cin == 1) ? (g.KH / 2 + 1) * g.Wt + 8 : (g.KH / 2) * g.Wt + g.KW - 1;
+  const int region_full = c.NT * 128 + halo;
+  const int n_tilesets = cdiv(g.n_tiles, c.NT);
+  L->region_pos = (n_tilesets == 1) ? g.PP : region_full;
+  const int N = g.Cout, taps = 3 * g.KH * g.KW;
+  std::vector<KStep> ks;
+  std::vector<uint16_t> wp;
+  auto wat = [&](int n, int ci, int kd, int kh, int kw) {
+    return w[(((static_cast<size_t>(n) * g.Cin + ci) * 3 + kd) * g.KH + kh) * g.KW + kw];
+  };
+  // one B tile = [2 K-halves][N][8] bf16; fill(hi/lo) appends it and returns its byte offset within the stage
+  auto push_tile = [&](size_t stage_begin, auto&& elem, int kind) {
+    const uint32_t off = static_cast<uint32_t>((wp.size() - stage_begin) * 2);
+    for (int half = 0; half < 2; ++half)
+      for (int n = 0; n < N; ++n)
+        for (int k = 0; k < 8; ++k) {
+          const float x = elem(half, n, k);
+          const uint16_t h = f2bf(x);
+          wp.push_back(kind == 0 ? h : f2bf(x - bf2f(h)));
+        }
+    return off;
+  };
+  const uint32_t arr_bytes = static_cast<uint32_t>(L->region_pos) * 16;  // one (chunk, parity) run in a unit slot
+  int n_units = 0;
+  if (g.Cin == 1) {
+    // layer 1: K index = (kh pair, kw'): pairs (0,2), (1,3), (4, zero)
+    L->ksteps_per_stage = split ? 9 : 3;
+    for (int kd = 0; kd < 3; ++kd) {
+      const size_t sb = wp.size();
+      uint32_t boff[3][2];
+      for (int pr = 0; pr < 3; ++pr) {
+        const int kha = (pr == 2) ? 4 : pr, khb = (pr == 2) ? -1 : pr + 2;
+        auto elem = [&](int half, int n, int k) {
+          const int kh = half == 0 ? kha : khb;
+          return (kh >= 0 && k < g.KW) ? wat(n, 0, kd, kh, k) : 0.f;
+        };
+        boff[pr][0] = push_tile(sb, elem, 0);
+        if (split) boff[pr][1] = push_tile(sb, elem, 1);
+      }
+      for (int pr = 0; pr < 3; ++pr) {
+        const int kha = (pr == 2) ? 4 : pr;
+        for (int v = 0; v < (split ? 3 : 1); ++v) {  // (A_hi,B_hi), (A_lo,B_hi), (A_hi,B_lo)
+          const int akind = (v == 1) ? 1 : 0, bkind = (v == 2) ? 1 : 0;
+          KStep s;
+          for (int a = 0; a < 2; ++a) {
+            const int par = (a + kha) & 1, dr = (a + kha) >> 1;
+            s.a_off[a] = (akind * 2 + par) * arr_bytes + dr * g.Wt * 16;
+          }
+          s.lbo = g.Wt * 16;
+          s.b_off = boff[pr][bkind];
+          s.kd = kd;
+          ks.push_back(s);
+        }
+      }
+      n_units++;
+    }
+    L->stage_bytes = static_cast<int>(wp.size() * 2 / 3);
+  } else {
+    // generic: unit = (kd, channel group); stage = (tap, channel group)
+    const int groups = (g.Cout == 96 && split) ? 2 : 1;
+    const int CG = g.Cin / groups, pairs = CG / 16;
+    L->ksteps_per_stage = pairs * (split ? 3 : 1);
+    const int kmul = split ? 2 : 1;
+    for (int kd = 0; kd < 3; ++kd)
+      for (int cg = 0; cg < groups; ++cg) {
+        const int chunk0 = cg * (CG / 8) * kmul;  // first chunk array of this unit
+        for (int kh = 0; kh < g.KH; ++kh)
+          for (int kw = 0; kw < g.KW; ++kw) {
+            const size_t sb = wp.size();
+            std::vector<uint32_t> bh(pairs), bl(pairs);
+            for (int pr = 0; pr < pairs; ++pr) {
+              auto elem = [&](int half, int n, int k) { return wat(n, cg * CG + pr * 16 + half * 8 + k, kd, kh, kw); };
+              bh[pr] = push_tile(sb, elem, 0);
+            }
+            if (split)
+              for (int pr = 0; pr < pairs; ++pr) {
+                auto elem = [&](int half, int n, int k) { return wat(n, cg * CG + pr * 16 + half * 8 + k, kd, kh, kw); };
+                bl[pr] = push_tile(sb, elem, 1);
+              }
+            for (int pr = 0; pr < pairs; ++pr)
+              for (int v = 0; v < (split ? 3 : 1); ++v) {
+                const int akind = (v == 1) ? 1 : 0, bkind = (v == 2) ? 1 : 0;
+                const int c8 = (cg * CG + pr * 16) / 8;              // global 8-channel chunk of the first K half
+                const int arr = (split ? 2 * c8 + akind : c8) - chunk0;  // chunk array index inside the unit
+                KStep s;
+                for (int a = 0; a < 2; ++a) {
+                  const int par = (a + kh) & 1, dr = (a + kh) >> 1;
+                  s.a_off[a] = (arr * 2 + par) * arr_bytes + (dr * g.Wt + kw) * 16;
+                }
+                s.lbo = kmul * 2 * arr_bytes;
+                s.b_off = bkind ? bl[pr] : bh[pr];
+                s.kd = kd;
+                ks.push_back(s);
+              }
+          }
+        n_units++;
+      }
+    L->stage_bytes = static_cast<int>(wp.size() * 2 / (taps * groups));
+  }
+  L->n_ksteps = static_cast<int>(ks.size());
+  L->n_stages = L->n_ksteps / L->ksteps_per_stage;
+  const int chunks_per_unit = g.n_chunks / (n_units / 3);
+  L->plane_slot_bytes = chunks_per_unit * 2 * static_cast<int>(arr_bytes);
+  L->smem_bytes = static_cast<size_t>(L->ring) * L->plane_slot_bytes + static_cast<size_t>(region_full - L->region_pos) * 16 +
+                  static_cast<size_t>(L->wstages) * L->stage_bytes + align_up(ks.size() * sizeof(KStep), 16) +
+                  (2 * kMaxRing + 2 * kMaxWStages + 4) * 8 + 16;
+  if (L->smem_bytes > 232448 || L->ring > kMaxRing || L->wstages > kMaxWStages || n_units > kMaxUnits ||
+      wp.size() * 2 != static_cast<size_t>(L->n_stages) * L->stage_bytes || L->stage_bytes % 16 != 0) {
+    set_error("umma layer config invalid: smem %zu stage_bytes %d n_stages %d packed %zu", L->smem_bytes, L->stage_bytes,
+              L->n_stages, wp.size() * 2);
+    return AVS_EINVAL;
+  }
+  AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&L->d_ksteps), ks.size() * sizeof(KStep)));
+  AVS_CUDA(cudaMemcpy(L->d_ksteps, ks.data(), ks.size() * sizeof(KStep), cudaMemcpyHostToDevice));
+  AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&L->d_w), wp.size() * 2));
+  AVS_CUDA(cudaMemcpy(L->d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+  AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&L->d_bias), N * sizeof(float)));
+  AVS_CUDA(cudaMemcpy(L->d_bias, bias, N * sizeof(float), cudaMemcpyHostToDevice));
+  AVS_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  return AVS_OK;
+}
+
+void umma_layer_free(UmmaLayer* L) {
+  cudaFree(L->d_ksteps);
+  cudaFree(L->d_w);
+  cudaFree(L->d_bias);
+  L->d_ksteps = nullptr; L->d_w = nullptr; L->d_bias = nullptr;
+}
+
+int umma_pack_frames(const float* frames, __nv_bfloat16* act, const LayerGeom& g, int split, int B, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * (AVS_T + 2) * 2 * g.PP;
+  pack_frames_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(frames, act, g, split, AVS_T, total);
+  AVS_LAUNCHED();
+  return AVS_OK;
+}
+
+int umma_unpack_act(const __nv_bfloat16* act, float* out, const LayerGeom& g, int split, int C, int B, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * C * AVS_T * g.H * g.W;
+  unpack_act_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(act, out, g, split, C, AVS_T, total);
+  AVS_LAUNCHED();
+  return AVS_OK;
+}
+
+int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const EpiOut& eo, int B, int n_sms, cudaStream_t st) {
+  ConvKernelParams p;
+  memset(&p, 0, sizeof(p));
+  const LayerGeom& g = L.g;
+  p.act = act_in; p.w = L.d_w; p.ksteps = L.d_ksteps; p.bias = L.d_bias; p.eo = eo;
+  const int units_per_kd = (g.Cout == 96 && L.split) ? 2 : 1;
+  p.n_units = 3 * units_per_kd;
+  const int chunks_per_unit = g.n_chunks / units_per_kd;
+  const int ks_per_unit = L.n_ksteps / p.n_units;
+  for (int u = 0; u < p.n_units; ++u)
+    p.units[u] = UnitDesc{u / units_per_kd, (u % units_per_kd) * chunks_per_unit, chunks_per_unit, (u + 1) * ks_per_unit};
+  p.N = g.Cout; p.acc_stride = L.acc_stride; p.NT = L.NT; p.NBUF = L.NBUF; p.ring = L.ring; p.wstages = L.wstages;
+  p.n_ksteps = L.n_ksteps; p.ksteps_per_stage = L.ksteps_per_stage; p.stage_bytes = L.stage_bytes; p.n_stages = L.n_stages;
+  p.unit_slot_bytes = L.plane_slot_bytes; p.region_pos = L.region_pos;
+  const int halo = (g.Cin == 1) ? (g.KH / 2 + 1) * g.Wt + 8 : (g.KH / 2) * g.Wt + g.KW - 1;
+  p.region_full = L.NT * 128 + halo;
+  p.n_chunks = g.n_chunks; p.PP = g.PP; p.Wt = g.Wt; p.Ho = g.Ho; p.Wo = g.Wo; p.n_tiles = g.n_tiles;
+  p.n_tilesets = cdiv(g.n_tiles, L.NT);
+  p.T = AVS_T;
+  const long long items = static_cast<long long>(B) * AVS_T * p.n_tilesets;
+  AVS_REQUIRE(items < (1LL << 31), "too many work items for one launch");
+  p.n_items = static_cast<int>(items);
+  p.plane_stride = static_cast<long long>(g.n_chunks) * 2 * g.PP * 8;
+  p.clip_stride = p.plane_stride * (AVS_T + 2);
+  const int grid = static_cast<int>(std::min<long long>(items, n_sms));
+  conv_umma_kernel<<<grid, kConvThreads, L.smem_bytes, st>>>(p);
+  AVS_LAUNCHED();
+  return AVS_OK;
+}
+
+}  // namespace avs

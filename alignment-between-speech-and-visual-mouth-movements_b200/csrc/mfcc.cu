@@ -1,0 +1,398 @@
+// K1 — MFCC statistics for every audio shift of every clip.
+//
+// Replaces compute_audio_stats(shift_audio(...)) (misalignment_detection_train.py:100-127), i.e.
+// librosa.feature.mfcc(y, sr, n_mfcc, hop_length=sr/40) followed by mean / unbiased std over frames.
+//
+// Structure:
+//   host plan   : every STFT frame of every shifted signal is a window [p, p+2048) of the ORIGINAL
+//                 signal restricted to a valid range [a, b) (zero elsewhere).  Frames with equal
+//                 (p, a, b) are identical, so the K*F frames collapse to U unique ones (745 instead
+//                 of 4961 for +-20 video frames at 25 fps / 16 kHz).
+//   logmel kernel: per unique frame: Hann window, 2048-point real FFT (1024-point complex radix-4
+//                 Stockham in shared memory + split post-pass), |X|^2, sparse Slaney mel filterbank,
+//                 10*log10(max(1e-10, .)).  fp32 throughout.
+//   stats kernel: per (clip, shift): gather the F frames through the map, global max, top_db clamp,
+//                 DCT-II (ortho) to n_mfcc coefficients, mean and unbiased std over frames.
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <tuple>
+#include <vector>
+#include "common.cuh"
+
+namespace avs {
+
+constexpr int kNfft = AVS_NFFT;
+constexpr int kHalf = kNfft / 2;      // 1024
+constexpr int kBins = kHalf + 1;      // 1025
+constexpr int kMels = AVS_NMELS;      // 128
+constexpr int kFftThreads = 256;
+constexpr int kFramesPerCta = 8;
+constexpr int kMaxQ = 40;
+
+}  // namespace avs
+
+struct avs_mfcc_plan {
+  int n_samples, sr, hop, n_mfcc, n_shifts, n_frames, n_unique;
+  int4* d_frames = nullptr;     // [U] (p, a, b, 0): window start, valid range in original-signal coordinates
+  int* d_map = nullptr;         // [K][F] -> unique frame id
+  float* d_window = nullptr;    // [2048] periodic Hann
+  float2* d_tw = nullptr;       // [1024] exp(-2 pi i e / 1024)
+  float2* d_tw2 = nullptr;      // [1025] exp(-2 pi i k / 2048)
+  int2* d_mel_rng = nullptr;    // [128] (first bin, count)
+  int* d_mel_off = nullptr;     // [128] offset into d_mel_w
+  float* d_mel_w = nullptr;     // concatenated non-zero filter weights
+  float* d_dct = nullptr;       // [128][kMaxQ] DCT-II ortho basis, transposed, zero padded
+};
+
+namespace avs {
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+__global__ void __launch_bounds__(kFftThreads)
+mfcc_logmel_kernel(const float* __restrict__ audio, int n_samples, const int4* __restrict__ frames, int n_unique,
+                   const float* __restrict__ window, const float2* __restrict__ tw, const float2* __restrict__ tw2,
+                   const int2* __restrict__ mel_rng, const int* __restrict__ mel_off,
+                   const float* __restrict__ mel_w, float* __restrict__ logmel) {
+  __shared__ float2 buf0[kHalf];
+  __shared__ float2 buf1[kHalf];
+  __shared__ float2 s_tw[kHalf];
+  __shared__ float s_pow[kBins + 3];
+
+  const int tid = threadIdx.x;
+  const int clip = blockIdx.y;
+  const float* x = audio + static_cast<size_t>(clip) * n_samples;
+  for (int i = tid; i < kHalf; i += kFftThreads) s_tw[i] = tw[i];
+
+  const int u0 = blockIdx.x * kFramesPerCta;
+  const int u1 = min(u0 + kFramesPerCta, n_unique);
+  for (int u = u0; u < u1; ++u) {
+    const int4 fr = frames[u];
+    __syncthreads();  // previous frame's consumers are done with buf/s_pow (and s_tw is loaded)
+    // z[n] = w[2n] x[p+2n] + i w[2n+1] x[p+2n+1], zero outside [a, b)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int n = tid + r * kFftThreads;
+      const int i0 = fr.x + 2 * n, i1 = i0 + 1;
+      const float2 w = reinterpret_cast<const float2*>(window)[n];
+      const float re = (i0 >= fr.y && i0 < fr.z) ? __ldg(x + i0) * w.x : 0.f;
+      const float im = (i1 >= fr.y && i1 < fr.z) ? __ldg(x + i1) * w.y : 0.f;
+      buf0[n] = make_float2(re, im);
+    }
+    __syncthreads();
+    // 5 radix-4 Stockham passes, Ns = 1, 4, 16, 64, 256
+    float2* src = buf0;
+    float2* dst = buf1;
+#pragma unroll
+    for (int pass = 0; pass < 5; ++pass) {
+      const int Ns = 1 << (2 * pass);
+      const int j = tid;
+      const int k = j & (Ns - 1);
+      float2 v0 = src[j], v1 = src[j + 256], v2 = src[j + 512], v3 = src[j + 768];
+      if (pass > 0) {
+        const int e = k * (256 / Ns);  // exponent of exp(-2 pi i / 1024)
+        v1 = cmul(v1, s_tw[e]);
+        v2 = cmul(v2, s_tw[2 * e]);
+        v3 = cmul(v3, s_tw[3 * e]);
+      }
+      const float2 a = make_float2(v0.x + v2.x, v0.y + v2.y);
+      const float2 b = make_float2(v0.x - v2.x, v0.y - v2.y);
+      const float2 c = make_float2(v1.x + v3.x, v1.y + v3.y);
+      const float2 d = make_float2(v1.y - v3.y, v3.x - v1.x);  // -i * (v1 - v3)
+      const int o = ((j - k) << 2) + k;
+      dst[o] = make_float2(a.x + c.x, a.y + c.y);
+      dst[o + Ns] = make_float2(b.x + d.x, b.y + d.y);
+      dst[o + 2 * Ns] = make_float2(a.x - c.x, a.y - c.y);
+      dst[o + 3 * Ns] = make_float2(b.x - d.x, b.y - d.y);
+      __syncthreads();
+      float2* t = src; src = dst; dst = t;
+    }
+    // split post-pass: X[k] = E[k] + W_2048^k O[k], k in [0, 1024]
+    for (int k = tid; k < kBins; k += kFftThreads) {
+      const float2 zk = src[k & (kHalf - 1)];
+      const float2 zn = src[(kHalf - k) & (kHalf - 1)];
+      const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));  // (zk - conj zn) / (2i)
+      const float2 wo = cmul(__ldg(tw2 + k), o);
+      const float xr = e.x + wo.x, xi = e.y + wo.y;
+      s_pow[k] = xr * xr + xi * xi;
+    }
+    __syncthreads();
+    // sparse mel projection: warp per mel band (16 bands per warp), lanes stride the band's bins
+    float* out = logmel + (static_cast<size_t>(clip) * n_unique + u) * kMels;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int m = warp; m < kMels; m += kFftThreads / 32) {
+      const int2 rg = mel_rng[m];
+      const float* w = mel_w + mel_off[m];
+      float acc = 0.f;
+      for (int i = lane; i < rg.y; i += 32) acc = fmaf(__ldg(w + i), s_pow[rg.x + i], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) out[m] = 10.0f * log10f(fmaxf(acc, 1e-10f));
+    }
+  }
+}
+
+// One CTA per (shift, clip).  128 threads; thread j owns frames j, j+128, ...
+template <int NQ>
+__global__ void __launch_bounds__(128)
+mfcc_stats_kernel(const float* __restrict__ logmel, const int* __restrict__ map, int n_unique, int n_frames,
+                  int n_shifts, int n_mfcc, const float* __restrict__ dct_t, float* __restrict__ out_stats,
+                  float* __restrict__ out_mfcc) {
+  extern __shared__ float smem[];
+  float* s_dct = smem;                       // [128][NQ]
+  float* s_mfcc = smem + kMels * NQ;         // [F][NQ]
+  __shared__ float s_red[4];
+  const int tid = threadIdx.x;
+  const int k = blockIdx.x, clip = blockIdx.y;
+  const int* mp = map + static_cast<size_t>(k) * n_frames;
+  const float* lm = logmel + static_cast<size_t>(clip) * n_unique * kMels;
+
+  for (int i = tid; i < kMels * NQ; i += 128) s_dct[i] = dct_t[(i / NQ) * kMaxQ + (i % NQ)];
+  // global max over this shifted signal's [n_mels, n_frames] log-mel array (power_to_db top_db reference)
+  float mx = -INFINITY;
+  for (int i = tid; i < n_frames * (kMels / 4); i += 128) {
+    const int j = i / (kMels / 4), c = i % (kMels / 4);
+    const float4 v = reinterpret_cast<const float4*>(lm + static_cast<size_t>(mp[j]) * kMels)[c];
+    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  mx = warp_max(mx);
+  if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  const float floor_db = mx - 80.0f;
+
+  for (int j = tid; j < n_frames; j += 128) {
+    const float4* row = reinterpret_cast<const float4*>(lm + static_cast<size_t>(mp[j]) * kMels);
+    float acc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
+    for (int c = 0; c < kMels / 4; ++c) {
+      const float4 v4 = row[c];
+      const float v[4] = {fmaxf(v4.x, floor_db), fmaxf(v4.y, floor_db), fmaxf(v4.z, floor_db),
+                          fmaxf(v4.w, floor_db)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4* d = reinterpret_cast<const float4*>(s_dct + (c * 4 + e) * NQ);
+#pragma unroll
+        for (int q4 = 0; q4 < NQ / 4; ++q4) {
+          const float4 dd = d[q4];
+          acc[q4 * 4 + 0] = fmaf(dd.x, v[e], acc[q4 * 4 + 0]);
+          acc[q4 * 4 + 1] = fmaf(dd.y, v[e], acc[q4 * 4 + 1]);
+          acc[q4 * 4 + 2] = fmaf(dd.z, v[e], acc[q4 * 4 + 2]);
+          acc[q4 * 4 + 3] = fmaf(dd.w, v[e], acc[q4 * 4 + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) s_mfcc[j * NQ + q] = acc[q];
+  }
+  __syncthreads();
+  if (out_mfcc != nullptr) {
+    float* om = out_mfcc + (static_cast<size_t>(clip) * n_shifts + k) * n_frames * n_mfcc;
+    for (int i = tid; i < n_frames * n_mfcc; i += 128) om[i] = s_mfcc[(i / n_mfcc) * NQ + (i % n_mfcc)];
+  }
+  if (tid < n_mfcc) {
+    float s = 0.f;
+    for (int j = 0; j < n_frames; ++j) s += s_mfcc[j * NQ + tid];
+    const float mean = s / static_cast<float>(n_frames);
+    float ss = 0.f;
+    for (int j = 0; j < n_frames; ++j) {
+      const float d = s_mfcc[j * NQ + tid] - mean;
+      ss = fmaf(d, d, ss);
+    }
+    float* o = out_stats + (static_cast<size_t>(clip) * n_shifts + k) * 2 * n_mfcc;
+    o[tid] = mean;
+    o[n_mfcc + tid] = sqrtf(ss / static_cast<float>(n_frames - 1));  // unbiased; NaN when n_frames == 1 (as torch.std)
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host tables
+static double hz_to_mel(double f) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+  return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+  return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+template <class T>
+static int upload(T** dst, const std::vector<T>& v) {
+  AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), std::max<size_t>(v.size(), 1) * sizeof(T)));
+  if (!v.empty()) AVS_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return AVS_OK;
+}
+
+}  // namespace avs
+
+using namespace avs;
+
+extern "C" int avs_mfcc_plan_create(int n_samples, int sample_rate, int n_mfcc, const int32_t* shift_samples,
+                                    int n_shifts, avs_mfcc_plan** out) {
+  AVS_REQUIRE(out != nullptr && shift_samples != nullptr, "null argument");
+  AVS_REQUIRE(n_samples > 0 && sample_rate > 0 && n_shifts > 0, "empty problem");
+  AVS_REQUIRE(n_mfcc >= 1 && n_mfcc <= kMaxQ, "n_mfcc must be in [1, 40]");
+  avs_mfcc_plan* p = new avs_mfcc_plan();
+  p->n_samples = n_samples;
+  p->sr = sample_rate;
+  p->hop = std::max(1, sample_rate / 40);  // misalignment_detection_train.py:120
+  p->n_mfcc = n_mfcc;
+  p->n_shifts = n_shifts;
+  p->n_frames = 1 + n_samples / p->hop;  // center=True: 1 + (n + 2*(n_fft/2) - n_fft) / hop
+
+  // ---- unique frame table
+  std::map<std::tuple<int, int, int>, int> ids;
+  std::vector<std::tuple<int, int, int>> uniq;
+  std::vector<int> map(static_cast<size_t>(n_shifts) * p->n_frames);
+  for (int k = 0; k < n_shifts; ++k) {
+    const long long s = shift_samples[k];
+    // shift_audio (:100-114): y[n] = x[n - s] for n in [max(0,s), min(N, N+s)), zero elsewhere;
+    // |s| >= N -> all zeros.  Valid x range:
+    long long lo = std::max<long long>(0, -s), hi = std::min<long long>(n_samples, n_samples - s);
+    if (s >= n_samples || -s >= n_samples) lo = hi = 0;
+    for (int j = 0; j < p->n_frames; ++j) {
+      const long long start = static_cast<long long>(p->hop) * j - kHalf - s;  // in x coordinates
+      long long a = std::max(start, lo), b = std::min(start + kNfft, hi);
+      std::tuple<int, int, int> key;
+      if (a >= b) key = std::make_tuple(0, 0, 0);  // all-zero frame
+      else key = std::make_tuple(static_cast<int>(start), static_cast<int>(a), static_cast<int>(b));
+      auto it = ids.find(key);
+      if (it == ids.end()) {
+        it = ids.emplace(key, static_cast<int>(uniq.size())).first;
+        uniq.push_back(key);
+      }
+      map[static_cast<size_t>(k) * p->n_frames + j] = it->second;
+    }
+  }
+  // sort unique frames by start so neighbouring CTAs touch neighbouring audio
+  std::vector<int> order(uniq.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return uniq[a] < uniq[b]; });
+  std::vector<int> rank(uniq.size());
+  std::vector<int4> frames(uniq.size());
+  for (size_t r = 0; r < order.size(); ++r) {
+    rank[order[r]] = static_cast<int>(r);
+    frames[r] = make_int4(std::get<0>(uniq[order[r]]), std::get<1>(uniq[order[r]]), std::get<2>(uniq[order[r]]), 0);
+  }
+  for (auto& m : map) m = rank[m];
+  p->n_unique = static_cast<int>(uniq.size());
+
+  // ---- constant tables (computed in double, stored in float)
+  const double kPi = 3.14159265358979323846;
+  std::vector<float> window(kNfft);
+  for (int n = 0; n < kNfft; ++n) window[n] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * kPi * n / kNfft));
+  std::vector<float2> tw(kHalf), tw2(kBins);
+  for (int e = 0; e < kHalf; ++e)
+    tw[e] = make_float2(static_cast<float>(std::cos(2.0 * kPi * e / kHalf)), static_cast<float>(-std::sin(2.0 * kPi * e / kHalf)));
+  for (int k = 0; k < kBins; ++k)
+    tw2[k] = make_float2(static_cast<float>(std::cos(2.0 * kPi * k / kNfft)), static_cast<float>(-std::sin(2.0 * kPi * k / kNfft)));
+  // librosa.filters.mel(sr, n_fft=2048, n_mels=128, fmin=0, fmax=sr/2, htk=False, norm='slaney')
+  std::vector<double> mel_f(kMels + 2);
+  const double mmin = hz_to_mel(0.0), mmax = hz_to_mel(sample_rate / 2.0);
+  for (int i = 0; i < kMels + 2; ++i) mel_f[i] = mel_to_hz(mmin + (mmax - mmin) * i / (kMels + 1));
+  std::vector<int2> rng(kMels);
+  std::vector<int> off(kMels);
+  std::vector<float> mw;
+  for (int m = 0; m < kMels; ++m) {
+    const double enorm = 2.0 / (mel_f[m + 2] - mel_f[m]);
+    int first = -1, last = -2;
+    std::vector<float> row(kBins);
+    for (int k = 0; k < kBins; ++k) {
+      const double f = static_cast<double>(k) * sample_rate / kNfft;
+      const double lower = (f - mel_f[m]) / (mel_f[m + 1] - mel_f[m]);
+      const double upper = (mel_f[m + 2] - f) / (mel_f[m + 2] - mel_f[m + 1]);
+      const float w32 = static_cast<float>(std::max(0.0, std::min(lower, upper)));
+      row[k] = static_cast<float>(static_cast<double>(w32) * enorm);
+      if (row[k] != 0.f) {
+        if (first < 0) first = k;
+        last = k;
+      }
+    }
+    if (first < 0) first = 0, last = -1;
+    rng[m] = make_int2(first, last - first + 1);
+    off[m] = static_cast<int>(mw.size());
+    for (int k = first; k <= last; ++k) mw.push_back(row[k]);
+  }
+  std::vector<float> dct(static_cast<size_t>(kMels) * kMaxQ, 0.f);
+  for (int q = 0; q < n_mfcc; ++q)
+    for (int m = 0; m < kMels; ++m) {
+      double v = std::cos(kPi * q * (2 * m + 1) / (2.0 * kMels)) * std::sqrt(2.0 / kMels);
+      if (q == 0) v *= std::sqrt(0.5);
+      dct[static_cast<size_t>(m) * kMaxQ + q] = static_cast<float>(v);
+    }
+  int rc;
+  if ((rc = upload(&p->d_frames, frames)) || (rc = upload(&p->d_map, map)) || (rc = upload(&p->d_window, window)) ||
+      (rc = upload(&p->d_tw, tw)) || (rc = upload(&p->d_tw2, tw2)) || (rc = upload(&p->d_mel_rng, rng)) ||
+      (rc = upload(&p->d_mel_off, off)) || (rc = upload(&p->d_mel_w, mw)) || (rc = upload(&p->d_dct, dct))) {
+    avs_mfcc_plan_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return AVS_OK;
+}
+
+extern "C" void avs_mfcc_plan_destroy(avs_mfcc_plan* p) {
+  if (!p) return;
+  cudaFree(p->d_frames); cudaFree(p->d_map); cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_tw2);
+  cudaFree(p->d_mel_rng); cudaFree(p->d_mel_off); cudaFree(p->d_mel_w); cudaFree(p->d_dct);
+  delete p;
+}
+extern "C" int avs_mfcc_plan_unique_frames(const avs_mfcc_plan* p) { return p ? p->n_unique : AVS_EINVAL; }
+extern "C" int avs_mfcc_plan_frames(const avs_mfcc_plan* p) { return p ? p->n_frames : AVS_EINVAL; }
+extern "C" size_t avs_mfcc_workspace_bytes(const avs_mfcc_plan* p, int n_clips) {
+  if (!p || n_clips <= 0) return 0;
+  return align_up(static_cast<size_t>(n_clips) * p->n_unique * kMels * sizeof(float), 256);
+}
+
+extern "C" int avs_mfcc_sweep_debug(const avs_mfcc_plan* p, const float* audio, int n_clips, float* out_stats,
+                                    float* out_mfcc, void* workspace, size_t workspace_bytes, void* stream) {
+  AVS_REQUIRE(p && audio && out_stats && workspace, "null argument");
+  if (n_clips <= 0) return AVS_OK;
+  if (workspace_bytes < avs_mfcc_workspace_bytes(p, n_clips)) {
+    set_error("mfcc workspace too small: %zu < %zu", workspace_bytes, avs_mfcc_workspace_bytes(p, n_clips));
+    return AVS_EWORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* logmel = static_cast<float*>(workspace);
+  for (int c0 = 0; c0 < n_clips; c0 += 32768) {  // gridDim.y limit
+    const int nc = std::min(32768, n_clips - c0);
+    dim3 g1(cdiv(p->n_unique, kFramesPerCta), nc);
+    mfcc_logmel_kernel<<<g1, kFftThreads, 0, st>>>(audio + static_cast<size_t>(c0) * p->n_samples, p->n_samples,
+                                                   p->d_frames, p->n_unique, p->d_window, p->d_tw, p->d_tw2,
+                                                   p->d_mel_rng, p->d_mel_off, p->d_mel_w,
+                                                   logmel + static_cast<size_t>(c0) * p->n_unique * kMels);
+    AVS_LAUNCHED();
+    dim3 g2(p->n_shifts, nc);
+    float* os = out_stats + static_cast<size_t>(c0) * p->n_shifts * 2 * p->n_mfcc;
+    float* om = out_mfcc ? out_mfcc + static_cast<size_t>(c0) * p->n_shifts * p->n_frames * p->n_mfcc : nullptr;
+    const float* lm = logmel + static_cast<size_t>(c0) * p->n_unique * kMels;
+    if (p->n_mfcc <= 20) {
+      const size_t sm = (static_cast<size_t>(kMels) * 20 + static_cast<size_t>(p->n_frames) * 20) * sizeof(float);
+      AVS_CUDA(cudaFuncSetAttribute(mfcc_stats_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)));
+      mfcc_stats_kernel<20><<<g2, 128, sm, st>>>(lm, p->d_map, p->n_unique, p->n_frames, p->n_shifts, p->n_mfcc,
+                                                 p->d_dct, os, om);
+    } else {
+      const size_t sm = (static_cast<size_t>(kMels) * kMaxQ + static_cast<size_t>(p->n_frames) * kMaxQ) * sizeof(float);
+      AVS_CUDA(cudaFuncSetAttribute(mfcc_stats_kernel<kMaxQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)));
+      mfcc_stats_kernel<kMaxQ><<<g2, 128, sm, st>>>(lm, p->d_map, p->n_unique, p->n_frames, p->n_shifts, p->n_mfcc,
+                                                    p->d_dct, os, om);
+    }
+    AVS_LAUNCHED();
+  }
+  return AVS_OK;
+}
+
+extern "C" int avs_mfcc_stats_sweep(const avs_mfcc_plan* p, const float* audio, int n_clips, float* out_stats,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  return avs_mfcc_sweep_debug(p, audio, n_clips, out_stats, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" __attribute__((visibility("hidden"))) int avs_mfcc_plan_nshifts_internal(const avs_mfcc_plan* p, int* K, int* n_mfcc, int* n_samples) {
+  *K = p->n_shifts;
+  *n_mfcc = p->n_mfcc;
+  *n_samples = p->n_samples;
+  return AVS_OK;
+}

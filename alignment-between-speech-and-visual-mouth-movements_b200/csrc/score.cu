@@ -1,0 +1,145 @@
+// K4 — shift-sweep detector score, and K5 — greedy CTC decode.
+//
+// K4 replaces sigmoid(MisalignmentDetector(cat[vstats, astats_k])) for all shifts k of a clip
+// (misalignment_detection_train.py:207,243-250,267).  13 824 of the 13 864 input features do not
+// depend on the shift, so  W1 . cat[v, a_k] = W1[:, :Dv] . v  +  W1[:, Dv:] . a_k :
+//   (1) hv[B, H] = vstats . W1v^T + b1          one fp32 GEMM per batch (sgemm_nt)
+//   (2) per clip: for each shift  score = sigmoid(w2 . relu(hv + W1a . a_k) + b2), then arg-max.
+#include "common.cuh"
+#include "sgemm.cuh"
+
+namespace avs {
+
+// One CTA (128 threads) per clip.  W1a ([H, Da] slice of W1, row stride ldw) is re-read from L2 by
+// every CTA (H*Da*4 = 80 KB); vstats never enter this kernel.
+__global__ void __launch_bounds__(128)
+sweep_score_kernel(const float* __restrict__ hv, const float* __restrict__ astats, int n_shifts, int a_dim,
+                   const float* __restrict__ w1a, int ldw, const float* __restrict__ w2,
+                   const float* __restrict__ b2, int hidden, float* __restrict__ out_scores,
+                   int32_t* __restrict__ out_best) {
+  extern __shared__ float sm[];
+  float* s_a = sm;                         // [K][Da]
+  float* s_sc = sm + n_shifts * a_dim;     // [K]
+  __shared__ float s_part[4];
+  const int clip = blockIdx.x, tid = threadIdx.x;
+  const float* a = astats + static_cast<size_t>(clip) * n_shifts * a_dim;
+  for (int i = tid; i < n_shifts * a_dim; i += 128) s_a[i] = a[i];
+  __syncthreads();
+  for (int k = 0; k < n_shifts; ++k) {
+    float part = 0.f;
+    for (int h = tid; h < hidden; h += 128) {
+      float acc = hv[static_cast<size_t>(clip) * hidden + h];
+      const float* w = w1a + static_cast<size_t>(h) * ldw;
+      for (int i = 0; i < a_dim; ++i) acc = fmaf(__ldg(w + i), s_a[k * a_dim + i], acc);
+      part = fmaf(fmaxf(acc, 0.f), __ldg(w2 + h), part);
+    }
+    part = warp_sum(part);
+    if ((tid & 31) == 0) s_part[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+      const float logit = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]) + b2[0];
+      const float sc = 1.0f / (1.0f + expf(-logit));
+      s_sc[k] = sc;
+      out_scores[static_cast<size_t>(clip) * n_shifts + k] = sc;
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && out_best != nullptr) {
+    int best = 0;
+    float bv = s_sc[0];
+    for (int k = 1; k < n_shifts; ++k)
+      if (s_sc[k] > bv || (isnan(s_sc[k]) && !isnan(bv))) bv = s_sc[k], best = k;  // first maximum (np.argmax)
+    out_best[clip] = best;
+  }
+}
+
+// K5: one CTA per clip; thread t takes the arg-max of step t (first index on ties, NaN wins like
+// torch.max), then the collapse (utils.py:24-30) is a flag + block-wide exclusive scan.
+__global__ void __launch_bounds__(128)
+ctc_greedy_kernel(const float* __restrict__ logp, int n_steps, int vocab, int blank, int32_t* __restrict__ out_ids,
+                  int32_t* __restrict__ out_len) {
+  extern __shared__ int s_arg[];           // [n_steps + 1], s_arg[0] = blank (prev of step 0)
+  __shared__ int s_warp[4];
+  __shared__ int s_base;
+  const int clip = blockIdx.x, tid = threadIdx.x;
+  const float* lp = logp + static_cast<size_t>(clip) * n_steps * vocab;
+  if (tid == 0) s_arg[0] = blank, s_base = 0;
+  for (int t = tid; t < n_steps; t += 128) {
+    const float* row = lp + static_cast<size_t>(t) * vocab;
+    float bv = row[0];
+    int bi = 0;
+    for (int v = 1; v < vocab; ++v) {
+      const float x = row[v];
+      if (x > bv || (isnan(x) && !isnan(bv))) bv = x, bi = v;
+    }
+    s_arg[t + 1] = bi;
+  }
+  __syncthreads();
+  int32_t* ids = out_ids + static_cast<size_t>(clip) * n_steps;
+  for (int t0 = 0; t0 < n_steps; t0 += 128) {
+    const int t = t0 + tid;
+    int c = -1, keep = 0;
+    if (t < n_steps) {
+      c = s_arg[t + 1];
+      keep = (c != s_arg[t] && c != blank) ? 1 : 0;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    off += __popc(bal & ((1u << lane) - 1u));
+    if (keep) ids[off] = c;
+    __syncthreads();
+    if (tid == 0) s_base += s_warp[0] + s_warp[1] + s_warp[2] + s_warp[3];
+    __syncthreads();
+  }
+  const int len = s_base;
+  for (int t = len + tid; t < n_steps; t += 128) ids[t] = -1;
+  if (tid == 0) out_len[clip] = len;
+}
+
+}  // namespace avs
+
+using namespace avs;
+
+extern "C" size_t avs_sweep_score_workspace_bytes(int n_clips, int hidden) {
+  if (n_clips <= 0 || hidden <= 0) return 0;
+  return align_up(static_cast<size_t>(n_clips) * hidden * sizeof(float), 256);
+}
+
+extern "C" int avs_sweep_score(const float* vstats, const float* astats, int n_clips, int n_shifts, int v_dim,
+                               int a_dim, const float* w1, const float* b1, const float* w2, const float* b2,
+                               int hidden, float* out_scores, int32_t* out_best, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  AVS_REQUIRE(vstats && astats && w1 && b1 && w2 && b2 && out_scores && workspace, "null argument");
+  AVS_REQUIRE(n_shifts > 0 && v_dim > 0 && a_dim > 0 && hidden > 0, "bad shape");
+  if (n_clips <= 0) return AVS_OK;
+  if (workspace_bytes < avs_sweep_score_workspace_bytes(n_clips, hidden)) {
+    set_error("sweep_score workspace too small");
+    return AVS_EWORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* hv = static_cast<float*>(workspace);
+  const int ld = v_dim + a_dim;
+  int rc = sgemm_nt(vstats, v_dim, w1, ld, b1, hv, hidden, n_clips, hidden, v_dim, st);
+  if (rc) return rc;
+  const size_t sm = (static_cast<size_t>(n_shifts) * a_dim + n_shifts) * sizeof(float);
+  AVS_REQUIRE(sm <= 48 * 1024, "n_shifts * a_dim too large for the score kernel");
+  sweep_score_kernel<<<n_clips, 128, sm, st>>>(hv, astats, n_shifts, a_dim, w1 + v_dim, ld, w2, b2, hidden,
+                                               out_scores, out_best);
+  AVS_LAUNCHED();
+  return AVS_OK;
+}
+
+extern "C" int avs_ctc_greedy(const float* logp, int n_clips, int n_steps, int vocab, int blank, int32_t* out_ids,
+                              int32_t* out_len, void* stream) {
+  AVS_REQUIRE(logp && out_ids && out_len, "null argument");
+  AVS_REQUIRE(n_steps > 0 && vocab > 0 && n_steps <= 8192, "bad shape");
+  if (n_clips <= 0) return AVS_OK;
+  ctc_greedy_kernel<<<n_clips, 128, (n_steps + 1) * sizeof(int), static_cast<cudaStream_t>(stream)>>>(
+      logp, n_steps, vocab, blank, out_ids, out_len);
+  AVS_LAUNCHED();
+  return AVS_OK;
+}

@@ -1,0 +1,78 @@
+#include "sgemm.cuh"
+namespace avs {
+
+constexpr int BM = 128, BN = 128, BK = 8;
+
+__global__ void __launch_bounds__(256)
+sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N, int K) {
+  __shared__ float As[2][BK][BM + 4];
+  __shared__ float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int lr = tid >> 1, lk = (tid & 1) * 4;  // each thread stages one float4 of A and one of B per k-tile
+  const int tx = tid & 15, ty = tid >> 4;       // 16 x 16 threads, 8 x 8 outputs each (strided by 16)
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const bool a_ok = (m0 + lr) < M, b_ok = (n0 + lr) < N;
+  const float* ap = A + static_cast<size_t>(m0 + lr) * lda + lk;
+  const float* bp = B + static_cast<size_t>(n0 + lr) * ldb + lk;
+  float4 ra = a_ok ? *reinterpret_cast<const float4*>(ap) : make_float4(0, 0, 0, 0);
+  float4 rb = b_ok ? *reinterpret_cast<const float4*>(bp) : make_float4(0, 0, 0, 0);
+  const int nk = K / BK;  // K % 8 == 0 is enforced by the host wrapper via padding check
+  int buf = 0;
+  As[0][lk + 0][lr] = ra.x; As[0][lk + 1][lr] = ra.y; As[0][lk + 2][lr] = ra.z; As[0][lk + 3][lr] = ra.w;
+  Bs[0][lk + 0][lr] = rb.x; Bs[0][lk + 1][lr] = rb.y; Bs[0][lk + 2][lr] = rb.z; Bs[0][lk + 3][lr] = rb.w;
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    if (kt + 1 < nk) {
+      ra = a_ok ? *reinterpret_cast<const float4*>(ap + (kt + 1) * BK) : make_float4(0, 0, 0, 0);
+      rb = b_ok ? *reinterpret_cast<const float4*>(bp + (kt + 1) * BK) : make_float4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = As[buf][k][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = Bs[buf][k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      const int nb = buf ^ 1;
+      As[nb][lk + 0][lr] = ra.x; As[nb][lk + 1][lr] = ra.y; As[nb][lk + 2][lr] = ra.z; As[nb][lk + 3][lr] = ra.w;
+      Bs[nb][lk + 0][lr] = rb.x; Bs[nb][lk + 1][lr] = rb.y; Bs[nb][lk + 2][lr] = rb.z; Bs[nb][lk + 3][lr] = rb.w;
+      __syncthreads();
+      buf = nb;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty + 16 * i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n < N) C[static_cast<size_t>(m) * ldc + n] = acc[i][j] + (bias ? bias[n] : 0.f);
+    }
+  }
+}
+
+int sgemm_nt(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N,
+             int K, cudaStream_t st) {
+  AVS_REQUIRE(K % BK == 0 && lda % 4 == 0 && ldb % 4 == 0, "sgemm_nt needs K % 8 == 0 and 16-byte aligned rows");
+  if (M <= 0 || N <= 0) return AVS_OK;
+  dim3 grid(cdiv(N, BN), cdiv(M, BM));
+  sgemm_nt_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+  AVS_LAUNCHED();
+  return AVS_OK;
+}
+
+}  // namespace avs

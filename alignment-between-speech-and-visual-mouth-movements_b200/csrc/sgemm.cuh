@@ -1,0 +1,10 @@
+// fp32 CUDA-core GEMM used where fp32-exact accumulation matters more than tensor throughput
+// (detector hidden layer, GRU projections in AVS_PREC_FP32):  C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]).
+#pragma once
+#include "common.cuh"
+namespace avs {
+// A row-major with leading dimension lda, B row-major [N, K] with ldb (torch Linear weight), C with ldc.
+// Requires K % 4 == 0, lda % 4 == 0, ldb % 4 == 0 and 16-byte aligned A / B.
+int sgemm_nt(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N,
+             int K, cudaStream_t st);
+}  // namespace avs

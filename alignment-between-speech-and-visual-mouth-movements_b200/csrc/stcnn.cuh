@@ -1,0 +1,65 @@
+// internal interfaces of the STCNN implementation (conv_ffma.cu, conv_umma.cu, stcnn.cu)
+#pragma once
+#include "common.cuh"
+
+namespace avs {
+
+// fp32 CUDA-core layer: in NCDHW f32, w OIDHW f32, out addressed as b*o_sb + c*o_sc + t*o_st + ho*Wo + wo
+int conv_pool_ffma(const float* in, const float* w, const float* bias, float* out, int B, int Cin, int Cout, int T,
+                   int H, int W, int KH, int KW, long long o_sb, long long o_sc, long long o_st, cudaStream_t st);
+int vstats(const float* emb, float* out, int B, int F, cudaStream_t st);
+
+// ---- tcgen05 path ------------------------------------------------------------------------------
+// Geometry of one layer in the "parity-plane" activation layout.
+struct LayerGeom {
+  int Cin, Cout, H, W, KH, KW;    // conv input dims / kernel (KD = 3)
+  int ph, pw;                     // spatial padding = KH/2, KW/2
+  int Ho, Wo;                     // pooled output dims (floor)
+  int Wt;                         // row pitch in positions = W + pw (even)
+  int Hh;                         // rows per parity array
+  int n_q;                        // output positions per plane in pooled-row space = Ho * Wt
+  int n_tiles;                    // ceil(n_q / 128)
+  int PP;                         // positions per (plane, chunk, parity) array in HBM
+  int n_chunks;                   // 16-byte chunk arrays per (plane, parity): Cin/8 (conv1: 1), x2 when split
+};
+
+struct KStep {                    // one tcgen05.mma (K = 16) of the per-output-step schedule
+  uint32_t a_off[2];              // byte offset of the A tile inside a plane slot, for acc 0 (even rows) / 1 (odd rows)
+  uint32_t lbo;                   // byte stride between the two 8-wide K halves of A
+  uint32_t b_off;                 // byte offset of the B tile inside its weight stage
+  int32_t kd;                     // which of the 3 time planes A comes from
+};
+
+struct UmmaLayer {                // device-resident, built once by stcnn_create
+  LayerGeom g;
+  int split;                      // 1: hi/lo bf16 split (BF16X3)
+  int NT;                         // M tiles (of 128 positions) per work item
+  int NBUF;                       // TMEM accumulator buffers (1 or 2)
+  int ring;                       // plane slots in shared memory
+  int wstages;                    // weight stages in shared memory
+  int n_ksteps, ksteps_per_stage, stage_bytes, n_stages;
+  int plane_slot_bytes;           // bytes of one plane slot in shared memory
+  int region_pos;                 // positions loaded per (chunk, parity) for a full NT-tile item
+  int acc_stride;                 // TMEM columns between accumulators
+  KStep* d_ksteps = nullptr;
+  __nv_bfloat16* d_w = nullptr;   // packed B tiles, n_stages * stage_bytes
+  float* d_bias = nullptr;
+  size_t smem_bytes;
+};
+
+struct EpiOut {                   // where the fused bias+ReLU+pool epilogue writes
+  int mode;                       // 0: next layer's parity-plane bf16 layout, 1: emb f32 [B, T, C*Ho*Wo]
+  __nv_bfloat16* act;             // mode 0
+  int n_chunks_next, PP_next, Wt_next, ph_next, pw_next, split_next;
+  float* emb;                     // mode 1
+};
+
+void geom_finalize(LayerGeom& g, int split);  // fills the derived fields from Cin, Cout, H, W, KH, KW
+int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w_host, const float* b_host);
+void umma_layer_free(UmmaLayer* L);
+size_t umma_act_bytes(const LayerGeom& g, int split, int B);   // bytes of the input activation buffer of a layer
+int umma_pack_frames(const float* frames, __nv_bfloat16* act, const LayerGeom& g1, int split, int B, cudaStream_t st);
+int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const EpiOut& eo, int B, int n_sms, cudaStream_t st);
+int umma_unpack_act(const __nv_bfloat16* act, float* out_ncdhw, const LayerGeom& g_next, int split, int C, int B, cudaStream_t st);
+
+}  // namespace avs

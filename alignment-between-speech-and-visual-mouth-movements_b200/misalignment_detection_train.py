@@ -1,0 +1,340 @@
+"""Drop-in for the feature pipeline + detector of ``misalignment_detection_train.py`` (reference
+lines 79-250, 299-318) and the batched +-S sync sweep built from it.
+
+Kept names / signatures: ``DetectorConfig``, ``shift_audio``, ``compute_audio_stats``,
+``extract_visual_embeddings``, ``FeatureExtractor`` (``build_feature``), ``MisalignmentDetector``,
+``load_lipnet``, ``save_detector``, ``load_detector``.  New batched entry points: ``SyncSweeper`` /
+``sync_sweep`` (all clips x all shifts in three kernels).
+All arithmetic runs in libavsync_b200 (K1, K2, K4); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _native as N
+from .model import LipNet
+
+
+@dataclass
+class DetectorConfig:                      # reference :79-88
+    img_width: int = 100
+    img_height: int = 50
+    max_video_length: int = 75
+    sample_rate: int = 16000
+    n_mfcc: int = 20
+    max_shift_frames: int = 10
+    num_negative_samples: int = 1
+    default_fps: float = 25.0
+
+
+def shift_samples(shift_frames: int, fps: float, sample_rate: int) -> int:
+    """Signed integer sample delay the reference applies for ``shift_frames`` (:101-105)."""
+    if shift_frames == 0:
+        return 0
+    return int(shift_frames / max(fps, 1e-5) * sample_rate)
+
+
+def shift_audio(audio: np.ndarray, shift_frames: int, fps: float, sample_rate: int) -> np.ndarray:
+    """Host-side index arithmetic of the reference (:100-114): integer delay with zero fill.
+    The sweep never materialises shifted copies (the delay is folded into the K1 frame plan);
+    this function exists for callers that want the shifted signal itself."""
+    s = shift_samples(shift_frames, fps, sample_rate)
+    if s == 0:
+        return audio.copy()
+    out = np.zeros_like(audio)
+    n = len(audio)
+    if 0 < s < n:
+        out[s:] = audio[:n - s]
+    elif -n < s < 0:
+        out[:n + s] = audio[-s:]
+    return out
+
+
+# ---------------------------------------------------------------------------------- K1
+class _MfccPlan:
+    def __init__(self, n_samples: int, sample_rate: int, n_mfcc: int, shifts: Sequence[int]):
+        arr = (ctypes.c_int32 * len(shifts))(*[int(s) for s in shifts])
+        h = N.c_void_p()
+        N.check(N.lib().avs_mfcc_plan_create(int(n_samples), int(sample_rate), int(n_mfcc), arr, len(shifts),
+                                             ctypes.byref(h)), "mfcc_plan_create")
+        self.handle = N.Handle(h, N.lib().avs_mfcc_plan_destroy)
+        self.n_shifts = len(shifts)
+        self.n_mfcc = n_mfcc
+        self.n_samples = n_samples
+        self.n_frames = N.lib().avs_mfcc_plan_frames(h)
+        self.n_unique = N.lib().avs_mfcc_plan_unique_frames(h)
+
+
+_plan_cache: Dict[tuple, _MfccPlan] = {}
+
+
+def mfcc_plan(n_samples: int, sample_rate: int, n_mfcc: int, shifts: Sequence[int]) -> _MfccPlan:
+    N.device_check()
+    key = (torch.cuda.current_device(), n_samples, sample_rate, n_mfcc, tuple(int(s) for s in shifts))
+    p = _plan_cache.get(key)
+    if p is None:
+        if len(_plan_cache) > 64:
+            _plan_cache.clear()
+        p = _plan_cache[key] = _MfccPlan(n_samples, sample_rate, n_mfcc, shifts)
+    return p
+
+
+def audio_stats_sweep(audio: torch.Tensor, shifts_samples: Sequence[int], sample_rate: int = 16000,
+                      n_mfcc: int = 20, return_mfcc: bool = False):
+    """K1: audio [B, n] CUDA f32 -> stats [B, K, 2*n_mfcc] for every integer sample delay in
+    ``shifts_samples`` (== compute_audio_stats(shift_audio(.)) per (clip, shift), :100-127)."""
+    N.require_cuda(audio, "audio")
+    audio = N.f32c(audio)
+    B, n = audio.shape
+    plan = mfcc_plan(n, sample_rate, n_mfcc, shifts_samples)
+    L = N.lib()
+    out = torch.empty((B, plan.n_shifts, 2 * n_mfcc), dtype=torch.float32, device=audio.device)
+    ws = N.workspace(L.avs_mfcc_workspace_bytes(plan.handle.h, B), audio.device)
+    if return_mfcc:
+        m = torch.empty((B, plan.n_shifts, plan.n_frames, n_mfcc), dtype=torch.float32, device=audio.device)
+        N.check(L.avs_mfcc_sweep_debug(plan.handle.h, N.ptr(audio), B, N.ptr(out), N.ptr(m), N.ptr(ws), ws.numel(),
+                                       N.stream_ptr()), "mfcc_sweep_debug")
+        return out, m
+    N.check(L.avs_mfcc_stats_sweep(plan.handle.h, N.ptr(audio), B, N.ptr(out), N.ptr(ws), ws.numel(),
+                                   N.stream_ptr()), "mfcc_stats_sweep")
+    return out
+
+
+def compute_audio_stats(audio: np.ndarray, sample_rate: int, n_mfcc: int) -> torch.Tensor:
+    """Reference contract (:117-127): 1-D float audio -> CPU tensor [2*n_mfcc] = cat(mean, std)
+    of ``librosa.feature.mfcc(y, sr, n_mfcc, hop_length=sr//40)`` over frames."""
+    audio = np.asarray(audio)
+    if audio.size == 0:
+        return torch.zeros(n_mfcc * 2, dtype=torch.float32)
+    N.device_check()
+    a = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32)).cuda().unsqueeze(0)
+    return audio_stats_sweep(a, [0], sample_rate, n_mfcc)[0, 0].cpu()
+
+
+# ---------------------------------------------------------------------------------- K2
+def extract_visual_embeddings(lipnet: LipNet, frames: torch.Tensor) -> torch.Tensor:
+    """Reference contract (:130-144): frames [B,1,75,50,100] -> [B,75,6912] on ``frames.device``."""
+    with torch.no_grad():
+        return lipnet.stcnn(frames)
+
+
+def visual_stats(lipnet: LipNet, frames: torch.Tensor) -> torch.Tensor:
+    """[B,1,75,50,100] -> [B,13824] = cat(emb.mean(t), emb.std(t)) per clip (:165), on device."""
+    with torch.no_grad():
+        return lipnet.stcnn(frames, want_vstats=True)[1]
+
+
+# ---------------------------------------------------------------------------------- detector
+class MisalignmentDetector(nn.Module):
+    """Reference :237-250; stays a trainable torch module (config 5 trains it with autograd).
+    Inference over a shift sweep goes through ``SyncSweeper`` / K4 instead of this forward."""
+
+    def __init__(self, input_dim: int, hidden_dim: int = 256, dropout: float = 0.3):
+        super().__init__()
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim
+        self.classifier = nn.Sequential(
+            nn.Linear(input_dim, hidden_dim), nn.ReLU(), nn.Dropout(dropout), nn.Linear(hidden_dim, 1))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.classifier(x).squeeze(-1)
+
+
+def sweep_score(vstats: torch.Tensor, astats: torch.Tensor, detector: MisalignmentDetector):
+    """K4: vstats [B,Dv], astats [B,K,Da] -> (scores [B,K] = sigmoid(detector(cat[v, a_k])), best [B])."""
+    N.require_cuda(vstats, "vstats")
+    N.require_cuda(astats, "astats")
+    vstats, astats = N.f32c(vstats), N.f32c(astats)
+    B, K, Da = astats.shape
+    Dv = vstats.shape[1]
+    lin1, lin2 = detector.classifier[0], detector.classifier[3]
+    if lin1.in_features != Dv + Da:
+        raise RuntimeError(f"detector expects {lin1.in_features} features, got {Dv}+{Da}")
+    w1, b1, w2, b2 = (N.f32c(t) for t in (lin1.weight, lin1.bias, lin2.weight, lin2.bias))
+    for t in (w1, b1, w2, b2):
+        N.require_cuda(t, "detector parameters")
+    H = lin1.out_features
+    L = N.lib()
+    scores = torch.empty((B, K), dtype=torch.float32, device=vstats.device)
+    best = torch.empty((B,), dtype=torch.int32, device=vstats.device)
+    ws = N.workspace(L.avs_sweep_score_workspace_bytes(B, H), vstats.device)
+    if B:
+        N.check(L.avs_sweep_score(N.ptr(vstats), N.ptr(astats), B, K, Dv, Da, N.ptr(w1), N.ptr(b1), N.ptr(w2),
+                                  N.ptr(b2), H, N.ptr(scores), N.ptr(best), N.ptr(ws), ws.numel(), N.stream_ptr()),
+                "sweep_score")
+    return scores, best
+
+
+class SyncSweeper:
+    """All clips x all shifts of the +-``max_shift_frames`` sweep in one pipeline (K2 | K1 -> K4).
+
+    ``run(frames, audio)`` takes device tensors; ``run_host(frames, audio)`` takes host arrays and
+    pipelines the H2D/D2H copies against compute chunk by chunk.  Both return
+    ``(scores [B, 2S+1], best_shift_frames [B])`` where ``best_shift_frames = argmax_k - S``.
+    """
+
+    def __init__(self, lipnet: LipNet, detector: MisalignmentDetector, max_shift_frames: int,
+                 n_samples: int = 48000, fps: float = 25.0, sample_rate: int = 16000, n_mfcc: int = 20,
+                 chunk_clips: int = 64):
+        N.device_check()
+        self.S = int(max_shift_frames)
+        self.shift_frames = list(range(-self.S, self.S + 1))
+        self.shifts = [shift_samples(k, fps, sample_rate) for k in self.shift_frames]
+        self.n_samples, self.n_mfcc = n_samples, n_mfcc
+        self.lipnet, self.detector = lipnet, detector
+        self.plan = mfcc_plan(n_samples, sample_rate, n_mfcc, self.shifts)
+        self.net = lipnet._stcnn()
+        lin1, lin2 = detector.classifier[0], detector.classifier[3]
+        self._w = [N.f32c(t) for t in (lin1.weight, lin1.bias, lin2.weight, lin2.bias)]
+        for t in self._w:
+            N.require_cuda(t, "detector parameters")
+        if lin1.in_features != 2 * lipnet.conv_output_dim + 2 * n_mfcc:
+            raise RuntimeError("detector input_dim does not match 2*conv_output_dim + 2*n_mfcc")
+        h = N.c_void_p()
+        N.check(N.lib().avs_sweep_create(self.net.h, self.plan.handle.h, *[N.ptr(t) for t in self._w],
+                                         lin1.out_features, int(chunk_clips), ctypes.byref(h)), "sweep_create")
+        self.handle = N.Handle(h, N.lib().avs_sweep_destroy)
+        self.chunk_clips = int(chunk_clips)
+        self.K = len(self.shifts)
+
+    def run(self, frames: torch.Tensor, audio: torch.Tensor):
+        N.require_cuda(frames, "frames")
+        N.require_cuda(audio, "audio")
+        frames = self.lipnet._check_frames(frames)
+        audio = N.f32c(audio)
+        B = frames.shape[0]
+        if audio.shape != (B, self.n_samples):
+            raise RuntimeError(f"audio must be [{B}, {self.n_samples}], got {tuple(audio.shape)}")
+        scores = torch.empty((B, self.K), dtype=torch.float32, device=frames.device)
+        best = torch.empty((B,), dtype=torch.int32, device=frames.device)
+        N.check(N.lib().avs_sweep_run(self.handle.h, N.ptr(frames), N.ptr(audio), B, N.ptr(scores), N.ptr(best),
+                                      N.stream_ptr()), "sweep_run")
+        return scores, best - self.S
+
+    def run_host(self, frames: np.ndarray, audio: np.ndarray):
+        frames = np.ascontiguousarray(frames, dtype=np.float32)
+        audio = np.ascontiguousarray(audio, dtype=np.float32)
+        B = frames.shape[0]
+        if frames.shape[1:] != (1, 75, 50, 100) or audio.shape != (B, self.n_samples):
+            raise RuntimeError("frames must be [B,1,75,50,100] and audio [B, n_samples]")
+        scores = np.empty((B, self.K), dtype=np.float32)
+        best = np.empty((B,), dtype=np.int32)
+        N.check(N.lib().avs_sweep_run_host(self.handle.h, frames.ctypes.data_as(N.c_void_p),
+                                           audio.ctypes.data_as(N.c_void_p), B,
+                                           scores.ctypes.data_as(N.c_void_p), best.ctypes.data_as(N.c_void_p)),
+                "sweep_run_host")
+        return scores, best - self.S
+
+
+def sync_sweep(lipnet: LipNet, detector: MisalignmentDetector, frames: torch.Tensor, audio: torch.Tensor,
+               max_shift_frames: int, fps: float = 25.0, sample_rate: int = 16000, n_mfcc: int = 20):
+    """One-shot form of ``SyncSweeper.run``."""
+    sw = SyncSweeper(lipnet, detector, max_shift_frames, audio.shape[1], fps, sample_rate, n_mfcc,
+                     chunk_clips=min(64, max(1, frames.shape[0])))
+    return sw.run(frames, audio)
+
+
+# ---------------------------------------------------------------------------------- FeatureExtractor
+class FeatureExtractor:
+    """Reference :147-208.  ``grid_dataset`` must provide ``process_video(path) -> Tensor[1,T,H,W]``;
+    audio comes from ``audio_loader(path) -> (np.ndarray, sr)`` (the reference's librosa/moviepy
+    loaders are file IO and out of scope; pass a loader, or pre-fill ``audio_cache``)."""
+
+    def __init__(self, grid_dataset, lipnet: LipNet, device: torch.device, cfg: DetectorConfig,
+                 audio_loader=None):
+        self.grid = grid_dataset
+        self.lipnet = lipnet.to(device)
+        self.device = device
+        self.cfg = cfg
+        self.audio_loader = audio_loader
+        self.visual_cache: dict = {}
+        self.audio_cache: dict = {}
+        self.fps_cache: dict = {}
+
+    def _load_visual_stats(self, video_path: str) -> Tuple[torch.Tensor, float]:
+        if video_path in self.visual_cache:
+            return self.visual_cache[video_path], self.fps_cache[video_path]
+        frames = self.grid.process_video(video_path)
+        fps = self.cfg.default_fps                       # .npy / synthetic clips (:91-93)
+        getter = getattr(self.grid, "get_video_fps", None)
+        if getter is not None:
+            fps = getter(video_path) or fps
+        stats = visual_stats(self.lipnet, frames.unsqueeze(0).to(self.device))[0].cpu()
+        self.visual_cache[video_path] = stats
+        self.fps_cache[video_path] = fps
+        return stats, fps
+
+    def _load_audio(self, video_path: str) -> Tuple[np.ndarray, int]:
+        if video_path in self.audio_cache:
+            return self.audio_cache[video_path]
+        if self.audio_loader is None:
+            raise RuntimeError(f"Failed to load audio from {video_path}: no audio_loader configured")
+        try:
+            audio, sr = self.audio_loader(video_path)
+        except Exception as e:                            # same error class as the reference (:191)
+            raise RuntimeError(f"Failed to load audio from {video_path}: {e}")
+        if audio.ndim > 1:
+            audio = np.mean(audio, axis=0)
+        audio = audio.astype(np.float32)
+        self.audio_cache[video_path] = (audio, sr)
+        return audio, sr
+
+    def build_feature(self, video_path: str, shift_frames: int) -> Tuple[torch.Tensor, dict]:
+        visual_stats_, fps = self._load_visual_stats(video_path)
+        audio, sr = self._load_audio(video_path)
+        if sr != self.cfg.sample_rate:
+            raise RuntimeError("resampling (librosa.resample, :202-204) is outside the B200 path: "
+                               f"provide {self.cfg.sample_rate} Hz audio")
+        s = shift_samples(shift_frames, fps, sr)
+        a = torch.from_numpy(np.ascontiguousarray(audio)).to(self.device).unsqueeze(0)
+        audio_stats = audio_stats_sweep(a, [s], sr, self.cfg.n_mfcc)[0, 0].cpu()
+        feature = torch.cat([visual_stats_, audio_stats], dim=0)
+        return feature, {"video_path": video_path, "shift_frames": shift_frames, "fps": fps}
+
+    def build_features_sweep(self, video_path: str, max_shift_frames: int) -> torch.Tensor:
+        """All 2S+1 features of one clip at once: [2S+1, 13864]."""
+        visual_stats_, fps = self._load_visual_stats(video_path)
+        audio, sr = self._load_audio(video_path)
+        shifts = [shift_samples(k, fps, sr) for k in range(-max_shift_frames, max_shift_frames + 1)]
+        a = torch.from_numpy(np.ascontiguousarray(audio)).to(self.device).unsqueeze(0)
+        ast = audio_stats_sweep(a, shifts, sr, self.cfg.n_mfcc)[0].cpu()
+        return torch.cat([visual_stats_.unsqueeze(0).expand(len(shifts), -1), ast], dim=1)
+
+
+# ---------------------------------------------------------------------------------- checkpoints
+def load_lipnet(checkpoint_path: str, vocab_size: int, device: torch.device, precision: str = "bf16x3") -> LipNet:
+    """Reference :299-309 — accepts a bare state_dict or ``{'model_state_dict': ...}``."""
+    lipnet = LipNet(vocab_size=vocab_size, precision=precision)
+    checkpoint = torch.load(checkpoint_path, map_location=device)
+    if isinstance(checkpoint, dict) and "model_state_dict" in checkpoint:
+        lipnet.load_state_dict(checkpoint["model_state_dict"])
+    else:
+        lipnet.load_state_dict(checkpoint)
+    lipnet.eval()
+    for p in lipnet.parameters():
+        p.requires_grad = False
+    return lipnet.to(device)
+
+
+def save_detector(model: MisalignmentDetector, path: str, cfg: DetectorConfig) -> None:
+    """Reference :312-318 checkpoint format."""
+    torch.save({
+        "model_state_dict": model.state_dict(),
+        "input_dim": model.input_dim,
+        "hidden_dim": model.hidden_dim,
+        "config": {"sample_rate": cfg.sample_rate, "n_mfcc": cfg.n_mfcc, "max_shift_frames": cfg.max_shift_frames},
+    }, path)
+
+
+def load_detector(path: str, device: torch.device) -> MisalignmentDetector:
+    """misalignment_detection_demo.py:204-209."""
+    ckpt = torch.load(path, map_location=device)
+    model = MisalignmentDetector(ckpt["input_dim"], ckpt.get("hidden_dim", 256))
+    model.load_state_dict(ckpt["model_state_dict"])
+    return model.to(device).eval()

@@ -1,0 +1,169 @@
+/*
+ * avsync.h — C-ABI of the B200-native AV sync-scoring hot path (libavsync_b200.so).
+ *
+ * The reference (Hu-xiao-max/Alignment-Between-Speech-and-Visual-Mouth-Movements)
+ * has no FFI of its own: its seam is plain Python callables.  Each
+ * entry point below replaces the arithmetic behind one of those callables; the
+ * Python shims in alignment-between-speech-and-visual-mouth-movements_b200/ keep the
+ * reference names and signatures and are the only callers.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types cross the ABI.
+ *   - every function returns 0 (AVS_OK) or a negative AVS_E* code and never throws;
+ *     avs_last_error_string() describes the last failure on the calling thread.
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and the
+ *     call returns without synchronising (except the *_host entry points, which
+ *     synchronise before returning because their outputs are host buffers).
+ *   - device pointers are owned by the caller and must stay alive until the stream
+ *     has drained; outputs are fully overwritten.
+ *   - sm_100a only: avs_device_check() fails on anything else; there is no CPU path.
+ */
+#ifndef AVSYNC_H_
+#define AVSYNC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVS_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define AVS_API __attribute__((visibility("default")))
+#else
+#define AVS_API
+#endif
+
+enum {
+  AVS_OK = 0,
+  AVS_EINVAL = -1,     /* bad argument (null pointer, unsupported shape) */
+  AVS_ECUDA = -2,      /* a CUDA runtime call failed; see avs_last_error_string() */
+  AVS_EARCH = -3,      /* device is not sm_100 */
+  AVS_EWORKSPACE = -4, /* workspace too small */
+  AVS_ENOMEM = -5
+};
+
+/* arithmetic the STCNN / GRU input GEMMs run in */
+enum {
+  AVS_PREC_FP32 = 0,   /* CUDA-core FFMA, fp32 throughout (slow; bring-up / cross-check path) */
+  AVS_PREC_BF16 = 1,   /* tcgen05 kind::f16 bf16 x bf16 -> fp32 accum, single pass */
+  AVS_PREC_BF16X3 = 2  /* tcgen05, hi/lo bf16 split, 3 passes (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo): fp32-grade */
+};
+
+/* geometry fixed by the reference model (model.py:22-52, misalignment_detection_train.py:79-88) */
+#define AVS_T 75
+#define AVS_H 50
+#define AVS_W 100
+#define AVS_EMB 6912      /* 96 * 6 * 12 */
+#define AVS_VSTATS 13824  /* 2 * AVS_EMB */
+#define AVS_NFFT 2048
+#define AVS_NMELS 128
+
+AVS_API int avs_version(void);
+AVS_API const char* avs_last_error_string(void);
+/* 0 iff `device` is compute capability 10.x. */
+AVS_API int avs_device_check(int device);
+
+/* ---------------------------------------------------------------- K1: MFCC statistics sweep
+ * Replaces compute_audio_stats(shift_audio(audio, k, fps, sr), sr, n_mfcc)
+ * (misalignment_detection_train.py:100-127, librosa.feature.mfcc at :121) for all K shifts
+ * of B clips in one call.  shift_samples[k] is the signed integer delay shift_audio applies
+ * (:103).  The plan de-duplicates STFT frames shared between shifts on the host. */
+typedef struct avs_mfcc_plan avs_mfcc_plan;
+AVS_API int avs_mfcc_plan_create(int n_samples, int sample_rate, int n_mfcc,
+                         const int32_t* shift_samples, int n_shifts, avs_mfcc_plan** out);
+AVS_API void avs_mfcc_plan_destroy(avs_mfcc_plan* plan);
+AVS_API int avs_mfcc_plan_unique_frames(const avs_mfcc_plan* plan); /* distinct STFT frames per clip */
+AVS_API int avs_mfcc_plan_frames(const avs_mfcc_plan* plan);        /* STFT frames per shifted signal */
+AVS_API size_t avs_mfcc_workspace_bytes(const avs_mfcc_plan* plan, int n_clips);
+/* audio: device f32 [n_clips, n_samples]; out_stats: device f32 [n_clips, n_shifts, 2*n_mfcc]
+ * = [mean(n_mfcc), unbiased std(n_mfcc)] per (clip, shift). */
+AVS_API int avs_mfcc_stats_sweep(const avs_mfcc_plan* plan, const float* audio, int n_clips,
+                         float* out_stats, void* workspace, size_t workspace_bytes, void* stream);
+/* debug/parity: also write the per-frame MFCC table f32 [n_clips, n_shifts, n_frames, n_mfcc] */
+AVS_API int avs_mfcc_sweep_debug(const avs_mfcc_plan* plan, const float* audio, int n_clips,
+                         float* out_stats, float* out_mfcc, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ---------------------------------------------------------------- K2: STCNN
+ * Replaces extract_visual_embeddings (misalignment_detection_train.py:130-144) == the
+ * conv half of LipNet.forward (model.py:67-82), eval mode, plus the visual statistics of
+ * misalignment_detection_train.py:165.  Weights are the reference's state_dict tensors
+ * (device f32, OIDHW): conv1 [32,1,3,5,5], conv2 [64,32,3,5,5], conv3 [96,64,3,3,3]. */
+typedef struct avs_stcnn avs_stcnn;
+AVS_API int avs_stcnn_create(const float* w1, const float* b1, const float* w2, const float* b2,
+                     const float* w3, const float* b3, int precision, void* stream,
+                     avs_stcnn** out);
+AVS_API void avs_stcnn_destroy(avs_stcnn* net);
+AVS_API size_t avs_stcnn_workspace_bytes(const avs_stcnn* net, int n_clips);
+/* frames: device f32 [n_clips,1,75,50,100].  out_emb (f32 [n_clips,75,6912], feature index
+ * c*72+h*12+w) and out_vstats (f32 [n_clips,13824] = [mean_t, unbiased std_t]) may each be NULL. */
+AVS_API int avs_stcnn_forward(const avs_stcnn* net, const float* frames, int n_clips, float* out_emb,
+                      float* out_vstats, void* workspace, size_t workspace_bytes, void* stream);
+/* debug/parity: copy the pooled activations of layer 1/2 out as f32 NCDHW
+ * ([n,32,75,25,50] / [n,64,75,12,25]); either pointer may be NULL. */
+AVS_API int avs_stcnn_forward_debug(const avs_stcnn* net, const float* frames, int n_clips, float* out_emb,
+                            float* out_vstats, float* out_pool1, float* out_pool2, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- K3: Bi-GRU head
+ * Replaces gru1 -> gru2 -> fc -> log_softmax of LipNet.forward (model.py:84-95), eval mode.
+ * Weight pointers are the reference state_dict tensors, device f32:
+ *   w_ih [2][3H, in], w_hh [2][3H, H], b_ih [2][3H], b_hh [2][3H]  ([0]=forward, [1]=reverse),
+ *   gate order (r, z, n), H = hidden.  fc_w [V, 2H], fc_b [V]. */
+typedef struct avs_bigru avs_bigru;
+AVS_API int avs_bigru_create(int in_dim, int hidden, int vocab,
+                     const float* g1_w_ih, const float* g1_w_hh, const float* g1_b_ih, const float* g1_b_hh,
+                     const float* g2_w_ih, const float* g2_w_hh, const float* g2_b_ih, const float* g2_b_hh,
+                     const float* fc_w, const float* fc_b, int precision, void* stream, avs_bigru** out);
+AVS_API void avs_bigru_destroy(avs_bigru* head);
+AVS_API size_t avs_bigru_workspace_bytes(const avs_bigru* head, int n_clips, int n_steps);
+/* emb: device f32 [n_clips, n_steps, in_dim]; out_logp: device f32 [n_clips, n_steps, vocab]. */
+AVS_API int avs_bigru_forward(const avs_bigru* head, const float* emb, int n_clips, int n_steps,
+                      float* out_logp, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- K4: shift-sweep score
+ * Replaces, for every (clip, shift), torch.sigmoid(MisalignmentDetector(cat[vstats, astats_k]))
+ * (misalignment_detection_train.py:207,243-250,267; misalignment_detection_demo.py:249-250) and
+ * the arg-max over shifts.  w1 [hidden, v_dim + a_dim] row-major (classifier.0.weight), b1 [hidden],
+ * w2 [hidden] (classifier.3.weight), b2 [1]; all device f32.
+ * out_scores f32 [n_clips, n_shifts]; out_best int32 [n_clips] (first maximum). */
+AVS_API size_t avs_sweep_score_workspace_bytes(int n_clips, int hidden);
+AVS_API int avs_sweep_score(const float* vstats, const float* astats, int n_clips, int n_shifts, int v_dim,
+                    int a_dim, const float* w1, const float* b1, const float* w2, const float* b2,
+                    int hidden, float* out_scores, int32_t* out_best, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- K5: greedy CTC decode
+ * Replaces the arithmetic of decode_prediction (utils.py:20-30): per step arg-max over the vocab
+ * (first index on ties), drop repeats and blanks.  logp device f32 [n_clips, n_steps, vocab];
+ * out_ids int32 [n_clips, n_steps] (first out_len[i] entries valid, rest -1); out_len int32 [n_clips]. */
+AVS_API int avs_ctc_greedy(const float* logp, int n_clips, int n_steps, int vocab, int blank,
+                   int32_t* out_ids, int32_t* out_len, void* stream);
+
+/* ---------------------------------------------------------------- whole sweep (K2 + K1 + K4)
+ * The composed +-S sync sweep of SURVEY.md §3.2: for each clip, visual stats once, audio stats
+ * per shift, detector score per shift, arg-max.  The handle owns its device workspace, two
+ * streams and (for the host entry point) pinned staging buffers; clips are processed in chunks
+ * of at most `chunk_clips`. */
+typedef struct avs_sweep avs_sweep;
+AVS_API int avs_sweep_create(const avs_stcnn* net, const avs_mfcc_plan* plan, const float* w1,
+                     const float* b1, const float* w2, const float* b2, int hidden,
+                     int chunk_clips, avs_sweep** out);
+AVS_API void avs_sweep_destroy(avs_sweep* sw);
+/* frames/audio/out_* are DEVICE buffers; enqueues on `stream`, no sync. */
+AVS_API int avs_sweep_run(avs_sweep* sw, const float* frames, const float* audio, int n_clips,
+                  float* out_scores, int32_t* out_best, void* stream);
+/* frames/audio/out_* are HOST buffers (pageable or pinned); copies are pipelined against
+ * compute chunk by chunk; returns after the results are in the host buffers. */
+AVS_API int avs_sweep_run_host(avs_sweep* sw, const float* frames_host, const float* audio_host,
+                       int n_clips, float* out_scores_host, int32_t* out_best_host);
+/* number of kernel launches this library has enqueued since load (all handles, this process) */
+AVS_API long long avs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVSYNC_H_ */
