@@ -26,6 +26,9 @@ SIGNATURES = {
     "avs_last_error_string": (c_char_p, []),
     "avs_device_check": (c_int, [c_int]),
     "avs_launch_count": (c_longlong, []),
+    "avs_prof_enable": (None, [c_int]),
+    "avs_prof_reset": (None, []),
+    "avs_prof_read": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(c_int)]),
     "avs_mfcc_plan_create": (c_int, [c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(_P)]),
     "avs_mfcc_plan_destroy": (None, [_P]),
     "avs_mfcc_plan_unique_frames": (c_int, [_P]),

@@ -11,7 +11,52 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+// ---- per-kernel timing
+int g_prof_on = 0;
+namespace {
+constexpr int kProfRing = 8192;
+struct ProfState {
+  cudaEvent_t ev[kProfRing][2];
+  int used = 0;
+  bool made = false;
+} g_prof[PROF_NSLOTS];
+}
+void prof_begin(int slot, cudaStream_t st) {
+  ProfState& p = g_prof[slot];
+  if (p.used >= kProfRing) return;
+  if (!p.made) {
+    for (int i = 0; i < kProfRing; ++i) cudaEventCreate(&p.ev[i][0]), cudaEventCreate(&p.ev[i][1]);
+    p.made = true;
+  }
+  cudaEventRecord(p.ev[p.used][0], st);
+}
+void prof_end(int slot, cudaStream_t st) {
+  ProfState& p = g_prof[slot];
+  if (p.used >= kProfRing || !p.made) return;
+  cudaEventRecord(p.ev[p.used][1], st);
+  ++p.used;
+}
 }  // namespace avs
+
+extern "C" void avs_prof_enable(int on) { avs::g_prof_on = on; }
+extern "C" void avs_prof_reset(void) {
+  for (int s = 0; s < avs::PROF_NSLOTS; ++s) avs::g_prof[s].used = 0;
+}
+extern "C" int avs_prof_read(int slot, double* total_ms, int* count) {
+  if (slot < 0 || slot >= avs::PROF_NSLOTS || !total_ms || !count) return AVS_EINVAL;
+  auto& p = avs::g_prof[slot];
+  double t = 0;
+  for (int i = 0; i < p.used; ++i) {
+    AVS_CUDA(cudaEventSynchronize(p.ev[i][1]));
+    float ms = 0;
+    AVS_CUDA(cudaEventElapsedTime(&ms, p.ev[i][0], p.ev[i][1]));
+    t += ms;
+  }
+  *total_ms = t;
+  *count = p.used;
+  return AVS_OK;
+}
 
 extern "C" int avs_version(void) { return AVS_VERSION; }
 extern "C" const char* avs_last_error_string(void) { return avs::g_err; }

@@ -37,6 +37,18 @@ extern long long g_launches;
     AVS_CUDA(cudaPeekAtLastError());   \
   } while (0)
 
+// ---- optional per-kernel timing (avs_prof_*): CUDA events recorded on the launching stream
+enum ProfSlot { PROF_PACK = 0, PROF_CONV1, PROF_CONV2, PROF_CONV3, PROF_VSTATS, PROF_LOGMEL, PROF_MFCC_STATS,
+                PROF_SCORE_GEMM, PROF_SCORE, PROF_NSLOTS };
+extern int g_prof_on;
+void prof_begin(int slot, cudaStream_t st);
+void prof_end(int slot, cudaStream_t st);
+struct ProfScope {
+  int slot; cudaStream_t st;
+  ProfScope(int s, cudaStream_t t) : slot(s), st(t) { if (g_prof_on) prof_begin(slot, st); }
+  ~ProfScope() { if (g_prof_on) prof_end(slot, st); }
+};
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
@@ -102,8 +114,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded spin: a protocol bug must surface as a launch failure, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+      printf("avsync: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+             smem_u32(bar), parity);
+      __trap();
+    }
   }
 }
 

@@ -91,6 +91,7 @@ int conv_pool_ffma(const float* in, const float* w, const float* bias, float* ou
                    int H, int W, int KH, int KW, long long o_sb, long long o_sc, long long o_st, cudaStream_t st) {
   const int Ho = H / 2, Wo = W / 2;
   dim3 grid(cdiv(Ho, 16) * cdiv(Wo, 16), B * T, cdiv(Cout, 8));
+  ProfScope ps(Cin == 1 ? PROF_CONV1 : (Cout == 64 ? PROF_CONV2 : PROF_CONV3), st);
   AVS_REQUIRE(static_cast<long long>(B) * T <= 65535, "FFMA conv path: n_clips * T must be <= 65535 per call");
   if (KH == 5 && KW == 5)
     conv_pool_ffma_kernel<5, 5><<<grid, 256, 0, st>>>(in, w, bias, out, Cin, Cout, T, H, W, o_sb, o_sc, o_st);
@@ -131,6 +132,7 @@ vstats_kernel(const float* __restrict__ emb, float* __restrict__ out, int F) {
 
 int vstats(const float* emb, float* out, int B, int F, cudaStream_t st) {
   if (B <= 0) return AVS_OK;
+  ProfScope ps(PROF_VSTATS, st);
   for (int b0 = 0; b0 < B; b0 += 32768) {
     const int nb = B - b0 < 32768 ? B - b0 : 32768;
     vstats_kernel<AVS_T><<<dim3(cdiv(F, 128), nb), 128, 0, st>>>(emb + static_cast<size_t>(b0) * AVS_T * F,

@@ -503,6 +503,7 @@ void umma_layer_free(UmmaLayer* L) {
 
 int umma_pack_frames(const float* frames, __nv_bfloat16* act, const LayerGeom& g, int split, int B, cudaStream_t st) {
   const long long total = static_cast<long long>(B) * (AVS_T + 2) * 2 * g.PP;
+  ProfScope ps(PROF_PACK, st);
   pack_frames_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(frames, act, g, split, AVS_T, total);
   AVS_LAUNCHED();
   return AVS_OK;
@@ -540,6 +541,7 @@ int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const Epi
   p.plane_stride = static_cast<long long>(g.n_chunks) * 2 * g.PP * 8;
   p.clip_stride = p.plane_stride * (AVS_T + 2);
   const int grid = static_cast<int>(std::min<long long>(items, n_sms));
+  ProfScope ps(L.g.Cin == 1 ? PROF_CONV1 : (L.g.Cout == 64 ? PROF_CONV2 : PROF_CONV3), st);
   conv_umma_kernel<<<grid, kConvThreads, L.smem_bytes, st>>>(p);
   AVS_LAUNCHED();
   return AVS_OK;

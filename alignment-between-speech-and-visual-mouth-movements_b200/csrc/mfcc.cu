@@ -360,15 +360,17 @@ extern "C" int avs_mfcc_sweep_debug(const avs_mfcc_plan* p, const float* audio, 
   for (int c0 = 0; c0 < n_clips; c0 += 32768) {  // gridDim.y limit
     const int nc = std::min(32768, n_clips - c0);
     dim3 g1(cdiv(p->n_unique, kFramesPerCta), nc);
+    { ProfScope ps(PROF_LOGMEL, st);
     mfcc_logmel_kernel<<<g1, kFftThreads, 0, st>>>(audio + static_cast<size_t>(c0) * p->n_samples, p->n_samples,
                                                    p->d_frames, p->n_unique, p->d_window, p->d_tw, p->d_tw2,
                                                    p->d_mel_rng, p->d_mel_off, p->d_mel_w,
-                                                   logmel + static_cast<size_t>(c0) * p->n_unique * kMels);
+                                                   logmel + static_cast<size_t>(c0) * p->n_unique * kMels); }
     AVS_LAUNCHED();
     dim3 g2(p->n_shifts, nc);
     float* os = out_stats + static_cast<size_t>(c0) * p->n_shifts * 2 * p->n_mfcc;
     float* om = out_mfcc ? out_mfcc + static_cast<size_t>(c0) * p->n_shifts * p->n_frames * p->n_mfcc : nullptr;
     const float* lm = logmel + static_cast<size_t>(c0) * p->n_unique * kMels;
+    ProfScope ps2(PROF_MFCC_STATS, st);
     if (p->n_mfcc <= 20) {
       const size_t sm = (static_cast<size_t>(kMels) * 20 + static_cast<size_t>(p->n_frames) * 20) * sizeof(float);
       AVS_CUDA(cudaFuncSetAttribute(mfcc_stats_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)));

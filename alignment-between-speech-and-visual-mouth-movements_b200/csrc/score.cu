@@ -123,8 +123,10 @@ extern "C" int avs_sweep_score(const float* vstats, const float* astats, int n_c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* hv = static_cast<float*>(workspace);
   const int ld = v_dim + a_dim;
-  int rc = sgemm_nt(vstats, v_dim, w1, ld, b1, hv, hidden, n_clips, hidden, v_dim, st);
+  int rc;
+  { ProfScope ps(PROF_SCORE_GEMM, st); rc = sgemm_nt(vstats, v_dim, w1, ld, b1, hv, hidden, n_clips, hidden, v_dim, st); }
   if (rc) return rc;
+  ProfScope ps(PROF_SCORE, st);
   const size_t sm = (static_cast<size_t>(n_shifts) * a_dim + n_shifts) * sizeof(float);
   AVS_REQUIRE(sm <= 48 * 1024, "n_shifts * a_dim too large for the score kernel");
   sweep_score_kernel<<<n_clips, 128, sm, st>>>(hv, astats, n_shifts, a_dim, w1 + v_dim, ld, w2, b2, hidden,

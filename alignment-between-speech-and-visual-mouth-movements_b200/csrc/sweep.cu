@@ -112,6 +112,15 @@ extern "C" int avs_sweep_run(avs_sweep* s, const float* frames, const float* aud
   return AVS_OK;
 }
 
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 static int host_init(avs_sweep* s) {
   if (s->host_ready) return AVS_OK;
   const size_t fb = static_cast<size_t>(s->chunk) * kFrameElems * sizeof(float);
@@ -143,6 +152,8 @@ extern "C" int avs_sweep_run_host(avs_sweep* s, const float* frames_host, const 
   int rc = host_init(s);
   if (rc) return rc;
   const int n_chunks = cdiv(n_clips, s->chunk);
+  // page-locked caller buffers are copied from directly; pageable ones go through the pinned staging slots
+  const bool direct = is_pinned(frames_host) && is_pinned(audio_host);
   // software pipeline over chunks: stage(i) -> H2D(i) on the copy stream | compute(i) on main | D2H(i) on copy
   for (int i = 0; i < n_chunks; ++i) {
     const int sl = i & 1, c0 = i * s->chunk, n = std::min(s->chunk, n_clips - c0);
@@ -152,10 +163,17 @@ extern "C" int avs_sweep_run_host(avs_sweep* s, const float* frames_host, const 
       memcpy(out_scores_host + static_cast<size_t>(p0) * s->K, s->h_scores[sl], static_cast<size_t>(pn) * s->K * sizeof(float));
       memcpy(out_best_host + p0, s->h_best[sl], static_cast<size_t>(pn) * sizeof(int32_t));
     }
-    memcpy(s->h_frames[sl], frames_host + c0 * kFrameElems, n * kFrameElems * sizeof(float));
-    memcpy(s->h_audio[sl], audio_host + static_cast<size_t>(c0) * s->n_samples, static_cast<size_t>(n) * s->n_samples * sizeof(float));
-    AVS_CUDA(cudaMemcpyAsync(s->d_frames[sl], s->h_frames[sl], n * kFrameElems * sizeof(float), cudaMemcpyHostToDevice, s->copy));
-    AVS_CUDA(cudaMemcpyAsync(s->d_audio[sl], s->h_audio[sl], static_cast<size_t>(n) * s->n_samples * sizeof(float), cudaMemcpyHostToDevice, s->copy));
+    const float* fsrc = frames_host + c0 * kFrameElems;
+    const float* asrc = audio_host + static_cast<size_t>(c0) * s->n_samples;
+    if (i >= 2) AVS_CUDA(cudaStreamWaitEvent(s->copy, s->ev_done[sl], 0));  // d_frames[sl] is free once chunk i-2 computed
+    if (!direct) {
+      memcpy(s->h_frames[sl], fsrc, n * kFrameElems * sizeof(float));
+      memcpy(s->h_audio[sl], asrc, static_cast<size_t>(n) * s->n_samples * sizeof(float));
+      fsrc = s->h_frames[sl];
+      asrc = s->h_audio[sl];
+    }
+    AVS_CUDA(cudaMemcpyAsync(s->d_frames[sl], fsrc, n * kFrameElems * sizeof(float), cudaMemcpyHostToDevice, s->copy));
+    AVS_CUDA(cudaMemcpyAsync(s->d_audio[sl], asrc, static_cast<size_t>(n) * s->n_samples * sizeof(float), cudaMemcpyHostToDevice, s->copy));
     AVS_CUDA(cudaEventRecord(s->ev_in[sl], s->copy));
     AVS_CUDA(cudaStreamWaitEvent(s->main, s->ev_in[sl], 0));
     if ((rc = run_chunk(s, s->d_frames[sl], s->d_audio[sl], n, s->d_scores[sl], s->d_best[sl], s->main))) return rc;

@@ -160,6 +160,12 @@ AVS_API int avs_sweep_run(avs_sweep* sw, const float* frames, const float* audio
  * compute chunk by chunk; returns after the results are in the host buffers. */
 AVS_API int avs_sweep_run_host(avs_sweep* sw, const float* frames_host, const float* audio_host,
                        int n_clips, float* out_scores_host, int32_t* out_best_host);
+/* Optional per-kernel timing: when enabled, every launch of a profiled kernel is bracketed by CUDA
+ * events on its own stream.  slot: 0 pack, 1 conv1, 2 conv2, 3 conv3, 4 vstats, 5 mfcc log-mel,
+ * 6 mfcc stats, 7 score GEMM, 8 score.  avs_prof_read synchronises on the recorded events. */
+AVS_API void avs_prof_enable(int on);
+AVS_API void avs_prof_reset(void);
+AVS_API int avs_prof_read(int slot, double* total_ms, int* count);
 /* number of kernel launches this library has enqueued since load (all handles, this process) */
 AVS_API long long avs_launch_count(void);
 

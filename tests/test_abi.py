@@ -1,0 +1,56 @@
+"""The C-ABI library loads and exports every symbol include/avsync.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "avsync.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"AVS_API\s+[\w\s\*]+?\b(avs_\w+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def native():
+    import avsync_b200
+    N = avsync_b200._native
+    if not os.path.isfile(N.LIB_PATH):
+        N.build()
+    return N
+
+
+def test_header_declares_the_expected_surface():
+    syms = declared_symbols()
+    for must in ("avs_mfcc_stats_sweep", "avs_stcnn_forward", "avs_bigru_forward", "avs_sweep_score",
+                 "avs_ctc_greedy", "avs_sweep_run", "avs_sweep_run_host", "avs_version", "avs_last_error_string"):
+        assert must in syms
+    assert len(syms) >= 27
+
+
+def test_library_exports_every_declared_symbol(native):
+    L = ctypes.CDLL(native.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(L, s), f"{s} declared in avsync.h but not exported"
+
+
+def test_binding_covers_every_declared_symbol(native):
+    assert sorted(native.SIGNATURES) == declared_symbols()
+    assert native.lib().avs_version() == 100
+
+
+def test_no_cpu_fallback_without_cuda(native):
+    import torch
+    import avsync_b200 as A
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    net = A.LipNet(39).eval()
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 1, 75, 50, 100))
+    with pytest.raises(RuntimeError):
+        A.compute_audio_stats(__import__("numpy").zeros(48000, dtype="float32"), 16000, 20)
+    with pytest.raises(RuntimeError):
+        A.ctc_greedy_decode(torch.zeros(1, 75, 39))

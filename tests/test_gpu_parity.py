@@ -1,0 +1,305 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle and the golden vectors minted
+from the reference.  Run on the B200 box: python -m pytest tests -m gpu.
+
+Tolerances (north_star): integer outputs (CTC ids, best offsets) bit-exact; fp32 / bf16x3 features,
+logits and scores within rtol 1e-3 (atol stated per test); single-pass bf16 within the looser
+tolerance written in each test."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lipnet_ref, sweep_ref
+
+pytestmark = pytest.mark.gpu
+
+SHIFTS41 = [640 * k for k in range(-20, 21)]
+
+
+@pytest.fixture(scope="module")
+def A():
+    import avsync_b200
+    avsync_b200._native.device_check()
+    return avsync_b200
+
+
+def make_lipnet(A, sd, precision):
+    net = A.LipNet(39, precision=precision)
+    net.load_state_dict(sd)
+    return net.cuda().eval()
+
+
+def make_detector(A, det_sd):
+    det = A.MisalignmentDetector(13864, 512)
+    det.load_state_dict(det_sd)
+    return det.cuda().eval()
+
+
+def report(name, got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    err = np.abs(got - want)
+    rel = err / np.maximum(np.abs(want), 1e-6)
+    print(f"[parity] {name}: max_abs={err.max():.3e} mean_abs={err.mean():.3e} "
+          f"max_rel(|want|>1e-2)={rel[np.abs(want) > 1e-2].max() if (np.abs(want) > 1e-2).any() else 0:.3e} "
+          f"ref_absmax={np.abs(want).max():.3e}")
+
+
+# ------------------------------------------------------------------------------------------ K5
+def test_ctc_greedy_golden_cases(A, golden):
+    g = golden("decode")
+    names = sorted({k.split("__")[0] for k in g.files})
+
+    class DS:
+        idx_to_char = lipnet_ref.make_vocab()
+    for n in names:
+        t = torch.from_numpy(g[f"{n}__in"]).cuda()
+        ids, lens = A.ctc_greedy_decode(t.unsqueeze(0))
+        L = int(lens[0])
+        assert ids[0, :L].tolist() == g[f"{n}__ids"].tolist(), n
+        assert (ids[0, L:] == -1).all()
+        assert A.decode_prediction(t, DS) == str(g[f"{n}__text"]), n
+
+
+def test_ctc_greedy_random_batch256_bit_exact(A):
+    rng = np.random.default_rng(3)
+    logp = rng.normal(-3.66, 0.05, (256, 75, 39)).astype(np.float32)
+    logp[5, :, :] = logp[5, 0, 0]                 # all ties -> blank everywhere -> empty
+    logp[6, 10:20, 7] = 1.0                       # a run of the same symbol
+    logp[7, 3, 4] = np.nan                        # NaN wins the max like torch.max
+    ids, lens = A.ctc_greedy_decode(torch.from_numpy(logp).cuda())
+    ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
+    for i in range(256):
+        want = lipnet_ref.greedy_ids(logp[i])
+        assert ids[i, :lens[i]].tolist() == want, i
+    # ragged shapes
+    for (B, T, V) in ((1, 1, 2), (3, 200, 5), (2, 75, 39)):
+        x = rng.normal(size=(B, T, V)).astype(np.float32)
+        ids, lens = A.ctc_greedy_decode(torch.from_numpy(x).cuda())
+        for i in range(B):
+            assert ids[i, :int(lens[i])].tolist() == lipnet_ref.greedy_ids(x[i])
+    ids, lens = A.ctc_greedy_decode(torch.zeros((0, 75, 39), device="cuda"))
+    assert ids.shape == (0, 75) and lens.shape == (0,)
+
+
+# ------------------------------------------------------------------------------------------ K1
+def test_mfcc_stats_vs_golden_all_shifts(A, golden):
+    g = golden("astats")
+    for kind in ("noise", "halfsilent", "chirp", "speechlike"):
+        a = torch.from_numpy(sweep_ref.synth_audio(1, seed=1234, kind=kind)).cuda()
+        got = A.audio_stats_sweep(a, SHIFTS41, 16000, 20)[0].cpu().numpy()
+        report(f"astats[{kind}]", got, g[kind])
+        np.testing.assert_allclose(got, g[kind], rtol=1e-3, atol=2e-3, err_msg=kind)
+
+
+def test_mfcc_per_frame_table_vs_oracle(A):
+    from oracle import mfcc_ref
+    a = sweep_ref.synth_audio(1, seed=77, kind="speechlike")
+    st, m = A.audio_stats_sweep(torch.from_numpy(a).cuda(), [0, 640 * 7, -640 * 20], 16000, 20, return_mfcc=True)
+    for j, k in enumerate((0, 7, -20)):
+        want = mfcc_ref.mfcc(sweep_ref.shift_audio(a[0], k, 25.0, 16000), 16000, 20, 400).T     # [121, 20]
+        report(f"mfcc[k={k}]", m[0, j].cpu().numpy(), want)
+        np.testing.assert_allclose(m[0, j].cpu().numpy(), want, rtol=1e-3, atol=5e-3)
+
+
+def test_mfcc_frame_dedup_is_exact(A):
+    """The 41-shift plan shares STFT frames between shifts (745 unique of 4961); results must be
+    bit-identical to running every shift on its own plan."""
+    a = torch.from_numpy(sweep_ref.synth_audio(3, seed=5, kind="speechlike")).cuda()
+    full = A.audio_stats_sweep(a, SHIFTS41, 16000, 20)
+    from avsync_b200.misalignment_detection_train import mfcc_plan
+    p = mfcc_plan(48000, 16000, 20, SHIFTS41)
+    assert p.n_frames == 121 and p.n_unique < 800, (p.n_frames, p.n_unique)
+    for j in (0, 1, 19, 20, 21, 40):
+        single = A.audio_stats_sweep(a, [SHIFTS41[j]], 16000, 20)
+        assert torch.equal(full[:, j], single[:, 0]), j
+
+
+def test_mfcc_edge_cases(A):
+    from oracle import mfcc_ref
+    # silence: every mel = amin -> -100 dB everywhere -> only c0 non-zero, std 0
+    z = torch.zeros((1, 48000), device="cuda")
+    st = A.audio_stats_sweep(z, [0, 640], 16000, 20).cpu().numpy()
+    want = sweep_ref.compute_audio_stats(np.zeros(48000, np.float32), 16000, 20).numpy()
+    np.testing.assert_allclose(st[0, 0], want, rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(st[0, 1], want, rtol=1e-5, atol=1e-3)
+    # |shift| >= len -> shifted signal is all zeros (misalignment_detection_train.py:107-113)
+    a = sweep_ref.synth_audio(1, seed=9)
+    st = A.audio_stats_sweep(torch.from_numpy(a).cuda(), [48000, -50000, 47999], 16000, 20).cpu().numpy()
+    np.testing.assert_allclose(st[0, 0], want, rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(st[0, 1], want, rtol=1e-5, atol=1e-3)
+    w3 = sweep_ref.compute_audio_stats(np.concatenate([np.zeros(47999, np.float32), a[0, :1]]), 16000, 20).numpy()
+    np.testing.assert_allclose(st[0, 2], w3, rtol=1e-3, atol=2e-3)
+    # shifts that are not on the 80-sample grid (29.97 fps) and other lengths / rates
+    for (n, sr, fps) in ((48000, 16000, 29.97), (16000, 16000, 25.0), (12345, 8000, 25.0), (4000, 16000, 25.0)):
+        x = sweep_ref.synth_audio(1, seed=11, n_samples=n, kind="speechlike")
+        ks = (-3, 0, 2, 5)
+        shifts = [sweep_ref.shift_samples(k, fps, sr) for k in ks]
+        got = A.audio_stats_sweep(torch.from_numpy(x).cuda(), shifts, sr, 20).cpu().numpy()
+        for j, k in enumerate(ks):
+            w = sweep_ref.compute_audio_stats(sweep_ref.shift_audio(x[0], k, fps, sr), sr, 20).numpy()
+            np.testing.assert_allclose(got[0, j], w, rtol=1e-3, atol=2e-3, err_msg=str((n, sr, fps, k)))
+    # reference-shaped entry point: numpy in, CPU tensor out; n_mfcc != 20
+    x = sweep_ref.synth_audio(1, seed=13)[0]
+    for nm in (13, 20, 40):
+        got = A.compute_audio_stats(x, 16000, nm)
+        assert got.device.type == "cpu" and got.shape == (2 * nm,)
+        np.testing.assert_allclose(got.numpy(), sweep_ref.compute_audio_stats(x, 16000, nm).numpy(), rtol=1e-3, atol=2e-3)
+    # a single STFT frame: torch.std of one sample is NaN, mean still defined
+    one = A.compute_audio_stats(x[:300], 16000, 20).numpy()
+    w1 = sweep_ref.compute_audio_stats(x[:300], 16000, 20).numpy()
+    np.testing.assert_allclose(one[:20], w1[:20], rtol=1e-3, atol=2e-3)
+    assert np.isnan(one[20:]).all() and np.isnan(w1[20:]).all()
+
+
+# ------------------------------------------------------------------------------------------ K2
+TOL = {"fp32": dict(rtol=1e-3, atol=1e-5), "bf16x3": dict(rtol=1e-3, atol=1e-4), "bf16": dict(rtol=3e-2, atol=6e-3)}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_stcnn_vs_oracle_and_golden(A, golden, lipnet_sd, precision):
+    frames = sweep_ref.synth_frames(2, seed=1234)
+    with torch.no_grad():
+        emb_ref, p1_ref, p2_ref, _ = lipnet_ref.stcnn(lipnet_sd, frames, return_intermediates=True)
+    net = make_lipnet(A, lipnet_sd, precision)
+    emb, vst, p1, p2 = net.stcnn(frames.cuda(), want_vstats=True, debug=True)
+    torch.cuda.synchronize()
+    tol = TOL[precision]
+    report(f"pool1[{precision}]", p1.cpu().numpy(), p1_ref.numpy())
+    report(f"pool2[{precision}]", p2.cpu().numpy(), p2_ref.numpy())
+    report(f"emb[{precision}]", emb.cpu().numpy(), emb_ref.numpy())
+    np.testing.assert_allclose(p1.cpu().numpy(), p1_ref.numpy(), **tol)
+    np.testing.assert_allclose(p2.cpu().numpy(), p2_ref.numpy(), **tol)
+    np.testing.assert_allclose(emb.cpu().numpy(), emb_ref.numpy(), **tol)
+    g = golden("stcnn")
+    flat = emb.reshape(2, -1).cpu().numpy()
+    np.testing.assert_allclose(flat[:, ::int(g["emb_stride"])], g["emb_sample"], **tol)
+    report(f"vstats[{precision}]", vst.cpu().numpy(), g["vstats"])
+    np.testing.assert_allclose(vst.cpu().numpy(), g["vstats"], **tol)
+    # drop-in entry point
+    e2 = A.extract_visual_embeddings(net, frames.cuda())
+    assert e2.is_cuda and torch.equal(e2, emb)
+
+
+def test_stcnn_wrong_shape_raises(A, lipnet_sd):
+    net = make_lipnet(A, lipnet_sd, "bf16")
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 75, 50, 100, device="cuda"))      # 3-channel input fails like conv1 would
+    with pytest.raises(RuntimeError):
+        net.train()(torch.zeros(1, 1, 75, 50, 100, device="cuda"))
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_stcnn_batch_independence(A, lipnet_sd, precision):
+    """Clips are independent units: a clip's embedding must not depend on its batch neighbours."""
+    frames = sweep_ref.synth_frames(5, seed=42).cuda()
+    net = make_lipnet(A, lipnet_sd, precision)
+    full = net.stcnn(frames)
+    for i in (0, 2, 4):
+        assert torch.equal(net.stcnn(frames[i:i + 1])[0], full[i]), i
+
+
+# ------------------------------------------------------------------------------------------ K3
+def test_bigru_head_vs_oracle(A, lipnet_sd):
+    g = torch.Generator().manual_seed(0)
+    emb = torch.rand((3, 75, 6912), generator=g) * 0.2
+    with torch.no_grad():
+        want = lipnet_ref.gru_head(lipnet_sd, emb).numpy()
+    net = make_lipnet(A, lipnet_sd, "fp32")
+    got = net.gru_head(emb.cuda()).cpu().numpy()
+    report("logp[gru_head]", got, want)
+    np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(np.exp(got).sum(-1), 1.0, atol=1e-4)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_lipnet_forward_and_decode_vs_golden(A, golden, lipnet_sd, precision):
+    g = golden("lipnet")
+    frames = sweep_ref.synth_frames(2, seed=1234).cuda()
+    net = make_lipnet(A, lipnet_sd, precision)
+    logp = net(frames)
+    assert logp.shape == (2, 75, 39)
+    report(f"logp[{precision}]", logp.cpu().numpy(), g["logp"])
+    np.testing.assert_allclose(logp.cpu().numpy(), g["logp"], rtol=1e-3, atol=2e-4)
+
+    class DS:
+        idx_to_char = lipnet_ref.make_vocab()
+    texts = A.decode_batch(logp, DS)
+    assert texts == [str(t) for t in g["texts"]]
+    assert [A.decode_prediction(logp[i], DS) for i in range(2)] == texts
+
+
+# ------------------------------------------------------------------------------------------ K4 + sweep
+def test_sweep_score_kernel_vs_oracle(A, det_sd):
+    g = torch.Generator().manual_seed(4)
+    v = torch.rand((7, 13824), generator=g)
+    a = torch.randn((7, 31, 40), generator=g) * 20
+    x = torch.cat([v[:, None, :].expand(-1, 31, -1), a], dim=-1)
+    want = torch.sigmoid(sweep_ref.detector_logits(det_sd, x)).numpy()
+    det = make_detector(A, det_sd)
+    sc, best = A.sweep_score(v.cuda(), a.cuda(), det)
+    report("scores[K4]", sc.cpu().numpy(), want)
+    np.testing.assert_allclose(sc.cpu().numpy(), want, rtol=1e-3, atol=1e-5)
+    assert best.cpu().tolist() == sc.cpu().numpy().argmax(1).tolist()
+    # ties -> first maximum, like np.argmax
+    det0 = A.MisalignmentDetector(13864, 512)
+    for p in det0.parameters():
+        torch.nn.init.zeros_(p)
+    sc0, best0 = A.sweep_score(v.cuda(), a.cuda(), det0.cuda().eval())
+    assert (sc0 == 0.5).all() and (best0 == 0).all()
+
+
+@pytest.mark.parametrize("precision,atol", [("fp32", 2e-5), ("bf16x3", 2e-5), ("bf16", 3e-3)])
+def test_sync_sweep_vs_golden(A, golden, lipnet_sd, det_sd, precision, atol):
+    g = golden("sweep")
+    frames = sweep_ref.synth_frames(2, seed=1234).cuda()
+    audio = np.stack([sweep_ref.synth_audio(1, seed=1234, kind="noise")[0],
+                      sweep_ref.synth_audio(1, seed=1235, kind="speechlike")[0]])
+    net, det = make_lipnet(A, lipnet_sd, precision), make_detector(A, det_sd)
+    scores, best = A.sync_sweep(net, det, frames, torch.from_numpy(audio).cuda(), 20)
+    got = scores.cpu().numpy()
+    report(f"sweep scores[{precision}]", got, g["scores"])
+    print("[parity] golden top-2 margins", g["margin"], "best", g["best"] - 20, "got", best.cpu().numpy())
+    np.testing.assert_allclose(got, g["scores"], rtol=1e-3, atol=atol)
+    for i in range(2):
+        if g["margin"][i] > 2 * atol:              # best-offset arg-max must be exact when the margin is resolvable
+            assert int(best[i]) == int(g["best"][i]) - 20
+    assert best.cpu().tolist() == (got.argmax(1) - 20).tolist()
+
+
+def test_sweeper_host_entry_and_chunking(A, lipnet_sd, det_sd):
+    """run_host (host buffers, pipelined copies, chunks of 4 with a ragged tail) == run (device buffers)."""
+    n = 10
+    frames = sweep_ref.synth_frames(n, seed=7)
+    audio = sweep_ref.synth_audio(n, seed=7, kind="speechlike")
+    net, det = make_lipnet(A, lipnet_sd, "bf16"), make_detector(A, det_sd)
+    sw = A.SyncSweeper(net, det, 15, chunk_clips=4)
+    s_dev, b_dev = sw.run(frames.cuda(), torch.from_numpy(audio).cuda())
+    s_host, b_host = sw.run_host(frames.numpy(), audio)
+    assert s_dev.shape == (n, 31)
+    assert np.array_equal(s_dev.cpu().numpy(), s_host) and np.array_equal(b_dev.cpu().numpy(), b_host)
+    big = A.SyncSweeper(net, det, 15, chunk_clips=16)
+    s_big, b_big = big.run(frames.cuda(), torch.from_numpy(audio).cuda())
+    assert torch.equal(s_big, s_dev) and torch.equal(b_big, b_dev)
+
+
+def test_config2_batch64_properties(A, lipnet_sd, det_sd):
+    """BASELINE config 2 size (64 clips, +-15): size-independent properties instead of a CPU oracle run —
+    (i) every clip's row equals the row it gets when swept alone; (ii) scores are probabilities;
+    (iii) swapping two clips swaps their rows; (iv) the oracle agrees on a sample of 2 clips."""
+    n = 64
+    frames = sweep_ref.synth_frames(n, seed=21).cuda()
+    audio = torch.from_numpy(sweep_ref.synth_audio(n, seed=21, kind="speechlike")).cuda()
+    net, det = make_lipnet(A, lipnet_sd, "bf16x3"), make_detector(A, det_sd)
+    sw = A.SyncSweeper(net, det, 15, chunk_clips=32)
+    scores, best = sw.run(frames, audio)
+    assert scores.shape == (n, 31) and ((scores > 0) & (scores < 1)).all()
+    for i in (0, 31, 32, 63):
+        si, bi = sw.run(frames[i:i + 1], audio[i:i + 1])
+        assert torch.equal(si[0], scores[i]) and int(bi[0]) == int(best[i])
+    perm = torch.arange(n).flip(0).cuda()
+    s2, b2 = sw.run(frames[perm], audio[perm])
+    assert torch.equal(s2, scores[perm]) and torch.equal(b2, best[perm])
+    det_cpu = det_sd
+    for i in (3, 40):
+        r = sweep_ref.sweep_clip(lipnet_sd, det_cpu, frames[i].cpu(), audio[i].cpu().numpy(), list(range(-15, 16)),
+                                 batched=True)
+        np.testing.assert_allclose(scores[i].cpu().numpy(), r["scores"], rtol=1e-3, atol=2e-5)

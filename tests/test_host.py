@@ -1,0 +1,102 @@
+"""Host-side logic of the drop-in package (CPU only): reference-compatible names, shapes, state_dict keys,
+checkpoint formats, shift arithmetic, shard arithmetic."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import avsync_b200 as A
+from oracle import lipnet_ref, sweep_ref
+
+
+def test_shift_audio_matches_oracle_everywhere():
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=997).astype(np.float32)
+    for fps, sr in ((25.0, 16000), (29.97, 16000), (25.0, 8000), (0.0, 16000)):
+        for k in (-40, -20, -3, -1, 0, 1, 2, 7, 20, 40):
+            got = A.shift_audio(a, k, fps, sr)
+            want = sweep_ref.shift_audio(a, k, fps, sr)
+            assert np.array_equal(got, want), (fps, sr, k)
+            assert got is not a
+            assert A.shift_samples(k, fps, sr) == sweep_ref.shift_samples(k, fps, sr)
+    assert A.shift_audio(np.zeros(0, np.float32), 3, 25.0, 16000).size == 0
+
+
+def test_compute_audio_stats_empty_input_guard():
+    # reference returns zeros before touching librosa (misalignment_detection_train.py:118-119)
+    assert A.compute_audio_stats(np.zeros(0, np.float32), 16000, 20).tolist() == [0.0] * 40
+
+
+def test_lipnet_state_dict_is_reference_compatible(lipnet_sd):
+    net = A.LipNet(vocab_size=39)
+    assert list(net.state_dict().keys()) == list(lipnet_sd.keys())
+    for k, v in net.state_dict().items():
+        assert v.shape == lipnet_sd[k].shape, k
+    net.load_state_dict(lipnet_sd)                     # bare form
+    assert net.conv_output_dim == 6912 and sum(p.numel() for p in net.parameters()) == 12537927
+    torch.manual_seed(0)
+    fresh = A.LipNet(vocab_size=39)                    # same default init as the reference under the same seed
+    for k, v in fresh.state_dict().items():
+        assert torch.equal(v, lipnet_sd[k]), k
+    for attr in ("conv1", "conv2", "conv3", "pool1", "pool2", "pool3", "dropout1", "dropout2", "dropout3",
+                 "gru1", "gru2", "fc"):
+        assert hasattr(net, attr)
+
+
+def test_load_lipnet_accepts_both_checkpoint_forms(tmp_path, lipnet_sd):
+    p1, p2 = tmp_path / "bare.pth", tmp_path / "wrapped.pth"
+    torch.save(lipnet_sd, p1)
+    torch.save({"epoch": 3, "model_state_dict": lipnet_sd, "train_loss": 0.0}, p2)
+    for p in (p1, p2):
+        net = A.load_lipnet(str(p), 39, torch.device("cpu"))
+        assert not net.training and all(not q.requires_grad for q in net.parameters())
+        assert torch.equal(net.fc.weight, lipnet_sd["fc.weight"])
+
+
+def test_detector_module_and_checkpoint_format(tmp_path, det_sd):
+    det = A.MisalignmentDetector(13864, 512)
+    assert list(det.state_dict().keys()) == list(det_sd.keys())
+    det.load_state_dict(det_sd)
+    det.eval()
+    x = torch.randn(5, 13864)
+    with torch.no_grad():
+        np.testing.assert_allclose(det(x).numpy(), sweep_ref.detector_logits(det_sd, x).numpy(), rtol=1e-5, atol=1e-6)
+    path = str(tmp_path / "det.pth")
+    A.save_detector(det, path, A.DetectorConfig(max_shift_frames=20))
+    ck = torch.load(path)
+    assert set(ck) == {"model_state_dict", "input_dim", "hidden_dim", "config"}
+    assert ck["config"] == {"sample_rate": 16000, "n_mfcc": 20, "max_shift_frames": 20}
+    back = A.load_detector(path, torch.device("cpu"))
+    assert back.hidden_dim == 512 and torch.equal(back.classifier[0].weight, det.classifier[0].weight)
+
+
+def test_detector_config_defaults():
+    c = A.DetectorConfig()
+    assert (c.img_width, c.img_height, c.max_video_length, c.sample_rate, c.n_mfcc, c.max_shift_frames,
+            c.num_negative_samples, c.default_fps) == (100, 50, 75, 16000, 20, 10, 1, 25.0)
+
+
+def test_ids_to_text_matches_reference_table():
+    class DS:
+        idx_to_char = lipnet_ref.make_vocab()
+    assert A.utils.ids_to_text([1, 1, 37, 38, 27, 99], DS) == "aa <pad>0"
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 64, 8192, 8191):
+        for w in (1, 2, 3, 8):
+            spans = [A.distributed.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_feature_extractor_errors_like_reference():
+    class Grid:
+        def process_video(self, p):
+            return torch.zeros(1, 75, 50, 100)
+    fx = A.FeatureExtractor(Grid(), A.LipNet(39).eval(), torch.device("cpu"), A.DetectorConfig())
+    with pytest.raises(RuntimeError, match="Failed to load audio"):
+        fx._load_audio("nope.mpg")
