@@ -26,6 +26,7 @@ SIGNATURES = {
     "avs_last_error_string": (c_char_p, []),
     "avs_device_check": (c_int, [c_int]),
     "avs_launch_count": (c_longlong, []),
+    "avs_debug_set": (None, [c_int]),
     "avs_prof_enable": (None, [c_int]),
     "avs_prof_reset": (None, []),
     "avs_prof_read": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(c_int)]),

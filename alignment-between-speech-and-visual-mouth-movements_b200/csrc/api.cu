@@ -58,6 +58,9 @@ extern "C" int avs_prof_read(int slot, double* total_ms, int* count) {
   return AVS_OK;
 }
 
+namespace avs { extern int g_conv_dbg; }
+extern "C" void avs_debug_set(int flags) { avs::g_conv_dbg = flags; }
+
 extern "C" int avs_version(void) { return AVS_VERSION; }
 extern "C" const char* avs_last_error_string(void) { return avs::g_err; }
 extern "C" long long avs_launch_count(void) { return avs::g_launches; }

@@ -23,6 +23,7 @@
 //   warp 2         : TMEM allocator
 //   warps 4..7     : epilogue     — tcgen05.ld, pool, bias, ReLU, bf16 (hi/lo) pack, store
 // mbarrier rings: a_full/a_empty[RING], w_full/w_empty[WSTAGES], acc_full/acc_empty[NBUF].
+#include <stdlib.h>
 #include <vector>
 #include "stcnn.cuh"
 
@@ -50,6 +51,7 @@ struct ConvKernelParams {
   int unit_slot_bytes, region_pos, region_full;
   int n_chunks, PP, Wt, Ho, Wo, n_tiles, n_tilesets;
   int T, n_items;
+  int dbg;  // experiment switches (avs_debug_set): 1 = weights loaded once, 2 = A units loaded once, 4 = epilogue skips math/stores
   long long clip_stride, plane_stride;  // elements (bf16) between clips / time planes of `act`
 };
 
@@ -104,6 +106,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       const int len = min(p.region_pos, p.PP - q0);  // positions per (chunk, parity) run
       for (int u = 0; u < p.n_units; ++u, ++seq) {
         const int slot = seq % p.ring;
+        if ((p.dbg & 2) && seq >= static_cast<uint32_t>(p.ring)) continue;
         mbar_wait(&a_empty[slot], ((seq / p.ring) & 1) ^ 1);
         const UnitDesc ud = p.units[u];
         const uint32_t bytes = static_cast<uint32_t>(len) * 16u;
@@ -122,6 +125,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       for (int s = 0; s < p.n_stages; ++s, ++seq) {
         const int slot = seq % p.wstages;
+        if ((p.dbg & 1) && seq >= static_cast<uint32_t>(p.wstages)) continue;
         mbar_wait(&w_empty[slot], ((seq / p.wstages) & 1) ^ 1);
         mbar_expect_tx(&w_full[slot], p.stage_bytes);
         bulk_g2s(s_w + static_cast<size_t>(slot) * p.stage_bytes,
@@ -147,13 +151,13 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       for (int e = 0; e < p.n_ksteps; ++e) {
         if (e == (u == 0 ? 0 : p.units[u - 1].kstep_end)) {  // first K-step of unit u
           const int slot = useq % p.ring;
-          mbar_wait(&a_full[slot], (useq / p.ring) & 1);
+          if (!(p.dbg & 2) || useq < static_cast<uint32_t>(p.ring)) mbar_wait(&a_full[slot], (useq / p.ring) & 1);
           tc_fence_after();
           unit_base = units_addr + slot * p.unit_slot_bytes;
         }
         if (e % p.ksteps_per_stage == 0) {
           const int slot = wseq % p.wstages;
-          mbar_wait(&w_full[slot], (wseq / p.wstages) & 1);
+          if (!(p.dbg & 1) || wseq < static_cast<uint32_t>(p.wstages)) mbar_wait(&w_full[slot], (wseq / p.wstages) & 1);
           tc_fence_after();
           stage_base = w_addr + slot * p.stage_bytes;
         }
@@ -167,11 +171,11 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
           }
         }
         if ((e + 1) % p.ksteps_per_stage == 0) {
-          tc_commit(&w_empty[wseq % p.wstages]);
+          if (!(p.dbg & 1)) tc_commit(&w_empty[wseq % p.wstages]);
           ++wseq;
         }
         if (e + 1 == p.units[u].kstep_end) {
-          tc_commit(&a_empty[useq % p.ring]);
+          if (!(p.dbg & 2)) tc_commit(&a_empty[useq % p.ring]);
           ++useq;
           ++u;
         }
@@ -190,7 +194,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       mbar_wait(&acc_full[buf], (step / p.NBUF) & 1);
       tc_fence_after();
       const uint32_t d_base = tmem_base + buf * (p.NT * 2 * p.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
-      for (int i = 0; i < nt; ++i) {
+      for (int i = 0; i < ((p.dbg & 4) ? 0 : nt); ++i) {
         const int Q = (ts * p.NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
         const int r = Q / p.Wt, wc = Q % p.Wt;                // pooled row, conv column
         const int wo = wc >> 1;
@@ -337,11 +341,27 @@ static float bf2f(uint16_t h) {
 
 struct LayerCfg { int NT, NBUF, ring, wstages; };
 
-static LayerCfg pick_cfg(const LayerGeom& g, int split) {
-  if (g.Cin == 1) return {4, 2, 3, 4};
-  if (g.Cout == 64) return split ? LayerCfg{1, 2, 3, 3} : LayerCfg{2, 2, 3, 4};
-  return {2, 1, 3, 4};  // Cout = 96 (TMEM: 2 tiles x 2 accs x 128 columns)
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
 }
+
+static LayerCfg pick_cfg(const LayerGeom& g, int split) {
+  LayerCfg c;
+  if (g.Cin == 1) c = {4, 2, 3, 4};
+  else if (g.Cout == 64) c = split ? LayerCfg{1, 2, 3, 3} : LayerCfg{2, 2, 3, 4};
+  else c = {2, 1, 3, 4};  // Cout = 96 (TMEM: 2 tiles x 2 accs x 128 columns)
+  // tuning overrides (experiments only; an over-large value fails the smem check in umma_layer_build)
+  const char* tag = g.Cin == 1 ? "1" : (g.Cout == 64 ? "2" : "3");
+  char name[32];
+  snprintf(name, sizeof(name), "AVS_CONV%s_WSTAGES", tag);
+  c.wstages = env_int(name, c.wstages);
+  snprintf(name, sizeof(name), "AVS_CONV%s_RING", tag);
+  c.ring = env_int(name, c.ring);
+  return c;
+}
+
+int g_conv_dbg = 0;
 
 void geom_finalize(LayerGeom& g, int split) {
   g.ph = g.KH / 2;
@@ -535,6 +555,7 @@ int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const Epi
   p.n_chunks = g.n_chunks; p.PP = g.PP; p.Wt = g.Wt; p.Ho = g.Ho; p.Wo = g.Wo; p.n_tiles = g.n_tiles;
   p.n_tilesets = cdiv(g.n_tiles, L.NT);
   p.T = AVS_T;
+  p.dbg = g_conv_dbg;
   const long long items = static_cast<long long>(B) * AVS_T * p.n_tilesets;
   AVS_REQUIRE(items < (1LL << 31), "too many work items for one launch");
   p.n_items = static_cast<int>(items);

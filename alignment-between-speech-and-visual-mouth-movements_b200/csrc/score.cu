@@ -104,9 +104,17 @@ ctc_greedy_kernel(const float* __restrict__ logp, int n_steps, int vocab, int bl
 
 using namespace avs;
 
+// K slices of the hidden-layer GEMM.  Fixed (not a function of the batch) so that a clip's scores are
+// bit-identical whatever batch it is scored in; 16 slices give >= 64 CTAs even for a single clip.
+static int score_splits(int /*n_clips*/, int /*hidden*/, int v_dim) {
+  int s = 1;
+  while (s < 16 && v_dim % (s * 2 * 8) == 0) s *= 2;
+  return s;
+}
+
 extern "C" size_t avs_sweep_score_workspace_bytes(int n_clips, int hidden) {
   if (n_clips <= 0 || hidden <= 0) return 0;
-  return align_up(static_cast<size_t>(n_clips) * hidden * sizeof(float), 256);
+  return align_up(static_cast<size_t>(n_clips) * hidden * sizeof(float), 256) * 17;  // hv + up to 16 split-K partials
 }
 
 extern "C" int avs_sweep_score(const float* vstats, const float* astats, int n_clips, int n_shifts, int v_dim,
@@ -124,7 +132,12 @@ extern "C" int avs_sweep_score(const float* vstats, const float* astats, int n_c
   float* hv = static_cast<float*>(workspace);
   const int ld = v_dim + a_dim;
   int rc;
-  { ProfScope ps(PROF_SCORE_GEMM, st); rc = sgemm_nt(vstats, v_dim, w1, ld, b1, hv, hidden, n_clips, hidden, v_dim, st); }
+  {
+    ProfScope ps(PROF_SCORE_GEMM, st);
+    float* partial = hv + align_up(static_cast<size_t>(n_clips) * hidden * sizeof(float), 256) / sizeof(float);
+    rc = sgemm_nt_splitk(vstats, v_dim, w1, ld, b1, hv, n_clips, hidden, v_dim, score_splits(n_clips, hidden, v_dim),
+                         partial, st);
+  }
   if (rc) return rc;
   ProfScope ps(PROF_SCORE, st);
   const size_t sm = (static_cast<size_t>(n_shifts) * a_dim + n_shifts) * sizeof(float);

@@ -6,6 +6,10 @@ constexpr int BM = 128, BN = 128, BK = 8;
 __global__ void __launch_bounds__(256)
 sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                 const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N, int K) {
+  // split-K: slice z covers k in [z*K, (z+1)*K) and writes its own [M, ldc] partial (bias must be null then)
+  A += static_cast<size_t>(blockIdx.z) * K;
+  B += static_cast<size_t>(blockIdx.z) * K;
+  C += static_cast<size_t>(blockIdx.z) * M * ldc;
   __shared__ float As[2][BK][BM + 4];
   __shared__ float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x;
@@ -63,6 +67,32 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
       if (n < N) C[static_cast<size_t>(m) * ldc + n] = acc[i][j] + (bias ? bias[n] : 0.f);
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias, float* __restrict__ C, int M, int N,
+                     int splits) {
+  const size_t n = static_cast<size_t>(M) * N;
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[z * n + i];
+    C[i] = s + (bias ? bias[i % N] : 0.f);
+  }
+}
+
+// skinny-M variant: K is cut into `splits` slices (deterministic two-phase reduction through `partial`,
+// which must hold splits * M * N floats); C is dense [M, N].
+int sgemm_nt_splitk(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int M, int N, int K,
+                    int splits, float* partial, cudaStream_t st) {
+  AVS_REQUIRE(splits >= 1 && K % (splits * BK) == 0 && lda % 4 == 0 && ldb % 4 == 0, "bad split-K configuration");
+  if (M <= 0 || N <= 0) return AVS_OK;
+  if (splits == 1) return sgemm_nt(A, lda, B, ldb, bias, C, N, M, N, K, st);
+  dim3 grid(cdiv(N, BN), cdiv(M, BM), splits);
+  sgemm_nt_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, nullptr, partial, N, M, N, K / splits);
+  AVS_LAUNCHED();
+  splitk_reduce_kernel<<<cdiv(M * N, 1024), 256, 0, st>>>(partial, bias, C, M, N, splits);
+  AVS_LAUNCHED();
+  return AVS_OK;
 }
 
 int sgemm_nt(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N,

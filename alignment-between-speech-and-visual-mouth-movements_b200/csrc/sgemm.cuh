@@ -7,4 +7,6 @@ namespace avs {
 // Requires K % 4 == 0, lda % 4 == 0, ldb % 4 == 0 and 16-byte aligned A / B.
 int sgemm_nt(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N,
              int K, cudaStream_t st);
+int sgemm_nt_splitk(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int M, int N, int K,
+                    int splits, float* partial, cudaStream_t st);
 }  // namespace avs

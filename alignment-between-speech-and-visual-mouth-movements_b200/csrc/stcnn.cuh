@@ -54,6 +54,7 @@ struct EpiOut {                   // where the fused bias+ReLU+pool epilogue wri
   float* emb;                     // mode 1
 };
 
+extern int g_conv_dbg;
 void geom_finalize(LayerGeom& g, int split);  // fills the derived fields from Cin, Cout, H, W, KH, KW
 int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w_host, const float* b_host);
 void umma_layer_free(UmmaLayer* L);

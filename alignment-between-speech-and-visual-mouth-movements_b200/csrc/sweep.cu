@@ -14,8 +14,10 @@ struct avs_sweep {
   void* ws_stcnn = nullptr; size_t ws_stcnn_bytes = 0;
   void* ws_mfcc = nullptr;  size_t ws_mfcc_bytes = 0;
   void* ws_score = nullptr; size_t ws_score_bytes = 0;
-  float* vstats = nullptr;  // [chunk, 13824]
-  float* astats = nullptr;  // [chunk, K, 2*n_mfcc]
+  float* vstats = nullptr;  // [cap, 13824]   (cap = largest n_clips seen; grown on demand)
+  float* astats = nullptr;  // [cap, K, 2*n_mfcc]
+  float* d_scores_all = nullptr; int32_t* d_best_all = nullptr;  // host entry point results
+  int cap = 0;
   cudaStream_t side = nullptr, copy = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // host entry point: double-buffered device inputs/outputs + pinned staging
@@ -48,14 +50,11 @@ extern "C" int avs_sweep_create(const avs_stcnn* net, const avs_mfcc_plan* plan,
   avs_mfcc_plan_nshifts_internal(plan, &s->K, &s->n_mfcc, &s->n_samples);
   s->ws_stcnn_bytes = avs_stcnn_workspace_bytes(net, chunk_clips);
   s->ws_mfcc_bytes = avs_mfcc_workspace_bytes(plan, chunk_clips);
-  s->ws_score_bytes = avs_sweep_score_workspace_bytes(chunk_clips, hidden);
+  s->ws_score_bytes = 0;
   int rc = AVS_OK;
   auto ck = [&](cudaError_t e) { if (e != cudaSuccess && rc == AVS_OK) { set_error("sweep_create: %s", cudaGetErrorString(e)); rc = AVS_ECUDA; } };
   ck(cudaMalloc(&s->ws_stcnn, s->ws_stcnn_bytes));
   ck(cudaMalloc(&s->ws_mfcc, s->ws_mfcc_bytes));
-  ck(cudaMalloc(&s->ws_score, s->ws_score_bytes));
-  ck(cudaMalloc(reinterpret_cast<void**>(&s->vstats), static_cast<size_t>(chunk_clips) * AVS_VSTATS * sizeof(float)));
-  ck(cudaMalloc(reinterpret_cast<void**>(&s->astats), static_cast<size_t>(chunk_clips) * s->K * 2 * s->n_mfcc * sizeof(float)));
   ck(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
   ck(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
   ck(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
@@ -70,6 +69,7 @@ extern "C" int avs_sweep_create(const avs_stcnn* net, const avs_mfcc_plan* plan,
 extern "C" void avs_sweep_destroy(avs_sweep* s) {
   if (!s) return;
   cudaFree(s->ws_stcnn); cudaFree(s->ws_mfcc); cudaFree(s->ws_score); cudaFree(s->vstats); cudaFree(s->astats);
+  cudaFree(s->d_scores_all); cudaFree(s->d_best_all);
   for (int i = 0; i < 2; ++i) {
     cudaFree(s->d_frames[i]); cudaFree(s->d_audio[i]); cudaFree(s->d_scores[i]); cudaFree(s->d_best[i]);
     cudaFreeHost(s->h_frames[i]); cudaFreeHost(s->h_audio[i]); cudaFreeHost(s->h_scores[i]); cudaFreeHost(s->h_best[i]);
@@ -85,31 +85,56 @@ extern "C" void avs_sweep_destroy(avs_sweep* s) {
   delete s;
 }
 
-// one chunk (n <= s->chunk clips), everything device resident; audio branch on the side stream
-static int run_chunk(avs_sweep* s, const float* frames, const float* audio, int n, float* scores, int32_t* best,
-                     cudaStream_t st) {
+// per-call buffers sized by the number of clips (statistics of all clips, K4 workspace, results)
+static int ensure_capacity(avs_sweep* s, int n_clips) {
+  if (n_clips <= s->cap) return AVS_OK;
+  AVS_CUDA(cudaDeviceSynchronize());
+  cudaFree(s->vstats); cudaFree(s->astats); cudaFree(s->ws_score); cudaFree(s->d_scores_all); cudaFree(s->d_best_all);
+  s->vstats = s->astats = nullptr; s->ws_score = nullptr; s->d_scores_all = nullptr; s->d_best_all = nullptr;
+  s->cap = 0;
+  s->ws_score_bytes = avs_sweep_score_workspace_bytes(n_clips, s->hidden);
+  AVS_CUDA(cudaMalloc(&s->ws_score, s->ws_score_bytes));
+  AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->vstats), static_cast<size_t>(n_clips) * AVS_VSTATS * sizeof(float)));
+  AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->astats), static_cast<size_t>(n_clips) * s->K * 2 * s->n_mfcc * sizeof(float)));
+  AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_scores_all), static_cast<size_t>(n_clips) * s->K * sizeof(float)));
+  AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_best_all), static_cast<size_t>(n_clips) * sizeof(int32_t)));
+  s->cap = n_clips;
+  return AVS_OK;
+}
+
+// statistics of one chunk (n <= s->chunk clips starting at clip c0); audio branch on the side stream.
+// The join with the side stream is left to the caller (ev_join is recorded here).
+static int run_chunk(avs_sweep* s, const float* frames, const float* audio, int c0, int n, cudaStream_t st) {
   int rc;
+  float* vst = s->vstats + static_cast<size_t>(c0) * AVS_VSTATS;
+  float* ast = s->astats + static_cast<size_t>(c0) * s->K * 2 * s->n_mfcc;
   AVS_CUDA(cudaEventRecord(s->ev_fork, st));
   AVS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
-  if ((rc = avs_mfcc_stats_sweep(s->plan, audio, n, s->astats, s->ws_mfcc, s->ws_mfcc_bytes, s->side))) return rc;
+  if ((rc = avs_mfcc_stats_sweep(s->plan, audio, n, ast, s->ws_mfcc, s->ws_mfcc_bytes, s->side))) return rc;
   AVS_CUDA(cudaEventRecord(s->ev_join, s->side));
-  if ((rc = avs_stcnn_forward(s->net, frames, n, nullptr, s->vstats, s->ws_stcnn, s->ws_stcnn_bytes, st))) return rc;
+  if ((rc = avs_stcnn_forward(s->net, frames, n, nullptr, vst, s->ws_stcnn, s->ws_stcnn_bytes, st))) return rc;
   AVS_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
-  return avs_sweep_score(s->vstats, s->astats, n, s->K, AVS_VSTATS, 2 * s->n_mfcc, s->w1, s->b1, s->w2, s->b2, s->hidden,
-                         scores, best, s->ws_score, s->ws_score_bytes, st);
+  return AVS_OK;
+}
+
+// K4 over all clips of the call: one hidden-layer GEMM for the whole batch, then the per-shift scores
+static int score_all(avs_sweep* s, int n_clips, float* scores, int32_t* best, cudaStream_t st) {
+  return avs_sweep_score(s->vstats, s->astats, n_clips, s->K, AVS_VSTATS, 2 * s->n_mfcc, s->w1, s->b1, s->w2, s->b2,
+                         s->hidden, scores, best, s->ws_score, s->ws_score_bytes, st);
 }
 
 extern "C" int avs_sweep_run(avs_sweep* s, const float* frames, const float* audio, int n_clips, float* out_scores,
                              int32_t* out_best, void* stream) {
   AVS_REQUIRE(s && frames && audio && out_scores && out_best, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_clips <= 0) return AVS_OK;
+  int rc = ensure_capacity(s, n_clips);
+  if (rc) return rc;
   for (int c0 = 0; c0 < n_clips; c0 += s->chunk) {
     const int n = std::min(s->chunk, n_clips - c0);
-    int rc = run_chunk(s, frames + c0 * kFrameElems, audio + static_cast<size_t>(c0) * s->n_samples, n,
-                       out_scores + static_cast<size_t>(c0) * s->K, out_best + c0, st);
-    if (rc) return rc;
+    if ((rc = run_chunk(s, frames + c0 * kFrameElems, audio + static_cast<size_t>(c0) * s->n_samples, c0, n, st))) return rc;
   }
-  return AVS_OK;
+  return score_all(s, n_clips, out_scores, out_best, st);
 }
 
 static bool is_pinned(const void* p) {
@@ -149,23 +174,22 @@ static int host_init(avs_sweep* s) {
 extern "C" int avs_sweep_run_host(avs_sweep* s, const float* frames_host, const float* audio_host, int n_clips,
                                   float* out_scores_host, int32_t* out_best_host) {
   AVS_REQUIRE(s && frames_host && audio_host && out_scores_host && out_best_host, "null argument");
+  if (n_clips <= 0) return AVS_OK;
   int rc = host_init(s);
   if (rc) return rc;
+  if ((rc = ensure_capacity(s, n_clips))) return rc;
   const int n_chunks = cdiv(n_clips, s->chunk);
   // page-locked caller buffers are copied from directly; pageable ones go through the pinned staging slots
   const bool direct = is_pinned(frames_host) && is_pinned(audio_host);
-  // software pipeline over chunks: stage(i) -> H2D(i) on the copy stream | compute(i) on main | D2H(i) on copy
+  // software pipeline over chunks: H2D(i+1) on the copy stream overlaps the kernels of chunk i on main
   for (int i = 0; i < n_chunks; ++i) {
     const int sl = i & 1, c0 = i * s->chunk, n = std::min(s->chunk, n_clips - c0);
-    if (i >= 2) {  // slot reuse: results of chunk i-2 must have landed in pinned memory, then drain them
-      AVS_CUDA(cudaEventSynchronize(s->ev_out[sl]));
-      const int p0 = (i - 2) * s->chunk, pn = std::min(s->chunk, n_clips - p0);
-      memcpy(out_scores_host + static_cast<size_t>(p0) * s->K, s->h_scores[sl], static_cast<size_t>(pn) * s->K * sizeof(float));
-      memcpy(out_best_host + p0, s->h_best[sl], static_cast<size_t>(pn) * sizeof(int32_t));
-    }
     const float* fsrc = frames_host + c0 * kFrameElems;
     const float* asrc = audio_host + static_cast<size_t>(c0) * s->n_samples;
-    if (i >= 2) AVS_CUDA(cudaStreamWaitEvent(s->copy, s->ev_done[sl], 0));  // d_frames[sl] is free once chunk i-2 computed
+    if (i >= 2) {
+      AVS_CUDA(cudaStreamWaitEvent(s->copy, s->ev_done[sl], 0));  // device slot is free once chunk i-2 has been consumed
+      if (!direct) AVS_CUDA(cudaEventSynchronize(s->ev_in[sl]));    // pinned staging slot has been read by its H2D
+    }
     if (!direct) {
       memcpy(s->h_frames[sl], fsrc, n * kFrameElems * sizeof(float));
       memcpy(s->h_audio[sl], asrc, static_cast<size_t>(n) * s->n_samples * sizeof(float));
@@ -176,18 +200,12 @@ extern "C" int avs_sweep_run_host(avs_sweep* s, const float* frames_host, const 
     AVS_CUDA(cudaMemcpyAsync(s->d_audio[sl], asrc, static_cast<size_t>(n) * s->n_samples * sizeof(float), cudaMemcpyHostToDevice, s->copy));
     AVS_CUDA(cudaEventRecord(s->ev_in[sl], s->copy));
     AVS_CUDA(cudaStreamWaitEvent(s->main, s->ev_in[sl], 0));
-    if ((rc = run_chunk(s, s->d_frames[sl], s->d_audio[sl], n, s->d_scores[sl], s->d_best[sl], s->main))) return rc;
+    if ((rc = run_chunk(s, s->d_frames[sl], s->d_audio[sl], c0, n, s->main))) return rc;
     AVS_CUDA(cudaEventRecord(s->ev_done[sl], s->main));
-    AVS_CUDA(cudaStreamWaitEvent(s->copy, s->ev_done[sl], 0));
-    AVS_CUDA(cudaMemcpyAsync(s->h_scores[sl], s->d_scores[sl], static_cast<size_t>(n) * s->K * sizeof(float), cudaMemcpyDeviceToHost, s->copy));
-    AVS_CUDA(cudaMemcpyAsync(s->h_best[sl], s->d_best[sl], static_cast<size_t>(n) * sizeof(int32_t), cudaMemcpyDeviceToHost, s->copy));
-    AVS_CUDA(cudaEventRecord(s->ev_out[sl], s->copy));
   }
-  for (int i = std::max(0, n_chunks - 2); i < n_chunks; ++i) {
-    const int sl = i & 1, c0 = i * s->chunk, n = std::min(s->chunk, n_clips - c0);
-    AVS_CUDA(cudaEventSynchronize(s->ev_out[sl]));
-    memcpy(out_scores_host + static_cast<size_t>(c0) * s->K, s->h_scores[sl], static_cast<size_t>(n) * s->K * sizeof(float));
-    memcpy(out_best_host + c0, s->h_best[sl], static_cast<size_t>(n) * sizeof(int32_t));
-  }
+  if ((rc = score_all(s, n_clips, s->d_scores_all, s->d_best_all, s->main))) return rc;
+  AVS_CUDA(cudaMemcpyAsync(out_scores_host, s->d_scores_all, static_cast<size_t>(n_clips) * s->K * sizeof(float), cudaMemcpyDeviceToHost, s->main));
+  AVS_CUDA(cudaMemcpyAsync(out_best_host, s->d_best_all, static_cast<size_t>(n_clips) * sizeof(int32_t), cudaMemcpyDeviceToHost, s->main));
+  AVS_CUDA(cudaStreamSynchronize(s->main));
   return AVS_OK;
 }

@@ -1,0 +1,60 @@
+"""Attribute the time of the tcgen05 conv layers: run the STCNN with the experiment switches of
+avs_debug_set (1 = weights loaded once, 2 = activations loaded once, 4 = no epilogue work) and with
+different pipeline depths, and print per-layer CUDA-event times.  GPU box only."""
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import avsync_b200 as A
+from oracle import lipnet_ref, sweep_ref
+
+L = A._native.lib()
+B = int(os.environ.get("MB_CLIPS", "32"))
+frames = sweep_ref.synth_frames(B, seed=3).cuda()
+sd = lipnet_ref.init_lipnet_state(39, 256, seed=0)
+
+
+def run(precision, flags, label):
+    net = A.LipNet(39, precision=precision)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    L.avs_debug_set(0)
+    net.stcnn(frames)
+    L.avs_debug_set(flags)
+    for _ in range(2):
+        net.stcnn(frames)
+    torch.cuda.synchronize()
+    L.avs_prof_reset()
+    L.avs_prof_enable(1)
+    for _ in range(3):
+        net.stcnn(frames)
+    torch.cuda.synchronize()
+    L.avs_prof_enable(0)
+    L.avs_debug_set(0)
+    out = []
+    for slot, name in ((0, "pack"), (1, "conv1"), (2, "conv2"), (3, "conv3")):
+        t, c = ctypes.c_double(), ctypes.c_int()
+        L.avs_prof_read(slot, ctypes.byref(t), ctypes.byref(c))
+        out.append(f"{name} {1e3 * t.value / max(c.value, 1) / B:8.2f} us/clip")
+    print(f"{label:44s} " + " | ".join(out), flush=True)
+
+
+for prec in ("bf16",):
+    for flags in (0, 1, 2, 3, 4, 7):
+        run(prec, flags, f"{prec} dbg={flags}")
+for ws, ring in ((8, 3), (12, 3), (12, 4)):
+    for l in ("1", "2", "3"):
+        os.environ[f"AVS_CONV{l}_WSTAGES"] = str(ws)
+        os.environ[f"AVS_CONV{l}_RING"] = str(ring)
+    try:
+        run("bf16", 0, f"bf16 wstages={ws} ring={ring}")
+        run("bf16", 1, f"bf16 wstages={ws} ring={ring} dbg=1")
+    except Exception as e:
+        print(f"wstages={ws} ring={ring}: {e}")
+for l in ("1", "2", "3"):
+    os.environ.pop(f"AVS_CONV{l}_WSTAGES", None)
+    os.environ.pop(f"AVS_CONV{l}_RING", None)
+run("bf16x3", 0, "bf16x3 dbg=0")

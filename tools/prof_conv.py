@@ -1,0 +1,20 @@
+"""Tiny driver for ncu: two STCNN forwards (bf16) on a few clips, so `-k regex:conv_umma -s 4 -c 1`
+captures layer 2 of the second forward.  GPU box only."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import avsync_b200 as A
+from oracle import lipnet_ref, sweep_ref
+
+B = int(os.environ.get("PROF_CLIPS", "8"))
+net = A.LipNet(39, precision=os.environ.get("PROF_PRECISION", "bf16"))
+net.load_state_dict(lipnet_ref.init_lipnet_state(39, 256, seed=0))
+net = net.cuda().eval()
+frames = sweep_ref.synth_frames(B, seed=3).cuda()
+for _ in range(2):
+    emb = net.stcnn(frames)
+torch.cuda.synchronize()
+print("ok", float(emb.sum()))
