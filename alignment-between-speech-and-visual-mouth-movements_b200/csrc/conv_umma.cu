@@ -41,7 +41,7 @@ struct UnitDesc {
 struct ConvKernelParams {
   const __nv_bfloat16* act;
   const __nv_bfloat16* w;
-  const KStep* ksteps;
+  const KStepDev* ksteps;
   const float* bias;
   EpiOut eo;
   UnitDesc units[kMaxUnits];
@@ -62,6 +62,7 @@ __device__ __forceinline__ void decode_item(const ConvKernelParams& p, int item,
   b = r / p.T;
 }
 
+template <int NT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -69,9 +70,9 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   uint8_t* s_units = smem;
   uint8_t* s_w = s_units + static_cast<size_t>(p.ring) * p.unit_slot_bytes +
                  static_cast<size_t>(p.region_full - p.region_pos) * 16;  // slack for garbage-lane over-reads
-  KStep* s_ks = reinterpret_cast<KStep*>(s_w + static_cast<size_t>(p.wstages) * p.stage_bytes);
+  KStepDev* s_ks = reinterpret_cast<KStepDev*>(s_w + static_cast<size_t>(p.wstages) * p.stage_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(
-      reinterpret_cast<uint8_t*>(s_ks) + ((static_cast<size_t>(p.n_ksteps) * sizeof(KStep) + 15) / 16) * 16);
+      reinterpret_cast<uint8_t*>(s_ks) + static_cast<size_t>(p.n_ksteps) * sizeof(KStepDev));
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kMaxRing;
   uint64_t* w_full = a_empty + kMaxRing;
@@ -82,7 +83,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < p.n_ksteps * static_cast<int>(sizeof(KStep) / 4); i += kConvThreads)
+  for (int i = threadIdx.x; i < p.n_ksteps * static_cast<int>(sizeof(KStepDev) / 4); i += kConvThreads)
     reinterpret_cast<uint32_t*>(s_ks)[i] = reinterpret_cast<const uint32_t*>(p.ksteps)[i];
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.ring; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 1);
@@ -98,16 +99,15 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
 
   if (warp == 0 && lane == 0) {
     // ============================================================ A producer
-    uint32_t seq = 0;
+    uint32_t seq = 0, slot = 0, phase = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       int b, t, ts;
       decode_item(p, item, b, t, ts);
       const int q0 = ts * p.NT * 128;
       const int len = min(p.region_pos, p.PP - q0);  // positions per (chunk, parity) run
-      for (int u = 0; u < p.n_units; ++u, ++seq) {
-        const int slot = seq % p.ring;
+      for (int u = 0; u < p.n_units; ++u, ++seq, slot = (slot + 1 == static_cast<uint32_t>(p.ring)) ? 0 : slot + 1, phase ^= (slot == 0)) {
         if ((p.dbg & 2) && seq >= static_cast<uint32_t>(p.ring)) continue;
-        mbar_wait(&a_empty[slot], ((seq / p.ring) & 1) ^ 1);
+        mbar_wait(&a_empty[slot], phase ^ 1);
         const UnitDesc ud = p.units[u];
         const uint32_t bytes = static_cast<uint32_t>(len) * 16u;
         mbar_expect_tx(&a_full[slot], bytes * 2u * ud.nchunks);
@@ -121,77 +121,83 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     }
   } else if (warp == 2 && lane == 0) {
     // ============================================================ B (weights) producer
-    uint32_t seq = 0;
+    uint32_t seq = 0, slot = 0, phase = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      for (int s = 0; s < p.n_stages; ++s, ++seq) {
-        const int slot = seq % p.wstages;
+      for (int s = 0; s < p.n_stages; ++s, ++seq, slot = (slot + 1 == static_cast<uint32_t>(p.wstages)) ? 0 : slot + 1, phase ^= (slot == 0)) {
         if ((p.dbg & 1) && seq >= static_cast<uint32_t>(p.wstages)) continue;
-        mbar_wait(&w_empty[slot], ((seq / p.wstages) & 1) ^ 1);
+        mbar_wait(&w_empty[slot], phase ^ 1);
         mbar_expect_tx(&w_full[slot], p.stage_bytes);
         bulk_g2s(s_w + static_cast<size_t>(slot) * p.stage_bytes,
                  reinterpret_cast<const uint8_t*>(p.w) + static_cast<size_t>(s) * p.stage_bytes, p.stage_bytes,
                  &w_full[slot]);
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ============================================================ MMA issuer
+    // The whole warp walks the schedule converged (all lanes hold identical values, so descriptors
+    // live in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit.
     const uint32_t idesc = umma_idesc_bf16(128, p.N);
-    const uint32_t units_addr = smem_u32(s_units), w_addr = smem_u32(s_w);
-    uint32_t useq = 0, wseq = 0, step = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++step) {
-      int b, t, ts;
-      decode_item(p, item, b, t, ts);
-      const int nt = min(p.NT, p.n_tiles - ts * p.NT);
-      const int buf = step % p.NBUF;
-      mbar_wait(&acc_empty[buf], ((step / p.NBUF) & 1) ^ 1);
+    const uint32_t units_lo = smem_u32(s_units) >> 4, w_lo = smem_u32(s_w) >> 4;
+    const uint32_t unit_step = static_cast<uint32_t>(p.unit_slot_bytes) >> 4, stage_step = static_cast<uint32_t>(p.stage_bytes) >> 4;
+    constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
+    uint32_t a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0, acc_buf = 0, acc_phase = 0;
+    uint32_t a_loaded = 0, w_loaded = 0;  // only used by the dbg switches
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int ts = item % p.n_tilesets;
+      const int nt = min(NT, p.n_tiles - ts * NT);
+      mbar_wait(&acc_empty[acc_buf], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_base = tmem_base + buf * (p.NT * 2 * p.acc_stride);
-      int u = 0;
-      uint32_t unit_base = 0, stage_base = 0;
+      const uint32_t d_base = tmem_base + acc_buf * (NT * 2 * p.acc_stride);
+      uint32_t unit_lo = 0, stage_lo = 0;
       for (int e = 0; e < p.n_ksteps; ++e) {
-        if (e == (u == 0 ? 0 : p.units[u - 1].kstep_end)) {  // first K-step of unit u
-          const int slot = useq % p.ring;
-          if (!(p.dbg & 2) || useq < static_cast<uint32_t>(p.ring)) mbar_wait(&a_full[slot], (useq / p.ring) & 1);
+        const KStepDev ks = s_ks[e];
+        if (ks.flags & KS_FIRST_OF_UNIT) {
+          if (!(p.dbg & 2) || a_loaded < static_cast<uint32_t>(p.ring)) mbar_wait(&a_full[a_slot], a_phase);
+          ++a_loaded;
           tc_fence_after();
-          unit_base = units_addr + slot * p.unit_slot_bytes;
+          unit_lo = units_lo + a_slot * unit_step;
         }
-        if (e % p.ksteps_per_stage == 0) {
-          const int slot = wseq % p.wstages;
-          if (!(p.dbg & 1) || wseq < static_cast<uint32_t>(p.wstages)) mbar_wait(&w_full[slot], (wseq / p.wstages) & 1);
+        if (ks.flags & KS_FIRST_OF_STAGE) {
+          if (!(p.dbg & 1) || w_loaded < static_cast<uint32_t>(p.wstages)) mbar_wait(&w_full[w_slot], w_phase);
+          ++w_loaded;
           tc_fence_after();
-          stage_base = w_addr + slot * p.stage_bytes;
+          stage_lo = w_lo + w_slot * stage_step;
         }
-        const KStep ks = s_ks[e];
-        const uint64_t bdesc = umma_desc_kmajor(stage_base + ks.b_off, p.N * 16, 128);
-        for (int i = 0; i < nt; ++i) {
+        const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (ks.b_lo + stage_lo);
+        const uint32_t a0 = ks.a_lo[0] + unit_lo, a1 = ks.a_lo[1] + unit_lo;
+        const uint32_t acc = e > 0 ? 1u : 0u;
+        if (elect_one()) {
 #pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            const uint64_t adesc = umma_desc_kmajor(unit_base + ks.a_off[a] + i * (128 * 16), ks.lbo, 128);
-            umma_f16(d_base + (i * 2 + a) * p.acc_stride, adesc, bdesc, idesc, e > 0 ? 1u : 0u);
+          for (int i = 0; i < NT; ++i) {
+            if (i < nt) {
+              umma_f16(d_base + (i * 2 + 0) * p.acc_stride, (static_cast<uint64_t>(kDescHi) << 32) | (a0 + i * 128), bdesc, idesc, acc);
+              umma_f16(d_base + (i * 2 + 1) * p.acc_stride, (static_cast<uint64_t>(kDescHi) << 32) | (a1 + i * 128), bdesc, idesc, acc);
+            }
           }
+          if ((ks.flags & KS_LAST_OF_STAGE) && !(p.dbg & 1)) tc_commit(&w_empty[w_slot]);
+          if ((ks.flags & KS_LAST_OF_UNIT) && !(p.dbg & 2)) tc_commit(&a_empty[a_slot]);
         }
-        if ((e + 1) % p.ksteps_per_stage == 0) {
-          if (!(p.dbg & 1)) tc_commit(&w_empty[wseq % p.wstages]);
-          ++wseq;
+        __syncwarp();
+        if (ks.flags & KS_LAST_OF_STAGE) {
+          if (++w_slot == static_cast<uint32_t>(p.wstages)) w_slot = 0, w_phase ^= 1;
         }
-        if (e + 1 == p.units[u].kstep_end) {
-          if (!(p.dbg & 2)) tc_commit(&a_empty[useq % p.ring]);
-          ++useq;
-          ++u;
+        if (ks.flags & KS_LAST_OF_UNIT) {
+          if (++a_slot == static_cast<uint32_t>(p.ring)) a_slot = 0, a_phase ^= 1;
         }
       }
-      tc_commit(&acc_full[buf]);
+      if (elect_one()) tc_commit(&acc_full[acc_buf]);
+      __syncwarp();
+      if (++acc_buf == static_cast<uint32_t>(p.NBUF)) acc_buf = 0, acc_phase ^= 1;
     }
   } else if (warp >= 4) {
     // ============================================================ epilogue
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    uint32_t step = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++step) {
+    uint32_t buf = 0, phase = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, buf = (buf + 1 == static_cast<uint32_t>(p.NBUF)) ? 0 : buf + 1, phase ^= (buf == 0)) {
       int b, t, ts;
       decode_item(p, item, b, t, ts);
       const int nt = min(p.NT, p.n_tiles - ts * p.NT);
-      const int buf = step % p.NBUF;
-      mbar_wait(&acc_full[buf], (step / p.NBUF) & 1);
+      mbar_wait(&acc_full[buf], phase);
       tc_fence_after();
       const uint32_t d_base = tmem_base + buf * (p.NT * 2 * p.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
       for (int i = 0; i < ((p.dbg & 4) ? 0 : nt); ++i) {
@@ -496,7 +502,7 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
   const int chunks_per_unit = g.n_chunks / (n_units / 3);
   L->plane_slot_bytes = chunks_per_unit * 2 * static_cast<int>(arr_bytes);
   L->smem_bytes = static_cast<size_t>(L->ring) * L->plane_slot_bytes + static_cast<size_t>(region_full - L->region_pos) * 16 +
-                  static_cast<size_t>(L->wstages) * L->stage_bytes + align_up(ks.size() * sizeof(KStep), 16) +
+                  static_cast<size_t>(L->wstages) * L->stage_bytes + ks.size() * sizeof(KStepDev) +
                   (2 * kMaxRing + 2 * kMaxWStages + 4) * 8 + 16;
   if (L->smem_bytes > 232448 || L->ring > kMaxRing || L->wstages > kMaxWStages || n_units > kMaxUnits ||
       wp.size() * 2 != static_cast<size_t>(L->n_stages) * L->stage_bytes || L->stage_bytes % 16 != 0) {
@@ -504,13 +510,27 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
               L->n_stages, wp.size() * 2);
     return AVS_EINVAL;
   }
-  AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&L->d_ksteps), ks.size() * sizeof(KStep)));
-  AVS_CUDA(cudaMemcpy(L->d_ksteps, ks.data(), ks.size() * sizeof(KStep), cudaMemcpyHostToDevice));
+  std::vector<KStepDev> kd(ks.size());
+  const int ks_per_unit = L->n_ksteps / n_units;
+  for (size_t e = 0; e < ks.size(); ++e) {
+    for (int a = 0; a < 2; ++a) kd[e].a_lo[a] = (ks[e].a_off[a] >> 4) | ((ks[e].lbo >> 4) << 16);
+    kd[e].b_lo = (ks[e].b_off >> 4) | (static_cast<uint32_t>(N) << 16);  // LBO of B = N * 16 B
+    uint32_t f = 0;
+    if (e % ks_per_unit == 0) f |= KS_FIRST_OF_UNIT;
+    if ((e + 1) % ks_per_unit == 0) f |= KS_LAST_OF_UNIT;
+    if (e % L->ksteps_per_stage == 0) f |= KS_FIRST_OF_STAGE;
+    if ((e + 1) % L->ksteps_per_stage == 0) f |= KS_LAST_OF_STAGE;
+    kd[e].flags = f;
+  }
+  AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&L->d_ksteps), kd.size() * sizeof(KStepDev)));
+  AVS_CUDA(cudaMemcpy(L->d_ksteps, kd.data(), kd.size() * sizeof(KStepDev), cudaMemcpyHostToDevice));
   AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&L->d_w), wp.size() * 2));
   AVS_CUDA(cudaMemcpy(L->d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
   AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&L->d_bias), N * sizeof(float)));
   AVS_CUDA(cudaMemcpy(L->d_bias, bias, N * sizeof(float), cudaMemcpyHostToDevice));
-  AVS_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  AVS_CUDA(cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  AVS_CUDA(cudaFuncSetAttribute(conv_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  AVS_CUDA(cudaFuncSetAttribute(conv_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   return AVS_OK;
 }
 
@@ -563,7 +583,9 @@ int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const Epi
   p.clip_stride = p.plane_stride * (AVS_T + 2);
   const int grid = static_cast<int>(std::min<long long>(items, n_sms));
   ProfScope ps(L.g.Cin == 1 ? PROF_CONV1 : (L.g.Cout == 64 ? PROF_CONV2 : PROF_CONV3), st);
-  conv_umma_kernel<<<grid, kConvThreads, L.smem_bytes, st>>>(p);
+  if (L.NT == 1) conv_umma_kernel<1><<<grid, kConvThreads, L.smem_bytes, st>>>(p);
+  else if (L.NT == 2) conv_umma_kernel<2><<<grid, kConvThreads, L.smem_bytes, st>>>(p);
+  else conv_umma_kernel<4><<<grid, kConvThreads, L.smem_bytes, st>>>(p);
   AVS_LAUNCHED();
   return AVS_OK;
 }

@@ -30,6 +30,17 @@ struct KStep {                    // one tcgen05.mma (K = 16) of the per-output-
   int32_t kd;                     // which of the 3 time planes A comes from
 };
 
+// device form of a K-step: descriptor low words with the slot-independent parts pre-folded
+//   a_lo[a] = (a_off[a] >> 4) | ((lbo >> 4) << 16),  b_lo = (b_off >> 4) | ((N * 16 >> 4) << 16)
+// the issuer only adds (slot base >> 4) (+ tile * 128) — smem addresses are < 256 KB so the 14-bit
+// address field never carries into the LBO field.
+enum : uint32_t { KS_FIRST_OF_UNIT = 1, KS_LAST_OF_UNIT = 2, KS_FIRST_OF_STAGE = 4, KS_LAST_OF_STAGE = 8 };
+struct KStepDev {
+  uint32_t a_lo[2];
+  uint32_t b_lo;
+  uint32_t flags;
+};
+
 struct UmmaLayer {                // device-resident, built once by stcnn_create
   LayerGeom g;
   int split;                      // 1: hi/lo bf16 split (BF16X3)
@@ -41,7 +52,7 @@ struct UmmaLayer {                // device-resident, built once by stcnn_create
   int plane_slot_bytes;           // bytes of one plane slot in shared memory
   int region_pos;                 // positions loaded per (chunk, parity) for a full NT-tile item
   int acc_stride;                 // TMEM columns between accumulators
-  KStep* d_ksteps = nullptr;
+  KStepDev* d_ksteps = nullptr;
   __nv_bfloat16* d_w = nullptr;   // packed B tiles, n_stages * stage_bytes
   float* d_bias = nullptr;
   size_t smem_bytes;

@@ -45,16 +45,17 @@ def run(precision, flags, label):
 for prec in ("bf16",):
     for flags in (0, 1, 2, 3, 4, 7):
         run(prec, flags, f"{prec} dbg={flags}")
-for ws, ring in ((8, 3), (12, 3), (12, 4)):
-    for l in ("1", "2", "3"):
-        os.environ[f"AVS_CONV{l}_WSTAGES"] = str(ws)
-        os.environ[f"AVS_CONV{l}_RING"] = str(ring)
+for ws in (2, 8):
+    os.environ["AVS_CONV2_WSTAGES"] = str(ws)
     try:
-        run("bf16", 0, f"bf16 wstages={ws} ring={ring}")
-        run("bf16", 1, f"bf16 wstages={ws} ring={ring} dbg=1")
+        run("bf16", 0, f"bf16 conv2 wstages={ws}")
     except Exception as e:
-        print(f"wstages={ws} ring={ring}: {e}")
-for l in ("1", "2", "3"):
-    os.environ.pop(f"AVS_CONV{l}_WSTAGES", None)
-    os.environ.pop(f"AVS_CONV{l}_RING", None)
+        print(f"wstages={ws}: {e}")
+os.environ.pop("AVS_CONV2_WSTAGES", None)
+os.environ["AVS_CONV2_RING"] = "4"
+try:
+    run("bf16", 0, "bf16 conv2 ring=4")
+except Exception as e:
+    print(f"ring=4: {e}")
+os.environ.pop("AVS_CONV2_RING", None)
 run("bf16x3", 0, "bf16x3 dbg=0")
