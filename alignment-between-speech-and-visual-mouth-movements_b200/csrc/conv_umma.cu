@@ -62,7 +62,7 @@ __device__ __forceinline__ void decode_item(const ConvKernelParams& p, int item,
   b = r / p.T;
 }
 
-template <int NT>
+template <int NT, int KPS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -134,60 +134,62 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer
-    // The whole warp walks the schedule converged (all lanes hold identical values, so descriptors
-    // live in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit.
+    // The whole warp walks the schedule converged; one elected lane issues tcgen05.mma / .commit.
+    // Loop nest: item -> weight stage -> KPS K-steps (unrolled) -> NT tiles x 2 accumulators.
+    // A units are made of whole stages, so unit boundaries are only checked once per stage.
     const uint32_t idesc = umma_idesc_bf16(128, p.N);
     const uint32_t units_lo = smem_u32(s_units) >> 4, w_lo = smem_u32(s_w) >> 4;
     const uint32_t unit_step = static_cast<uint32_t>(p.unit_slot_bytes) >> 4, stage_step = static_cast<uint32_t>(p.stage_bytes) >> 4;
-    constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
+    const uint32_t ring = p.ring, wstages = p.wstages, nbuf = p.NBUF, acc_stride = p.acc_stride;
+    const int n_stages = p.n_stages, n_tilesets = p.n_tilesets, n_tiles = p.n_tiles, dbg = p.dbg;
+    constexpr uint64_t kDescHi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, version 1
     uint32_t a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0, acc_buf = 0, acc_phase = 0;
     uint32_t a_loaded = 0, w_loaded = 0;  // only used by the dbg switches
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int ts = item % p.n_tilesets;
-      const int nt = min(NT, p.n_tiles - ts * NT);
+      const int ts = item % n_tilesets;
+      const int nt = min(NT, n_tiles - ts * NT);
       mbar_wait(&acc_empty[acc_buf], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_base = tmem_base + acc_buf * (NT * 2 * p.acc_stride);
-      uint32_t unit_lo = 0, stage_lo = 0;
-      for (int e = 0; e < p.n_ksteps; ++e) {
-        const KStepDev ks = s_ks[e];
-        if (ks.flags & KS_FIRST_OF_UNIT) {
-          if (!(p.dbg & 2) || a_loaded < static_cast<uint32_t>(p.ring)) mbar_wait(&a_full[a_slot], a_phase);
+      const uint32_t d_base = tmem_base + acc_buf * (NT * 2 * acc_stride);
+      uint32_t unit_lo = 0;
+      for (int st = 0; st < n_stages; ++st) {
+        const KStepDev* ks = s_ks + st * KPS;
+        const uint32_t f0 = ks[0].flags, f1 = ks[KPS - 1].flags;
+        if (f0 & KS_FIRST_OF_UNIT) {
+          if (!(dbg & 2) || a_loaded < ring) mbar_wait(&a_full[a_slot], a_phase);
           ++a_loaded;
-          tc_fence_after();
           unit_lo = units_lo + a_slot * unit_step;
         }
-        if (ks.flags & KS_FIRST_OF_STAGE) {
-          if (!(p.dbg & 1) || w_loaded < static_cast<uint32_t>(p.wstages)) mbar_wait(&w_full[w_slot], w_phase);
-          ++w_loaded;
-          tc_fence_after();
-          stage_lo = w_lo + w_slot * stage_step;
-        }
-        const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (ks.b_lo + stage_lo);
-        const uint32_t a0 = ks.a_lo[0] + unit_lo, a1 = ks.a_lo[1] + unit_lo;
-        const uint32_t acc = e > 0 ? 1u : 0u;
+        if (!(dbg & 1) || w_loaded < wstages) mbar_wait(&w_full[w_slot], w_phase);
+        ++w_loaded;
+        tc_fence_after();
+        const uint32_t stage_lo = w_lo + w_slot * stage_step;
         if (elect_one()) {
 #pragma unroll
-          for (int i = 0; i < NT; ++i) {
-            if (i < nt) {
-              umma_f16(d_base + (i * 2 + 0) * p.acc_stride, (static_cast<uint64_t>(kDescHi) << 32) | (a0 + i * 128), bdesc, idesc, acc);
-              umma_f16(d_base + (i * 2 + 1) * p.acc_stride, (static_cast<uint64_t>(kDescHi) << 32) | (a1 + i * 128), bdesc, idesc, acc);
+          for (int j = 0; j < KPS; ++j) {
+            const uint4 k4 = *reinterpret_cast<const uint4*>(ks + j);  // a_lo[0], a_lo[1], b_lo, flags
+            const uint64_t bdesc = kDescHi | (k4.z + stage_lo);
+            const uint32_t a0 = k4.x + unit_lo, a1 = k4.y + unit_lo;
+            const uint32_t acc = (st | j) != 0 ? 1u : 0u;
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+              if (i < nt) {
+                umma_f16(d_base + (i * 2 + 0) * acc_stride, kDescHi | (a0 + i * 128), bdesc, idesc, acc);
+                umma_f16(d_base + (i * 2 + 1) * acc_stride, kDescHi | (a1 + i * 128), bdesc, idesc, acc);
+              }
             }
           }
-          if ((ks.flags & KS_LAST_OF_STAGE) && !(p.dbg & 1)) tc_commit(&w_empty[w_slot]);
-          if ((ks.flags & KS_LAST_OF_UNIT) && !(p.dbg & 2)) tc_commit(&a_empty[a_slot]);
+          if (!(dbg & 1)) tc_commit(&w_empty[w_slot]);
+          if ((f1 & KS_LAST_OF_UNIT) && !(dbg & 2)) tc_commit(&a_empty[a_slot]);
+          if (st == n_stages - 1) tc_commit(&acc_full[acc_buf]);
         }
         __syncwarp();
-        if (ks.flags & KS_LAST_OF_STAGE) {
-          if (++w_slot == static_cast<uint32_t>(p.wstages)) w_slot = 0, w_phase ^= 1;
-        }
-        if (ks.flags & KS_LAST_OF_UNIT) {
-          if (++a_slot == static_cast<uint32_t>(p.ring)) a_slot = 0, a_phase ^= 1;
+        if (++w_slot == wstages) w_slot = 0, w_phase ^= 1;
+        if (f1 & KS_LAST_OF_UNIT) {
+          if (++a_slot == ring) a_slot = 0, a_phase ^= 1;
         }
       }
-      if (elect_one()) tc_commit(&acc_full[acc_buf]);
-      __syncwarp();
-      if (++acc_buf == static_cast<uint32_t>(p.NBUF)) acc_buf = 0, acc_phase ^= 1;
+      if (++acc_buf == nbuf) acc_buf = 0, acc_phase ^= 1;
     }
   } else if (warp >= 4) {
     // ============================================================ epilogue
@@ -265,6 +267,18 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
+}
+
+using ConvKernel = void (*)(const ConvKernelParams);
+// (tiles per item, K-steps per weight stage) of the six layer x precision configurations
+static ConvKernel conv_kernel_for(int NT, int KPS) {
+  if (NT == 4 && KPS == 3) return conv_umma_kernel<4, 3>;   // conv1 bf16
+  if (NT == 4 && KPS == 9) return conv_umma_kernel<4, 9>;   // conv1 bf16x3
+  if (NT == 2 && KPS == 2) return conv_umma_kernel<2, 2>;   // conv2 bf16
+  if (NT == 1 && KPS == 6) return conv_umma_kernel<1, 6>;   // conv2 bf16x3
+  if (NT == 2 && KPS == 4) return conv_umma_kernel<2, 4>;   // conv3 bf16
+  if (NT == 2 && KPS == 6) return conv_umma_kernel<2, 6>;   // conv3 bf16x3 (channel halves)
+  return nullptr;
 }
 
 // ------------------------------------------------------------------------------------------------ layout kernels
@@ -528,9 +542,11 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
   AVS_CUDA(cudaMemcpy(L->d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
   AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&L->d_bias), N * sizeof(float)));
   AVS_CUDA(cudaMemcpy(L->d_bias, bias, N * sizeof(float), cudaMemcpyHostToDevice));
-  AVS_CUDA(cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-  AVS_CUDA(cudaFuncSetAttribute(conv_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-  AVS_CUDA(cudaFuncSetAttribute(conv_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  if (conv_kernel_for(L->NT, L->ksteps_per_stage) == nullptr) {
+    set_error("no conv_umma_kernel instantiation for NT=%d KPS=%d", L->NT, L->ksteps_per_stage);
+    return AVS_EINVAL;
+  }
+  AVS_CUDA(cudaFuncSetAttribute(conv_kernel_for(L->NT, L->ksteps_per_stage), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   return AVS_OK;
 }
 
@@ -583,9 +599,7 @@ int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const Epi
   p.clip_stride = p.plane_stride * (AVS_T + 2);
   const int grid = static_cast<int>(std::min<long long>(items, n_sms));
   ProfScope ps(L.g.Cin == 1 ? PROF_CONV1 : (L.g.Cout == 64 ? PROF_CONV2 : PROF_CONV3), st);
-  if (L.NT == 1) conv_umma_kernel<1><<<grid, kConvThreads, L.smem_bytes, st>>>(p);
-  else if (L.NT == 2) conv_umma_kernel<2><<<grid, kConvThreads, L.smem_bytes, st>>>(p);
-  else conv_umma_kernel<4><<<grid, kConvThreads, L.smem_bytes, st>>>(p);
+  conv_kernel_for(L.NT, L.ksteps_per_stage)<<<grid, kConvThreads, L.smem_bytes, st>>>(p);
   AVS_LAUNCHED();
   return AVS_OK;
 }
