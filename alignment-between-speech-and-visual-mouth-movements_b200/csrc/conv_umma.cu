@@ -165,6 +165,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         tc_fence_after();
         const uint32_t stage_lo = w_lo + w_slot * stage_step;
         if (elect_one()) {
+          for (int rep = 0; rep < ((dbg & 8) ? 2 : 1); ++rep)  // dbg 8: issue every MMA twice (tensor-vs-issue bound test)
 #pragma unroll
           for (int j = 0; j < KPS; ++j) {
             const uint4 k4 = *reinterpret_cast<const uint4*>(ks + j);  // a_lo[0], a_lo[1], b_lo, flags
@@ -274,7 +275,9 @@ using ConvKernel = void (*)(const ConvKernelParams);
 static ConvKernel conv_kernel_for(int NT, int KPS) {
   if (NT == 4 && KPS == 3) return conv_umma_kernel<4, 3>;   // conv1 bf16
   if (NT == 4 && KPS == 9) return conv_umma_kernel<4, 9>;   // conv1 bf16x3
-  if (NT == 2 && KPS == 2) return conv_umma_kernel<2, 2>;   // conv2 bf16
+  if (NT == 2 && KPS == 2) return conv_umma_kernel<2, 2>;   // conv2 bf16, 1 tap per stage
+  if (NT == 2 && KPS == 10) return conv_umma_kernel<2, 10>; // conv2 bf16, 5 taps per stage
+  if (NT == 2 && KPS == 12) return conv_umma_kernel<2, 12>; // conv3 bf16, 3 taps per stage
   if (NT == 1 && KPS == 6) return conv_umma_kernel<1, 6>;   // conv2 bf16x3
   if (NT == 2 && KPS == 4) return conv_umma_kernel<2, 4>;   // conv3 bf16
   if (NT == 2 && KPS == 6) return conv_umma_kernel<2, 6>;   // conv3 bf16x3 (channel halves)
@@ -359,7 +362,7 @@ static float bf2f(uint16_t h) {
   return x;
 }
 
-struct LayerCfg { int NT, NBUF, ring, wstages; };
+struct LayerCfg { int NT, NBUF, ring, wstages, TPS; };  // TPS = filter taps per weight stage
 
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -368,12 +371,16 @@ static int env_int(const char* name, int dflt) {
 
 static LayerCfg pick_cfg(const LayerGeom& g, int split) {
   LayerCfg c;
-  if (g.Cin == 1) c = {4, 2, 3, 4};
-  else if (g.Cout == 64) c = split ? LayerCfg{1, 2, 3, 3} : LayerCfg{2, 2, 3, 4};
-  else c = {2, 1, 3, 4};  // Cout = 96 (TMEM: 2 tiles x 2 accs x 128 columns)
+  // Big weight stages amortise the issuer's per-stage cost (two mbarrier waits + descriptor setup,
+  // ~330 cycles) over more MMAs: conv2 bf16 uses one kernel row (5 taps, 40 MMAs) per stage.
+  if (g.Cin == 1) c = {4, 2, 3, 4, 1};
+  else if (g.Cout == 64) c = split ? LayerCfg{1, 2, 3, 3, 1} : LayerCfg{2, 2, 3, 3, 5};
+  else c = split ? LayerCfg{2, 1, 3, 4, 1} : LayerCfg{2, 1, 2, 3, 3};  // Cout = 96 (TMEM: 2 tiles x 2 accs x 128 columns)
   // tuning overrides (experiments only; an over-large value fails the smem check in umma_layer_build)
   const char* tag = g.Cin == 1 ? "1" : (g.Cout == 64 ? "2" : "3");
   char name[32];
+  snprintf(name, sizeof(name), "AVS_CONV%s_TPS", tag);
+  c.TPS = env_int(name, c.TPS);
   snprintf(name, sizeof(name), "AVS_CONV%s_WSTAGES", tag);
   c.wstages = env_int(name, c.wstages);
   snprintf(name, sizeof(name), "AVS_CONV%s_RING", tag);
@@ -473,14 +480,20 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
     // generic: unit = (kd, channel group); stage = (tap, channel group)
     const int groups = (g.Cout == 96 && split) ? 2 : 1;
     const int CG = g.Cin / groups, pairs = CG / 16;
-    L->ksteps_per_stage = pairs * (split ? 3 : 1);
+    const int TPS = c.TPS;
+    if ((g.KH * g.KW) % TPS != 0) {
+      set_error("taps per stage %d does not divide %d", TPS, g.KH * g.KW);
+      return AVS_EINVAL;
+    }
+    L->ksteps_per_stage = TPS * pairs * (split ? 3 : 1);
     const int kmul = split ? 2 : 1;
     for (int kd = 0; kd < 3; ++kd)
       for (int cg = 0; cg < groups; ++cg) {
         const int chunk0 = cg * (CG / 8) * kmul;  // first chunk array of this unit
+        size_t sb = 0;
         for (int kh = 0; kh < g.KH; ++kh)
           for (int kw = 0; kw < g.KW; ++kw) {
-            const size_t sb = wp.size();
+            if ((kh * g.KW + kw) % TPS == 0) sb = wp.size();  // a new weight stage starts here
             std::vector<uint32_t> bh(pairs), bl(pairs);
             for (int pr = 0; pr < pairs; ++pr) {
               auto elem = [&](int half, int n, int k) { return wat(n, cg * CG + pr * 16 + half * 8 + k, kd, kh, kw); };
@@ -509,7 +522,7 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
           }
         n_units++;
       }
-    L->stage_bytes = static_cast<int>(wp.size() * 2 / (taps * groups));
+    L->stage_bytes = static_cast<int>(wp.size() * 2 / (taps * groups / TPS));
   }
   L->n_ksteps = static_cast<int>(ks.size());
   L->n_stages = L->n_ksteps / L->ksteps_per_stage;

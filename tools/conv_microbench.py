@@ -43,19 +43,8 @@ def run(precision, flags, label):
 
 
 for prec in ("bf16",):
-    for flags in (0, 1, 2, 3, 4, 7):
+    for flags in (0, 7, 8, 15):
         run(prec, flags, f"{prec} dbg={flags}")
-for ws in (2, 8):
-    os.environ["AVS_CONV2_WSTAGES"] = str(ws)
-    try:
-        run("bf16", 0, f"bf16 conv2 wstages={ws}")
-    except Exception as e:
-        print(f"wstages={ws}: {e}")
-os.environ.pop("AVS_CONV2_WSTAGES", None)
-os.environ["AVS_CONV2_RING"] = "4"
-try:
-    run("bf16", 0, "bf16 conv2 ring=4")
-except Exception as e:
-    print(f"ring=4: {e}")
-os.environ.pop("AVS_CONV2_RING", None)
 run("bf16x3", 0, "bf16x3 dbg=0")
+run("bf16x3", 7, "bf16x3 dbg=7")
+run("bf16x3", 15, "bf16x3 dbg=15")
