@@ -29,7 +29,7 @@
 
 namespace avs {
 
-constexpr int kConvThreads = 256;
+constexpr int kConvThreads = 384;  // 4 control warps + 2 epilogue groups of 4 warps
 constexpr int kMaxUnits = 6;
 constexpr int kMaxRing = 4;
 constexpr int kMaxWStages = 8;
@@ -88,7 +88,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.ring; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 1);
     for (int i = 0; i < p.wstages; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
-    for (int i = 0; i < p.NBUF; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 4);
+    for (int i = 0; i < p.NBUF; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 8);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<512>(s_tmem);
@@ -194,7 +194,9 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     }
   } else if (warp >= 4) {
     // ============================================================ epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    // Two groups of four warps (warps 4-7 and 8-11); warp w may read TMEM lanes 32*(w%4)..+31.  The
+    // (tile, 32-column block) work units of an item alternate between the groups.
+    const int q = warp & 3, grp = (warp - 4) >> 2;
     uint32_t buf = 0, phase = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, buf = (buf + 1 == static_cast<uint32_t>(p.NBUF)) ? 0 : buf + 1, phase ^= (buf == 0)) {
       int b, t, ts;
@@ -210,18 +212,22 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         const bool valid = (r < p.Ho) && (wo < p.Wo);
         const int half = lane & 1;                            // even lane: channels 0..15 of the block, odd: 16..31
         for (int cb = 0; cb < p.N; cb += 32) {
+          if ((((i * p.N) >> 5) + (cb >> 5) & 1) != grp) continue;  // warp-uniform
           uint32_t v0[32], v1[32];
           tmem_ld32(d_base + (i * 2 + 0) * p.acc_stride + cb, v0);
           tmem_ld32(d_base + (i * 2 + 1) * p.acc_stride + cb, v1);
           tmem_ld_wait();
           float o[16];
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            float m = fmaxf(__uint_as_float(v0[c]), __uint_as_float(v1[c]));  // rows 2r, 2r+1
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));                 // columns 2wo, 2wo+1
-            if ((c >> 4) == half) o[c & 15] = fmaxf(m + __ldg(p.bias + cb + c), 0.f);
-          }
           const int ch0 = cb + half * 16;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            // rows 2r, 2r+1: max of the two accumulators; columns 2wo, 2wo+1: exchange with the
+            // neighbouring lane — each lane keeps 16 of the 32 channels and ships the other 16
+            const float lo = fmaxf(__uint_as_float(v0[c]), __uint_as_float(v1[c]));
+            const float hi = fmaxf(__uint_as_float(v0[c + 16]), __uint_as_float(v1[c + 16]));
+            const float got = __shfl_xor_sync(0xffffffffu, half ? lo : hi, 1);
+            o[c] = fmaxf(fmaxf(half ? hi : lo, got) + __ldg(p.bias + ch0 + c), 0.f);
+          }
           if (valid && p.eo.mode == 0) {
             const int hp = r + p.eo.ph_next;
             const long long pos = p.eo.pw_next + (hp >> 1) * p.eo.Wt_next + wo;
@@ -286,42 +292,49 @@ static ConvKernel conv_kernel_for(int NT, int KPS) {
 
 // ------------------------------------------------------------------------------------------------ layout kernels
 // frames f32 [B,1,T,H,W] -> layer-1 input: X8 layout, position p holds the 8 consecutive padded-row values
-// val(p) .. val(p+7) (so the kw taps are the K index of the MMA).  One thread per (clip, tp, parity, position).
+// val(p) .. val(p+7) (so the kw taps are the K index of the MMA).  One CTA per (clip, tp, parity): the
+// flattened padded parity array is staged in shared memory as bf16 (hi and lo residual) with coalesced
+// row loads, then every thread emits 16-byte X8 entries for consecutive positions.
 __global__ void __launch_bounds__(256)
-pack_frames_kernel(const float* __restrict__ frames, __nv_bfloat16* __restrict__ act, LayerGeom g, int split, int T,
-                   long long total) {
-  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  if (idx >= total) return;
-  const int pos = static_cast<int>(idx % g.PP);
-  long long r = idx / g.PP;
-  const int par = static_cast<int>(r % 2);
-  r /= 2;
-  const int tp = static_cast<int>(r % (T + 2));
-  const long long b = r / (T + 2);
-  float v[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int pe = pos + e - g.pw;
-    float x = 0.f;
-    if (pe >= 0 && tp >= 1 && tp <= T) {
-      const int row = pe / g.Wt, wq = pe % g.Wt;
+pack_frames_kernel(const float* __restrict__ frames, __nv_bfloat16* __restrict__ act, LayerGeom g, int split, int T) {
+  extern __shared__ uint16_t s_val[];           // [2][PP + 8]: hi, lo
+  const int n = g.PP + 8;
+  uint16_t* s_hi = s_val;
+  uint16_t* s_lo = s_val + n;
+  const int par = blockIdx.x & 1, tp = (blockIdx.x >> 1) % (T + 2);
+  const long long b = (blockIdx.x >> 1) / (T + 2);
+  for (int i = threadIdx.x; i < 2 * n; i += 256) s_val[i] = 0;
+  __syncthreads();
+  if (tp >= 1 && tp <= T) {
+    const float* f = frames + (b * T + (tp - 1)) * static_cast<long long>(g.H) * g.W;
+    for (int i = threadIdx.x; i < g.Hh * g.W; i += 256) {
+      const int row = i / g.W, wq = i - row * g.W;
       const int h = 2 * row + par - g.ph;
-      if (h >= 0 && h < g.H && wq < g.W) x = frames[((b * T + (tp - 1)) * g.H + h) * g.W + wq];
+      if (h >= 0 && h < g.H) {
+        const float v = f[h * g.W + wq];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const int pos = g.pw + row * g.Wt + wq;
+        s_hi[pos] = __bfloat16_as_ushort(hi);
+        s_lo[pos] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hi)));
+      }
     }
-    v[e] = x;
   }
-  uint32_t hi[4], lo[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
-    hi[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-    lo[e] = pack_bf16x2(v[2 * e] - __bfloat162float(h0), v[2 * e + 1] - __bfloat162float(h1));
-  }
+  __syncthreads();
   const int nch = split ? 2 : 1;
   __nv_bfloat16* base = act + ((b * (T + 2) + tp) * nch) * 2 * static_cast<long long>(g.PP) * 8;
-  *reinterpret_cast<uint4*>(base + (static_cast<long long>(par) * g.PP + pos) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  if (split)
-    *reinterpret_cast<uint4*>(base + ((2LL + par) * g.PP + pos) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  uint4* out_hi = reinterpret_cast<uint4*>(base + static_cast<long long>(par) * g.PP * 8);
+  uint4* out_lo = reinterpret_cast<uint4*>(base + (2LL + par) * g.PP * 8);
+  for (int p = threadIdx.x; p < g.PP; p += 256) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) w[e] = static_cast<uint32_t>(s_hi[p + 2 * e]) | (static_cast<uint32_t>(s_hi[p + 2 * e + 1]) << 16);
+    out_hi[p] = make_uint4(w[0], w[1], w[2], w[3]);
+    if (split) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) w[e] = static_cast<uint32_t>(s_lo[p + 2 * e]) | (static_cast<uint32_t>(s_lo[p + 2 * e + 1]) << 16);
+      out_lo[p] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
 }
 
 // debug: parity-plane input of a layer (C channels, geometry g) -> f32 NCDHW [B, C, T, H, W]
@@ -571,9 +584,9 @@ void umma_layer_free(UmmaLayer* L) {
 }
 
 int umma_pack_frames(const float* frames, __nv_bfloat16* act, const LayerGeom& g, int split, int B, cudaStream_t st) {
-  const long long total = static_cast<long long>(B) * (AVS_T + 2) * 2 * g.PP;
   ProfScope ps(PROF_PACK, st);
-  pack_frames_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(frames, act, g, split, AVS_T, total);
+  const size_t sm = static_cast<size_t>(2) * (g.PP + 8) * sizeof(uint16_t);
+  pack_frames_kernel<<<static_cast<unsigned>(B) * (AVS_T + 2) * 2, 256, sm, st>>>(frames, act, g, split, AVS_T);
   AVS_LAUNCHED();
   return AVS_OK;
 }

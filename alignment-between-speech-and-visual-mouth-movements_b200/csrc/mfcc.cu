@@ -57,21 +57,20 @@ mfcc_logmel_kernel(const float* __restrict__ audio, int n_samples, const int4* _
                    const float* __restrict__ window, const float2* __restrict__ tw, const float2* __restrict__ tw2,
                    const int2* __restrict__ mel_rng, const int* __restrict__ mel_off,
                    const float* __restrict__ mel_w, float* __restrict__ logmel) {
+  // 16 KB of shared memory per CTA, so that these CTAs can share an SM with the persistent conv
+  // kernels (which leave ~24 KB): twiddles come from L1, the power spectrum reuses the idle buffer.
   __shared__ float2 buf0[kHalf];
   __shared__ float2 buf1[kHalf];
-  __shared__ float2 s_tw[kHalf];
-  __shared__ float s_pow[kBins + 3];
 
   const int tid = threadIdx.x;
   const int clip = blockIdx.y;
   const float* x = audio + static_cast<size_t>(clip) * n_samples;
-  for (int i = tid; i < kHalf; i += kFftThreads) s_tw[i] = tw[i];
 
   const int u0 = blockIdx.x * kFramesPerCta;
   const int u1 = min(u0 + kFramesPerCta, n_unique);
   for (int u = u0; u < u1; ++u) {
     const int4 fr = frames[u];
-    __syncthreads();  // previous frame's consumers are done with buf/s_pow (and s_tw is loaded)
+    __syncthreads();  // previous frame's consumers are done with the buffers
     // z[n] = w[2n] x[p+2n] + i w[2n+1] x[p+2n+1], zero outside [a, b)
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -94,9 +93,9 @@ mfcc_logmel_kernel(const float* __restrict__ audio, int n_samples, const int4* _
       float2 v0 = src[j], v1 = src[j + 256], v2 = src[j + 512], v3 = src[j + 768];
       if (pass > 0) {
         const int e = k * (256 / Ns);  // exponent of exp(-2 pi i / 1024)
-        v1 = cmul(v1, s_tw[e]);
-        v2 = cmul(v2, s_tw[2 * e]);
-        v3 = cmul(v3, s_tw[3 * e]);
+        v1 = cmul(v1, __ldg(tw + e));
+        v2 = cmul(v2, __ldg(tw + 2 * e));
+        v3 = cmul(v3, __ldg(tw + 3 * e));
       }
       const float2 a = make_float2(v0.x + v2.x, v0.y + v2.y);
       const float2 b = make_float2(v0.x - v2.x, v0.y - v2.y);
@@ -110,7 +109,8 @@ mfcc_logmel_kernel(const float* __restrict__ audio, int n_samples, const int4* _
       __syncthreads();
       float2* t = src; src = dst; dst = t;
     }
-    // split post-pass: X[k] = E[k] + W_2048^k O[k], k in [0, 1024]
+    // split post-pass: X[k] = E[k] + W_2048^k O[k], k in [0, 1024]; 5 passes -> the spectrum is in buf1
+    float* s_pow = reinterpret_cast<float*>(dst);
     for (int k = tid; k < kBins; k += kFftThreads) {
       const float2 zk = src[k & (kHalf - 1)];
       const float2 zn = src[(kHalf - k) & (kHalf - 1)];

@@ -105,14 +105,18 @@ extern "C" size_t avs_stcnn_workspace_bytes(const avs_stcnn* net, int n_clips) {
   return carve(net, n_clips, nullptr, true).total;
 }
 
-extern "C" int avs_stcnn_forward_debug(const avs_stcnn* net, const float* frames, int B, float* out_emb,
-                                       float* out_vstats, float* out_pool1, float* out_pool2, void* workspace,
-                                       size_t workspace_bytes, void* stream) {
+// cap_clips: the workspace is carved for this many clips (>= B), so that repeated calls with different
+// B see the same buffer placement; pads_clean: the caller guarantees that the padding positions of the
+// parity-plane buffers are still zero (zeroed once, and kernels only ever write data positions).
+int avs::stcnn_forward_impl(const avs_stcnn* net, const float* frames, int B, int cap_clips, bool pads_clean,
+                            float* out_emb, float* out_vstats, float* out_pool1, float* out_pool2, void* workspace,
+                            size_t workspace_bytes, void* stream) {
   AVS_REQUIRE(net && frames && workspace, "null argument");
   AVS_REQUIRE(out_emb || out_vstats, "nothing to compute");
+  AVS_REQUIRE(cap_clips >= B, "workspace capacity below batch");
   if (B <= 0) return AVS_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  StcnnWs w = carve(net, B, workspace, out_emb == nullptr);
+  StcnnWs w = carve(net, cap_clips, workspace, out_emb == nullptr);
   if (workspace_bytes < w.total) {
     set_error("stcnn workspace too small: %zu < %zu", workspace_bytes, w.total);
     return AVS_EWORKSPACE;
@@ -142,8 +146,10 @@ extern "C" int avs_stcnn_forward_debug(const avs_stcnn* net, const float* frames
   } else {
     const int split = net->precision == AVS_PREC_BF16X3;
     // padding rows / gaps / time halo of the layer-2 and layer-3 inputs are never written: clear them
-    AVS_CUDA(cudaMemsetAsync(w.act[1], 0, w.act_bytes[1], st));
-    AVS_CUDA(cudaMemsetAsync(w.act[2], 0, w.act_bytes[2], st));
+    if (!pads_clean) {
+      AVS_CUDA(cudaMemsetAsync(w.act[1], 0, umma_act_bytes(net->L[1].g, split, B), st));
+      AVS_CUDA(cudaMemsetAsync(w.act[2], 0, umma_act_bytes(net->L[2].g, split, B), st));
+    }
     if ((rc = umma_pack_frames(frames, w.act[0], net->L[0].g, split, B, st))) return rc;
     for (int l = 0; l < 3; ++l) {
       EpiOut eo{};
@@ -164,6 +170,13 @@ extern "C" int avs_stcnn_forward_debug(const avs_stcnn* net, const float* frames
   }
   if (out_vstats && (rc = vstats(emb, out_vstats, B, AVS_EMB, st))) return rc;
   return AVS_OK;
+}
+
+extern "C" int avs_stcnn_forward_debug(const avs_stcnn* net, const float* frames, int B, float* out_emb,
+                                       float* out_vstats, float* out_pool1, float* out_pool2, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  return stcnn_forward_impl(net, frames, B, B, false, out_emb, out_vstats, out_pool1, out_pool2, workspace,
+                            workspace_bytes, stream);
 }
 
 extern "C" int avs_stcnn_forward(const avs_stcnn* net, const float* frames, int n_clips, float* out_emb,

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 
+struct avs_stcnn;
 namespace avs {
 
 // fp32 CUDA-core layer: in NCDHW f32, w OIDHW f32, out addressed as b*o_sb + c*o_sc + t*o_st + ho*Wo + wo
@@ -74,4 +75,7 @@ int umma_pack_frames(const float* frames, __nv_bfloat16* act, const LayerGeom& g
 int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const EpiOut& eo, int B, int n_sms, cudaStream_t st);
 int umma_unpack_act(const __nv_bfloat16* act, float* out_ncdhw, const LayerGeom& g_next, int split, int C, int B, cudaStream_t st);
 
+int stcnn_forward_impl(const avs_stcnn* net, const float* frames, int B, int cap_clips, bool pads_clean, float* out_emb,
+                       float* out_vstats, float* out_pool1, float* out_pool2, void* workspace, size_t workspace_bytes,
+                       void* stream);
 }  // namespace avs

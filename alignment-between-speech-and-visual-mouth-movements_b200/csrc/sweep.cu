@@ -3,7 +3,7 @@
 // stream for the audio branch and, for the host entry point, pinned staging buffers so that the
 // H2D copy of chunk i+1 overlaps the compute of chunk i.
 #include <algorithm>
-#include "common.cuh"
+#include "stcnn.cuh"
 
 struct avs_sweep {
   const avs_stcnn* net;
@@ -54,6 +54,7 @@ extern "C" int avs_sweep_create(const avs_stcnn* net, const avs_mfcc_plan* plan,
   int rc = AVS_OK;
   auto ck = [&](cudaError_t e) { if (e != cudaSuccess && rc == AVS_OK) { set_error("sweep_create: %s", cudaGetErrorString(e)); rc = AVS_ECUDA; } };
   ck(cudaMalloc(&s->ws_stcnn, s->ws_stcnn_bytes));
+  if (rc == AVS_OK) ck(cudaMemset(s->ws_stcnn, 0, s->ws_stcnn_bytes));  // parity-plane pads stay zero from here on
   ck(cudaMalloc(&s->ws_mfcc, s->ws_mfcc_bytes));
   ck(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
   ck(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
@@ -112,7 +113,9 @@ static int run_chunk(avs_sweep* s, const float* frames, const float* audio, int 
   AVS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
   if ((rc = avs_mfcc_stats_sweep(s->plan, audio, n, ast, s->ws_mfcc, s->ws_mfcc_bytes, s->side))) return rc;
   AVS_CUDA(cudaEventRecord(s->ev_join, s->side));
-  if ((rc = avs_stcnn_forward(s->net, frames, n, nullptr, vst, s->ws_stcnn, s->ws_stcnn_bytes, st))) return rc;
+  if ((rc = stcnn_forward_impl(s->net, frames, n, s->chunk, true, nullptr, vst, nullptr, nullptr, s->ws_stcnn,
+                               s->ws_stcnn_bytes, st)))
+    return rc;
   AVS_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
   return AVS_OK;
 }

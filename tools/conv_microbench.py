@@ -48,3 +48,20 @@ for prec in ("bf16",):
 run("bf16x3", 0, "bf16x3 dbg=0")
 run("bf16x3", 7, "bf16x3 dbg=7")
 run("bf16x3", 15, "bf16x3 dbg=15")
+
+# ---- K1 in isolation (nothing else on the GPU)
+audio = torch.from_numpy(sweep_ref.synth_audio(64, seed=3, kind="speechlike")).cuda()
+shifts = [640 * k for k in range(-20, 21)]
+for _ in range(2):
+    A.audio_stats_sweep(audio, shifts)
+torch.cuda.synchronize()
+L.avs_prof_reset()
+L.avs_prof_enable(1)
+for _ in range(3):
+    A.audio_stats_sweep(audio, shifts)
+torch.cuda.synchronize()
+L.avs_prof_enable(0)
+for slot, name in ((5, "mfcc_logmel"), (6, "mfcc_stats")):
+    t, c = ctypes.c_double(), ctypes.c_int()
+    L.avs_prof_read(slot, ctypes.byref(t), ctypes.byref(c))
+    print(f"{name} alone: {1e3 * t.value / max(c.value, 1) / 64:8.2f} us/clip", flush=True)
