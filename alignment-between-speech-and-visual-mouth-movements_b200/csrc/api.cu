@@ -17,23 +17,23 @@ int g_prof_on = 0;
 namespace {
 constexpr int kProfRing = 8192;
 struct ProfState {
-  cudaEvent_t ev[kProfRing][2];
-  int used = 0;
-  bool made = false;
+  cudaEvent_t ev[kProfRing][2] = {};
+  int used = 0, made = 0;   // events [0, made) exist
 } g_prof[PROF_NSLOTS];
 }
 void prof_begin(int slot, cudaStream_t st) {
   ProfState& p = g_prof[slot];
   if (p.used >= kProfRing) return;
-  if (!p.made) {
-    for (int i = 0; i < kProfRing; ++i) cudaEventCreate(&p.ev[i][0]), cudaEventCreate(&p.ev[i][1]);
-    p.made = true;
+  if (p.used >= p.made) {
+    cudaEventCreate(&p.ev[p.made][0]);
+    cudaEventCreate(&p.ev[p.made][1]);
+    ++p.made;
   }
   cudaEventRecord(p.ev[p.used][0], st);
 }
 void prof_end(int slot, cudaStream_t st) {
   ProfState& p = g_prof[slot];
-  if (p.used >= kProfRing || !p.made) return;
+  if (p.used >= kProfRing || p.used >= p.made) return;
   cudaEventRecord(p.ev[p.used][1], st);
   ++p.used;
 }

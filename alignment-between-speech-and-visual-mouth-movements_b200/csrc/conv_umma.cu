@@ -35,7 +35,7 @@ constexpr int kMaxRing = 4;
 constexpr int kMaxWStages = 8;
 
 struct UnitDesc {
-  int kd, chunk0, nchunks, kstep_end;  // ksteps [prev.kstep_end, kstep_end) read this unit
+  int kd, nplanes, chunk0, nchunks;  // time planes t+kd .. t+kd+nplanes-1, chunk arrays [chunk0, chunk0+nchunks)
 };
 
 struct ConvKernelParams {
@@ -110,13 +110,14 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         mbar_wait(&a_empty[slot], phase ^ 1);
         const UnitDesc ud = p.units[u];
         const uint32_t bytes = static_cast<uint32_t>(len) * 16u;
-        mbar_expect_tx(&a_full[slot], bytes * 2u * ud.nchunks);
-        const __nv_bfloat16* src = p.act + b * p.clip_stride + (t + ud.kd) * p.plane_stride +
-                                   (static_cast<long long>(ud.chunk0) * 2 * p.PP + q0) * 8;
+        mbar_expect_tx(&a_full[slot], bytes * 2u * ud.nchunks * ud.nplanes);
         uint8_t* dst = s_units + static_cast<size_t>(slot) * p.unit_slot_bytes;
-        for (int c = 0; c < ud.nchunks * 2; ++c)
-          bulk_g2s(dst + static_cast<size_t>(c) * p.region_pos * 16, src + static_cast<long long>(c) * p.PP * 8, bytes,
-                   &a_full[slot]);
+        for (int pl = 0; pl < ud.nplanes; ++pl) {
+          const __nv_bfloat16* src = p.act + b * p.clip_stride + (t + ud.kd + pl) * p.plane_stride +
+                                     (static_cast<long long>(ud.chunk0) * 2 * p.PP + q0) * 8;
+          for (int c = 0; c < ud.nchunks * 2; ++c, dst += static_cast<size_t>(p.region_pos) * 16)
+            bulk_g2s(dst, src + static_cast<long long>(c) * p.PP * 8, bytes, &a_full[slot]);
+        }
       }
     }
   } else if (warp == 2 && lane == 0) {
@@ -386,7 +387,7 @@ static LayerCfg pick_cfg(const LayerGeom& g, int split) {
   LayerCfg c;
   // Big weight stages amortise the issuer's per-stage cost (two mbarrier waits + descriptor setup,
   // ~330 cycles) over more MMAs: conv2 bf16 uses one kernel row (5 taps, 40 MMAs) per stage.
-  if (g.Cin == 1) c = {4, 2, 3, 4, 1};
+  if (g.Cin == 1) c = split ? LayerCfg{4, 2, 3, 4, 1} : LayerCfg{4, 2, 2, 2, 1};
   else if (g.Cout == 64) c = split ? LayerCfg{1, 2, 3, 3, 1} : LayerCfg{2, 2, 3, 3, 5};
   else c = split ? LayerCfg{2, 1, 3, 4, 1} : LayerCfg{2, 1, 2, 3, 3};  // Cout = 96 (TMEM: 2 tiles x 2 accs x 128 columns)
   // tuning overrides (experiments only; an over-large value fails the smem check in umma_layer_build)
@@ -458,9 +459,13 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
   int n_units = 0;
   if (g.Cin == 1) {
     // layer 1: K index = (kh pair, kw'): pairs (0,2), (1,3), (4, zero)
-    L->ksteps_per_stage = split ? 9 : 3;
+    // bf16: the three time planes form ONE unit and all nine K-steps ONE weight stage (72 MMAs per
+    // issuer iteration); split: one plane per unit, one stage per plane (shared memory is the limit)
+    const bool merged = !split;
+    L->ksteps_per_stage = 9;
+    const uint32_t plane_bytes = (split ? 2 : 1) * 2 * arr_bytes;
     for (int kd = 0; kd < 3; ++kd) {
-      const size_t sb = wp.size();
+      const size_t sb = merged ? 0 : wp.size();
       uint32_t boff[3][2];
       for (int pr = 0; pr < 3; ++pr) {
         const int kha = (pr == 2) ? 4 : pr, khb = (pr == 2) ? -1 : pr + 2;
@@ -478,7 +483,7 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
           KStep s;
           for (int a = 0; a < 2; ++a) {
             const int par = (a + kha) & 1, dr = (a + kha) >> 1;
-            s.a_off[a] = (akind * 2 + par) * arr_bytes + dr * g.Wt * 16;
+            s.a_off[a] = (merged ? kd * plane_bytes : 0) + (akind * 2 + par) * arr_bytes + dr * g.Wt * 16;
           }
           s.lbo = g.Wt * 16;
           s.b_off = boff[pr][bkind];
@@ -486,9 +491,10 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
           ks.push_back(s);
         }
       }
-      n_units++;
+      if (!merged || kd == 2) n_units++;
     }
-    L->stage_bytes = static_cast<int>(wp.size() * 2 / 3);
+    L->stage_bytes = static_cast<int>(wp.size() * 2 / (merged ? 1 : 3));
+    L->unit_planes = merged ? 3 : 1;
   } else {
     // generic: unit = (kd, channel group); stage = (tap, channel group)
     const int groups = (g.Cout == 96 && split) ? 2 : 1;
@@ -539,8 +545,10 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
   }
   L->n_ksteps = static_cast<int>(ks.size());
   L->n_stages = L->n_ksteps / L->ksteps_per_stage;
-  const int chunks_per_unit = g.n_chunks / (n_units / 3);
-  L->plane_slot_bytes = chunks_per_unit * 2 * static_cast<int>(arr_bytes);
+  if (g.Cin != 1) L->unit_planes = 1;
+  L->n_units = n_units;
+  L->chunks_per_unit = g.n_chunks / (n_units * L->unit_planes / 3);
+  L->plane_slot_bytes = L->unit_planes * L->chunks_per_unit * 2 * static_cast<int>(arr_bytes);
   L->smem_bytes = static_cast<size_t>(L->ring) * L->plane_slot_bytes + static_cast<size_t>(region_full - L->region_pos) * 16 +
                   static_cast<size_t>(L->wstages) * L->stage_bytes + ks.size() * sizeof(KStepDev) +
                   (2 * kMaxRing + 2 * kMaxWStages + 4) * 8 + 16;
@@ -603,12 +611,11 @@ int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const Epi
   memset(&p, 0, sizeof(p));
   const LayerGeom& g = L.g;
   p.act = act_in; p.w = L.d_w; p.ksteps = L.d_ksteps; p.bias = L.d_bias; p.eo = eo;
-  const int units_per_kd = (g.Cout == 96 && L.split) ? 2 : 1;
-  p.n_units = 3 * units_per_kd;
-  const int chunks_per_unit = g.n_chunks / units_per_kd;
-  const int ks_per_unit = L.n_ksteps / p.n_units;
+  p.n_units = L.n_units;
+  const int units_per_kd = L.n_units * L.unit_planes / 3;  // 2 for conv3-split (channel halves), else 1
   for (int u = 0; u < p.n_units; ++u)
-    p.units[u] = UnitDesc{u / units_per_kd, (u % units_per_kd) * chunks_per_unit, chunks_per_unit, (u + 1) * ks_per_unit};
+    p.units[u] = UnitDesc{L.unit_planes == 3 ? 0 : u / units_per_kd, L.unit_planes, (u % units_per_kd) * L.chunks_per_unit,
+                          L.chunks_per_unit};
   p.N = g.Cout; p.acc_stride = L.acc_stride; p.NT = L.NT; p.NBUF = L.NBUF; p.ring = L.ring; p.wstages = L.wstages;
   p.n_ksteps = L.n_ksteps; p.ksteps_per_stage = L.ksteps_per_stage; p.stage_bytes = L.stage_bytes; p.n_stages = L.n_stages;
   p.unit_slot_bytes = L.plane_slot_bytes; p.region_pos = L.region_pos;

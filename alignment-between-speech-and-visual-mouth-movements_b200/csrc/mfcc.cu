@@ -52,7 +52,7 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-__global__ void __launch_bounds__(kFftThreads)
+__global__ void __launch_bounds__(kFftThreads, 4)
 mfcc_logmel_kernel(const float* __restrict__ audio, int n_samples, const int4* __restrict__ frames, int n_unique,
                    const float* __restrict__ window, const float2* __restrict__ tw, const float2* __restrict__ tw2,
                    const int2* __restrict__ mel_rng, const int* __restrict__ mel_off,

@@ -50,7 +50,8 @@ struct UmmaLayer {                // device-resident, built once by stcnn_create
   int ring;                       // plane slots in shared memory
   int wstages;                    // weight stages in shared memory
   int n_ksteps, ksteps_per_stage, stage_bytes, n_stages;
-  int plane_slot_bytes;           // bytes of one plane slot in shared memory
+  int n_units, unit_planes, chunks_per_unit;  // A units per work item; time planes and chunk arrays per unit
+  int plane_slot_bytes;           // bytes of one unit slot in shared memory
   int region_pos;                 // positions loaded per (chunk, parity) for a full NT-tile item
   int acc_stride;                 // TMEM columns between accumulators
   KStepDev* d_ksteps = nullptr;
