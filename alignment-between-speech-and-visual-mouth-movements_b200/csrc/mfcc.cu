@@ -39,8 +39,7 @@ struct avs_mfcc_plan {
   float* d_window = nullptr;    // [2048] periodic Hann
   float2* d_tw = nullptr;       // [1024] exp(-2 pi i e / 1024)
   float2* d_tw2 = nullptr;      // [1025] exp(-2 pi i k / 2048)
-  int2* d_mel_rng = nullptr;    // [128] (first bin, count)
-  int* d_mel_off = nullptr;     // [128] offset into d_mel_w
+  int4* d_mel_tab = nullptr;    // [128] (first bin, count, offset into d_mel_w, 0)
   float* d_mel_w = nullptr;     // concatenated non-zero filter weights
   float* d_dct = nullptr;       // [128][kMaxQ] DCT-II ortho basis, transposed, zero padded
 };
@@ -55,8 +54,7 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 __global__ void __launch_bounds__(kFftThreads, 4)
 mfcc_logmel_kernel(const float* __restrict__ audio, int n_samples, const int4* __restrict__ frames, int n_unique,
                    const float* __restrict__ window, const float2* __restrict__ tw, const float2* __restrict__ tw2,
-                   const int2* __restrict__ mel_rng, const int* __restrict__ mel_off,
-                   const float* __restrict__ mel_w, float* __restrict__ logmel) {
+                   const int4* __restrict__ mel_tab, const float* __restrict__ mel_w, float* __restrict__ logmel) {
   // 16 KB of shared memory per CTA, so that these CTAs can share an SM with the persistent conv
   // kernels (which leave ~24 KB): twiddles come from L1, the power spectrum reuses the idle buffer.
   __shared__ float2 buf0[kHalf];
@@ -121,16 +119,25 @@ mfcc_logmel_kernel(const float* __restrict__ audio, int n_samples, const int4* _
       s_pow[k] = xr * xr + xi * xi;
     }
     __syncthreads();
-    // sparse mel projection: warp per mel band (16 bands per warp), lanes stride the band's bins
+    // sparse mel projection: two threads per mel band, each streams half of the band's non-zero
+    // weights (independent loads, L1-resident after the CTA's first frame); partner lanes combine
     float* out = logmel + (static_cast<size_t>(clip) * n_unique + u) * kMels;
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int m = warp; m < kMels; m += kFftThreads / 32) {
-      const int2 rg = mel_rng[m];
-      const float* w = mel_w + mel_off[m];
-      float acc = 0.f;
-      for (int i = lane; i < rg.y; i += 32) acc = fmaf(__ldg(w + i), s_pow[rg.x + i], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) out[m] = 10.0f * log10f(fmaxf(acc, 1e-10f));
+    {
+      const int m = tid >> 1, h = tid & 1;
+      const int4 rg = __ldg(mel_tab + m);  // (first bin, count, offset into mel_w, -)
+      const int n0 = (rg.y + 1) >> 1;
+      const int lo = h ? n0 : 0, hi = h ? rg.y : n0;
+      const float* w = mel_w + rg.z;
+      float acc0 = 0.f, acc1 = 0.f;
+      int i = lo;
+      for (; i + 1 < hi; i += 2) {
+        acc0 = fmaf(__ldg(w + i), s_pow[rg.x + i], acc0);
+        acc1 = fmaf(__ldg(w + i + 1), s_pow[rg.x + i + 1], acc1);
+      }
+      if (i < hi) acc0 = fmaf(__ldg(w + i), s_pow[rg.x + i], acc0);
+      float acc = acc0 + acc1;
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (h == 0) out[m] = 10.0f * log10f(fmaxf(acc, 1e-10f));
     }
   }
 }
@@ -293,8 +300,7 @@ extern "C" int avs_mfcc_plan_create(int n_samples, int sample_rate, int n_mfcc, 
   std::vector<double> mel_f(kMels + 2);
   const double mmin = hz_to_mel(0.0), mmax = hz_to_mel(sample_rate / 2.0);
   for (int i = 0; i < kMels + 2; ++i) mel_f[i] = mel_to_hz(mmin + (mmax - mmin) * i / (kMels + 1));
-  std::vector<int2> rng(kMels);
-  std::vector<int> off(kMels);
+  std::vector<int4> rng(kMels);
   std::vector<float> mw;
   for (int m = 0; m < kMels; ++m) {
     const double enorm = 2.0 / (mel_f[m + 2] - mel_f[m]);
@@ -312,8 +318,7 @@ extern "C" int avs_mfcc_plan_create(int n_samples, int sample_rate, int n_mfcc, 
       }
     }
     if (first < 0) first = 0, last = -1;
-    rng[m] = make_int2(first, last - first + 1);
-    off[m] = static_cast<int>(mw.size());
+    rng[m] = make_int4(first, last - first + 1, static_cast<int>(mw.size()), 0);
     for (int k = first; k <= last; ++k) mw.push_back(row[k]);
   }
   std::vector<float> dct(static_cast<size_t>(kMels) * kMaxQ, 0.f);
@@ -325,8 +330,7 @@ extern "C" int avs_mfcc_plan_create(int n_samples, int sample_rate, int n_mfcc, 
     }
   int rc;
   if ((rc = upload(&p->d_frames, frames)) || (rc = upload(&p->d_map, map)) || (rc = upload(&p->d_window, window)) ||
-      (rc = upload(&p->d_tw, tw)) || (rc = upload(&p->d_tw2, tw2)) || (rc = upload(&p->d_mel_rng, rng)) ||
-      (rc = upload(&p->d_mel_off, off)) || (rc = upload(&p->d_mel_w, mw)) || (rc = upload(&p->d_dct, dct))) {
+      (rc = upload(&p->d_tw, tw)) || (rc = upload(&p->d_tw2, tw2)) || (rc = upload(&p->d_mel_tab, rng)) || (rc = upload(&p->d_mel_w, mw)) || (rc = upload(&p->d_dct, dct))) {
     avs_mfcc_plan_destroy(p);
     return rc;
   }
@@ -337,7 +341,7 @@ extern "C" int avs_mfcc_plan_create(int n_samples, int sample_rate, int n_mfcc, 
 extern "C" void avs_mfcc_plan_destroy(avs_mfcc_plan* p) {
   if (!p) return;
   cudaFree(p->d_frames); cudaFree(p->d_map); cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_tw2);
-  cudaFree(p->d_mel_rng); cudaFree(p->d_mel_off); cudaFree(p->d_mel_w); cudaFree(p->d_dct);
+  cudaFree(p->d_mel_tab); cudaFree(p->d_mel_w); cudaFree(p->d_dct);
   delete p;
 }
 extern "C" int avs_mfcc_plan_unique_frames(const avs_mfcc_plan* p) { return p ? p->n_unique : AVS_EINVAL; }
@@ -363,7 +367,7 @@ extern "C" int avs_mfcc_sweep_debug(const avs_mfcc_plan* p, const float* audio, 
     { ProfScope ps(PROF_LOGMEL, st);
     mfcc_logmel_kernel<<<g1, kFftThreads, 0, st>>>(audio + static_cast<size_t>(c0) * p->n_samples, p->n_samples,
                                                    p->d_frames, p->n_unique, p->d_window, p->d_tw, p->d_tw2,
-                                                   p->d_mel_rng, p->d_mel_off, p->d_mel_w,
+                                                   p->d_mel_tab, p->d_mel_w,
                                                    logmel + static_cast<size_t>(c0) * p->n_unique * kMels); }
     AVS_LAUNCHED();
     dim3 g2(p->n_shifts, nc);
