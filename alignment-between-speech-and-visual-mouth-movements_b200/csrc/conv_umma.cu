@@ -63,7 +63,8 @@ __device__ __forceinline__ void decode_item(const ConvKernelParams& p, int item,
 }
 
 template <int NT, int KPS>
-__global__ void __launch_bounds__(kConvThreads, 1)
+// 128 registers per thread so that one FFT CTA (256 x 64 registers) of the audio branch fits beside it on the SM
+__global__ void __maxnreg__(128)
 conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // carve: [unit slots][weight stages][kstep table][barriers][tmem ptr]

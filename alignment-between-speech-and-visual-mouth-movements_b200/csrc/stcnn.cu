@@ -109,7 +109,7 @@ extern "C" size_t avs_stcnn_workspace_bytes(const avs_stcnn* net, int n_clips) {
 // B see the same buffer placement; pads_clean: the caller guarantees that the padding positions of the
 // parity-plane buffers are still zero (zeroed once, and kernels only ever write data positions).
 int avs::stcnn_forward_impl(const avs_stcnn* net, const float* frames, int B, int cap_clips, bool pads_clean,
-                            float* out_emb, float* out_vstats, float* out_pool1, float* out_pool2, void* workspace,
+                            cudaEvent_t after_layer1, float* out_emb, float* out_vstats, float* out_pool1, float* out_pool2, void* workspace,
                             size_t workspace_bytes, void* stream) {
   AVS_REQUIRE(net && frames && workspace, "null argument");
   AVS_REQUIRE(out_emb || out_vstats, "nothing to compute");
@@ -133,6 +133,7 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const float* frames, int B, in
       if ((rc = conv_pool_ffma(f, net->w[0], net->b[0], p1, nb, 1, 32, AVS_T, 50, 100, 5, 5, 32LL * AVS_T * 1250,
                                AVS_T * 1250LL, 1250, st)))
         return rc;
+      if (b0 == 0 && after_layer1) AVS_CUDA(cudaEventRecord(after_layer1, st));
       if ((rc = conv_pool_ffma(p1, net->w[1], net->b[1], p2, nb, 32, 64, AVS_T, 25, 50, 5, 5, 64LL * AVS_T * 300,
                                AVS_T * 300LL, 300, st)))
         return rc;
@@ -164,6 +165,7 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const float* frames, int B, in
         eo.emb = emb;
       }
       if ((rc = umma_conv_forward(net->L[l], w.act[l], eo, B, net->n_sms, st))) return rc;
+      if (l == 0 && after_layer1) AVS_CUDA(cudaEventRecord(after_layer1, st));
     }
     if (out_pool1 && (rc = umma_unpack_act(w.act[1], out_pool1, net->L[1].g, split, 32, B, st))) return rc;
     if (out_pool2 && (rc = umma_unpack_act(w.act[2], out_pool2, net->L[2].g, split, 64, B, st))) return rc;
@@ -175,7 +177,7 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const float* frames, int B, in
 extern "C" int avs_stcnn_forward_debug(const avs_stcnn* net, const float* frames, int B, float* out_emb,
                                        float* out_vstats, float* out_pool1, float* out_pool2, void* workspace,
                                        size_t workspace_bytes, void* stream) {
-  return stcnn_forward_impl(net, frames, B, B, false, out_emb, out_vstats, out_pool1, out_pool2, workspace,
+  return stcnn_forward_impl(net, frames, B, B, false, nullptr, out_emb, out_vstats, out_pool1, out_pool2, workspace,
                             workspace_bytes, stream);
 }
 

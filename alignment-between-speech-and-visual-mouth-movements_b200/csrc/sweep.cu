@@ -109,13 +109,14 @@ static int run_chunk(avs_sweep* s, const float* frames, const float* audio, int 
   int rc;
   float* vst = s->vstats + static_cast<size_t>(c0) * AVS_VSTATS;
   float* ast = s->astats + static_cast<size_t>(c0) * s->K * 2 * s->n_mfcc;
-  AVS_CUDA(cudaEventRecord(s->ev_fork, st));
+  // The audio branch forks AFTER layer 1: conv1 is the one layer that is CUDA-core sensitive (thin MMAs,
+  // heavy epilogue), while conv2/conv3 are tensor/smem bound and leave the ALUs to the FFT kernels.
+  if ((rc = stcnn_forward_impl(s->net, frames, n, s->chunk, true, s->ev_fork, nullptr, vst, nullptr, nullptr,
+                               s->ws_stcnn, s->ws_stcnn_bytes, st)))
+    return rc;
   AVS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
   if ((rc = avs_mfcc_stats_sweep(s->plan, audio, n, ast, s->ws_mfcc, s->ws_mfcc_bytes, s->side))) return rc;
   AVS_CUDA(cudaEventRecord(s->ev_join, s->side));
-  if ((rc = stcnn_forward_impl(s->net, frames, n, s->chunk, true, nullptr, vst, nullptr, nullptr, s->ws_stcnn,
-                               s->ws_stcnn_bytes, st)))
-    return rc;
   AVS_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
   return AVS_OK;
 }
