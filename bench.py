@@ -43,6 +43,15 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def conv2_traffic(clips_per_launch: int, precision: str):
+    """DRAM bytes per launch of the layer-2 conv kernel from the committed `ncu --set full` capture
+    (profiles/r01_conv2_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum = 74.8 MB for an
+    8-clip bf16 launch = 9.36 MB per clip), scaled to the clips one bench launch processes."""
+    if precision != "bf16":
+        return None
+    return 9.36e6 * clips_per_launch
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -273,7 +282,7 @@ def main():
         roof = {"kernel": "conv_umma_kernel[layer 2: Conv3d 32->64, 3x5x5 + bias + ReLU + pool]" if args.precision != "fp32"
                 else "conv_pool_ffma_kernel[layer 2]",
                 "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": achieved / tensor_peak, "traffic": None,
+                "frac": achieved / tensor_peak, "traffic": conv2_traffic(clips_per_launch, args.precision),
                 "peak_source": f"{pk_src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "algorithmic_flop_per_launch": CONV_FLOP[2] * clips_per_launch,
                 "issued_mma_multiplier": mult, "avg_launch_ms": avg_ms, "launches_timed": conv2["launches"],
