@@ -5,17 +5,22 @@
 //       TRANSPOSED ([k][3H]) so the per-step matrix-vector products read it coalesced; h lives in
 //       shared memory; PyTorch gate order (r, z, n), h0 = 0, n = tanh(gi_n + r * (W_hn h + b_hn)).
 //   (3) fc GEMM + row-wise log_softmax.
+#include <algorithm>
 #include "common.cuh"
 #include "sgemm.cuh"
+#include "gemm_umma.cuh"
 
 struct avs_bigru {
   int in_dim, H, V, precision;
   float* w_ih[2] = {nullptr, nullptr};   // [2*3H, in]
   float* b_ih[2] = {nullptr, nullptr};   // [2*3H]
-  float* w_hh_t[2] = {nullptr, nullptr}; // [2][H][3H]  (transposed)
+  float* w_hh_t[2] = {nullptr, nullptr}; // [2][H][3H]  (transposed; generic-H kernel)
+  float* w_hh[2] = {nullptr, nullptr};   // [2][3H][H]  (reference layout; cluster kernel)
   float* b_hh[2] = {nullptr, nullptr};   // [2*3H]
   float* fc_w = nullptr;                 // [V, 2H]
   float* fc_b = nullptr;
+  __nv_bfloat16* w_ih_packed[2] = {nullptr, nullptr};  // tensor-core modes: hi/lo chunked form of w_ih
+  int n_sms = 0;
 };
 
 namespace avs {
@@ -77,6 +82,111 @@ gru_recurrence_kernel(const float* __restrict__ xp, const float* __restrict__ w_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Persistent cluster recurrence (H = 256): one cluster of 8 CTAs per (16 clips, direction).  CTA r keeps
+// the W_hh rows of hidden units [32r, 32r+32) for all three gates RESIDENT in shared memory for the whole
+// sequence (96 rows x 256 k fp32 = 96 KB); every step each CTA computes its 32 units for the 16 clips,
+// writes the new h values into the h buffers of all 8 CTAs through distributed shared memory and the
+// cluster synchronises once (h is double-buffered, so one barrier per step is enough).
+//   thread = (unit = lane, clip pair = warp): W reads are conflict-free LDS.128, h reads are broadcasts.
+constexpr int kClu = 8, kCluClips = 16, kCluUnits = 32, kCluH = 256;
+constexpr size_t kCluSmem = static_cast<size_t>(kCluH / 4) * 3 * kCluUnits * 16 + 2ull * kCluClips * kCluH * 4;
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t local_addr, uint32_t rank, float v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1)
+gru_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
+                   float* __restrict__ out, int B, int T) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float4* s_w = reinterpret_cast<float4*>(smem_raw);                                  // [64 k4][3 gates][32 units]
+  float* s_h = reinterpret_cast<float*>(smem_raw + static_cast<size_t>(kCluH / 4) * 3 * kCluUnits * 16);  // [2][16][256]
+  constexpr int H = kCluH;
+  const uint32_t rank = cluster_rank();
+  const int dir = blockIdx.y, group = blockIdx.x / kClu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int J = rank * kCluUnits + lane;              // global hidden unit of this thread
+  const int c0 = 2 * warp, c1 = c0 + 1;               // this thread's two clips inside the group
+  const int b0 = group * kCluClips + c0, b1 = b0 + 1;
+  // resident weights: w_hh [2][3H][H] (reference layout) -> s_w[k4][gate][unit]
+  const float* w = w_hh + static_cast<size_t>(dir) * 3 * H * H;
+  for (int i = threadIdx.x; i < (H / 4) * 3 * kCluUnits; i += 256) {
+    const int u = i % kCluUnits, g = (i / kCluUnits) % 3, k4 = i / (3 * kCluUnits);
+    s_w[i] = *reinterpret_cast<const float4*>(w + (static_cast<size_t>(g) * H + rank * kCluUnits + u) * H + k4 * 4);
+  }
+  for (int i = threadIdx.x; i < 2 * kCluClips * H; i += 256) s_h[i] = 0.f;
+  const float br = b_hh[dir * 3 * H + J], bz = b_hh[dir * 3 * H + H + J], bn = b_hh[dir * 3 * H + 2 * H + J];
+  float h0 = 0.f, h1 = 0.f;
+  __syncthreads();
+  cluster_sync_all();
+  const uint32_t s_h_addr = smem_u32(s_h);
+  for (int s = 0; s < T; ++s) {
+    const int t = dir ? T - 1 - s : s;
+    const int cur = s & 1;
+    // input-projection terms first: their latency hides behind the mat-vec
+    float gi0[3] = {0.f, 0.f, 0.f}, gi1[3] = {0.f, 0.f, 0.f};
+    if (b0 < B) {
+      const float* g = xp + (static_cast<size_t>(b0) * T + t) * 6 * H + dir * 3 * H + J;
+      gi0[0] = g[0]; gi0[1] = g[H]; gi0[2] = g[2 * H];
+    }
+    if (b1 < B) {
+      const float* g = xp + (static_cast<size_t>(b1) * T + t) * 6 * H + dir * 3 * H + J;
+      gi1[0] = g[0]; gi1[1] = g[H]; gi1[2] = g[2 * H];
+    }
+    float r0 = 0.f, z0 = 0.f, n0 = 0.f, r1 = 0.f, z1 = 0.f, n1 = 0.f;
+    const float4* hv0 = reinterpret_cast<const float4*>(s_h + (cur * kCluClips + c0) * H);
+    const float4* hv1 = reinterpret_cast<const float4*>(s_h + (cur * kCluClips + c1) * H);
+#pragma unroll 4
+    for (int k4 = 0; k4 < H / 4; ++k4) {
+      const float4 wr = s_w[(k4 * 3 + 0) * kCluUnits + lane];
+      const float4 wz = s_w[(k4 * 3 + 1) * kCluUnits + lane];
+      const float4 wn = s_w[(k4 * 3 + 2) * kCluUnits + lane];
+      const float4 a = hv0[k4], b = hv1[k4];
+      r0 = fmaf(wr.x, a.x, r0); r0 = fmaf(wr.y, a.y, r0); r0 = fmaf(wr.z, a.z, r0); r0 = fmaf(wr.w, a.w, r0);
+      z0 = fmaf(wz.x, a.x, z0); z0 = fmaf(wz.y, a.y, z0); z0 = fmaf(wz.z, a.z, z0); z0 = fmaf(wz.w, a.w, z0);
+      n0 = fmaf(wn.x, a.x, n0); n0 = fmaf(wn.y, a.y, n0); n0 = fmaf(wn.z, a.z, n0); n0 = fmaf(wn.w, a.w, n0);
+      r1 = fmaf(wr.x, b.x, r1); r1 = fmaf(wr.y, b.y, r1); r1 = fmaf(wr.z, b.z, r1); r1 = fmaf(wr.w, b.w, r1);
+      z1 = fmaf(wz.x, b.x, z1); z1 = fmaf(wz.y, b.y, z1); z1 = fmaf(wz.z, b.z, z1); z1 = fmaf(wz.w, b.w, z1);
+      n1 = fmaf(wn.x, b.x, n1); n1 = fmaf(wn.y, b.y, n1); n1 = fmaf(wn.z, b.z, n1); n1 = fmaf(wn.w, b.w, n1);
+    }
+    {
+      const float r = 1.f / (1.f + expf(-(gi0[0] + r0 + br)));
+      const float z = 1.f / (1.f + expf(-(gi0[1] + z0 + bz)));
+      const float n = tanhf(gi0[2] + r * (n0 + bn));
+      h0 = (1.f - z) * n + z * h0;
+      if (b0 < B) out[(static_cast<size_t>(b0) * T + t) * 2 * H + dir * H + J] = h0;
+    }
+    {
+      const float r = 1.f / (1.f + expf(-(gi1[0] + r1 + br)));
+      const float z = 1.f / (1.f + expf(-(gi1[1] + z1 + bz)));
+      const float n = tanhf(gi1[2] + r * (n1 + bn));
+      h1 = (1.f - z) * n + z * h1;
+      if (b1 < B) out[(static_cast<size_t>(b1) * T + t) * 2 * H + dir * H + J] = h1;
+    }
+    // publish h(t) to every CTA of the cluster (next buffer), then one cluster barrier
+    const uint32_t a0 = s_h_addr + (((cur ^ 1) * kCluClips + c0) * H + J) * 4;
+    const uint32_t a1 = s_h_addr + (((cur ^ 1) * kCluClips + c1) * H + J) * 4;
+#pragma unroll
+    for (uint32_t rr = 0; rr < kClu; ++rr) {
+      st_cluster_f32(a0, rr, h0);
+      st_cluster_f32(a1, rr, h1);
+    }
+    cluster_sync_all();
+  }
+}
+
 // in-place row-wise log_softmax over V (one warp per row)
 __global__ void __launch_bounds__(128)
 log_softmax_kernel(float* __restrict__ x, int rows, int V) {
@@ -103,13 +213,15 @@ __global__ void transpose_whh_kernel(const float* __restrict__ w, float* __restr
   }
 }
 
-struct GruWs { float* xp; float* o1; float* o2; size_t total; };
+struct GruWs { float* xp; float* o1; float* o2; __nv_bfloat16* ap; size_t total; };
 static GruWs carve(const avs_bigru* g, int B, int T, void* ws) {
   Carver c(ws);
   GruWs r{};
   r.xp = c.take<float>(static_cast<size_t>(B) * T * 6 * g->H);
   r.o1 = c.take<float>(static_cast<size_t>(B) * T * 2 * g->H);
   r.o2 = c.take<float>(static_cast<size_t>(B) * T * 2 * g->H);
+  if (g->precision != AVS_PREC_FP32)
+    r.ap = reinterpret_cast<__nv_bfloat16*>(c.take<uint8_t>(gemm_packed_bytes(B * T, std::max(g->in_dim, 2 * g->H), 128)));
   r.total = align_up(c.off, 256);
   return r;
 }
@@ -146,9 +258,24 @@ extern "C" int avs_bigru_create(int in_dim, int hidden, int vocab, const float* 
     if ((rc = dup(&g->w_ih[l], wih[l], 6 * H * ins[l], st))) break;
     if ((rc = dup(&g->b_ih[l], bih[l], 6 * H, st))) break;
     if ((rc = dup(&g->b_hh[l], bhh[l], 6 * H, st))) break;
+    if ((rc = dup(&g->w_hh[l], whh[l], 6 * H * H, st))) break;
     if (cudaMalloc(reinterpret_cast<void**>(&g->w_hh_t[l]), 6 * H * H * sizeof(float)) != cudaSuccess) { rc = AVS_ENOMEM; break; }
     transpose_whh_kernel<<<256, 256, 0, st>>>(whh[l], g->w_hh_t[l], hidden);
     ++g_launches;
+  }
+  if (!rc && precision != AVS_PREC_FP32) {
+    // input projections run on tcgen05 (hi/lo bf16 split, fp32-grade): pack both layers' w_ih once
+    if (in_dim % 32 != 0 || (2 * hidden) % 32 != 0 || (6 * hidden) % 4 != 0) {
+      set_error("tensor-core GRU projections need in_dim and 2*hidden to be multiples of 32");
+      rc = AVS_EINVAL;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g->n_sms, cudaDevAttrMultiProcessorCount, dev);
+    for (int l = 0; l < 2 && !rc; ++l) {
+      if (cudaMalloc(reinterpret_cast<void**>(&g->w_ih_packed[l]), gemm_packed_bytes(6 * hidden, static_cast<int>(ins[l]), 256)) != cudaSuccess) { rc = AVS_ENOMEM; break; }
+      rc = gemm_pack(g->w_ih[l], static_cast<int>(ins[l]), 6 * hidden, static_cast<int>(ins[l]), 256, g->w_ih_packed[l], st);
+    }
   }
   if (!rc) rc = dup(&g->fc_w, fc_w, static_cast<size_t>(vocab) * 2 * H, st);
   if (!rc) rc = dup(&g->fc_b, fc_b, vocab, st);
@@ -164,7 +291,7 @@ extern "C" int avs_bigru_create(int in_dim, int hidden, int vocab, const float* 
 extern "C" void avs_bigru_destroy(avs_bigru* g) {
   if (!g) return;
   for (int l = 0; l < 2; ++l) {
-    cudaFree(g->w_ih[l]); cudaFree(g->b_ih[l]); cudaFree(g->w_hh_t[l]); cudaFree(g->b_hh[l]);
+    cudaFree(g->w_ih[l]); cudaFree(g->b_ih[l]); cudaFree(g->w_hh_t[l]); cudaFree(g->b_hh[l]); cudaFree(g->w_ih_packed[l]); cudaFree(g->w_hh[l]);
   }
   cudaFree(g->fc_w); cudaFree(g->fc_b);
   delete g;
@@ -192,9 +319,30 @@ extern "C" int avs_bigru_forward(const avs_bigru* g, const float* emb, int B, in
   const int ins[2] = {g->in_dim, 2 * H};
   int rc;
   for (int l = 0; l < 2; ++l) {
-    if ((rc = sgemm_nt(x, ins[l], g->w_ih[l], ins[l], g->b_ih[l], w.xp, 6 * H, rows, 6 * H, ins[l], st))) return rc;
-    gru_recurrence_kernel<kGruClips><<<dim3(cdiv(B, kGruClips), 2), H, sm, st>>>(w.xp, g->w_hh_t[l], g->b_hh[l], outs[l], B, T, H);
-    AVS_LAUNCHED();
+    if (g->precision == AVS_PREC_FP32) {
+      if ((rc = sgemm_nt(x, ins[l], g->w_ih[l], ins[l], g->b_ih[l], w.xp, 6 * H, rows, 6 * H, ins[l], st))) return rc;
+    } else {
+      if ((rc = gemm_pack(x, ins[l], rows, ins[l], 128, w.ap, st))) return rc;
+      if ((rc = gemm_umma_nt(w.ap, g->w_ih_packed[l], g->b_ih[l], w.xp, 6 * H, rows, 6 * H, ins[l], g->n_sms, st))) return rc;
+    }
+    if (H == kCluH) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(kClu * cdiv(B, kCluClips), 2, 1);
+      cfg.blockDim = dim3(256, 1, 1);
+      cfg.dynamicSmemBytes = kCluSmem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = kClu; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      AVS_CUDA(cudaFuncSetAttribute(gru_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCluSmem)));
+      AVS_CUDA(cudaLaunchKernelEx(&cfg, gru_cluster_kernel, static_cast<const float*>(w.xp), static_cast<const float*>(g->w_hh[l]),
+                                  static_cast<const float*>(g->b_hh[l]), outs[l], B, T));
+      AVS_LAUNCHED();
+    } else {
+      gru_recurrence_kernel<kGruClips><<<dim3(cdiv(B, kGruClips), 2), H, sm, st>>>(w.xp, g->w_hh_t[l], g->b_hh[l], outs[l], B, T, H);
+      AVS_LAUNCHED();
+    }
     x = outs[l];
   }
   if ((rc = sgemm_nt(w.o2, 2 * H, g->fc_w, 2 * H, g->fc_b, out_logp, g->V, rows, g->V, 2 * H, st))) return rc;

@@ -198,14 +198,17 @@ def test_stcnn_batch_independence(A, lipnet_sd, precision):
 
 
 # ------------------------------------------------------------------------------------------ K3
-def test_bigru_head_vs_oracle(A, lipnet_sd):
+@pytest.mark.parametrize("precision,n_clips", [("fp32", 3), ("bf16x3", 3), ("bf16x3", 19)])
+def test_bigru_head_vs_oracle(A, lipnet_sd, precision, n_clips):
+    """fp32: CUDA-core GEMM; bf16x3 / bf16: tcgen05 hi/lo-split GEMM (fp32-grade).  19 clips = two cluster
+    groups with a ragged tail, 1425 GEMM rows = 11.1 M-tiles."""
     g = torch.Generator().manual_seed(0)
-    emb = torch.rand((3, 75, 6912), generator=g) * 0.2
+    emb = torch.rand((n_clips, 75, 6912), generator=g) * 0.2
     with torch.no_grad():
         want = lipnet_ref.gru_head(lipnet_sd, emb).numpy()
-    net = make_lipnet(A, lipnet_sd, "fp32")
+    net = make_lipnet(A, lipnet_sd, precision)
     got = net.gru_head(emb.cuda()).cpu().numpy()
-    report("logp[gru_head]", got, want)
+    report(f"logp[gru_head {precision} B={n_clips}]", got, want)
     np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-4)
     np.testing.assert_allclose(np.exp(got).sum(-1), 1.0, atol=1e-4)
 
@@ -225,6 +228,26 @@ def test_lipnet_forward_and_decode_vs_golden(A, golden, lipnet_sd, precision):
     texts = A.decode_batch(logp, DS)
     assert texts == [str(t) for t in g["texts"]]
     assert [A.decode_prediction(logp[i], DS) for i in range(2)] == texts
+
+
+def test_config4_batch256_forward_and_decode(A, lipnet_sd):
+    """BASELINE config 4 size: 256 clips -> LipNet.forward -> greedy decode.  Properties at full size:
+    decoded ids bit-exact vs the oracle's collapse rule applied to the same log-probs, rows are
+    log-probabilities, a clip's log-probs do not depend on its batch; oracle agreement on a 2-clip sample."""
+    n = 256
+    frames = sweep_ref.synth_frames(n, seed=77).cuda()
+    net = make_lipnet(A, lipnet_sd, "bf16x3")
+    logp = net(frames)
+    assert logp.shape == (n, 75, 39)
+    np.testing.assert_allclose(torch.exp(logp).sum(-1).cpu().numpy(), 1.0, atol=1e-4)
+    ids, lens = A.ctc_greedy_decode(logp)
+    lp, ids, lens = logp.cpu().numpy(), ids.cpu().numpy(), lens.cpu().numpy()
+    for i in range(n):
+        assert ids[i, :lens[i]].tolist() == lipnet_ref.greedy_ids(lp[i]), i
+    for i in (0, 100, 255):
+        assert torch.equal(net(frames[i:i + 1])[0], logp[i]), i
+    want = lipnet_ref.lipnet_forward(lipnet_sd, frames[[5, 200]].cpu()).numpy()
+    np.testing.assert_allclose(lp[[5, 200]], want, rtol=1e-3, atol=2e-4)
 
 
 # ------------------------------------------------------------------------------------------ K4 + sweep

@@ -1,0 +1,36 @@
+"""Time the LipNet eval path (config 4: B=256 forward + greedy decode) stage by stage.  GPU box only."""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import avsync_b200 as A
+from oracle import lipnet_ref, sweep_ref
+
+B = int(os.environ.get("K3_CLIPS", "256"))
+prec = os.environ.get("K3_PRECISION", "bf16x3")
+net = A.LipNet(39, precision=prec)
+net.load_state_dict(lipnet_ref.init_lipnet_state(39, 256, seed=0))
+net = net.cuda().eval()
+frames = sweep_ref.synth_frames(B, seed=3).cuda()
+
+
+def timed(fn, n=3):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n, out
+
+
+t_stcnn, emb = timed(lambda: net.stcnn(frames))
+t_gru, logp = timed(lambda: net.gru_head(emb))
+t_dec, (ids, lens) = timed(lambda: A.ctc_greedy_decode(logp))
+print(f"B={B} precision={prec}: stcnn {t_stcnn:.2f} ms ({1e3 * t_stcnn / B:.1f} us/clip) | gru_head {t_gru:.2f} ms "
+      f"({1e3 * t_gru / B:.1f} us/clip) | ctc {t_dec:.3f} ms | total {B / (t_stcnn + t_gru + t_dec) * 1e3:.0f} clips/s")
