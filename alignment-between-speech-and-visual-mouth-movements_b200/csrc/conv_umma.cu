@@ -286,7 +286,9 @@ static ConvKernel conv_kernel_for(int NT, int KPS) {
   if (NT == 2 && KPS == 2) return conv_umma_kernel<2, 2>;   // conv2 bf16, 1 tap per stage
   if (NT == 2 && KPS == 10) return conv_umma_kernel<2, 10>; // conv2 bf16, 5 taps per stage
   if (NT == 2 && KPS == 12) return conv_umma_kernel<2, 12>; // conv3 bf16, 3 taps per stage
-  if (NT == 1 && KPS == 6) return conv_umma_kernel<1, 6>;   // conv2 bf16x3
+  if (NT == 1 && KPS == 6) return conv_umma_kernel<1, 6>;   // conv2 bf16x3, 1 tap per stage
+  if (NT == 1 && KPS == 30) return conv_umma_kernel<1, 30>; // conv2 bf16x3, 5 taps per stage
+  if (NT == 2 && KPS == 18) return conv_umma_kernel<2, 18>; // conv3 bf16x3, 3 taps per stage (channel halves)
   if (NT == 2 && KPS == 4) return conv_umma_kernel<2, 4>;   // conv3 bf16
   if (NT == 2 && KPS == 6) return conv_umma_kernel<2, 6>;   // conv3 bf16x3 (channel halves)
   return nullptr;
@@ -389,8 +391,8 @@ static LayerCfg pick_cfg(const LayerGeom& g, int split) {
   // Big weight stages amortise the issuer's per-stage cost (two mbarrier waits + descriptor setup,
   // ~330 cycles) over more MMAs: conv2 bf16 uses one kernel row (5 taps, 40 MMAs) per stage.
   if (g.Cin == 1) c = split ? LayerCfg{4, 2, 3, 4, 1} : LayerCfg{4, 2, 2, 2, 1};
-  else if (g.Cout == 64) c = split ? LayerCfg{1, 2, 3, 3, 1} : LayerCfg{2, 2, 3, 3, 5};
-  else c = split ? LayerCfg{2, 1, 3, 4, 1} : LayerCfg{2, 1, 2, 3, 3};  // Cout = 96 (TMEM: 2 tiles x 2 accs x 128 columns)
+  else if (g.Cout == 64) c = split ? LayerCfg{1, 2, 2, 2, 5} : LayerCfg{2, 2, 3, 3, 5};
+  else c = split ? LayerCfg{2, 1, 3, 2, 3} : LayerCfg{2, 1, 2, 3, 3};  // Cout = 96 (TMEM: 2 tiles x 2 accs x 128 columns)
   // tuning overrides (experiments only; an over-large value fails the smem check in umma_layer_build)
   const char* tag = g.Cin == 1 ? "1" : (g.Cout == 64 ? "2" : "3");
   char name[32];
