@@ -179,7 +179,6 @@ def main():
 
     import torch.distributed as dist
     import avsync_b200 as A
-    from oracle import lipnet_ref, sweep_ref      # weights only (seeded random init), never on the timed path
 
     torch.cuda.set_device(local_rank)
     A._native.device_check()
@@ -189,12 +188,12 @@ def main():
     dev = torch.device("cuda", local_rank)
     L = A._native.lib()
 
-    net = A.LipNet(39, precision=args.precision)
-    net.load_state_dict(lipnet_ref.init_lipnet_state(39, 256, seed=0))
-    net = net.to(dev).eval()
-    det = A.MisalignmentDetector(13864, 512)
-    det.load_state_dict(sweep_ref.init_detector_state(13864, 512, seed=1))
-    det = det.to(dev).eval()
+    # random-init weights of the reference architecture (PyTorch default initialisers, seeded); the
+    # product package only — oracle/ is imported by the cpu_baseline leg alone
+    torch.manual_seed(0)
+    net = A.LipNet(39, precision=args.precision).to(dev).eval()
+    torch.manual_seed(1)
+    det = A.MisalignmentDetector(13864, 512).to(dev).eval()
     C = args.clips_per_gpu
     n_total = C * world
     sw = A.SyncSweeper(net, det, S_FRAMES, N_SAMPLES, chunk_clips=min(args.chunk, C))

@@ -7,13 +7,11 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import avsync_b200 as A
-from oracle import lipnet_ref, sweep_ref
 
 B = int(os.environ.get("PROF_CLIPS", "8"))
-net = A.LipNet(39, precision=os.environ.get("PROF_PRECISION", "bf16"))
-net.load_state_dict(lipnet_ref.init_lipnet_state(39, 256, seed=0))
-net = net.cuda().eval()
-frames = sweep_ref.synth_frames(B, seed=3).cuda()
+torch.manual_seed(0)
+net = A.LipNet(39, precision=os.environ.get("PROF_PRECISION", "bf16")).cuda().eval()
+frames = torch.rand((B, 1, 75, 50, 100), generator=torch.Generator().manual_seed(3)).cuda()
 for _ in range(2):
     emb = net.stcnn(frames)
 torch.cuda.synchronize()
