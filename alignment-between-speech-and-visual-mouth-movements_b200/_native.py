@@ -32,6 +32,7 @@ SIGNATURES = {
     "avs_prof_read": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(c_int)]),
     "avs_mfcc_plan_create": (c_int, [c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(_P)]),
     "avs_mfcc_plan_destroy": (None, [_P]),
+    "avs_mfcc_plan_describe": (c_int, [c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int32), POINTER(c_int32)]),
     "avs_mfcc_plan_unique_frames": (c_int, [_P]),
     "avs_mfcc_plan_frames": (c_int, [_P]),
     "avs_mfcc_workspace_bytes": (c_size_t, [_P, c_int]),

@@ -6,7 +6,7 @@
 // Structure:
 //   host plan   : every STFT frame of every shifted signal is a window [p, p+2048) of the ORIGINAL
 //                 signal restricted to a valid range [a, b) (zero elsewhere).  Frames with equal
-//                 (p, a, b) are identical, so the K*F frames collapse to U unique ones (745 instead
+//                 (p, a, b) are identical, so the K*F frames collapse to U unique ones (746 instead
 //                 of 4961 for +-20 video frames at 25 fps / 16 kHz).
 //   logmel kernel: per unique frame: Hann window, 2048-point real FFT (1024-point complex radix-4
 //                 Stockham in shared memory + split post-pass), |X|^2, sparse Slaney mel filterbank,
@@ -233,9 +233,69 @@ static int upload(T** dst, const std::vector<T>& v) {
   return AVS_OK;
 }
 
+// Host-side frame plan: every (shift, frame) pair becomes a key (start, lo, hi) in ORIGINAL-signal
+// coordinates — the 2048-sample window starting at `start`, zero outside [lo, hi).  Equal keys are the
+// same STFT frame.  Returns the unique frames sorted by start and the [n_shifts][n_frames] -> id map.
+static void build_frame_plan(int n_samples, int hop, const int32_t* shift_samples, int n_shifts, int n_frames,
+                             std::vector<int4>& frames, std::vector<int>& map) {
+  std::map<std::tuple<int, int, int>, int> ids;
+  std::vector<std::tuple<int, int, int>> uniq;
+  map.assign(static_cast<size_t>(n_shifts) * n_frames, 0);
+  for (int k = 0; k < n_shifts; ++k) {
+    const long long s = shift_samples[k];
+    // shift_audio (:100-114): y[n] = x[n - s] for n in [max(0,s), min(N, N+s)), zero elsewhere;
+    // |s| >= N -> all zeros.  Valid x range:
+    long long lo = std::max<long long>(0, -s), hi = std::min<long long>(n_samples, n_samples - s);
+    if (s >= n_samples || -s >= n_samples) lo = hi = 0;
+    for (int j = 0; j < n_frames; ++j) {
+      const long long start = static_cast<long long>(hop) * j - kHalf - s;  // in x coordinates
+      long long a = std::max(start, lo), b = std::min(start + kNfft, hi);
+      std::tuple<int, int, int> key;
+      if (a >= b) key = std::make_tuple(0, 0, 0);  // all-zero frame
+      else key = std::make_tuple(static_cast<int>(start), static_cast<int>(a), static_cast<int>(b));
+      auto it = ids.find(key);
+      if (it == ids.end()) {
+        it = ids.emplace(key, static_cast<int>(uniq.size())).first;
+        uniq.push_back(key);
+      }
+      map[static_cast<size_t>(k) * n_frames + j] = it->second;
+    }
+  }
+  // sort unique frames by start so neighbouring CTAs touch neighbouring audio
+  std::vector<int> order(uniq.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return uniq[a] < uniq[b]; });
+  std::vector<int> rank(uniq.size());
+  frames.resize(uniq.size());
+  for (size_t r = 0; r < order.size(); ++r) {
+    rank[order[r]] = static_cast<int>(r);
+    frames[r] = make_int4(std::get<0>(uniq[order[r]]), std::get<1>(uniq[order[r]]), std::get<2>(uniq[order[r]]), 0);
+  }
+  for (auto& m : map) m = rank[m];
+}
+
 }  // namespace avs
 
 using namespace avs;
+
+extern "C" int avs_mfcc_plan_describe(int n_samples, int sample_rate, const int32_t* shift_samples, int n_shifts,
+                                      int* n_frames_out, int* n_unique_out, int32_t* frames_out, int32_t* map_out) {
+  AVS_REQUIRE(shift_samples && n_frames_out && n_unique_out, "null argument");
+  AVS_REQUIRE(n_samples > 0 && sample_rate > 0 && n_shifts > 0, "empty problem");
+  const int hop = std::max(1, sample_rate / 40);
+  const int n_frames = 1 + n_samples / hop;
+  std::vector<int4> frames;
+  std::vector<int> map;
+  build_frame_plan(n_samples, hop, shift_samples, n_shifts, n_frames, frames, map);
+  *n_frames_out = n_frames;
+  *n_unique_out = static_cast<int>(frames.size());
+  if (frames_out)
+    for (size_t i = 0; i < frames.size(); ++i) {
+      frames_out[3 * i] = frames[i].x; frames_out[3 * i + 1] = frames[i].y; frames_out[3 * i + 2] = frames[i].z;
+    }
+  if (map_out) std::copy(map.begin(), map.end(), map_out);
+  return AVS_OK;
+}
 
 extern "C" int avs_mfcc_plan_create(int n_samples, int sample_rate, int n_mfcc, const int32_t* shift_samples,
                                     int n_shifts, avs_mfcc_plan** out) {
@@ -250,42 +310,10 @@ extern "C" int avs_mfcc_plan_create(int n_samples, int sample_rate, int n_mfcc, 
   p->n_shifts = n_shifts;
   p->n_frames = 1 + n_samples / p->hop;  // center=True: 1 + (n + 2*(n_fft/2) - n_fft) / hop
 
-  // ---- unique frame table
-  std::map<std::tuple<int, int, int>, int> ids;
-  std::vector<std::tuple<int, int, int>> uniq;
-  std::vector<int> map(static_cast<size_t>(n_shifts) * p->n_frames);
-  for (int k = 0; k < n_shifts; ++k) {
-    const long long s = shift_samples[k];
-    // shift_audio (:100-114): y[n] = x[n - s] for n in [max(0,s), min(N, N+s)), zero elsewhere;
-    // |s| >= N -> all zeros.  Valid x range:
-    long long lo = std::max<long long>(0, -s), hi = std::min<long long>(n_samples, n_samples - s);
-    if (s >= n_samples || -s >= n_samples) lo = hi = 0;
-    for (int j = 0; j < p->n_frames; ++j) {
-      const long long start = static_cast<long long>(p->hop) * j - kHalf - s;  // in x coordinates
-      long long a = std::max(start, lo), b = std::min(start + kNfft, hi);
-      std::tuple<int, int, int> key;
-      if (a >= b) key = std::make_tuple(0, 0, 0);  // all-zero frame
-      else key = std::make_tuple(static_cast<int>(start), static_cast<int>(a), static_cast<int>(b));
-      auto it = ids.find(key);
-      if (it == ids.end()) {
-        it = ids.emplace(key, static_cast<int>(uniq.size())).first;
-        uniq.push_back(key);
-      }
-      map[static_cast<size_t>(k) * p->n_frames + j] = it->second;
-    }
-  }
-  // sort unique frames by start so neighbouring CTAs touch neighbouring audio
-  std::vector<int> order(uniq.size());
-  for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
-  std::sort(order.begin(), order.end(), [&](int a, int b) { return uniq[a] < uniq[b]; });
-  std::vector<int> rank(uniq.size());
-  std::vector<int4> frames(uniq.size());
-  for (size_t r = 0; r < order.size(); ++r) {
-    rank[order[r]] = static_cast<int>(r);
-    frames[r] = make_int4(std::get<0>(uniq[order[r]]), std::get<1>(uniq[order[r]]), std::get<2>(uniq[order[r]]), 0);
-  }
-  for (auto& m : map) m = rank[m];
-  p->n_unique = static_cast<int>(uniq.size());
+  std::vector<int4> frames;
+  std::vector<int> map;
+  build_frame_plan(n_samples, p->hop, shift_samples, n_shifts, p->n_frames, frames, map);
+  p->n_unique = static_cast<int>(frames.size());
 
   // ---- constant tables (computed in double, stored in float)
   const double kPi = 3.14159265358979323846;

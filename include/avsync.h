@@ -75,6 +75,11 @@ typedef struct avs_mfcc_plan avs_mfcc_plan;
 AVS_API int avs_mfcc_plan_create(int n_samples, int sample_rate, int n_mfcc,
                          const int32_t* shift_samples, int n_shifts, avs_mfcc_plan** out);
 AVS_API void avs_mfcc_plan_destroy(avs_mfcc_plan* plan);
+/* Host-only (no device needed): the frame plan itself.  frames_out (may be NULL) receives up to
+ * n_shifts*n_frames triples (start, lo, hi) — call once with NULL to size it by *n_unique_out —
+ * and map_out (may be NULL) the [n_shifts][n_frames] -> unique-frame-id table. */
+AVS_API int avs_mfcc_plan_describe(int n_samples, int sample_rate, const int32_t* shift_samples, int n_shifts,
+                           int* n_frames_out, int* n_unique_out, int32_t* frames_out, int32_t* map_out);
 AVS_API int avs_mfcc_plan_unique_frames(const avs_mfcc_plan* plan); /* distinct STFT frames per clip */
 AVS_API int avs_mfcc_plan_frames(const avs_mfcc_plan* plan);        /* STFT frames per shifted signal */
 AVS_API size_t avs_mfcc_workspace_bytes(const avs_mfcc_plan* plan, int n_clips);

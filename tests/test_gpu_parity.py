@@ -101,7 +101,7 @@ def test_mfcc_per_frame_table_vs_oracle(A):
 
 
 def test_mfcc_frame_dedup_is_exact(A):
-    """The 41-shift plan shares STFT frames between shifts (745 unique of 4961); results must be
+    """The 41-shift plan shares STFT frames between shifts (746 unique of 4961); results must be
     bit-identical to running every shift on its own plan."""
     a = torch.from_numpy(sweep_ref.synth_audio(3, seed=5, kind="speechlike")).cuda()
     full = A.audio_stats_sweep(a, SHIFTS41, 16000, 20)

@@ -100,3 +100,44 @@ def test_feature_extractor_errors_like_reference():
     fx = A.FeatureExtractor(Grid(), A.LipNet(39).eval(), torch.device("cpu"), A.DetectorConfig())
     with pytest.raises(RuntimeError, match="Failed to load audio"):
         fx._load_audio("nope.mpg")
+
+
+def _describe_plan(n, sr, shifts):
+    import ctypes
+    N = A._native
+    arr = (ctypes.c_int32 * len(shifts))(*shifts)
+    nf, nu = ctypes.c_int(), ctypes.c_int()
+    N.check(N.lib().avs_mfcc_plan_describe(n, sr, arr, len(shifts), ctypes.byref(nf), ctypes.byref(nu), None, None))
+    frames = (ctypes.c_int32 * (3 * nu.value))()
+    fmap = (ctypes.c_int32 * (len(shifts) * nf.value))()
+    N.check(N.lib().avs_mfcc_plan_describe(n, sr, arr, len(shifts), ctypes.byref(nf), ctypes.byref(nu), frames, fmap))
+    return nf.value, np.array(frames).reshape(-1, 3), np.array(fmap).reshape(len(shifts), nf.value)
+
+
+def test_mfcc_frame_plan_dedup_is_exact_on_host():
+    """The K1 host plan (no GPU needed): frames rebuilt from the unique (start, lo, hi) table through the
+    map must equal, sample for sample, the centre-padded frames of the np-shifted signal."""
+    rng = np.random.default_rng(0)
+    for (n, sr, fps, S) in ((48000, 16000, 25.0, 20), (48000, 16000, 29.97, 6), (5000, 8000, 25.0, 9), (900, 16000, 25.0, 2)):
+        x = rng.normal(size=n).astype(np.float32)
+        ks = list(range(-S, S + 1))
+        shifts = [sweep_ref.shift_samples(k, fps, sr) for k in ks]
+        nf, frames, fmap = _describe_plan(n, sr, shifts)
+        hop = max(1, sr // 40)
+        assert nf == 1 + n // hop
+        xz = np.concatenate([np.zeros(4096 + n, np.float32), x, np.zeros(4096 + n, np.float32)])   # x[i] at xz[4096+n+i]
+        for j, k in enumerate(ks):
+            y = np.pad(sweep_ref.shift_audio(x, k, fps, sr), (1024, 1024))
+            for f in (0, 1, 2, 3, nf // 2, nf - 4, nf - 3, nf - 2, nf - 1):
+                if not 0 <= f < nf:
+                    continue
+                start, lo, hi = frames[fmap[j, f]]
+                idx = np.arange(start, start + 2048)
+                got = np.where((idx >= lo) & (idx < hi), xz[4096 + n + idx], 0.0)
+                assert np.array_equal(got, y[hop * f: hop * f + 2048]), (n, sr, fps, k, f)
+    nf, frames, fmap = _describe_plan(48000, 16000, [640 * k for k in range(-20, 21)])
+    assert nf == 121 and len(frames) == 746            # 41 x 121 = 4961 (shift, frame) pairs -> 746 unique frames
+    nf, frames, _ = _describe_plan(48000, 16000, [640 * k for k in range(-15, 16)])
+    assert len(frames) < 31 * 121 / 5
+    _, frames, fmap = _describe_plan(1000, 16000, [5000, -5000, 0])      # |shift| >= len: all-zero frames
+    assert (fmap[0] == fmap[1]).all() and len(set(fmap[0])) == 1
