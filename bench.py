@@ -160,7 +160,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--clips-per-gpu", type=int, default=1024)
-    ap.add_argument("--chunk", type=int, default=64)
+    ap.add_argument("--chunk", type=int, default=128)
     ap.add_argument("--ref-clips", type=int, default=4, help="clips per step of the reference arm")
     ap.add_argument("--cpu-clips", type=int, default=12, help="clips of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
