@@ -6,7 +6,8 @@ error behaviour) over the C-ABI library ``libavsync_b200.so`` (``include/avsync.
     model.LipNet                               <- model.py
     utils.decode_prediction                    <- utils.py
     misalignment_detection_train.{DetectorConfig, shift_audio, compute_audio_stats,
-        extract_visual_embeddings, FeatureExtractor, MisalignmentDetector, load_lipnet, save_detector}
+        extract_visual_embeddings, FeatureExtractor, MisalignmentDataset, MisalignmentDetector, run_epoch,
+        load_lipnet, save_detector}                  utils.evaluate_model
     misalignment_detection_train.{SyncSweeper, sync_sweep}, utils.ctc_greedy_decode   (new, batched)
     distributed.{shard_range, sweep_sharded, gather_scores, ddp_detector_step}        (new, multi-GPU)
 
@@ -15,14 +16,15 @@ repo root aliases it).
 """
 from . import _native
 from .model import LipNet
-from .utils import ctc_greedy_decode, decode_batch, decode_prediction
-from .misalignment_detection_train import (DetectorConfig, FeatureExtractor, MisalignmentDetector, SyncSweeper,
+from .utils import ctc_greedy_decode, decode_batch, decode_prediction, evaluate_model
+from .misalignment_detection_train import (DetectorConfig, FeatureExtractor, MisalignmentDataset, MisalignmentDetector,
+                                           SyncSweeper, run_epoch,
                                            audio_stats_sweep, compute_audio_stats, extract_visual_embeddings,
                                            load_detector, load_lipnet, save_detector, shift_audio, shift_samples,
                                            sweep_score, sync_sweep, visual_stats)
 from . import distributed
 
 __all__ = ["LipNet", "ctc_greedy_decode", "decode_batch", "decode_prediction", "DetectorConfig", "FeatureExtractor",
-           "MisalignmentDetector", "SyncSweeper", "audio_stats_sweep", "compute_audio_stats",
+           "MisalignmentDataset", "MisalignmentDetector", "SyncSweeper", "run_epoch", "evaluate_model", "audio_stats_sweep", "compute_audio_stats",
            "extract_visual_embeddings", "load_detector", "load_lipnet", "save_detector", "shift_audio",
            "shift_samples", "sweep_score", "sync_sweep", "visual_stats", "distributed"]

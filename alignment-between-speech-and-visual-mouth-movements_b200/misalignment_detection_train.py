@@ -307,6 +307,76 @@ class FeatureExtractor:
         return torch.cat([visual_stats_.unsqueeze(0).expand(len(shifts), -1), ast], dim=1)
 
 
+# ---------------------------------------------------------------------------------- dataset / epoch
+class MisalignmentDataset(torch.utils.data.Dataset):
+    """Reference :211-234, same item semantics and the same RNG call order (``random.Random(seed)``:
+    ``randint(1, max_shift)`` then ``choice([-1, 1])`` per negative item, in access order).
+
+    ``precompute=True`` is the sweep-aware variant: the first access of a clip computes its
+    features for ALL 2S+1 shifts with one K1 launch and serves every later item of that clip from the table,
+    instead of one MFCC per item as the reference does in every epoch."""
+
+    def __init__(self, video_paths, extractor: FeatureExtractor, cfg: DetectorConfig, seed: int = 0,
+                 precompute: bool = False):
+        import random
+        self.video_paths = video_paths
+        self.extractor = extractor
+        self.cfg = cfg
+        self.rng = random.Random(seed)
+        self.precompute = precompute
+        self._table: Dict[str, torch.Tensor] = {}
+
+    def __len__(self) -> int:
+        return len(self.video_paths) * (1 + self.cfg.num_negative_samples)
+
+    def _feature(self, video_path: str, shift_frames: int) -> torch.Tensor:
+        if not self.precompute:
+            return self.extractor.build_feature(video_path, shift_frames)[0]
+        S = max(1, self.cfg.max_shift_frames)
+        tab = self._table.get(video_path)
+        if tab is None:
+            tab = self._table[video_path] = self.extractor.build_features_sweep(video_path, S)
+        return tab[shift_frames + S]
+
+    def __getitem__(self, idx: int):
+        base_idx = idx // (1 + self.cfg.num_negative_samples)
+        variant_idx = idx % (1 + self.cfg.num_negative_samples)
+        video_path = self.video_paths[base_idx]
+        if variant_idx == 0:
+            shift_frames, label = 0, 1.0
+        else:
+            magnitude = self.rng.randint(1, max(1, self.cfg.max_shift_frames))
+            direction = self.rng.choice([-1, 1])
+            shift_frames, label = magnitude * direction, 0.0
+        return self._feature(video_path, shift_frames), torch.tensor(label, dtype=torch.float32)
+
+
+def run_epoch(model, dataloader, criterion, device, optimizer=None):
+    """Reference :253-280 — one pass over ``dataloader``; trains when ``optimizer`` is given.  Returns the
+    same dict (loss, acc, auc, labels, probs); accuracy / ROC-AUC through scikit-learn on the concatenated
+    CPU arrays (AUC is NaN when only one class is present)."""
+    from .distributed import auc_acc
+    is_train = optimizer is not None
+    model.train() if is_train else model.eval()
+    total_loss = 0.0
+    all_labels, all_probs = [], []
+    for features, labels in dataloader:
+        features, labels = features.to(device), labels.to(device)
+        logits = model(features)
+        loss = criterion(logits, labels)
+        if is_train:
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
+        total_loss += loss.item() * features.size(0)
+        all_labels.append(labels.detach().cpu())
+        all_probs.append(torch.sigmoid(logits).detach().cpu())
+    labels_t = torch.cat(all_labels).numpy()
+    probs_t = torch.cat(all_probs).numpy()
+    acc, auc = auc_acc(labels_t, probs_t)
+    return {"loss": total_loss / len(dataloader.dataset), "acc": acc, "auc": auc, "labels": labels_t, "probs": probs_t}
+
+
 # ---------------------------------------------------------------------------------- checkpoints
 def load_lipnet(checkpoint_path: str, vocab_size: int, device: torch.device, precision: str = "bf16x3") -> LipNet:
     """Reference :299-309 — accepts a bare state_dict or ``{'model_state_dict': ...}``."""

@@ -43,3 +43,36 @@ def decode_batch(outputs: torch.Tensor, dataset, blank_index: int = 0) -> List[s
     ids, lens = ctc_greedy_decode(outputs, blank_index)
     ids_h, lens_h = ids.cpu().tolist(), lens.cpu().tolist()
     return [ids_to_text(row[:n], dataset) for row, n in zip(ids_h, lens_h)]
+
+
+def evaluate_model(model, test_loader, dataset, device, num_samples=5, verbose=True):
+    """Reference utils.py:38-86 — forward, decode, naive positional character accuracy for the first
+    ``num_samples`` items.  One batched decode (K5) per batch instead of one device sync per sample.
+    Prints the reference's lines when ``verbose`` and returns [(true_text, predicted_text, accuracy %)]."""
+    model.eval()
+    model.to(device)
+    results = []
+    if verbose:
+        print("\nModel Evaluation:")
+        print("-" * 50)
+    with torch.no_grad():
+        for i, (videos, labels, label_lengths) in enumerate(test_loader):
+            if i >= num_samples:
+                break
+            outputs = model(videos.to(device))
+            texts = decode_batch(outputs, dataset)
+            for j in range(videos.size(0)):
+                n = i * test_loader.batch_size + j
+                if n >= num_samples:
+                    break
+                true_label = labels[j][:label_lengths[j]]
+                true_text = "".join(dataset.idx_to_char.get(int(t), "") for t in true_label if int(t) != 0)
+                correct = sum(1 for a, b in zip(true_text, texts[j]) if a == b)
+                acc = correct / max(len(true_text), 1) * 100
+                results.append((true_text, texts[j], acc))
+                if verbose:
+                    print(f"\nSample {n + 1}:")
+                    print(f"True text: {true_text}")
+                    print(f"Predicted text: {texts[j]}")
+                    print(f"Character accuracy: {acc:.2f}%")
+    return results

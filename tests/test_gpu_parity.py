@@ -326,3 +326,62 @@ def test_config2_batch64_properties(A, lipnet_sd, det_sd):
         r = sweep_ref.sweep_clip(lipnet_sd, det_cpu, frames[i].cpu(), audio[i].cpu().numpy(), list(range(-15, 16)),
                                  batched=True)
         np.testing.assert_allclose(scores[i].cpu().numpy(), r["scores"], rtol=1e-3, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------ drop-in callers
+class _Grid:
+    """GridDataset stand-in: `process_video` returns seeded synthetic frames (the video decode is out of scope)."""
+    idx_to_char = lipnet_ref.make_vocab()
+
+    def process_video(self, path):
+        return sweep_ref.synth_frames(1, seed=int(path.split("_")[1]))[0]
+
+
+def _audio_loader(path):
+    return sweep_ref.synth_audio(1, seed=int(path.split("_")[1]), kind="speechlike")[0], 16000
+
+
+def test_feature_extractor_and_dataset_vs_oracle(A, lipnet_sd, det_sd):
+    net = make_lipnet(A, lipnet_sd, "bf16x3")
+    cfg = A.DetectorConfig(max_shift_frames=20)
+    fx = A.FeatureExtractor(_Grid(), net, torch.device("cuda"), cfg, audio_loader=_audio_loader)
+    path = "clip_31_.npy"
+    frames = sweep_ref.synth_frames(1, seed=31)
+    audio = sweep_ref.synth_audio(1, seed=31, kind="speechlike")[0]
+    with torch.no_grad():
+        v = sweep_ref.visual_stats(lipnet_ref.stcnn(lipnet_sd, frames)[0])
+    for k in (0, 7, -20):
+        feat, meta = fx.build_feature(path, k)
+        assert feat.device.type == "cpu" and feat.shape == (13864,) and meta == {"video_path": path, "shift_frames": k, "fps": 25.0}
+        want = torch.cat([v, sweep_ref.compute_audio_stats(sweep_ref.shift_audio(audio, k, 25.0, 16000), 16000, 20)])
+        np.testing.assert_allclose(feat.numpy(), want.numpy(), rtol=1e-3, atol=2e-3)
+    assert list(fx.visual_cache) == [path] and list(fx.audio_cache) == [path]
+    table = fx.build_features_sweep(path, 20)
+    assert table.shape == (41, 13864)
+    assert torch.equal(table[20 + 7], fx.build_feature(path, 7)[0])
+    ds = A.MisalignmentDataset([path, "clip_32_.npy"], fx, cfg, seed=3, precompute=True)
+    feat0, lab0 = ds[0]
+    assert float(lab0) == 1.0 and torch.equal(feat0, table[20])
+    feat1, lab1 = ds[1]
+    assert float(lab1) == 0.0 and any(torch.equal(feat1, table[j]) for j in range(41) if j != 20)
+    # sweep == detector over the table (the reference's per-shift loop, misalignment_detection_demo.py:244-250)
+    det = make_detector(A, det_sd)
+    with torch.no_grad():
+        per_shift = torch.sigmoid(det(table.cuda())).cpu().numpy()
+    scores, best = A.sync_sweep(net, det, frames.cuda(), torch.from_numpy(audio[None]).cuda(), 20)
+    np.testing.assert_allclose(scores[0].cpu().numpy(), per_shift, rtol=1e-3, atol=2e-5)
+
+
+def test_evaluate_model_drop_in(A, lipnet_sd, capsys):
+    net = make_lipnet(A, lipnet_sd, "bf16x3")
+    frames = sweep_ref.synth_frames(4, seed=5)
+    labels = torch.tensor([[2, 9, 14, 0], [1, 1, 0, 0], [6, 0, 0, 0], [38, 37, 3, 4]])
+    lens = torch.tensor([3, 2, 1, 4])
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(frames, labels, lens), batch_size=2)
+    res = A.evaluate_model(net, loader, _Grid(), torch.device("cuda"), num_samples=3)
+    out = capsys.readouterr().out
+    assert len(res) == 3 and "Model Evaluation:" in out and out.count("Character accuracy:") == 3
+    logp = lipnet_ref.lipnet_forward(lipnet_sd, frames)
+    for i, (true_text, pred, acc) in enumerate(res):
+        assert pred == lipnet_ref.decode_prediction(logp[i].numpy())
+    assert res[0][0] == "bin" and res[1][0] == "aa"

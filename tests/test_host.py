@@ -141,3 +141,71 @@ def test_mfcc_frame_plan_dedup_is_exact_on_host():
     assert len(frames) < 31 * 121 / 5
     _, frames, fmap = _describe_plan(1000, 16000, [5000, -5000, 0])      # |shift| >= len: all-zero frames
     assert (fmap[0] == fmap[1]).all() and len(set(fmap[0])) == 1
+
+
+class _FakeExtractor:
+    """Stands in for FeatureExtractor on the CPU: records (path, shift) and returns a feature that encodes them."""
+
+    def __init__(self):
+        self.calls = []
+
+    def build_feature(self, path, shift):
+        self.calls.append((path, shift))
+        return torch.full((4,), float(shift)), {"video_path": path, "shift_frames": shift, "fps": 25.0}
+
+    def build_features_sweep(self, path, S):
+        self.calls.append((path, "sweep", S))
+        return torch.arange(-S, S + 1, dtype=torch.float32)[:, None].expand(-1, 4).clone()
+
+
+def test_misalignment_dataset_matches_reference_rng_and_items():
+    from oracle import reference_import
+    cfg = A.DetectorConfig(max_shift_frames=20, num_negative_samples=2)
+    paths = [f"clip{i}.npy" for i in range(7)]
+    fx = _FakeExtractor()
+    ds = A.MisalignmentDataset(paths, fx, cfg, seed=42)
+    assert len(ds) == 21
+    items = [ds[i] for i in range(len(ds))]
+    labels = [float(l) for _, l in items]
+    assert labels == [1.0, 0.0, 0.0] * 7
+    shifts = [s for _, s in fx.calls]
+    assert all(s == 0 for s in shifts[0::3]) and all(1 <= abs(s) <= 20 for i, s in enumerate(shifts) if i % 3)
+    # sweep-aware variant: same RNG stream -> same shifts, features served from one table per clip
+    fx2 = _FakeExtractor()
+    ds2 = A.MisalignmentDataset(paths, fx2, cfg, seed=42, precompute=True)
+    got = [float(ds2[i][0][0]) for i in range(len(ds2))]
+    assert got == [float(s) for s in shifts]
+    assert len(fx2.calls) == len(paths) and all(c[1] == "sweep" for c in fx2.calls)
+    if reference_import.available():
+        _, _, _, mdt = reference_import.load()
+        fx3 = _FakeExtractor()
+        ref_cfg = mdt.DetectorConfig(max_shift_frames=20, num_negative_samples=2)
+        rds = mdt.MisalignmentDataset(paths, fx3, ref_cfg, seed=42)
+        ref_items = [rds[i] for i in range(len(rds))]
+        assert fx3.calls == fx.calls
+        assert [float(l) for _, l in ref_items] == labels
+
+
+def test_run_epoch_matches_reference_semantics():
+    from oracle import reference_import
+    torch.manual_seed(0)
+    x = torch.randn(40, 16)
+    y = (torch.rand(40) > 0.5).float()
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=8)
+    model = A.MisalignmentDetector(16, 8, dropout=0.0)
+    crit = torch.nn.BCEWithLogitsLoss()
+    ev = A.run_epoch(model, loader, crit, torch.device("cpu"))
+    assert set(ev) == {"loss", "acc", "auc", "labels", "probs"} and ev["probs"].shape == (40,)
+    if reference_import.available():
+        _, _, _, mdt = reference_import.load()
+        ref_model = mdt.MisalignmentDetector(16, 8, dropout=0.0)
+        ref_model.load_state_dict(model.state_dict())
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)
+        ropt = torch.optim.Adam(ref_model.parameters(), lr=1e-3, weight_decay=1e-5)
+        a = A.run_epoch(model, loader, crit, torch.device("cpu"), opt)
+        b = mdt.run_epoch(ref_model, loader, crit, torch.device("cpu"), ropt)
+        assert abs(a["loss"] - b["loss"]) < 1e-6 and a["acc"] == b["acc"] and abs(a["auc"] - b["auc"]) < 1e-9
+        for p, q in zip(model.parameters(), ref_model.parameters()):
+            assert torch.allclose(p, q, atol=1e-7)
+    one = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, torch.ones(40)), batch_size=8)
+    assert np.isnan(A.run_epoch(model, one, crit, torch.device("cpu"))["auc"])
