@@ -22,9 +22,10 @@ from .misalignment_detection_train import (DetectorConfig, FeatureExtractor, Mis
                                            audio_stats_sweep, compute_audio_stats, extract_visual_embeddings,
                                            load_detector, load_lipnet, save_detector, shift_audio, shift_samples,
                                            sweep_score, sync_sweep, visual_stats)
+from .dataset import GridPreprocessor
 from . import distributed
 
 __all__ = ["LipNet", "ctc_greedy_decode", "decode_batch", "decode_prediction", "DetectorConfig", "FeatureExtractor",
            "MisalignmentDataset", "MisalignmentDetector", "SyncSweeper", "run_epoch", "evaluate_model", "audio_stats_sweep", "compute_audio_stats",
            "extract_visual_embeddings", "load_detector", "load_lipnet", "save_detector", "shift_audio",
-           "shift_samples", "sweep_score", "sync_sweep", "visual_stats", "distributed"]
+           "shift_samples", "sweep_score", "sync_sweep", "visual_stats", "GridPreprocessor", "distributed"]

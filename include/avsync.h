@@ -165,6 +165,19 @@ AVS_API int avs_sweep_run(avs_sweep* sw, const float* frames, const float* audio
  * compute chunk by chunk; returns after the results are in the host buffers. */
 AVS_API int avs_sweep_run_host(avs_sweep* sw, const float* frames_host, const float* audio_host,
                        int n_clips, float* out_scores_host, int32_t* out_best_host);
+/* ---------------------------------------------------------------- pre-processing prologue
+ * The per-frame arithmetic of GridDataset.process_video (dataset.py:209-254) for decoded uint8 frames:
+ * BGR->gray, crop [0.6h:, 0.3w:0.7w], bilinear resize to 100x50, /255, pad/truncate to 75 frames.
+ * Bit-exact with OpenCV's 8-bit cvtColor / resize when the crop has >= 50 rows.
+ * frames: device u8 [n_clips, n_frames_in, h, w, channels]; lengths (device i32 [n_clips], may be NULL):
+ * valid frames per clip; out: device f32 [n_clips, 1, 75, 50, 100]. */
+typedef struct avs_preproc avs_preproc;
+AVS_API int avs_preproc_create(int h, int w, int channels, avs_preproc** out);
+AVS_API void avs_preproc_destroy(avs_preproc* p);
+AVS_API int avs_preproc_crop(const avs_preproc* p, int* y0, int* x0, int* crop_h, int* crop_w);
+AVS_API int avs_preproc_run(const avs_preproc* p, const uint8_t* frames, int n_clips, int n_frames_in,
+                    const int32_t* lengths, float* out, void* stream);
+
 /* Optional per-kernel timing: when enabled, every launch of a profiled kernel is bracketed by CUDA
  * events on its own stream.  slot: 0 pack, 1 conv1, 2 conv2, 3 conv3, 4 vstats, 5 mfcc log-mel,
  * 6 mfcc stats, 7 score GEMM, 8 score.  avs_prof_read synchronises on the recorded events. */

@@ -385,3 +385,24 @@ def test_evaluate_model_drop_in(A, lipnet_sd, capsys):
     for i, (true_text, pred, acc) in enumerate(res):
         assert pred == lipnet_ref.decode_prediction(logp[i].numpy())
     assert res[0][0] == "bin" and res[1][0] == "aa"
+
+
+def test_preprocessing_prologue_bit_exact_vs_opencv(A):
+    """gray -> crop -> resize -> /255 -> pad on the GPU == the reference's cv2 calls, bit for bit."""
+    pytest.importorskip("cv2")
+    from oracle import preproc_ref
+    rng = np.random.default_rng(5)
+    pre = A.GridPreprocessor()
+    for (n, h, w, c) in ((75, 288, 360, 3), (40, 240, 320, 3), (90, 480, 640, 3), (10, 288, 360, 1), (3, 126, 31, 3)):
+        shape = (n, h, w, 3) if c == 3 else (n, h, w)
+        frames = rng.integers(0, 256, shape, dtype=np.uint8)
+        got = pre.process_frames(frames)
+        want = preproc_ref.process_frames(frames)
+        assert got.is_cuda and got.shape == (1, 75, 50, 100)
+        assert torch.equal(got.cpu(), want), (n, h, w, c, float((got.cpu() - want).abs().max()))
+    assert pre.crop_box(288, 360) == (172, 108, 116, 144)
+    # batched, ragged lengths
+    fr = torch.from_numpy(rng.integers(0, 256, (3, 20, 288, 360, 3), dtype=np.uint8)).cuda()
+    out = pre.process_batch(fr, lengths=torch.tensor([20, 7, 0]))
+    for i, ln in enumerate((20, 7, 0)):
+        assert torch.equal(out[i].cpu(), preproc_ref.process_frames(fr[i, :ln].cpu().numpy()))

@@ -134,3 +134,28 @@ def test_oracle_vs_reference_modules_directly(lipnet_sd, det_sd):
     x = torch.randn(3, 13864)
     with torch.no_grad():
         np.testing.assert_allclose(sweep_ref.detector_logits(det_sd, x).numpy(), det(x).numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_preprocessing_restatement_vs_opencv():
+    """The two OpenCV 8-bit algorithms the GPU prologue implements, restated in numpy, against cv2 itself."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import preproc_ref
+    rng = np.random.default_rng(0)
+    b, g, r = np.meshgrid(np.arange(0, 256, 3), np.arange(0, 256, 5), np.arange(0, 256, 7), indexing="ij")
+    colours = np.stack([b, g, r], -1).astype(np.uint8)
+    assert np.array_equal(preproc_ref.gray_u8(colours), cv2.cvtColor(colours.reshape(-1, 37, 3), cv2.COLOR_BGR2GRAY).reshape(b.shape))
+    img = rng.integers(0, 256, (288, 360, 3), dtype=np.uint8)
+    assert np.array_equal(preproc_ref.gray_u8(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    for _ in range(60):
+        hh, ww = int(rng.integers(50, 500)), int(rng.integers(8, 700))
+        c = rng.integers(0, 256, (hh, ww), dtype=np.uint8)
+        assert np.array_equal(preproc_ref.resize_linear_u8(c, 100, 50), cv2.resize(c, (100, 50))), (hh, ww)
+    frames = rng.integers(0, 256, (5, 288, 360, 3), dtype=np.uint8)
+    out = preproc_ref.process_frames(frames)
+    assert out.shape == (1, 75, 50, 100) and out.dtype == torch.float32 and float(out[0, 5:].abs().max()) == 0.0
+    if reference_import.available():
+        # the same frames through the reference's own code path: an uncompressed .npy is returned /255 only, so
+        # compare instead against its per-frame operations applied by hand (dataset.py:209-231)
+        gray = cv2.cvtColor(frames[0], cv2.COLOR_BGR2GRAY)
+        want = cv2.resize(gray[int(288 * 0.6):, int(360 * 0.3):int(360 * 0.7)], (100, 50)) / 255.0
+        np.testing.assert_array_equal(out[0, 0].numpy(), want.astype(np.float32))
