@@ -400,7 +400,7 @@ def test_preprocessing_prologue_bit_exact_vs_opencv(A):
         want = preproc_ref.process_frames(frames)
         assert got.is_cuda and got.shape == (1, 75, 50, 100)
         assert torch.equal(got.cpu(), want), (n, h, w, c, float((got.cpu() - want).abs().max()))
-    assert pre.crop_box(288, 360) == (172, 108, 116, 144)
+    assert pre.crop_box(288, 360) == (172, 108, 116, 143)       # int(360 * 0.7) == 251 in double arithmetic
     # batched, ragged lengths
     fr = torch.from_numpy(rng.integers(0, 256, (3, 20, 288, 360, 3), dtype=np.uint8)).cuda()
     out = pre.process_batch(fr, lengths=torch.tensor([20, 7, 0]))
