@@ -16,7 +16,7 @@ repo root aliases it).
 """
 from . import _native
 from .model import LipNet
-from .utils import ctc_greedy_decode, decode_batch, decode_prediction, evaluate_model
+from .utils import ctc_greedy_decode, decode_batch, decode_metrics, decode_prediction, evaluate_model
 from .misalignment_detection_train import (DetectorConfig, FeatureExtractor, MisalignmentDataset, MisalignmentDetector,
                                            SyncSweeper, run_epoch,
                                            audio_stats_sweep, compute_audio_stats, extract_visual_embeddings,
@@ -26,6 +26,6 @@ from .dataset import GridPreprocessor
 from . import distributed
 
 __all__ = ["LipNet", "ctc_greedy_decode", "decode_batch", "decode_prediction", "DetectorConfig", "FeatureExtractor",
-           "MisalignmentDataset", "MisalignmentDetector", "SyncSweeper", "run_epoch", "evaluate_model", "audio_stats_sweep", "compute_audio_stats",
+           "MisalignmentDataset", "MisalignmentDetector", "SyncSweeper", "run_epoch", "evaluate_model", "decode_metrics", "audio_stats_sweep", "compute_audio_stats",
            "extract_visual_embeddings", "load_detector", "load_lipnet", "save_detector", "shift_audio",
            "shift_samples", "sweep_score", "sync_sweep", "visual_stats", "GridPreprocessor", "distributed"]

@@ -50,6 +50,7 @@ SIGNATURES = {
     "avs_sweep_score_workspace_bytes": (c_size_t, [c_int, c_int]),
     "avs_sweep_score": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
     "avs_ctc_greedy": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "avs_edit_metrics": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "avs_preproc_create": (c_int, [c_int, c_int, c_int, POINTER(_P)]),
     "avs_preproc_destroy": (None, [_P]),
     "avs_preproc_crop": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),

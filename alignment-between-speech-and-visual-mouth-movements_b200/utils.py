@@ -76,3 +76,28 @@ def evaluate_model(model, test_loader, dataset, device, num_samples=5, verbose=T
                     print(f"Predicted text: {texts[j]}")
                     print(f"Character accuracy: {acc:.2f}%")
     return results
+
+
+def decode_metrics(pred_ids: torch.Tensor, pred_lens: torch.Tensor, target_ids: torch.Tensor, target_lens: torch.Tensor,
+                   space_id: int = 37, pad_id: int = 38):
+    """Batched CER / WER / positional character accuracy on DEVICE id sequences, with the text
+    semantics of the reference: ``calculate_cer`` / ``calculate_wer`` (train.py:945-993) on the strings the ids
+    render to (id 38 renders as the 5 characters '<pad>'), and ``evaluate_model``'s accuracy (utils.py:83-86).
+    Returns a dict of CPU float tensors [B]: cer, wer, char_accuracy (percent), plus the raw int table."""
+    for t, n in ((pred_ids, "pred_ids"), (pred_lens, "pred_lens"), (target_ids, "target_ids"), (target_lens, "target_lens")):
+        N.require_cuda(t, n)
+    pred_ids, target_ids = pred_ids.to(torch.int32).contiguous(), target_ids.to(torch.int32).contiguous()
+    pred_lens, target_lens = pred_lens.to(torch.int32).contiguous(), target_lens.to(torch.int32).contiguous()
+    B = pred_ids.shape[0]
+    out = torch.empty((B, 6), dtype=torch.int32, device=pred_ids.device)
+    if B:
+        N.check(N.lib().avs_edit_metrics(N.ptr(pred_ids), N.ptr(pred_lens), pred_ids.shape[1], N.ptr(target_ids),
+                                         N.ptr(target_lens), target_ids.shape[1], B, space_id, pad_id, 16, 1, 4,
+                                         N.ptr(out), N.stream_ptr()), "edit_metrics")
+    r = out.cpu().to(torch.float64)
+    pred_n, tgt_n, tgt_w = r[:, 5], r[:, 1], r[:, 3]
+    cer = torch.where(tgt_n > 0, r[:, 0] / tgt_n.clamp(min=1), (pred_n > 0).to(torch.float64))
+    pred_w_nonzero = (r[:, 2] > 0) | (tgt_w > 0)          # target empty: WER = 1 if the prediction has any word
+    wer = torch.where(tgt_w > 0, r[:, 2] / tgt_w.clamp(min=1), ((r[:, 2] > 0) & pred_w_nonzero).to(torch.float64))
+    acc = r[:, 4] / tgt_n.clamp(min=1) * 100.0
+    return {"cer": cer, "wer": wer, "char_accuracy": acc, "raw": out.cpu()}

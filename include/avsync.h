@@ -165,6 +165,17 @@ AVS_API int avs_sweep_run(avs_sweep* sw, const float* frames, const float* audio
  * compute chunk by chunk; returns after the results are in the host buffers. */
 AVS_API int avs_sweep_run_host(avs_sweep* sw, const float* frames_host, const float* audio_host,
                        int n_clips, float* out_scores_host, int32_t* out_best_host);
+/* ---------------------------------------------------------------- decode metrics
+ * Edit distances behind calculate_cer / calculate_wer (train.py:945-993) and the positional character
+ * matches of evaluate_model (utils.py:83-86) for a batch of id sequences that are already on the device
+ * (e.g. straight from avs_ctc_greedy).  pad_id renders as the five characters "<pad>" like the reference
+ * table (p_id/a_id/d_id = ids of 'p','a','d'); words are runs of non-space symbols.
+ * out: device i32 [n_clips, 6] = {char distance, target chars, word distance, target words,
+ * positional matches, predicted chars}.  CER = out[0]/out[1], WER = out[2]/out[3]. */
+AVS_API int avs_edit_metrics(const int32_t* pred_ids, const int32_t* pred_len, int pred_stride,
+                     const int32_t* tgt_ids, const int32_t* tgt_len, int tgt_stride, int n_clips,
+                     int space_id, int pad_id, int p_id, int a_id, int d_id, int32_t* out, void* stream);
+
 /* ---------------------------------------------------------------- pre-processing prologue
  * The per-frame arithmetic of GridDataset.process_video (dataset.py:209-254) for decoded uint8 frames:
  * BGR->gray, crop [0.6h:, 0.3w:0.7w], bilinear resize to 100x50, /255, pad/truncate to 75 frames.

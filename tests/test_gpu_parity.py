@@ -406,3 +406,31 @@ def test_preprocessing_prologue_bit_exact_vs_opencv(A):
     out = pre.process_batch(fr, lengths=torch.tensor([20, 7, 0]))
     for i, ln in enumerate((20, 7, 0)):
         assert torch.equal(out[i].cpu(), preproc_ref.process_frames(fr[i, :ln].cpu().numpy()))
+
+
+def test_decode_metrics_vs_oracle(A):
+    """batched CER / WER / positional accuracy on device ids == the text metrics of the reference
+    (train.py:945-993, utils.py:83-86) on the rendered strings, including '<pad>' (id 38 -> 5 characters)."""
+    from oracle import metrics_ref as M
+    table = lipnet_ref.make_vocab()
+    rng = np.random.default_rng(9)
+    B, Tp, Tt = 64, 75, 40
+    pred = rng.integers(1, 39, (B, Tp)).astype(np.int32)
+    tgt = rng.integers(1, 38, (B, Tt)).astype(np.int32)
+    pred[rng.random((B, Tp)) < 0.2] = 37                      # plenty of spaces -> words
+    tgt[rng.random((B, Tt)) < 0.2] = 37
+    pl = rng.integers(0, Tp + 1, B).astype(np.int32)
+    tl = rng.integers(0, Tt + 1, B).astype(np.int32)
+    pl[:3], tl[:3] = (0, 5, 0), (0, 0, 7)                     # empty prediction / target combinations
+    pred[3, :6], pl[3] = (2, 9, 14, 37, 2, 12), 6             # "bin bl"
+    tgt[3, :8], tl[3] = (2, 9, 14, 37, 2, 12, 21, 5), 8       # "bin blue"
+    pred[4, :pl[4]] = 37                                      # only spaces -> no words
+    got = A.decode_metrics(torch.from_numpy(pred).cuda(), torch.from_numpy(pl).cuda(), torch.from_numpy(tgt).cuda(),
+                           torch.from_numpy(tl).cuda())
+    for i in range(B):
+        p = "".join(table[int(c)] for c in pred[i, :pl[i]])
+        t = "".join(table[int(c)] for c in tgt[i, :tl[i]])
+        assert abs(float(got["cer"][i]) - M.cer(p, t)) < 1e-12, (i, p, t)
+        assert abs(float(got["wer"][i]) - M.wer(p, t)) < 1e-12, (i, p, t)
+        assert abs(float(got["char_accuracy"][i]) - M.char_accuracy(t, p)) < 1e-9, (i, p, t)
+    assert abs(float(got["cer"][3]) - 0.25) < 1e-12 and float(got["wer"][3]) == 0.5

@@ -159,3 +159,12 @@ def test_preprocessing_restatement_vs_opencv():
         gray = cv2.cvtColor(frames[0], cv2.COLOR_BGR2GRAY)
         want = cv2.resize(gray[int(288 * 0.6):, int(360 * 0.3):int(360 * 0.7)], (100, 50)) / 255.0
         np.testing.assert_array_equal(out[0, 0].numpy(), want.astype(np.float32))
+
+
+def test_metrics_restatement_known_answers():
+    from oracle import metrics_ref as M
+    assert M.levenshtein("kitten", "sitting") == 3 and M.levenshtein("", "abc") == 3 and M.levenshtein("abc", "abc") == 0
+    assert M.cer("bin blue", "bin blue") == 0.0 and M.cer("", "") == 0.0 and M.cer("x", "") == 1.0
+    assert abs(M.cer("bin blu", "bin blue") - 1 / 8) < 1e-12
+    assert M.wer("bin  blue at", "bin blue at f") == 0.25 and M.wer("a b", "") == 1.0 and M.wer("   ", "") == 0.0
+    assert M.char_accuracy("abcd", "abxd") == 75.0 and M.char_accuracy("", "abc") == 0.0
