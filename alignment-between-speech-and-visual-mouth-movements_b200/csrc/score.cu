@@ -5,6 +5,7 @@
 // depend on the shift, so  W1 . cat[v, a_k] = W1[:, :Dv] . v  +  W1[:, Dv:] . a_k :
 //   (1) hv[B, H] = vstats . W1v^T + b1          one fp32 GEMM per batch (sgemm_nt)
 //   (2) per clip: for each shift  score = sigmoid(w2 . relu(hv + W1a . a_k) + b2), then arg-max.
+#include <algorithm>
 #include "common.cuh"
 #include "sgemm.cuh"
 
@@ -50,6 +51,57 @@ sweep_score_kernel(const float* __restrict__ hv, const float* __restrict__ astat
     for (int k = 1; k < n_shifts; ++k)
       if (s_sc[k] > bv || (isnan(s_sc[k]) && !isnan(bv))) bv = s_sc[k], best = k;  // first maximum (np.argmax)
     out_best[clip] = best;
+  }
+}
+
+// Persistent variant used whenever W1a^T (a_dim x hidden fp32, 80 KB for 40 x 512) fits in shared memory:
+// each CTA stages W1a^T once, then loops over clips; the 8 warps of a CTA take different shifts of the clip
+// (lane l owns hidden units l, l+32, ...: conflict-free shared-memory reads, a_k values broadcast), so there
+// is no block-wide reduction per shift and small batches no longer serialise 41 reductions per clip.
+__global__ void __launch_bounds__(256)
+sweep_score_persistent_kernel(const float* __restrict__ hv, const float* __restrict__ astats, int n_clips, int n_shifts,
+                              int a_dim, const float* __restrict__ w1a, int ldw, const float* __restrict__ w2,
+                              const float* __restrict__ b2, int hidden, float* __restrict__ out_scores,
+                              int32_t* __restrict__ out_best) {
+  extern __shared__ float sm[];
+  const int pitch = hidden + 1;                      // +1: conflict-free transposing stores
+  float* s_w = sm;                                   // [a_dim][hidden + 1]
+  float* s_a = s_w + a_dim * pitch;                  // [K][a_dim]
+  float* s_sc = s_a + n_shifts * a_dim;              // [K]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < a_dim * hidden; i += 256) {  // coalesced reads of the [hidden, a_dim] slice of W1
+    const int a = i % a_dim, h = i / a_dim;
+    s_w[a * pitch + h] = w1a[static_cast<size_t>(h) * ldw + a];
+  }
+  const float bias2 = b2[0];
+  for (int clip = blockIdx.x; clip < n_clips; clip += gridDim.x) {
+    __syncthreads();  // s_w staged / previous clip's s_a, s_sc consumed
+    const float* a = astats + static_cast<size_t>(clip) * n_shifts * a_dim;
+    for (int i = tid; i < n_shifts * a_dim; i += 256) s_a[i] = a[i];
+    __syncthreads();
+    const float* hrow = hv + static_cast<size_t>(clip) * hidden;
+    for (int k = warp; k < n_shifts; k += 8) {
+      float part = 0.f;
+      for (int h = lane; h < hidden; h += 32) {
+        float acc = __ldg(hrow + h);
+        for (int i = 0; i < a_dim; ++i) acc = fmaf(s_w[i * pitch + h], s_a[k * a_dim + i], acc);
+        part = fmaf(fmaxf(acc, 0.f), __ldg(w2 + h), part);
+      }
+      part = warp_sum(part);
+      if (lane == 0) {
+        const float sc = 1.0f / (1.0f + expf(-(part + bias2)));
+        s_sc[k] = sc;
+        out_scores[static_cast<size_t>(clip) * n_shifts + k] = sc;
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && out_best != nullptr) {
+      int best = 0;
+      float bv = s_sc[0];
+      for (int k = 1; k < n_shifts; ++k)
+        if (s_sc[k] > bv || (isnan(s_sc[k]) && !isnan(bv))) bv = s_sc[k], best = k;  // first maximum (np.argmax)
+      out_best[clip] = best;
+    }
   }
 }
 
@@ -142,8 +194,19 @@ extern "C" int avs_sweep_score(const float* vstats, const float* astats, int n_c
   ProfScope ps(PROF_SCORE, st);
   const size_t sm = (static_cast<size_t>(n_shifts) * a_dim + n_shifts) * sizeof(float);
   AVS_REQUIRE(sm <= 48 * 1024, "n_shifts * a_dim too large for the score kernel");
-  sweep_score_kernel<<<n_clips, 128, sm, st>>>(hv, astats, n_shifts, a_dim, w1 + v_dim, ld, w2, b2, hidden,
-                                               out_scores, out_best);
+  const size_t sm_p = sm + static_cast<size_t>(a_dim) * (hidden + 1) * sizeof(float);
+  if (sm_p <= 200 * 1024) {
+    int dev = 0, n_sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+    AVS_CUDA(cudaFuncSetAttribute(sweep_score_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_p)));
+    const int grid = std::min(n_clips, n_sms * (sm_p <= 100 * 1024 ? 2 : 1));
+    sweep_score_persistent_kernel<<<grid, 256, sm_p, st>>>(hv, astats, n_clips, n_shifts, a_dim, w1 + v_dim, ld, w2, b2,
+                                                           hidden, out_scores, out_best);
+  } else {
+    sweep_score_kernel<<<n_clips, 128, sm, st>>>(hv, astats, n_shifts, a_dim, w1 + v_dim, ld, w2, b2, hidden,
+                                                 out_scores, out_best);
+  }
   AVS_LAUNCHED();
   return AVS_OK;
 }
