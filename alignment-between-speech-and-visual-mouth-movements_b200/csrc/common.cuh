@@ -39,7 +39,7 @@ extern long long g_launches;
 
 // ---- optional per-kernel timing (avs_prof_*): CUDA events recorded on the launching stream
 enum ProfSlot { PROF_PACK = 0, PROF_CONV1, PROF_CONV2, PROF_CONV3, PROF_VSTATS, PROF_LOGMEL, PROF_MFCC_STATS,
-                PROF_SCORE_GEMM, PROF_SCORE, PROF_NSLOTS };
+                PROF_SCORE_GEMM, PROF_SCORE, PROF_GRU_PACK, PROF_GRU_GEMM, PROF_GRU_REC, PROF_GRU_FC, PROF_NSLOTS };
 extern int g_prof_on;
 void prof_begin(int slot, cudaStream_t st);
 void prof_end(int slot, cudaStream_t st);

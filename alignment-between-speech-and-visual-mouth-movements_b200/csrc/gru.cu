@@ -320,11 +320,14 @@ extern "C" int avs_bigru_forward(const avs_bigru* g, const float* emb, int B, in
   int rc;
   for (int l = 0; l < 2; ++l) {
     if (g->precision == AVS_PREC_FP32) {
+      ProfScope ps(PROF_GRU_GEMM, st);
       if ((rc = sgemm_nt(x, ins[l], g->w_ih[l], ins[l], g->b_ih[l], w.xp, 6 * H, rows, 6 * H, ins[l], st))) return rc;
     } else {
-      if ((rc = gemm_pack(x, ins[l], rows, ins[l], 128, w.ap, st))) return rc;
+      { ProfScope ps(PROF_GRU_PACK, st); if ((rc = gemm_pack(x, ins[l], rows, ins[l], 128, w.ap, st))) return rc; }
+      ProfScope ps(PROF_GRU_GEMM, st);
       if ((rc = gemm_umma_nt(w.ap, g->w_ih_packed[l], g->b_ih[l], w.xp, 6 * H, rows, 6 * H, ins[l], g->n_sms, st))) return rc;
     }
+    ProfScope psr(PROF_GRU_REC, st);
     if (H == kCluH) {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(kClu * cdiv(B, kCluClips), 2, 1);
@@ -345,6 +348,7 @@ extern "C" int avs_bigru_forward(const avs_bigru* g, const float* emb, int B, in
     }
     x = outs[l];
   }
+  ProfScope psf(PROF_GRU_FC, st);
   if ((rc = sgemm_nt(w.o2, 2 * H, g->fc_w, 2 * H, g->fc_b, out_logp, g->V, rows, g->V, 2 * H, st))) return rc;
   log_softmax_kernel<<<cdiv(rows, 4), 128, 0, st>>>(out_logp, rows, g->V);
   AVS_LAUNCHED();

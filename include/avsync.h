@@ -191,7 +191,8 @@ AVS_API int avs_preproc_run(const avs_preproc* p, const uint8_t* frames, int n_c
 
 /* Optional per-kernel timing: when enabled, every launch of a profiled kernel is bracketed by CUDA
  * events on its own stream.  slot: 0 pack, 1 conv1, 2 conv2, 3 conv3, 4 vstats, 5 mfcc log-mel,
- * 6 mfcc stats, 7 score GEMM, 8 score.  avs_prof_read synchronises on the recorded events. */
+ * 6 mfcc stats, 7 score GEMM, 8 score, 9 GRU operand pack, 10 GRU input GEMM, 11 GRU recurrence,
+ * 12 fc + log_softmax.  avs_prof_read synchronises on the recorded events. */
 AVS_API void avs_prof_enable(int on);
 AVS_API void avs_prof_reset(void);
 AVS_API int avs_prof_read(int slot, double* total_ms, int* count);

@@ -54,3 +54,24 @@ def test_no_cpu_fallback_without_cuda(native):
         A.compute_audio_stats(__import__("numpy").zeros(48000, dtype="float32"), 16000, 20)
     with pytest.raises(RuntimeError):
         A.ctc_greedy_decode(torch.zeros(1, 75, 39))
+
+
+def test_argument_validation_returns_error_codes_without_a_device(native):
+    """Bad arguments are rejected with AVS_EINVAL (-1) and a message before any CUDA call is made."""
+    import ctypes
+    L = native.lib()
+    arr = (ctypes.c_int32 * 3)(0, 640, -640)
+    h = ctypes.c_void_p()
+    assert L.avs_mfcc_plan_create(48000, 16000, 0, arr, 3, ctypes.byref(h)) == -1          # n_mfcc out of range
+    assert b"n_mfcc" in L.avs_last_error_string()
+    assert L.avs_mfcc_plan_create(48000, 16000, 41, arr, 3, ctypes.byref(h)) == -1
+    assert L.avs_mfcc_plan_create(0, 16000, 20, arr, 3, ctypes.byref(h)) == -1             # empty signal
+    assert L.avs_mfcc_plan_create(48000, 16000, 20, None, 3, ctypes.byref(h)) == -1        # null shifts
+    nf, nu = ctypes.c_int(), ctypes.c_int()
+    assert L.avs_mfcc_plan_describe(48000, 16000, arr, 0, ctypes.byref(nf), ctypes.byref(nu), None, None) == -1
+    assert L.avs_sweep_score(None, None, 1, 41, 13824, 40, None, None, None, None, 512, None, None, None, 0, None) == -1
+    assert L.avs_ctc_greedy(None, 1, 75, 39, 0, None, None, None) == -1
+    assert L.avs_preproc_create(288, 360, 2, ctypes.byref(h)) == -1                        # channels must be 1 or 3
+    with pytest.raises(ValueError):
+        import avsync_b200 as A
+        A.LipNet(39, precision="fp8")

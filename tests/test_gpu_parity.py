@@ -434,3 +434,33 @@ def test_decode_metrics_vs_oracle(A):
         assert abs(float(got["wer"][i]) - M.wer(p, t)) < 1e-12, (i, p, t)
         assert abs(float(got["char_accuracy"][i]) - M.char_accuracy(t, p)) < 1e-9, (i, p, t)
     assert abs(float(got["cer"][3]) - 0.25) < 1e-12 and float(got["wer"][3]) == 0.5
+
+
+def test_error_paths_on_device(A, lipnet_sd, det_sd):
+    """Status codes / exceptions instead of crashes: short workspace, wrong shapes, wrong devices."""
+    N = A._native
+    L = N.lib()
+    net = make_lipnet(A, lipnet_sd, "bf16")
+    h = net._stcnn().h
+    frames = torch.zeros((1, 1, 75, 50, 100), device="cuda")
+    emb = torch.empty((1, 75, 6912), device="cuda")
+    ws = torch.empty(1024, dtype=torch.uint8, device="cuda")
+    rc = L.avs_stcnn_forward(h, N.ptr(frames), 1, N.ptr(emb), None, N.ptr(ws), ws.numel(), N.stream_ptr())
+    assert rc == -4 and b"workspace" in L.avs_last_error_string()
+    rc = L.avs_stcnn_forward(h, N.ptr(frames), 1, None, None, N.ptr(ws), ws.numel(), N.stream_ptr())
+    assert rc == -1                                                   # nothing to compute
+    assert L.avs_stcnn_forward(h, N.ptr(frames), 0, N.ptr(emb), None, N.ptr(ws), ws.numel(), N.stream_ptr()) == 0   # empty batch
+    det = make_detector(A, det_sd)
+    sw = A.SyncSweeper(net, det, 15)
+    with pytest.raises(RuntimeError):
+        sw.run(frames, torch.zeros((1, 1000), device="cuda"))         # audio length differs from the plan
+    with pytest.raises(RuntimeError):
+        sw.run(frames.cpu(), torch.zeros((1, 48000)))                 # host tensors: no CPU fallback
+    with pytest.raises(RuntimeError):
+        A.sweep_score(torch.zeros((2, 100), device="cuda"), torch.zeros((2, 31, 40), device="cuda"), det)
+    with pytest.raises(RuntimeError):
+        A.MisalignmentDetector(13864, 512)  # CPU parameters
+        A.SyncSweeper(net, A.MisalignmentDetector(13864, 512), 15)
+    torch.cuda.synchronize()
+    s, b = sw.run(frames, torch.zeros((1, 48000), device="cuda"))     # the handle is still usable afterwards
+    assert s.shape == (1, 31) and torch.isfinite(s).all()

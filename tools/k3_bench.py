@@ -32,3 +32,18 @@ t_gru, logp = timed(lambda: net.gru_head(emb))
 t_dec, (ids, lens) = timed(lambda: A.ctc_greedy_decode(logp))
 print(f"B={B} precision={prec}: stcnn {t_stcnn:.2f} ms ({1e3 * t_stcnn / B:.1f} us/clip) | gru_head {t_gru:.2f} ms "
       f"({1e3 * t_gru / B:.1f} us/clip) | ctc {t_dec:.3f} ms | total {B / (t_stcnn + t_gru + t_dec) * 1e3:.0f} clips/s")
+
+import ctypes
+L = A._native.lib()
+L.avs_prof_reset()
+L.avs_prof_enable(1)
+for _ in range(3):
+    net.gru_head(emb)
+torch.cuda.synchronize()
+L.avs_prof_enable(0)
+parts = []
+for slot, name in ((9, "pack"), (10, "gemm"), (11, "recurrence"), (12, "fc+softmax")):
+    t, c = ctypes.c_double(), ctypes.c_int()
+    L.avs_prof_read(slot, ctypes.byref(t), ctypes.byref(c))
+    parts.append(f"{name} {t.value / 3:.3f} ms ({c.value // 3} launches)")
+print("gru_head breakdown per forward: " + " | ".join(parts))
