@@ -50,7 +50,7 @@ struct ConvKernelParams {
   int n_ksteps, ksteps_per_stage, stage_bytes, n_stages;
   int unit_slot_bytes, region_pos, region_full;
   int n_chunks, PP, Wt, Ho, Wo, n_tiles, n_tilesets;
-  int T, n_items;
+  int T, n_items, split;
   int dbg;  // experiment switches (avs_debug_set): 1 = weights loaded once, 2 = A units loaded once, 4 = epilogue skips math/stores
   long long clip_stride, plane_stride;  // elements (bf16) between clips / time planes of `act`
 };
@@ -139,7 +139,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     // The whole warp walks the schedule converged; one elected lane issues tcgen05.mma / .commit.
     // Loop nest: item -> weight stage -> KPS K-steps (unrolled) -> NT tiles x 2 accumulators.
     // A units are made of whole stages, so unit boundaries are only checked once per stage.
-    const uint32_t idesc = umma_idesc_bf16(128, p.N);
+    const uint32_t idesc_n = umma_idesc_bf16(128, p.N), idesc_w = umma_idesc_bf16(128, 2 * p.N);
     const uint32_t units_lo = smem_u32(s_units) >> 4, w_lo = smem_u32(s_w) >> 4;
     const uint32_t unit_step = static_cast<uint32_t>(p.unit_slot_bytes) >> 4, stage_step = static_cast<uint32_t>(p.stage_bytes) >> 4;
     const uint32_t ring = p.ring, wstages = p.wstages, nbuf = p.NBUF, acc_stride = p.acc_stride;
@@ -174,6 +174,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
             const uint64_t bdesc = kDescHi | (k4.z + stage_lo);
             const uint32_t a0 = k4.x + unit_lo, a1 = k4.y + unit_lo;
             const uint32_t acc = (st | j) != 0 ? 1u : 0u;
+            const uint32_t idesc = (k4.w & KS_WIDE) ? idesc_w : idesc_n;
 #pragma unroll
             for (int i = 0; i < NT; ++i) {
               if (i < nt) {
@@ -219,6 +220,17 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
           tmem_ld32(d_base + (i * 2 + 0) * p.acc_stride + cb, v0);
           tmem_ld32(d_base + (i * 2 + 1) * p.acc_stride + cb, v1);
           tmem_ld_wait();
+          if (p.split) {  // second column block: A_hi * B_lo, the small term, added last
+            uint32_t u0[32], u1[32];
+            tmem_ld32(d_base + (i * 2 + 0) * p.acc_stride + p.N + cb, u0);
+            tmem_ld32(d_base + (i * 2 + 1) * p.acc_stride + p.N + cb, u1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              v0[c] = __float_as_uint(__uint_as_float(v0[c]) + __uint_as_float(u0[c]));
+              v1[c] = __float_as_uint(__uint_as_float(v1[c]) + __uint_as_float(u1[c]));
+            }
+          }
           float o[16];
           const int ch0 = cb + half * 16;
 #pragma unroll
@@ -282,15 +294,14 @@ using ConvKernel = void (*)(const ConvKernelParams);
 // (tiles per item, K-steps per weight stage) of the six layer x precision configurations
 static ConvKernel conv_kernel_for(int NT, int KPS) {
   if (NT == 4 && KPS == 3) return conv_umma_kernel<4, 3>;   // conv1 bf16
-  if (NT == 4 && KPS == 9) return conv_umma_kernel<4, 9>;   // conv1 bf16x3
+  if (NT == 4 && KPS == 9) return conv_umma_kernel<4, 9>;   // conv1 bf16 (merged unit)
+  if (NT == 2 && KPS == 6) return conv_umma_kernel<2, 6>;   // conv1 bf16x3
+  if (NT == 1 && KPS == 20) return conv_umma_kernel<1, 20>; // conv2 bf16x3, 5 taps per stage
+  if (NT == 1 && KPS == 12) return conv_umma_kernel<1, 12>; // conv3 bf16x3, 3 taps per stage (channel halves)
   if (NT == 2 && KPS == 2) return conv_umma_kernel<2, 2>;   // conv2 bf16, 1 tap per stage
   if (NT == 2 && KPS == 10) return conv_umma_kernel<2, 10>; // conv2 bf16, 5 taps per stage
   if (NT == 2 && KPS == 12) return conv_umma_kernel<2, 12>; // conv3 bf16, 3 taps per stage
-  if (NT == 1 && KPS == 6) return conv_umma_kernel<1, 6>;   // conv2 bf16x3, 1 tap per stage
-  if (NT == 1 && KPS == 30) return conv_umma_kernel<1, 30>; // conv2 bf16x3, 5 taps per stage
-  if (NT == 2 && KPS == 18) return conv_umma_kernel<2, 18>; // conv3 bf16x3, 3 taps per stage (channel halves)
   if (NT == 2 && KPS == 4) return conv_umma_kernel<2, 4>;   // conv3 bf16
-  if (NT == 2 && KPS == 6) return conv_umma_kernel<2, 6>;   // conv3 bf16x3 (channel halves)
   return nullptr;
 }
 
@@ -390,9 +401,10 @@ static LayerCfg pick_cfg(const LayerGeom& g, int split) {
   LayerCfg c;
   // Big weight stages amortise the issuer's per-stage cost (two mbarrier waits + descriptor setup,
   // ~330 cycles) over more MMAs: conv2 bf16 uses one kernel row (5 taps, 40 MMAs) per stage.
-  if (g.Cin == 1) c = split ? LayerCfg{4, 2, 3, 4, 1} : LayerCfg{4, 2, 2, 2, 1};
+  // split mode doubles the accumulator width (hi*hi+lo*hi | hi*lo column blocks), so fewer tiles fit in TMEM
+  if (g.Cin == 1) c = split ? LayerCfg{2, 2, 3, 4, 1} : LayerCfg{4, 2, 2, 2, 1};
   else if (g.Cout == 64) c = split ? LayerCfg{1, 2, 2, 2, 5} : LayerCfg{2, 2, 3, 3, 5};
-  else c = split ? LayerCfg{2, 1, 3, 2, 3} : LayerCfg{2, 1, 2, 3, 3};  // Cout = 96 (TMEM: 2 tiles x 2 accs x 128 columns)
+  else c = split ? LayerCfg{1, 1, 3, 2, 3} : LayerCfg{2, 1, 2, 3, 3};  // Cout = 96 (TMEM: 2 tiles x 2 accs x 128 columns)
   // tuning overrides (experiments only; an over-large value fails the smem check in umma_layer_build)
   const char* tag = g.Cin == 1 ? "1" : (g.Cout == 64 ? "2" : "3");
   char name[32];
@@ -435,7 +447,7 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
   L->split = split;
   const LayerCfg c = pick_cfg(g, split);
   L->NT = c.NT; L->NBUF = c.NBUF; L->ring = c.ring; L->wstages = c.wstages;
-  L->acc_stride = (g.Cout == 96) ? 128 : g.Cout;
+  L->acc_stride = split ? (g.Cout == 96 ? 256 : 2 * g.Cout) : (g.Cout == 96 ? 128 : g.Cout);
   const int halo = (g.Cin == 1) ? (g.KH / 2 + 1) * g.Wt + 8 : (g.KH / 2) * g.Wt + g.KW - 1;
   const int region_full = c.NT * 128 + halo;
   const int n_tilesets = cdiv(g.n_tiles, c.NT);
@@ -446,16 +458,21 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
   auto wat = [&](int n, int ci, int kd, int kh, int kw) {
     return w[(((static_cast<size_t>(n) * g.Cin + ci) * 3 + kd) * g.KH + kh) * g.KW + kw];
   };
-  // one B tile = [2 K-halves][N][8] bf16; fill(hi/lo) appends it and returns its byte offset within the stage
-  auto push_tile = [&](size_t stage_begin, auto&& elem, int kind) {
+  // One B tile = [2 K-halves][rows][8] bf16, appended to the packed weights; returns its byte offset within
+  // the stage.  Plain bf16: rows = the N output channels.  Split: rows = N "hi" rows followed by N "lo"
+  // residual rows, so that ONE MMA of width 2N computes A_hi*B_hi and A_hi*B_lo with a single fetch of A
+  // (the two halves land in adjacent accumulator column blocks and are added in the epilogue), and the
+  // A_lo*B_hi MMA of width N reads the first N rows of the same tile.
+  auto push_tile = [&](size_t stage_begin, auto&& elem) {
     const uint32_t off = static_cast<uint32_t>((wp.size() - stage_begin) * 2);
     for (int half = 0; half < 2; ++half)
-      for (int n = 0; n < N; ++n)
-        for (int k = 0; k < 8; ++k) {
-          const float x = elem(half, n, k);
-          const uint16_t h = f2bf(x);
-          wp.push_back(kind == 0 ? h : f2bf(x - bf2f(h)));
-        }
+      for (int kind = 0; kind < (split ? 2 : 1); ++kind)
+        for (int n = 0; n < N; ++n)
+          for (int k = 0; k < 8; ++k) {
+            const float x = elem(half, n, k);
+            const uint16_t h = f2bf(x);
+            wp.push_back(kind == 0 ? h : f2bf(x - bf2f(h)));
+          }
     return off;
   };
   const uint32_t arr_bytes = static_cast<uint32_t>(L->region_pos) * 16;  // one (chunk, parity) run in a unit slot
@@ -465,31 +482,31 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
     // bf16: the three time planes form ONE unit and all nine K-steps ONE weight stage (72 MMAs per
     // issuer iteration); split: one plane per unit, one stage per plane (shared memory is the limit)
     const bool merged = !split;
-    L->ksteps_per_stage = 9;
+    L->ksteps_per_stage = split ? 6 : 9;
     const uint32_t plane_bytes = (split ? 2 : 1) * 2 * arr_bytes;
     for (int kd = 0; kd < 3; ++kd) {
       const size_t sb = merged ? 0 : wp.size();
-      uint32_t boff[3][2];
+      uint32_t boff[3];
       for (int pr = 0; pr < 3; ++pr) {
         const int kha = (pr == 2) ? 4 : pr, khb = (pr == 2) ? -1 : pr + 2;
         auto elem = [&](int half, int n, int k) {
           const int kh = half == 0 ? kha : khb;
           return (kh >= 0 && k < g.KW) ? wat(n, 0, kd, kh, k) : 0.f;
         };
-        boff[pr][0] = push_tile(sb, elem, 0);
-        if (split) boff[pr][1] = push_tile(sb, elem, 1);
+        boff[pr] = push_tile(sb, elem);
       }
       for (int pr = 0; pr < 3; ++pr) {
         const int kha = (pr == 2) ? 4 : pr;
-        for (int v = 0; v < (split ? 3 : 1); ++v) {  // (A_hi,B_hi), (A_lo,B_hi), (A_hi,B_lo)
-          const int akind = (v == 1) ? 1 : 0, bkind = (v == 2) ? 1 : 0;
+        for (int v = 0; v < (split ? 2 : 1); ++v) {  // split: A_hi x [B_hi | B_lo] (wide), then A_lo x B_hi
+          const int akind = v;
           KStep s;
+          s.wide = split && v == 0;
           for (int a = 0; a < 2; ++a) {
             const int par = (a + kha) & 1, dr = (a + kha) >> 1;
             s.a_off[a] = (merged ? kd * plane_bytes : 0) + (akind * 2 + par) * arr_bytes + dr * g.Wt * 16;
           }
           s.lbo = g.Wt * 16;
-          s.b_off = boff[pr][bkind];
+          s.b_off = boff[pr];
           s.kd = kd;
           ks.push_back(s);
         }
@@ -507,7 +524,7 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
       set_error("taps per stage %d does not divide %d", TPS, g.KH * g.KW);
       return AVS_EINVAL;
     }
-    L->ksteps_per_stage = TPS * pairs * (split ? 3 : 1);
+    L->ksteps_per_stage = TPS * pairs * (split ? 2 : 1);
     const int kmul = split ? 2 : 1;
     for (int kd = 0; kd < 3; ++kd)
       for (int cg = 0; cg < groups; ++cg) {
@@ -516,28 +533,24 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
         for (int kh = 0; kh < g.KH; ++kh)
           for (int kw = 0; kw < g.KW; ++kw) {
             if ((kh * g.KW + kw) % TPS == 0) sb = wp.size();  // a new weight stage starts here
-            std::vector<uint32_t> bh(pairs), bl(pairs);
+            std::vector<uint32_t> bt(pairs);
             for (int pr = 0; pr < pairs; ++pr) {
               auto elem = [&](int half, int n, int k) { return wat(n, cg * CG + pr * 16 + half * 8 + k, kd, kh, kw); };
-              bh[pr] = push_tile(sb, elem, 0);
+              bt[pr] = push_tile(sb, elem);
             }
-            if (split)
-              for (int pr = 0; pr < pairs; ++pr) {
-                auto elem = [&](int half, int n, int k) { return wat(n, cg * CG + pr * 16 + half * 8 + k, kd, kh, kw); };
-                bl[pr] = push_tile(sb, elem, 1);
-              }
             for (int pr = 0; pr < pairs; ++pr)
-              for (int v = 0; v < (split ? 3 : 1); ++v) {
-                const int akind = (v == 1) ? 1 : 0, bkind = (v == 2) ? 1 : 0;
+              for (int v = 0; v < (split ? 2 : 1); ++v) {  // split: A_hi x [B_hi | B_lo] (wide), then A_lo x B_hi
+                const int akind = v;
                 const int c8 = (cg * CG + pr * 16) / 8;              // global 8-channel chunk of the first K half
                 const int arr = (split ? 2 * c8 + akind : c8) - chunk0;  // chunk array index inside the unit
                 KStep s;
+                s.wide = split && v == 0;
                 for (int a = 0; a < 2; ++a) {
                   const int par = (a + kh) & 1, dr = (a + kh) >> 1;
                   s.a_off[a] = (arr * 2 + par) * arr_bytes + (dr * g.Wt + kw) * 16;
                 }
                 s.lbo = kmul * 2 * arr_bytes;
-                s.b_off = bkind ? bl[pr] : bh[pr];
+                s.b_off = bt[pr];
                 s.kd = kd;
                 ks.push_back(s);
               }
@@ -565,12 +578,13 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
   const int ks_per_unit = L->n_ksteps / n_units;
   for (size_t e = 0; e < ks.size(); ++e) {
     for (int a = 0; a < 2; ++a) kd[e].a_lo[a] = (ks[e].a_off[a] >> 4) | ((ks[e].lbo >> 4) << 16);
-    kd[e].b_lo = (ks[e].b_off >> 4) | (static_cast<uint32_t>(N) << 16);  // LBO of B = N * 16 B
+    kd[e].b_lo = (ks[e].b_off >> 4) | (static_cast<uint32_t>(split ? 2 * N : N) << 16);  // LBO of B = tile rows * 16 B
     uint32_t f = 0;
     if (e % ks_per_unit == 0) f |= KS_FIRST_OF_UNIT;
     if ((e + 1) % ks_per_unit == 0) f |= KS_LAST_OF_UNIT;
     if (e % L->ksteps_per_stage == 0) f |= KS_FIRST_OF_STAGE;
     if ((e + 1) % L->ksteps_per_stage == 0) f |= KS_LAST_OF_STAGE;
+    if (ks[e].wide) f |= KS_WIDE;
     kd[e].flags = f;
   }
   AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&L->d_ksteps), kd.size() * sizeof(KStepDev)));
@@ -627,6 +641,7 @@ int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const Epi
   p.n_chunks = g.n_chunks; p.PP = g.PP; p.Wt = g.Wt; p.Ho = g.Ho; p.Wo = g.Wo; p.n_tiles = g.n_tiles;
   p.n_tilesets = cdiv(g.n_tiles, L.NT);
   p.T = AVS_T;
+  p.split = L.split;
   p.dbg = g_conv_dbg;
   const long long items = static_cast<long long>(B) * AVS_T * p.n_tilesets;
   AVS_REQUIRE(items < (1LL << 31), "too many work items for one launch");

@@ -29,13 +29,14 @@ struct KStep {                    // one tcgen05.mma (K = 16) of the per-output-
   uint32_t lbo;                   // byte stride between the two 8-wide K halves of A
   uint32_t b_off;                 // byte offset of the B tile inside its weight stage
   int32_t kd;                     // which of the 3 time planes A comes from
+  bool wide = false;              // split mode: this MMA is 2N wide (B_hi | B_lo rows)
 };
 
 // device form of a K-step: descriptor low words with the slot-independent parts pre-folded
 //   a_lo[a] = (a_off[a] >> 4) | ((lbo >> 4) << 16),  b_lo = (b_off >> 4) | ((N * 16 >> 4) << 16)
 // the issuer only adds (slot base >> 4) (+ tile * 128) — smem addresses are < 256 KB so the 14-bit
 // address field never carries into the LBO field.
-enum : uint32_t { KS_FIRST_OF_UNIT = 1, KS_LAST_OF_UNIT = 2, KS_FIRST_OF_STAGE = 4, KS_LAST_OF_STAGE = 8 };
+enum : uint32_t { KS_FIRST_OF_UNIT = 1, KS_LAST_OF_UNIT = 2, KS_FIRST_OF_STAGE = 4, KS_LAST_OF_STAGE = 8, KS_WIDE = 16 };
 struct KStepDev {
   uint32_t a_lo[2];
   uint32_t b_lo;
