@@ -182,12 +182,15 @@ extern "C" int avs_sweep_run_host(avs_sweep* s, const float* frames_host, const 
   int rc = host_init(s);
   if (rc) return rc;
   if ((rc = ensure_capacity(s, n_clips))) return rc;
-  const int n_chunks = cdiv(n_clips, s->chunk);
   // page-locked caller buffers are copied from directly; pageable ones go through the pinned staging slots
   const bool direct = is_pinned(frames_host) && is_pinned(audio_host);
-  // software pipeline over chunks: H2D(i+1) on the copy stream overlaps the kernels of chunk i on main
-  for (int i = 0; i < n_chunks; ++i) {
-    const int sl = i & 1, c0 = i * s->chunk, n = std::min(s->chunk, n_clips - c0);
+  // software pipeline over chunks: H2D(i+1) on the copy stream overlaps the kernels of chunk i on main.
+  // The first chunks are small (16, 32, 64, ... clips) so that compute starts after a short copy instead of
+  // waiting for a full chunk to cross PCIe.
+  int c0 = 0, next = std::min(16, s->chunk);
+  for (int i = 0; c0 < n_clips; ++i) {
+    const int sl = i & 1, n = std::min(next, n_clips - c0);
+    next = std::min(next * 2, s->chunk);
     const float* fsrc = frames_host + c0 * kFrameElems;
     const float* asrc = audio_host + static_cast<size_t>(c0) * s->n_samples;
     if (i >= 2) {
@@ -206,6 +209,7 @@ extern "C" int avs_sweep_run_host(avs_sweep* s, const float* frames_host, const 
     AVS_CUDA(cudaStreamWaitEvent(s->main, s->ev_in[sl], 0));
     if ((rc = run_chunk(s, s->d_frames[sl], s->d_audio[sl], c0, n, s->main))) return rc;
     AVS_CUDA(cudaEventRecord(s->ev_done[sl], s->main));
+    c0 += n;
   }
   if ((rc = score_all(s, n_clips, s->d_scores_all, s->d_best_all, s->main))) return rc;
   AVS_CUDA(cudaMemcpyAsync(out_scores_host, s->d_scores_all, static_cast<size_t>(n_clips) * s->K * sizeof(float), cudaMemcpyDeviceToHost, s->main));
