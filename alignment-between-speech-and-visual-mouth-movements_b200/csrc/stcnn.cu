@@ -27,6 +27,9 @@ struct StcnnWs {  // workspace carve, shared by size query and forward
   size_t total;
 };
 
+int stcnn_fill(avs_stcnn* net, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+               const float* b3, int dev, cudaStream_t st);
+
 static StcnnWs carve(const avs_stcnn* net, int B, void* ws, bool need_emb) {
   Carver c(ws);
   StcnnWs r{};
@@ -60,6 +63,19 @@ extern "C" int avs_stcnn_create(const float* w1, const float* b1, const float* w
   if (rc) return rc;
   avs_stcnn* net = new avs_stcnn();
   net->precision = precision;
+  rc = avs::stcnn_fill(net, w1, b1, w2, b2, w3, b3, dev, st);
+  if (rc) {
+    avs_stcnn_destroy(net);
+    return rc;
+  }
+  *out = net;
+  return AVS_OK;
+}
+
+int avs::stcnn_fill(avs_stcnn* net, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                    const float* b3, int dev, cudaStream_t st) {
+  const int precision = net->precision;
+  int rc;
   AVS_CUDA(cudaDeviceGetAttribute(&net->n_sms, cudaDevAttrMultiProcessorCount, dev));
   const float* ws[3] = {w1, w2, w3};
   const float* bs[3] = {b1, b2, b3};
@@ -78,15 +94,10 @@ extern "C" int avs_stcnn_create(const float* w1, const float* b1, const float* w
       g.Cin = kCin[l]; g.Cout = kCout[l]; g.H = kHin[l]; g.W = kWin[l]; g.KH = kKH[l]; g.KW = kKW[l];
       const int split = precision == AVS_PREC_BF16X3;
       geom_finalize(g, split);
-      rc = umma_layer_build(&net->L[l], g, split, hw.data(), hb.data());
-      if (rc) {
-        avs_stcnn_destroy(net);
-        return rc;
-      }
+      if ((rc = umma_layer_build(&net->L[l], g, split, hw.data(), hb.data()))) return rc;
     }
   }
   AVS_CUDA(cudaStreamSynchronize(st));
-  *out = net;
   return AVS_OK;
 }
 

@@ -23,13 +23,9 @@ struct avs_sweep {
   // host entry point: double-buffered device inputs/outputs + pinned staging
   float* d_frames[2] = {nullptr, nullptr};
   float* d_audio[2] = {nullptr, nullptr};
-  float* d_scores[2] = {nullptr, nullptr};
-  int32_t* d_best[2] = {nullptr, nullptr};
   float* h_frames[2] = {nullptr, nullptr};
   float* h_audio[2] = {nullptr, nullptr};
-  float* h_scores[2] = {nullptr, nullptr};
-  int32_t* h_best[2] = {nullptr, nullptr};
-  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   cudaStream_t main = nullptr;
   bool host_ready = false;
 };
@@ -72,11 +68,10 @@ extern "C" void avs_sweep_destroy(avs_sweep* s) {
   cudaFree(s->ws_stcnn); cudaFree(s->ws_mfcc); cudaFree(s->ws_score); cudaFree(s->vstats); cudaFree(s->astats);
   cudaFree(s->d_scores_all); cudaFree(s->d_best_all);
   for (int i = 0; i < 2; ++i) {
-    cudaFree(s->d_frames[i]); cudaFree(s->d_audio[i]); cudaFree(s->d_scores[i]); cudaFree(s->d_best[i]);
-    cudaFreeHost(s->h_frames[i]); cudaFreeHost(s->h_audio[i]); cudaFreeHost(s->h_scores[i]); cudaFreeHost(s->h_best[i]);
+    cudaFree(s->d_frames[i]); cudaFree(s->d_audio[i]);
+    cudaFreeHost(s->h_frames[i]); cudaFreeHost(s->h_audio[i]);
     if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]);
     if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]);
-    if (s->ev_out[i]) cudaEventDestroy(s->ev_out[i]);
   }
   if (s->side) cudaStreamDestroy(s->side);
   if (s->copy) cudaStreamDestroy(s->copy);
@@ -154,20 +149,13 @@ static int host_init(avs_sweep* s) {
   if (s->host_ready) return AVS_OK;
   const size_t fb = static_cast<size_t>(s->chunk) * kFrameElems * sizeof(float);
   const size_t ab = static_cast<size_t>(s->chunk) * s->n_samples * sizeof(float);
-  const size_t sb = static_cast<size_t>(s->chunk) * s->K * sizeof(float);
-  const size_t bb = static_cast<size_t>(s->chunk) * sizeof(int32_t);
   for (int i = 0; i < 2; ++i) {
     AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_frames[i]), fb));
     AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_audio[i]), ab));
-    AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_scores[i]), sb));
-    AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_best[i]), bb));
     AVS_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s->h_frames[i]), fb, cudaHostAllocDefault));
     AVS_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s->h_audio[i]), ab, cudaHostAllocDefault));
-    AVS_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s->h_scores[i]), sb, cudaHostAllocDefault));
-    AVS_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s->h_best[i]), bb, cudaHostAllocDefault));
     AVS_CUDA(cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming));
     AVS_CUDA(cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming));
-    AVS_CUDA(cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming));
   }
   AVS_CUDA(cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking));
   AVS_CUDA(cudaStreamCreateWithFlags(&s->main, cudaStreamNonBlocking));
