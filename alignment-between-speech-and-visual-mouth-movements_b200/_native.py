@@ -47,6 +47,8 @@ SIGNATURES = {
     "avs_bigru_destroy": (None, [_P]),
     "avs_bigru_workspace_bytes": (c_size_t, [_P, c_int, c_int]),
     "avs_bigru_forward": (c_int, [_P, _P, c_int, c_int, _P, _P, c_size_t, _P]),
+    "avs_gemm_split_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "avs_gemm_split": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
     "avs_sweep_score_workspace_bytes": (c_size_t, [c_int, c_int]),
     "avs_sweep_score": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
     "avs_ctc_greedy": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),

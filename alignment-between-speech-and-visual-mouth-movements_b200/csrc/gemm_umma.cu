@@ -212,3 +212,31 @@ int gemm_umma_nt(const __nv_bfloat16* a_packed, const __nv_bfloat16* w_packed, c
 }
 
 }  // namespace avs
+
+// C-ABI wrapper (tests, and the DFT-as-GEMM comparison of tools/k1_gemm_vs_fft.py): packs both operands and
+// runs the split GEMM.  workspace >= avs_gemm_split_workspace_bytes(M, N, K).
+extern "C" size_t avs_gemm_split_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  return avs::align_up(avs::gemm_packed_bytes(M, K, 128), 256) + avs::align_up(avs::gemm_packed_bytes(N, K, 256), 256);
+}
+
+extern "C" int avs_gemm_split(const float* a, const float* w, const float* bias, float* c, int M, int N, int K,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace avs;
+  AVS_REQUIRE(a && w && bias && c && workspace, "null argument");
+  AVS_REQUIRE(K % 32 == 0 && N % 4 == 0, "avs_gemm_split needs K % 32 == 0 and N % 4 == 0");
+  if (workspace_bytes < avs_gemm_split_workspace_bytes(M, N, K)) {
+    set_error("gemm_split workspace too small");
+    return AVS_EWORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, n_sms = 148;
+  AVS_CUDA(cudaGetDevice(&dev));
+  AVS_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+  __nv_bfloat16* ap = static_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(workspace) + align_up(gemm_packed_bytes(M, K, 128), 256));
+  int rc;
+  if ((rc = gemm_pack(a, K, M, K, 128, ap, st))) return rc;
+  if ((rc = gemm_pack(w, K, N, K, 256, wp, st))) return rc;
+  return gemm_umma_nt(ap, wp, bias, c, N, M, N, K, n_sms, st);
+}

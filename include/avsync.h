@@ -129,6 +129,13 @@ AVS_API size_t avs_bigru_workspace_bytes(const avs_bigru* head, int n_clips, int
 AVS_API int avs_bigru_forward(const avs_bigru* head, const float* emb, int n_clips, int n_steps,
                       float* out_logp, void* workspace, size_t workspace_bytes, void* stream);
 
+/* fp32-grade GEMM on tcgen05 (the K3 input-projection kernel, exposed for unit tests and for the
+ * DFT-as-GEMM comparison in profiles/): C[M,N] = A[M,K] . W[N,K]^T + bias[N], all device f32 row-major,
+ * operands split hi/lo in bf16 (three products, fp32 accumulate).  K % 32 == 0, N % 4 == 0. */
+AVS_API size_t avs_gemm_split_workspace_bytes(int M, int N, int K);
+AVS_API int avs_gemm_split(const float* a, const float* w, const float* bias, float* c, int M, int N, int K,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- K4: shift-sweep score
  * Replaces, for every (clip, shift), torch.sigmoid(MisalignmentDetector(cat[vstats, astats_k]))
  * (misalignment_detection_train.py:207,243-250,267; misalignment_detection_demo.py:249-250) and
