@@ -464,3 +464,25 @@ def test_error_paths_on_device(A, lipnet_sd, det_sd):
     torch.cuda.synchronize()
     s, b = sw.run(frames, torch.zeros((1, 48000), device="cuda"))     # the handle is still usable afterwards
     assert s.shape == (1, 31) and torch.isfinite(s).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (300, 1536, 512), (77, 40, 96), (1425, 1536, 6912)])
+def test_split_gemm_vs_fp64(A, M, N, K):
+    """The tcgen05 hi/lo-split GEMM (K3's input projection) against a float64 product: fp32-grade accuracy,
+    ragged M / N tails, single- and multi-stage K."""
+    N_ = A._native
+    L = N_.lib()
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn((M, K), generator=g)
+    w = torch.randn((N, K), generator=g) / K ** 0.5
+    b = torch.randn((N,), generator=g)
+    want = (a.double() @ w.double().t() + b.double()).numpy()
+    ad, wd, bd = a.cuda(), w.cuda(), b.cuda()
+    c = torch.full((M, N), float("nan"), device="cuda")
+    ws = N_.workspace(L.avs_gemm_split_workspace_bytes(M, N, K), "cuda")
+    N_.check(L.avs_gemm_split(N_.ptr(ad), N_.ptr(wd), N_.ptr(bd), N_.ptr(c), M, N, K, N_.ptr(ws), ws.numel(), N_.stream_ptr()))
+    got = c.cpu().numpy()
+    report(f"split gemm {M}x{N}x{K}", got, want)
+    fp32 = (ad @ wd.t() + bd).cpu().numpy()
+    err, err32 = np.abs(got - want).max(), np.abs(fp32 - want).max()
+    assert np.isfinite(got).all() and err < 2e-5 * max(1.0, np.abs(want).max()), (err, err32)
