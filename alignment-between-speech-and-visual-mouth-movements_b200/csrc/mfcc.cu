@@ -142,6 +142,145 @@ mfcc_logmel_kernel(const float* __restrict__ audio, int n_samples, const int4* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-per-frame variant (the one launched): the 1024-point complex FFT is two rounds of 32-point FFTs held
+// entirely in registers (N = 32 x 32 Cooley-Tukey), with one transpose through shared memory in between —
+// no block barriers, no per-pass index arithmetic, compile-time twiddles inside the 32-point FFTs.  Per
+// frame this issues ~2x fewer instructions than the radix-4 block FFT above and keeps only 8.4 KB of shared
+// memory per warp (2 warps per CTA), so it still co-resides with the persistent conv kernels.
+constexpr int kWarpFftWarps = 2;
+
+template <int IDX>  // exp(-2 pi i IDX / 32)
+__device__ __forceinline__ float2 tw32() {
+  constexpr float c[9] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654757f,
+                          0.55557023301960218f, 0.38268343236508978f, 0.19509032201612825f, 0.0f};
+  constexpr int i = IDX & 31;
+  // cos(2 pi i / 32) and -sin(2 pi i / 32) from the first-octant table
+  constexpr int q = i & 15;
+  constexpr float cs = (q <= 8) ? c[q] : -c[16 - q];
+  constexpr float sn = (q <= 8) ? c[8 - q] : c[q - 8];
+  return (i < 16) ? make_float2(cs, -sn) : make_float2(-cs, sn);
+}
+
+template <int LEN, int BASE, int J>
+__device__ __forceinline__ void dif_butterfly(float2 (&v)[32]) {
+  constexpr int HALF = LEN / 2;
+  const float2 a = v[BASE + J], b = v[BASE + J + HALF];
+  v[BASE + J] = make_float2(a.x + b.x, a.y + b.y);
+  const float2 d = make_float2(a.x - b.x, a.y - b.y);
+  constexpr int T = J * (32 / LEN);  // twiddle exponent over 32
+  if constexpr (T == 0) v[BASE + J + HALF] = d;
+  else if constexpr (T == 8) v[BASE + J + HALF] = make_float2(d.y, -d.x);  // * (-i)
+  else {
+    const float2 w = tw32<T>();
+    v[BASE + J + HALF] = make_float2(d.x * w.x - d.y * w.y, d.x * w.y + d.y * w.x);
+  }
+}
+template <int LEN, int BASE, int J>
+__device__ __forceinline__ void dif_group(float2 (&v)[32]) {
+  if constexpr (J < LEN / 2) {
+    dif_butterfly<LEN, BASE, J>(v);
+    dif_group<LEN, BASE, J + 1>(v);
+  }
+}
+template <int LEN, int BASE>
+__device__ __forceinline__ void dif_stage(float2 (&v)[32]) {
+  if constexpr (BASE < 32) {
+    dif_group<LEN, BASE, 0>(v);
+    dif_stage<LEN, BASE + LEN>(v);
+  }
+}
+// in-place 32-point forward DFT, decimation in frequency: on return v[i] = X[bitrev5(i)]
+__device__ __forceinline__ void fft32(float2 (&v)[32]) {
+  dif_stage<32, 0>(v);
+  dif_stage<16, 0>(v);
+  dif_stage<8, 0>(v);
+  dif_stage<4, 0>(v);
+  dif_stage<2, 0>(v);
+}
+__host__ __device__ constexpr int bitrev5(int i) {
+  return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
+}
+
+__global__ void __launch_bounds__(32 * kWarpFftWarps)
+mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const int4* __restrict__ frames, int n_unique,
+                        const float* __restrict__ window, const float2* __restrict__ tw, const float2* __restrict__ tw2,
+                        const int4* __restrict__ mel_tab, const float* __restrict__ mel_w, float* __restrict__ logmel) {
+  __shared__ float2 s_z[kWarpFftWarps][32 * 33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int clip = blockIdx.y;
+  const int u = blockIdx.x * kWarpFftWarps + warp;
+  if (u >= n_unique) return;  // warp-uniform; no block barriers below
+  float2* z = s_z[warp];
+  const float* x = audio + static_cast<size_t>(clip) * n_samples;
+  const int4 fr = frames[u];
+  float2 v[32];
+  // z[n] = w[2n] x[p+2n] + i w[2n+1] x[p+2n+1] (zero outside [lo, hi)), n = 32*n1 + lane: lane = n2
+#pragma unroll
+  for (int n1 = 0; n1 < 32; ++n1) {
+    const int n = 32 * n1 + lane;
+    const int i0 = fr.x + 2 * n, i1 = i0 + 1;
+    const float2 w = __ldg(reinterpret_cast<const float2*>(window) + n);
+    v[n1] = make_float2((i0 >= fr.y && i0 < fr.z) ? __ldg(x + i0) * w.x : 0.f,
+                        (i1 >= fr.y && i1 < fr.z) ? __ldg(x + i1) * w.y : 0.f);
+  }
+  fft32(v);  // over n1: v[i] = Y[n2 = lane][k1 = bitrev5(i)]
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int k1 = bitrev5(i);
+    float2 y = v[i];
+    if (k1 != 0) y = cmul(y, __ldg(tw + ((lane * k1) & (kHalf - 1))));  // W_1024^(n2 k1)
+    z[lane * 33 + k1] = y;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) v[n2] = z[n2 * 33 + lane];  // lane = k1
+  fft32(v);  // over n2: v[i] = Z[k1 + 32 * bitrev5(i)]
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) z[lane + 32 * bitrev5(i)] = v[i];  // natural order, flat [1024]
+  __syncwarp();
+  // split post-pass for the real transform: bins k = lane + 32 i, i = 0..32 (k <= 1024)
+  float pw[33];
+#pragma unroll
+  for (int i = 0; i < 33; ++i) {
+    const int k = lane + 32 * i;
+    pw[i] = 0.f;
+    if (k <= kHalf) {
+      const float2 zk = z[k & (kHalf - 1)], zn = z[(kHalf - k) & (kHalf - 1)];
+      const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+      const float2 wo = cmul(__ldg(tw2 + k), o);
+      const float xr = e.x + wo.x, xi = e.y + wo.y;
+      pw[i] = xr * xr + xi * xi;
+    }
+  }
+  __syncwarp();
+  float* s_pow = reinterpret_cast<float*>(z);
+#pragma unroll
+  for (int i = 0; i < 33; ++i)
+    if (lane + 32 * i <= kHalf) s_pow[lane + 32 * i] = pw[i];
+  __syncwarp();
+  // sparse mel: lane takes one band of each quartile (bands lane, lane+32, lane+64, lane+96)
+  float* out = logmel + (static_cast<size_t>(clip) * n_unique + u) * kMels;
+#pragma unroll
+  for (int r = 0; r < kMels / 32; ++r) {
+    const int m = lane + 32 * r;
+    const int4 rg = __ldg(mel_tab + m);
+    const float* w = mel_w + rg.z;
+    float acc0 = 0.f, acc1 = 0.f;
+    int i = 0;
+    for (; i + 1 < rg.y; i += 2) {
+      acc0 = fmaf(__ldg(w + i), s_pow[rg.x + i], acc0);
+      acc1 = fmaf(__ldg(w + i + 1), s_pow[rg.x + i + 1], acc1);
+    }
+    if (i < rg.y) acc0 = fmaf(__ldg(w + i), s_pow[rg.x + i], acc0);
+    out[m] = 10.0f * log10f(fmaxf(acc0 + acc1, 1e-10f));
+  }
+}
+
 // One CTA per (shift, clip).  128 threads; thread j owns frames j, j+128, ...
 template <int NQ>
 __global__ void __launch_bounds__(128)
@@ -391,9 +530,9 @@ extern "C" int avs_mfcc_sweep_debug(const avs_mfcc_plan* p, const float* audio, 
   float* logmel = static_cast<float*>(workspace);
   for (int c0 = 0; c0 < n_clips; c0 += 32768) {  // gridDim.y limit
     const int nc = std::min(32768, n_clips - c0);
-    dim3 g1(cdiv(p->n_unique, kFramesPerCta), nc);
+    dim3 g1(cdiv(p->n_unique, kWarpFftWarps), nc);
     { ProfScope ps(PROF_LOGMEL, st);
-    mfcc_logmel_kernel<<<g1, kFftThreads, 0, st>>>(audio + static_cast<size_t>(c0) * p->n_samples, p->n_samples,
+    mfcc_logmel_warp_kernel<<<g1, 32 * kWarpFftWarps, 0, st>>>(audio + static_cast<size_t>(c0) * p->n_samples, p->n_samples,
                                                    p->d_frames, p->n_unique, p->d_window, p->d_tw, p->d_tw2,
                                                    p->d_mel_tab, p->d_mel_w,
                                                    logmel + static_cast<size_t>(c0) * p->n_unique * kMels); }
