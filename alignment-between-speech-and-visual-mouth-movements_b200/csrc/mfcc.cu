@@ -8,9 +8,9 @@
 //                 signal restricted to a valid range [a, b) (zero elsewhere).  Frames with equal
 //                 (p, a, b) are identical, so the K*F frames collapse to U unique ones (746 instead
 //                 of 4961 for +-20 video frames at 25 fps / 16 kHz).
-//   logmel kernel: per unique frame: Hann window, 2048-point real FFT (1024-point complex radix-4
-//                 Stockham in shared memory + split post-pass), |X|^2, sparse Slaney mel filterbank,
-//                 10*log10(max(1e-10, .)).  fp32 throughout.
+//   logmel kernel: per unique frame (one warp each): Hann window, 2048-point real FFT (1024-point complex
+//                 FFT as 32 x 32 register-resident 32-point FFTs + split post-pass), |X|^2, sparse Slaney mel
+//                 filterbank, 10*log10(max(1e-10, .)).  fp32 throughout.
 //   stats kernel: per (clip, shift): gather the F frames through the map, global max, top_db clamp,
 //                 DCT-II (ortho) to n_mfcc coefficients, mean and unbiased std over frames.
 #include <algorithm>
@@ -26,8 +26,6 @@ constexpr int kNfft = AVS_NFFT;
 constexpr int kHalf = kNfft / 2;      // 1024
 constexpr int kBins = kHalf + 1;      // 1025
 constexpr int kMels = AVS_NMELS;      // 128
-constexpr int kFftThreads = 256;
-constexpr int kFramesPerCta = 8;
 constexpr int kMaxQ = 40;
 
 }  // namespace avs
@@ -51,103 +49,13 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-__global__ void __launch_bounds__(kFftThreads, 4)
-mfcc_logmel_kernel(const float* __restrict__ audio, int n_samples, const int4* __restrict__ frames, int n_unique,
-                   const float* __restrict__ window, const float2* __restrict__ tw, const float2* __restrict__ tw2,
-                   const int4* __restrict__ mel_tab, const float* __restrict__ mel_w, float* __restrict__ logmel) {
-  // 16 KB of shared memory per CTA, so that these CTAs can share an SM with the persistent conv
-  // kernels (which leave ~24 KB): twiddles come from L1, the power spectrum reuses the idle buffer.
-  __shared__ float2 buf0[kHalf];
-  __shared__ float2 buf1[kHalf];
-
-  const int tid = threadIdx.x;
-  const int clip = blockIdx.y;
-  const float* x = audio + static_cast<size_t>(clip) * n_samples;
-
-  const int u0 = blockIdx.x * kFramesPerCta;
-  const int u1 = min(u0 + kFramesPerCta, n_unique);
-  for (int u = u0; u < u1; ++u) {
-    const int4 fr = frames[u];
-    __syncthreads();  // previous frame's consumers are done with the buffers
-    // z[n] = w[2n] x[p+2n] + i w[2n+1] x[p+2n+1], zero outside [a, b)
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int n = tid + r * kFftThreads;
-      const int i0 = fr.x + 2 * n, i1 = i0 + 1;
-      const float2 w = reinterpret_cast<const float2*>(window)[n];
-      const float re = (i0 >= fr.y && i0 < fr.z) ? __ldg(x + i0) * w.x : 0.f;
-      const float im = (i1 >= fr.y && i1 < fr.z) ? __ldg(x + i1) * w.y : 0.f;
-      buf0[n] = make_float2(re, im);
-    }
-    __syncthreads();
-    // 5 radix-4 Stockham passes, Ns = 1, 4, 16, 64, 256
-    float2* src = buf0;
-    float2* dst = buf1;
-#pragma unroll
-    for (int pass = 0; pass < 5; ++pass) {
-      const int Ns = 1 << (2 * pass);
-      const int j = tid;
-      const int k = j & (Ns - 1);
-      float2 v0 = src[j], v1 = src[j + 256], v2 = src[j + 512], v3 = src[j + 768];
-      if (pass > 0) {
-        const int e = k * (256 / Ns);  // exponent of exp(-2 pi i / 1024)
-        v1 = cmul(v1, __ldg(tw + e));
-        v2 = cmul(v2, __ldg(tw + 2 * e));
-        v3 = cmul(v3, __ldg(tw + 3 * e));
-      }
-      const float2 a = make_float2(v0.x + v2.x, v0.y + v2.y);
-      const float2 b = make_float2(v0.x - v2.x, v0.y - v2.y);
-      const float2 c = make_float2(v1.x + v3.x, v1.y + v3.y);
-      const float2 d = make_float2(v1.y - v3.y, v3.x - v1.x);  // -i * (v1 - v3)
-      const int o = ((j - k) << 2) + k;
-      dst[o] = make_float2(a.x + c.x, a.y + c.y);
-      dst[o + Ns] = make_float2(b.x + d.x, b.y + d.y);
-      dst[o + 2 * Ns] = make_float2(a.x - c.x, a.y - c.y);
-      dst[o + 3 * Ns] = make_float2(b.x - d.x, b.y - d.y);
-      __syncthreads();
-      float2* t = src; src = dst; dst = t;
-    }
-    // split post-pass: X[k] = E[k] + W_2048^k O[k], k in [0, 1024]; 5 passes -> the spectrum is in buf1
-    float* s_pow = reinterpret_cast<float*>(dst);
-    for (int k = tid; k < kBins; k += kFftThreads) {
-      const float2 zk = src[k & (kHalf - 1)];
-      const float2 zn = src[(kHalf - k) & (kHalf - 1)];
-      const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-      const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));  // (zk - conj zn) / (2i)
-      const float2 wo = cmul(__ldg(tw2 + k), o);
-      const float xr = e.x + wo.x, xi = e.y + wo.y;
-      s_pow[k] = xr * xr + xi * xi;
-    }
-    __syncthreads();
-    // sparse mel projection: two threads per mel band, each streams half of the band's non-zero
-    // weights (independent loads, L1-resident after the CTA's first frame); partner lanes combine
-    float* out = logmel + (static_cast<size_t>(clip) * n_unique + u) * kMels;
-    {
-      const int m = tid >> 1, h = tid & 1;
-      const int4 rg = __ldg(mel_tab + m);  // (first bin, count, offset into mel_w, -)
-      const int n0 = (rg.y + 1) >> 1;
-      const int lo = h ? n0 : 0, hi = h ? rg.y : n0;
-      const float* w = mel_w + rg.z;
-      float acc0 = 0.f, acc1 = 0.f;
-      int i = lo;
-      for (; i + 1 < hi; i += 2) {
-        acc0 = fmaf(__ldg(w + i), s_pow[rg.x + i], acc0);
-        acc1 = fmaf(__ldg(w + i + 1), s_pow[rg.x + i + 1], acc1);
-      }
-      if (i < hi) acc0 = fmaf(__ldg(w + i), s_pow[rg.x + i], acc0);
-      float acc = acc0 + acc1;
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      if (h == 0) out[m] = 10.0f * log10f(fmaxf(acc, 1e-10f));
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Warp-per-frame variant (the one launched): the 1024-point complex FFT is two rounds of 32-point FFTs held
-// entirely in registers (N = 32 x 32 Cooley-Tukey), with one transpose through shared memory in between —
-// no block barriers, no per-pass index arithmetic, compile-time twiddles inside the 32-point FFTs.  Per
-// frame this issues ~2x fewer instructions than the radix-4 block FFT above and keeps only 8.4 KB of shared
-// memory per warp (2 warps per CTA), so it still co-resides with the persistent conv kernels.
+// Log-mel of one unique STFT frame per WARP.  The 2048-point real transform is a 1024-point complex FFT of the
+// even/odd-packed frame plus a split post-pass; the complex FFT is two rounds of 32-point FFTs held entirely
+// in registers (N = 32 x 32 Cooley-Tukey, compile-time twiddles inside the 32-point FFTs) with one transpose
+// through shared memory in between — no block barriers and no per-pass index arithmetic (a first version
+// with a radix-4 Stockham FFT per 256-thread CTA issued ~2x the instructions and was 1.7x slower).  8.4 KB of
+// shared memory per warp, 2 warps per CTA, so these CTAs co-reside with the persistent conv kernels.
 constexpr int kWarpFftWarps = 2;
 
 template <int IDX>  // exp(-2 pi i IDX / 32)
