@@ -45,11 +45,12 @@ def peaks():
 
 def conv2_traffic(clips_per_launch: int, precision: str):
     """DRAM bytes per launch of the layer-2 conv kernel from the committed `ncu --set full` capture
-    (profiles/r01_conv2_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum = 74.8 MB for an
-    8-clip bf16 launch = 9.36 MB per clip), scaled to the clips one bench launch processes."""
+    (profiles/r01_conv2_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum = 740.1 MB for a
+    64-clip bf16 launch = 11.56 MB per clip; algorithmic: 8.6 MB padded input + 2.9 MB pooled output),
+    scaled to the clips one bench launch processes."""
     if precision != "bf16":
         return None
-    return 9.36e6 * clips_per_launch
+    return 11.56e6 * clips_per_launch
 
 
 class ClockSampler:
