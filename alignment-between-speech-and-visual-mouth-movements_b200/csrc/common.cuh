@@ -119,7 +119,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+    if (clock64() - t0 > 40000000000LL) {  // ~20 s at 2 GHz: far beyond any legitimate wait, even when time-sliced
       printf("avsync: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
              smem_u32(bar), parity);
       __trap();
