@@ -27,6 +27,22 @@ def timed(fn, n=5, warm=3):
 g = torch.Generator().manual_seed(3)
 torch.manual_seed(1)
 det = A.MisalignmentDetector(13864, 512).cuda().eval()
+# config 1: ONE clip, +-15 frames: STCNN + Bi-GRU head (log-probs) + detector scores — the reference's CPU-runnable case
+torch.manual_seed(0)
+net1 = A.LipNet(39, precision="bf16x3").cuda().eval()
+f1 = torch.rand((1, 1, 75, 50, 100), generator=g).cuda()
+a1 = (torch.randn((1, 48000), generator=g) * 0.1).clamp_(-1, 1).cuda()
+sw1 = A.SyncSweeper(net1, det, 15, chunk_clips=1)
+
+
+def config1():
+    sw1.run(f1, a1)
+    return A.ctc_greedy_decode(net1(f1))
+
+
+ms = timed(config1, n=20)
+print(json.dumps({"config": "1: one clip, +-15 frames, STCNN + Bi-GRU head + detector sweep + decode", "precision": "bf16x3",
+                  "ms": ms, "clips_per_s": 1e3 / ms}))
 for prec in ("bf16x3", "bf16"):
     torch.manual_seed(0)
     net = A.LipNet(39, precision=prec).cuda().eval()
