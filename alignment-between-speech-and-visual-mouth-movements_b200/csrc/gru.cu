@@ -89,8 +89,11 @@ gru_recurrence_kernel(const float* __restrict__ xp, const float* __restrict__ w_
 // writes the new h values into the h buffers of all 8 CTAs through distributed shared memory and the
 // cluster synchronises once (h is double-buffered, so one barrier per step is enough).
 //   thread = (unit = lane, clip pair = warp): W reads are conflict-free LDS.128, h reads are broadcasts.
-constexpr int kClu = 8, kCluClips = 16, kCluUnits = 32, kCluH = 256;
-constexpr size_t kCluSmem = static_cast<size_t>(kCluH / 4) * 3 * kCluUnits * 16 + 2ull * kCluClips * kCluH * 4;
+constexpr int kClu = 8, kCluClips = 16, kCluUnits = 32, kCluH = 256, kCluSlices = 8;
+constexpr size_t kCluWBytes = static_cast<size_t>(kCluH / 4) * 3 * kCluUnits * 16;      // 96 KB
+constexpr size_t kCluHBytes = 2ull * kCluClips * kCluH * 4;                              // 32 KB
+constexpr size_t kCluRBytes = static_cast<size_t>(kCluSlices) * 3 * kCluClips * kCluUnits * 4;  // 48 KB
+constexpr size_t kCluSmem = kCluWBytes + kCluHBytes + kCluRBytes;
 
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -107,18 +110,27 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t local_addr, uint32_t ran
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
 }
 
+// Per step, in two phases:
+//   (1) mat-vec, k-split: thread = (unit = lane, k slice = warp, 32 k each) accumulates the three gate rows of
+//       its unit against ALL clips of the group, so every W element is read from shared memory exactly once
+//       per step (conflict-free LDS.128) and h reads are warp broadcasts; work scales with the number of
+//       valid clips, which makes single-clip latency ~10x lower than a clip-parallel mapping;
+//   (2) the 8 partial sums meet in shared memory; thread = (unit, clip pair) finishes the gates, writes h(t)
+//       into the next h buffer of all 8 CTAs through DSMEM, and the cluster synchronises once.
 __global__ void __launch_bounds__(256, 1)
 gru_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                    float* __restrict__ out, int B, int T) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  float4* s_w = reinterpret_cast<float4*>(smem_raw);                                  // [64 k4][3 gates][32 units]
-  float* s_h = reinterpret_cast<float*>(smem_raw + static_cast<size_t>(kCluH / 4) * 3 * kCluUnits * 16);  // [2][16][256]
+  float4* s_w = reinterpret_cast<float4*>(smem_raw);                           // [64 k4][3 gates][32 units]
+  float* s_h = reinterpret_cast<float*>(smem_raw + kCluWBytes);                // [2][16 clips][256]
+  float* s_r = reinterpret_cast<float*>(smem_raw + kCluWBytes + kCluHBytes);   // [8 slices][3 gates][16 clips][32 units]
   constexpr int H = kCluH;
   const uint32_t rank = cluster_rank();
   const int dir = blockIdx.y, group = blockIdx.x / kClu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int J = rank * kCluUnits + lane;              // global hidden unit of this thread
-  const int c0 = 2 * warp, c1 = c0 + 1;               // this thread's two clips inside the group
+  const int n_valid = min(kCluClips, B - group * kCluClips);   // clips of this group that exist (>= 1)
+  const int c0 = 2 * warp, c1 = c0 + 1;               // phase 2: this thread's two clips inside the group
   const int b0 = group * kCluClips + c0, b1 = b0 + 1;
   // resident weights: w_hh [2][3H][H] (reference layout) -> s_w[k4][gate][unit]
   const float* w = w_hh + static_cast<size_t>(dir) * 3 * H * H;
@@ -135,7 +147,7 @@ gru_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
   for (int s = 0; s < T; ++s) {
     const int t = dir ? T - 1 - s : s;
     const int cur = s & 1;
-    // input-projection terms first: their latency hides behind the mat-vec
+    // input-projection terms of phase 2 first: their latency hides behind the mat-vec
     float gi0[3] = {0.f, 0.f, 0.f}, gi1[3] = {0.f, 0.f, 0.f};
     if (b0 < B) {
       const float* g = xp + (static_cast<size_t>(b0) * T + t) * 6 * H + dir * 3 * H + J;
@@ -145,45 +157,73 @@ gru_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
       const float* g = xp + (static_cast<size_t>(b1) * T + t) * 6 * H + dir * 3 * H + J;
       gi1[0] = g[0]; gi1[1] = g[H]; gi1[2] = g[2 * H];
     }
-    float r0 = 0.f, z0 = 0.f, n0 = 0.f, r1 = 0.f, z1 = 0.f, n1 = 0.f;
-    const float4* hv0 = reinterpret_cast<const float4*>(s_h + (cur * kCluClips + c0) * H);
-    const float4* hv1 = reinterpret_cast<const float4*>(s_h + (cur * kCluClips + c1) * H);
-#pragma unroll 4
-    for (int k4 = 0; k4 < H / 4; ++k4) {
+    // ---- phase 1: partial dot products over k in [32 warp, 32 warp + 32)
+    float ar[kCluClips], az[kCluClips], an[kCluClips];
+#pragma unroll
+    for (int c = 0; c < kCluClips; ++c) ar[c] = az[c] = an[c] = 0.f;
+    const float4* hv = reinterpret_cast<const float4*>(s_h + cur * kCluClips * H) + warp * 8;
+#pragma unroll 2
+    for (int kk = 0; kk < 8; ++kk) {
+      const int k4 = warp * 8 + kk;
       const float4 wr = s_w[(k4 * 3 + 0) * kCluUnits + lane];
       const float4 wz = s_w[(k4 * 3 + 1) * kCluUnits + lane];
       const float4 wn = s_w[(k4 * 3 + 2) * kCluUnits + lane];
-      const float4 a = hv0[k4], b = hv1[k4];
-      r0 = fmaf(wr.x, a.x, r0); r0 = fmaf(wr.y, a.y, r0); r0 = fmaf(wr.z, a.z, r0); r0 = fmaf(wr.w, a.w, r0);
-      z0 = fmaf(wz.x, a.x, z0); z0 = fmaf(wz.y, a.y, z0); z0 = fmaf(wz.z, a.z, z0); z0 = fmaf(wz.w, a.w, z0);
-      n0 = fmaf(wn.x, a.x, n0); n0 = fmaf(wn.y, a.y, n0); n0 = fmaf(wn.z, a.z, n0); n0 = fmaf(wn.w, a.w, n0);
-      r1 = fmaf(wr.x, b.x, r1); r1 = fmaf(wr.y, b.y, r1); r1 = fmaf(wr.z, b.z, r1); r1 = fmaf(wr.w, b.w, r1);
-      z1 = fmaf(wz.x, b.x, z1); z1 = fmaf(wz.y, b.y, z1); z1 = fmaf(wz.z, b.z, z1); z1 = fmaf(wz.w, b.w, z1);
-      n1 = fmaf(wn.x, b.x, n1); n1 = fmaf(wn.y, b.y, n1); n1 = fmaf(wn.z, b.z, n1); n1 = fmaf(wn.w, b.w, n1);
-    }
-    {
-      const float r = 1.f / (1.f + expf(-(gi0[0] + r0 + br)));
-      const float z = 1.f / (1.f + expf(-(gi0[1] + z0 + bz)));
-      const float n = tanhf(gi0[2] + r * (n0 + bn));
-      h0 = (1.f - z) * n + z * h0;
-      if (b0 < B) out[(static_cast<size_t>(b0) * T + t) * 2 * H + dir * H + J] = h0;
-    }
-    {
-      const float r = 1.f / (1.f + expf(-(gi1[0] + r1 + br)));
-      const float z = 1.f / (1.f + expf(-(gi1[1] + z1 + bz)));
-      const float n = tanhf(gi1[2] + r * (n1 + bn));
-      h1 = (1.f - z) * n + z * h1;
-      if (b1 < B) out[(static_cast<size_t>(b1) * T + t) * 2 * H + dir * H + J] = h1;
-    }
-    // publish h(t) to every CTA of the cluster (next buffer), then one cluster barrier
-    const uint32_t a0 = s_h_addr + (((cur ^ 1) * kCluClips + c0) * H + J) * 4;
-    const uint32_t a1 = s_h_addr + (((cur ^ 1) * kCluClips + c1) * H + J) * 4;
 #pragma unroll
-    for (uint32_t rr = 0; rr < kClu; ++rr) {
-      st_cluster_f32(a0, rr, h0);
-      st_cluster_f32(a1, rr, h1);
+      for (int c = 0; c < kCluClips; ++c) {
+        if (c < n_valid) {  // warp-uniform
+          const float4 a = hv[c * (H / 4) + kk];
+          ar[c] = fmaf(wr.x, a.x, ar[c]); ar[c] = fmaf(wr.y, a.y, ar[c]); ar[c] = fmaf(wr.z, a.z, ar[c]); ar[c] = fmaf(wr.w, a.w, ar[c]);
+          az[c] = fmaf(wz.x, a.x, az[c]); az[c] = fmaf(wz.y, a.y, az[c]); az[c] = fmaf(wz.z, a.z, az[c]); az[c] = fmaf(wz.w, a.w, az[c]);
+          an[c] = fmaf(wn.x, a.x, an[c]); an[c] = fmaf(wn.y, a.y, an[c]); an[c] = fmaf(wn.z, a.z, an[c]); an[c] = fmaf(wn.w, a.w, an[c]);
+        }
+      }
     }
-    cluster_sync_all();
+#pragma unroll
+    for (int c = 0; c < kCluClips; ++c) {
+      if (c < n_valid) {
+        s_r[((warp * 3 + 0) * kCluClips + c) * kCluUnits + lane] = ar[c];
+        s_r[((warp * 3 + 1) * kCluClips + c) * kCluUnits + lane] = az[c];
+        s_r[((warp * 3 + 2) * kCluClips + c) * kCluUnits + lane] = an[c];
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: thread = (unit, clips c0 / c1): sum the 8 slices in a fixed order, gates, publish h(t)
+    if (c0 < n_valid) {
+      float r0 = 0.f, z0 = 0.f, n0 = 0.f, r1 = 0.f, z1 = 0.f, n1 = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < kCluSlices; ++sl) {
+        r0 += s_r[((sl * 3 + 0) * kCluClips + c0) * kCluUnits + lane];
+        z0 += s_r[((sl * 3 + 1) * kCluClips + c0) * kCluUnits + lane];
+        n0 += s_r[((sl * 3 + 2) * kCluClips + c0) * kCluUnits + lane];
+        if (c1 < n_valid) {
+          r1 += s_r[((sl * 3 + 0) * kCluClips + c1) * kCluUnits + lane];
+          z1 += s_r[((sl * 3 + 1) * kCluClips + c1) * kCluUnits + lane];
+          n1 += s_r[((sl * 3 + 2) * kCluClips + c1) * kCluUnits + lane];
+        }
+      }
+      {
+        const float r = 1.f / (1.f + expf(-(gi0[0] + r0 + br)));
+        const float z = 1.f / (1.f + expf(-(gi0[1] + z0 + bz)));
+        const float n = tanhf(gi0[2] + r * (n0 + bn));
+        h0 = (1.f - z) * n + z * h0;
+        out[(static_cast<size_t>(b0) * T + t) * 2 * H + dir * H + J] = h0;
+      }
+      if (c1 < n_valid) {
+        const float r = 1.f / (1.f + expf(-(gi1[0] + r1 + br)));
+        const float z = 1.f / (1.f + expf(-(gi1[1] + z1 + bz)));
+        const float n = tanhf(gi1[2] + r * (n1 + bn));
+        h1 = (1.f - z) * n + z * h1;
+        out[(static_cast<size_t>(b1) * T + t) * 2 * H + dir * H + J] = h1;
+      }
+      const uint32_t a0 = s_h_addr + (((cur ^ 1) * kCluClips + c0) * H + J) * 4;
+      const uint32_t a1 = s_h_addr + (((cur ^ 1) * kCluClips + c1) * H + J) * 4;
+#pragma unroll
+      for (uint32_t rr = 0; rr < kClu; ++rr) {
+        st_cluster_f32(a0, rr, h0);
+        if (c1 < n_valid) st_cluster_f32(a1, rr, h1);
+      }
+    }
+    cluster_sync_all();  // also orders this step's s_r reads before the next step's s_r writes
   }
 }
 
