@@ -169,21 +169,31 @@ gru_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
       const float4 wz = s_w[(k4 * 3 + 1) * kCluUnits + lane];
       const float4 wn = s_w[(k4 * 3 + 2) * kCluUnits + lane];
 #pragma unroll
-      for (int c = 0; c < kCluClips; ++c) {
-        if (c < n_valid) {  // warp-uniform
-          const float4 a = hv[c * (H / 4) + kk];
-          ar[c] = fmaf(wr.x, a.x, ar[c]); ar[c] = fmaf(wr.y, a.y, ar[c]); ar[c] = fmaf(wr.z, a.z, ar[c]); ar[c] = fmaf(wr.w, a.w, ar[c]);
-          az[c] = fmaf(wz.x, a.x, az[c]); az[c] = fmaf(wz.y, a.y, az[c]); az[c] = fmaf(wz.z, a.z, az[c]); az[c] = fmaf(wz.w, a.w, az[c]);
-          an[c] = fmaf(wn.x, a.x, an[c]); an[c] = fmaf(wn.y, a.y, an[c]); an[c] = fmaf(wn.z, a.z, an[c]); an[c] = fmaf(wn.w, a.w, an[c]);
+      for (int cb = 0; cb < kCluClips; cb += 4) {
+        if (cb < n_valid) {  // warp-uniform; clips are taken four at a time (absent clips of a block have h = 0)
+          float4 a[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) a[c] = hv[(cb + c) * (H / 4) + kk];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { ar[cb + c] = fmaf(wr.x, a[c].x, ar[cb + c]); az[cb + c] = fmaf(wz.x, a[c].x, az[cb + c]); an[cb + c] = fmaf(wn.x, a[c].x, an[cb + c]); }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { ar[cb + c] = fmaf(wr.y, a[c].y, ar[cb + c]); az[cb + c] = fmaf(wz.y, a[c].y, az[cb + c]); an[cb + c] = fmaf(wn.y, a[c].y, an[cb + c]); }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { ar[cb + c] = fmaf(wr.z, a[c].z, ar[cb + c]); az[cb + c] = fmaf(wz.z, a[c].z, az[cb + c]); an[cb + c] = fmaf(wn.z, a[c].z, an[cb + c]); }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { ar[cb + c] = fmaf(wr.w, a[c].w, ar[cb + c]); az[cb + c] = fmaf(wz.w, a[c].w, az[cb + c]); an[cb + c] = fmaf(wn.w, a[c].w, an[cb + c]); }
         }
       }
     }
 #pragma unroll
-    for (int c = 0; c < kCluClips; ++c) {
-      if (c < n_valid) {
-        s_r[((warp * 3 + 0) * kCluClips + c) * kCluUnits + lane] = ar[c];
-        s_r[((warp * 3 + 1) * kCluClips + c) * kCluUnits + lane] = az[c];
-        s_r[((warp * 3 + 2) * kCluClips + c) * kCluUnits + lane] = an[c];
+    for (int cb = 0; cb < kCluClips; cb += 4) {
+      if (cb < n_valid) {
+#pragma unroll
+        for (int c = cb; c < cb + 4; ++c) {
+          s_r[((warp * 3 + 0) * kCluClips + c) * kCluUnits + lane] = ar[c];
+          s_r[((warp * 3 + 1) * kCluClips + c) * kCluUnits + lane] = az[c];
+          s_r[((warp * 3 + 2) * kCluClips + c) * kCluUnits + lane] = an[c];
+        }
       }
     }
     __syncthreads();
@@ -206,14 +216,12 @@ gru_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
         const float z = 1.f / (1.f + expf(-(gi0[1] + z0 + bz)));
         const float n = tanhf(gi0[2] + r * (n0 + bn));
         h0 = (1.f - z) * n + z * h0;
-        out[(static_cast<size_t>(b0) * T + t) * 2 * H + dir * H + J] = h0;
       }
       if (c1 < n_valid) {
         const float r = 1.f / (1.f + expf(-(gi1[0] + r1 + br)));
         const float z = 1.f / (1.f + expf(-(gi1[1] + z1 + bz)));
         const float n = tanhf(gi1[2] + r * (n1 + bn));
         h1 = (1.f - z) * n + z * h1;
-        out[(static_cast<size_t>(b1) * T + t) * 2 * H + dir * H + J] = h1;
       }
       const uint32_t a0 = s_h_addr + (((cur ^ 1) * kCluClips + c0) * H + J) * 4;
       const uint32_t a1 = s_h_addr + (((cur ^ 1) * kCluClips + c1) * H + J) * 4;
@@ -223,7 +231,15 @@ gru_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
         if (c1 < n_valid) st_cluster_f32(a1, rr, h1);
       }
     }
-    cluster_sync_all();  // also orders this step's s_r reads before the next step's s_r writes
+    // arrive (release: the DSMEM stores above) ... the global stores of h(t) ride between arrive and wait so
+    // the release fence does not have to drain them ... wait (acquire).  The barrier also orders this step's
+    // s_r reads before the next step's s_r writes.
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    if (c0 < n_valid) {
+      out[(static_cast<size_t>(b0) * T + t) * 2 * H + dir * H + J] = h0;
+      if (c1 < n_valid) out[(static_cast<size_t>(b1) * T + t) * 2 * H + dir * H + J] = h1;
+    }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
 }
 
