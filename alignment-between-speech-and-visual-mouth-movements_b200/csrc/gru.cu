@@ -5,10 +5,12 @@
 //       TRANSPOSED ([k][3H]) so the per-step matrix-vector products read it coalesced; h lives in
 //       shared memory; PyTorch gate order (r, z, n), h0 = 0, n = tanh(gi_n + r * (W_hn h + b_hn)).
 //   (3) fc GEMM + row-wise log_softmax.
+#include <stdlib.h>
 #include <algorithm>
 #include "common.cuh"
 #include "sgemm.cuh"
 #include "gemm_umma.cuh"
+#include "gru_umma.cuh"
 
 struct avs_bigru {
   int in_dim, H, V, precision;
@@ -20,6 +22,7 @@ struct avs_bigru {
   float* fc_w = nullptr;                 // [V, 2H]
   float* fc_b = nullptr;
   __nv_bfloat16* w_ih_packed[2] = {nullptr, nullptr};  // tensor-core modes: hi/lo chunked form of w_ih
+  __nv_bfloat16* w_hh_packed[2] = {nullptr, nullptr};  // tensor-core modes, H = 256: per-CTA UMMA slabs of w_hh
   int n_sms = 0;
 };
 
@@ -331,6 +334,10 @@ extern "C" int avs_bigru_create(int in_dim, int hidden, int vocab, const float* 
     for (int l = 0; l < 2 && !rc; ++l) {
       if (cudaMalloc(reinterpret_cast<void**>(&g->w_ih_packed[l]), gemm_packed_bytes(6 * hidden, static_cast<int>(ins[l]), 256)) != cudaSuccess) { rc = AVS_ENOMEM; break; }
       rc = gemm_pack(g->w_ih[l], static_cast<int>(ins[l]), 6 * hidden, static_cast<int>(ins[l]), 256, g->w_ih_packed[l], st);
+      if (!rc && hidden == 256) {
+        if (cudaMalloc(reinterpret_cast<void**>(&g->w_hh_packed[l]), gru_whh_packed_bytes()) != cudaSuccess) { rc = AVS_ENOMEM; break; }
+        rc = gru_pack_whh(g->w_hh[l], g->w_hh_packed[l], st);
+      }
     }
   }
   if (!rc) rc = dup(&g->fc_w, fc_w, static_cast<size_t>(vocab) * 2 * H, st);
@@ -347,7 +354,7 @@ extern "C" int avs_bigru_create(int in_dim, int hidden, int vocab, const float* 
 extern "C" void avs_bigru_destroy(avs_bigru* g) {
   if (!g) return;
   for (int l = 0; l < 2; ++l) {
-    cudaFree(g->w_ih[l]); cudaFree(g->b_ih[l]); cudaFree(g->w_hh_t[l]); cudaFree(g->b_hh[l]); cudaFree(g->w_ih_packed[l]); cudaFree(g->w_hh[l]);
+    cudaFree(g->w_ih[l]); cudaFree(g->b_ih[l]); cudaFree(g->w_hh_t[l]); cudaFree(g->b_hh[l]); cudaFree(g->w_ih_packed[l]); cudaFree(g->w_hh[l]); cudaFree(g->w_hh_packed[l]);
   }
   cudaFree(g->fc_w); cudaFree(g->fc_b);
   delete g;
@@ -384,7 +391,9 @@ extern "C" int avs_bigru_forward(const avs_bigru* g, const float* emb, int B, in
       if ((rc = gemm_umma_nt(w.ap, g->w_ih_packed[l], g->b_ih[l], w.xp, 6 * H, rows, 6 * H, ins[l], g->n_sms, st))) return rc;
     }
     ProfScope psr(PROF_GRU_REC, st);
-    if (H == kCluH) {
+    if (g->w_hh_packed[l] != nullptr && !getenv("AVS_GRU_FMA")) {
+      if ((rc = gru_recurrence_umma(w.xp, g->w_hh_packed[l], g->b_hh[l], outs[l], B, T, st))) return rc;
+    } else if (H == kCluH) {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(kClu * cdiv(B, kCluClips), 2, 1);
       cfg.blockDim = dim3(256, 1, 1);

@@ -1,0 +1,221 @@
+// K3 recurrence on the tensor cores (hidden = 256): the per-step mat-vec  gh[rows, clips] = W_hh[rows, :] . h[clips, :]^T
+// of one cluster CTA (96 gate rows of 32 hidden units, 16 clips) is 32 tcgen05.mma per step.
+//
+//   * W_hh slice resident in shared memory for the whole sequence, split hi/lo in bf16, in the K-major
+//     no-swizzle UMMA layout [k chunk][128 rows][8] (rows 96..127 are zero padding): the A operand.
+//   * h(t-1) of the 16 clips lives in every CTA of the cluster as the B operand, also split hi/lo:
+//     [k chunk][hi clips 0..15 | lo clips 0..15][8], double buffered.  One MMA of width 32 computes
+//     W_hi.h_hi and W_hi.h_lo, one of width 16 adds W_lo.h_hi (fp32-grade, like gemm_umma.cu).
+//   * per step: cluster barrier -> 32 MMAs + commit -> 4 warps read the accumulator (lane = gate row),
+//     exchange through shared memory so that thread (unit, clip pair) holds r, z, n -> gates in fp32 ->
+//     the CTA's 32 new hidden values go to all 8 CTAs' B operands as 16-byte DSMEM stores.
+// Cluster of 8 CTAs per (16 clips, direction), as in gru.cu's CUDA-core kernel (which remains the fp32 path).
+#include "common.cuh"
+#include "gru_umma.cuh"
+
+namespace avs {
+
+constexpr int kH = 256, kClu = 8, kClips = 16, kUnits = 32, kRows = 128, kChunks = kH / 8;
+constexpr int kABytes = kChunks * kRows * 16;             // one kind (hi or lo): 64 KB
+constexpr int kBBytes = kChunks * 2 * kClips * 16;        // one h buffer (hi + lo): 16 KB
+constexpr int kXsPitch = kClips + 1;
+constexpr size_t kSmem = 2ull * kABytes + 2ull * kBBytes + kRows * kXsPitch * 4 + 4 * 2 * kClips * 16 + 64;
+
+__device__ __forceinline__ uint32_t cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t local_addr, uint32_t rank, uint4 v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+// wp: packed W_hh [2 dirs][8 ranks][2 kinds][32 chunks][128 rows][8] bf16 (gru_pack_whh)
+__global__ void __launch_bounds__(256, 1)
+gru_cluster_umma_kernel(const float* __restrict__ xp, const __nv_bfloat16* __restrict__ wp, const float* __restrict__ b_hh,
+                        float* __restrict__ out, int B, int T) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_a = smem;                                               // [hi|lo][chunk][row][16 B]
+  uint8_t* s_b = s_a + 2 * kABytes;                                  // [2 buffers][chunk][hi|lo][clip][16 B]
+  float* s_x = reinterpret_cast<float*>(s_b + 2 * kBBytes);          // [128 rows][17]
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_x + kRows * kXsPitch);  // this CTA's 4 chunks: [chunk][hi|lo][clip][16 B]
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_stage + 4 * 2 * kClips * 16);
+  uint64_t* bar_mma = bar_w + 1;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = cta_rank();
+  const int dir = blockIdx.y, group = blockIdx.x / kClu;
+  const int J = rank * kUnits + lane;
+  const int n_valid = min(kClips, B - group * kClips);
+  const int c0 = 2 * warp, c1 = c0 + 1;
+  const int b0 = group * kClips + c0, b1 = b0 + 1;
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<32>(s_tmem);
+  for (int i = tid; i < 2 * kBBytes / 16; i += 256) reinterpret_cast<uint4*>(s_b)[i] = make_uint4(0, 0, 0, 0);  // h(-1) = 0
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *s_tmem;
+  if (tid == 0) {  // resident weights: 128 KB in 8 bulk copies
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(wp) + (static_cast<size_t>(dir) * kClu + rank) * 2 * kABytes;
+    mbar_expect_tx(bar_w, 2 * kABytes);
+    for (int i = 0; i < 8; ++i) bulk_g2s(s_a + i * (kABytes / 4), src + static_cast<size_t>(i) * (kABytes / 4), kABytes / 4, bar_w);
+  }
+  const float br = b_hh[dir * 3 * kH + J], bz = b_hh[dir * 3 * kH + kH + J], bn = b_hh[dir * 3 * kH + 2 * kH + J];
+  float h0 = 0.f, h1 = 0.f;
+  fence_proxy_async();  // the zeroed h buffers are read by the async proxy (tcgen05.mma)
+  mbar_wait(bar_w, 0);
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+  const uint32_t a_lo32 = smem_u32(s_a) >> 4, b_lo32 = smem_u32(s_b) >> 4, stage_addr = smem_u32(s_stage);
+  constexpr uint64_t kHi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;  // SBO 128 B, descriptor version 1
+  constexpr uint32_t kLboA = ((kRows * 16) >> 4) << 16, kLboB = ((2 * kClips * 16) >> 4) << 16;
+  const uint32_t idesc_w = umma_idesc_bf16(128, 2 * kClips), idesc_n = umma_idesc_bf16(128, kClips);
+
+  for (int s = 0; s < T; ++s) {
+    const int t = dir ? T - 1 - s : s;
+    const int cur = s & 1;
+    // ---- mat-vec on the tensor core: D[row, 0:16] = W_hi.h_hi + W_lo.h_hi, D[row, 16:32] = W_hi.h_lo
+    if (tid == 0) {
+      fence_proxy_async();  // h(t-1) arrived through generic-proxy DSMEM stores
+      tc_fence_after();
+      const uint32_t bb = b_lo32 + cur * (kBBytes >> 4);
+#pragma unroll
+      for (int j = 0; j < kChunks / 2; ++j) {
+        const uint32_t a_hi = a_lo32 + (2 * j) * (kRows * 16 >> 4), a_lo = a_hi + (kABytes >> 4);
+        const uint32_t bj = bb + (2 * j) * (2 * kClips * 16 >> 4);
+        umma_f16(tmem_d, kHi | kLboA | a_hi, kHi | kLboB | bj, idesc_w, j != 0 ? 1u : 0u);
+        umma_f16(tmem_d, kHi | kLboA | a_lo, kHi | kLboB | bj, idesc_n, 1u);
+      }
+      tc_commit(bar_mma);
+    }
+    // input-projection terms: their latency hides behind the MMAs
+    float gi0[3] = {0.f, 0.f, 0.f}, gi1[3] = {0.f, 0.f, 0.f};
+    if (b0 < B) {
+      const float* g = xp + (static_cast<size_t>(b0) * T + t) * 6 * kH + dir * 3 * kH + J;
+      gi0[0] = g[0]; gi0[1] = g[kH]; gi0[2] = g[2 * kH];
+    }
+    if (b1 < B) {
+      const float* g = xp + (static_cast<size_t>(b1) * T + t) * 6 * kH + dir * 3 * kH + J;
+      gi1[0] = g[0]; gi1[1] = g[kH]; gi1[2] = g[2 * kH];
+    }
+    if (warp < 4) {  // lane of TMEM = gate row (gate * 32 + unit); rows >= 96 are padding
+      mbar_wait(bar_mma, s & 1);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem_d + (static_cast<uint32_t>(warp * 32) << 16), v);
+      tmem_ld_wait();
+      float* xr = s_x + (warp * 32 + lane) * kXsPitch;
+#pragma unroll
+      for (int c = 0; c < kClips; ++c) xr[c] = __uint_as_float(v[c]) + __uint_as_float(v[kClips + c]);
+      tc_fence_before();
+    }
+    __syncthreads();
+    // ---- gates: thread = (unit, clips c0 / c1)
+    if (c0 < n_valid) {
+      {
+        const float r = 1.f / (1.f + expf(-(gi0[0] + s_x[(0 * kUnits + lane) * kXsPitch + c0] + br)));
+        const float z = 1.f / (1.f + expf(-(gi0[1] + s_x[(1 * kUnits + lane) * kXsPitch + c0] + bz)));
+        const float n = tanhf(gi0[2] + r * (s_x[(2 * kUnits + lane) * kXsPitch + c0] + bn));
+        h0 = (1.f - z) * n + z * h0;
+      }
+      if (c1 < n_valid) {
+        const float r = 1.f / (1.f + expf(-(gi1[0] + s_x[(0 * kUnits + lane) * kXsPitch + c1] + br)));
+        const float z = 1.f / (1.f + expf(-(gi1[1] + s_x[(1 * kUnits + lane) * kXsPitch + c1] + bz)));
+        const float n = tanhf(gi1[2] + r * (s_x[(2 * kUnits + lane) * kXsPitch + c1] + bn));
+        h1 = (1.f - z) * n + z * h1;
+      }
+    }
+    {  // this CTA's 32 units of h(t), split hi/lo, in operand layout [chunk (4)][hi|lo][clip][8]
+      const __nv_bfloat16 h0h = __float2bfloat16_rn(h0), h1h = __float2bfloat16_rn(h1);
+      __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(s_stage) + (lane >> 3) * (2 * kClips * 8) + (lane & 7);
+      st[c0 * 8] = h0h;
+      st[c1 * 8] = h1h;
+      st[kClips * 8 + c0 * 8] = __float2bfloat16_rn(h0 - __bfloat162float(h0h));
+      st[kClips * 8 + c1 * 8] = __float2bfloat16_rn(h1 - __bfloat162float(h1h));
+    }
+    __syncthreads();
+    // 128 16-byte vectors to each of the 8 CTAs' next h buffer (chunks 4*rank .. 4*rank+3)
+    for (int i = tid; i < 128 * kClu; i += 256) {
+      const int vec = i & 127, dst = i >> 7;
+      const uint4 val = reinterpret_cast<const uint4*>(s_stage)[vec];
+      const uint32_t off = static_cast<uint32_t>((cur ^ 1) * kBBytes + (rank * 4) * (2 * kClips * 16) + vec * 16);
+      st_cluster_v4(smem_u32(s_b) + off, dst, val);
+    }
+    (void)stage_addr;
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    if (c0 < n_valid) {
+      out[(static_cast<size_t>(b0) * T + t) * 2 * kH + dir * kH + J] = h0;
+      if (c1 < n_valid) out[(static_cast<size_t>(b1) * T + t) * 2 * kH + dir * kH + J] = h1;
+    }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<32>(tmem_d);
+  }
+}
+
+// w_hh [2][3H][H] f32 (reference layout) -> [2 dirs][8 ranks][hi|lo][32 chunks][128 rows][8] bf16
+__global__ void __launch_bounds__(256)
+gru_pack_whh_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;  // one thread per (dir, rank, chunk, row)
+  if (idx >= 2 * kClu * kChunks * kRows) return;
+  const int row = idx % kRows, chunk = (idx / kRows) % kChunks, rank = (idx / (kRows * kChunks)) % kClu,
+            dir = idx / (kRows * kChunks * kClu);
+  uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+  if (row < 3 * kUnits) {
+    const int gate = row / kUnits, unit = rank * kUnits + row % kUnits;
+    const float* src = w + (static_cast<size_t>(dir) * 3 * kH + gate * kH + unit) * kH + chunk * 8;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = src[2 * e], x1 = src[2 * e + 1];
+      const __nv_bfloat16 a = __float2bfloat16_rn(x0), b = __float2bfloat16_rn(x1);
+      hi[e] = static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+      lo[e] = pack_bf16x2(x0 - __bfloat162float(a), x1 - __bfloat162float(b));
+    }
+  }
+  uint4* o = reinterpret_cast<uint4*>(out) + (static_cast<size_t>(dir) * kClu + rank) * 2 * kChunks * kRows;
+  o[chunk * kRows + row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  o[kChunks * kRows + chunk * kRows + row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+size_t gru_whh_packed_bytes() { return static_cast<size_t>(2) * kClu * 2 * kABytes; }
+
+int gru_pack_whh(const float* w_hh, __nv_bfloat16* out, cudaStream_t st) {
+  gru_pack_whh_kernel<<<cdiv(2 * kClu * kChunks * kRows, 256), 256, 0, st>>>(w_hh, out);
+  AVS_LAUNCHED();
+  return AVS_OK;
+}
+
+int gru_recurrence_umma(const float* xp, const __nv_bfloat16* w_packed, const float* b_hh, float* out, int B, int T,
+                        cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kClu * cdiv(B, kClips), 2, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kClu; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  AVS_CUDA(cudaFuncSetAttribute(gru_cluster_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem)));
+  AVS_CUDA(cudaLaunchKernelEx(&cfg, gru_cluster_umma_kernel, xp, w_packed, b_hh, out, B, T));
+  AVS_LAUNCHED();
+  return AVS_OK;
+}
+
+}  // namespace avs
