@@ -140,7 +140,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     // Loop nest: item -> weight stage -> KPS K-steps (unrolled) -> NT tiles x 2 accumulators.
     // A units are made of whole stages, so unit boundaries are only checked once per stage.
     const uint32_t idesc_n = umma_idesc_bf16(128, p.N), idesc_w = umma_idesc_bf16(128, 2 * p.N);
-    const uint32_t units_lo = smem_u32(s_units) >> 4, w_lo = smem_u32(s_w) >> 4;
+    const uint32_t units_lo = (smem_u32(s_units) & 0x3FFFFu) >> 4, w_lo = (smem_u32(s_w) & 0x3FFFFu) >> 4;
     const uint32_t unit_step = static_cast<uint32_t>(p.unit_slot_bytes) >> 4, stage_step = static_cast<uint32_t>(p.stage_bytes) >> 4;
     const uint32_t ring = p.ring, wstages = p.wstages, nbuf = p.NBUF, acc_stride = p.acc_stride;
     const int n_stages = p.n_stages, n_tilesets = p.n_tilesets, n_tiles = p.n_tiles, dbg = p.dbg;
@@ -206,6 +206,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       decode_item(p, item, b, t, ts);
       const int nt = min(p.NT, p.n_tiles - ts * p.NT);
       mbar_wait(&acc_full[buf], phase);
+      __syncwarp();  // tcgen05.ld below is .aligned
       tc_fence_after();
       const uint32_t d_base = tmem_base + buf * (p.NT * 2 * p.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
       for (int i = 0; i < ((p.dbg & 4) ? 0 : nt); ++i) {

@@ -77,7 +77,7 @@ gemm_umma_kernel(const __grid_constant__ GemmParams p) {
     const uint32_t idesc = umma_idesc_bf16(kGM, kGN);
     constexpr uint64_t kHi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;           // SBO 128 B, version 1
     constexpr uint32_t kLboA = ((kGM * 16) >> 4) << 16, kLboB = ((kGN * 16) >> 4) << 16;
-    const uint32_t base = smem_u32(smem) >> 4;
+    const uint32_t base = (smem_u32(smem) & 0x3FFFFu) >> 4;
     uint32_t slot = 0, phase = 0, buf = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       mbar_wait(&acc_empty[buf], aphase ^ 1);
@@ -111,6 +111,7 @@ gemm_umma_kernel(const __grid_constant__ GemmParams p) {
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.tiles_n) * kGM, n0 = (tile % p.tiles_n) * kGN;
       mbar_wait(&acc_full[buf], aphase);
+      __syncwarp();  // tcgen05.ld below is .aligned
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       float* crow = p.c + static_cast<size_t>(row) * p.ldc + n0;

@@ -10,6 +10,7 @@
 //     exchange through shared memory so that thread (unit, clip pair) holds r, z, n -> gates in fp32 ->
 //     the CTA's 32 new hidden values go to all 8 CTAs' B operands as 16-byte DSMEM stores.
 // Cluster of 8 CTAs per (16 clips, direction), as in gru.cu's CUDA-core kernel (which remains the fp32 path).
+#include <stdlib.h>
 #include "common.cuh"
 #include "gru_umma.cuh"
 
@@ -19,21 +20,33 @@ constexpr int kH = 256, kClu = 8, kClips = 16, kUnits = 32, kRows = 128, kChunks
 constexpr int kABytes = kChunks * kRows * 16;             // one kind (hi or lo): 64 KB
 constexpr int kBBytes = kChunks * 2 * kClips * 16;        // one h buffer (hi + lo): 16 KB
 constexpr int kXsPitch = kClips + 1;
-constexpr size_t kSmem = 2ull * kABytes + 2ull * kBBytes + kRows * kXsPitch * 4 + 4 * 2 * kClips * 16 + 64;
+constexpr int kStageBytes = 4 * 2 * kClips * 16;          // this CTA's 32 units (4 chunks) of h, hi + lo: 2 KB
+constexpr size_t kSmem = 2ull * kABytes + 2ull * kBBytes + kRows * kXsPitch * 4 + 2 * kStageBytes + 64;
 
 __device__ __forceinline__ uint32_t cta_rank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t local_addr, uint32_t rank, uint4 v) {
+
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+  return remote;
+}
+// bulk copy local shared memory -> shared memory of another CTA of the cluster; completes on THAT CTA's mbarrier
+__device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster_addr, const void* src_smem, uint32_t bytes, uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster_addr),
+               "r"(smem_u32(src_smem)), "r"(bytes), "r"(mbar_cluster_addr)
                : "memory");
 }
 
 // wp: packed W_hh [2 dirs][8 ranks][2 kinds][32 chunks][128 rows][8] bf16 (gru_pack_whh)
+//
+// Step protocol (no cluster barrier inside the loop): h(t) travels between CTAs as bulk async copies that
+// complete on the RECEIVER's mbarrier bar_h[buffer] (8 x 2 KB per step), so the tensor core only ever reads
+// operand bytes written through the async proxy.  Buffer reuse is safe by data dependence: a CTA can start
+// step s+1 only after every peer delivered h(s), which each peer sends after its own step-s MMAs finished.
 __global__ void __launch_bounds__(256, 1)
 gru_cluster_umma_kernel(const float* __restrict__ xp, const __nv_bfloat16* __restrict__ wp, const float* __restrict__ b_hh,
                         float* __restrict__ out, int B, int T) {
@@ -41,10 +54,11 @@ gru_cluster_umma_kernel(const float* __restrict__ xp, const __nv_bfloat16* __res
   uint8_t* s_a = smem;                                               // [hi|lo][chunk][row][16 B]
   uint8_t* s_b = s_a + 2 * kABytes;                                  // [2 buffers][chunk][hi|lo][clip][16 B]
   float* s_x = reinterpret_cast<float*>(s_b + 2 * kBBytes);          // [128 rows][17]
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_x + kRows * kXsPitch);  // this CTA's 4 chunks: [chunk][hi|lo][clip][16 B]
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_stage + 4 * 2 * kClips * 16);
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_x + kRows * kXsPitch);  // [2][this CTA's 4 chunks: chunk][hi|lo][clip][16 B]
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_stage + 2 * kStageBytes);
   uint64_t* bar_mma = bar_w + 1;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  uint64_t* bar_h = bar_mma + 1;                                     // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_h + 2);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = cta_rank();
@@ -57,37 +71,48 @@ gru_cluster_umma_kernel(const float* __restrict__ xp, const __nv_bfloat16* __res
   if (tid == 0) {
     mbar_init(bar_w, 1);
     mbar_init(bar_mma, 1);
+    mbar_init(&bar_h[0], 1);
+    mbar_init(&bar_h[1], 1);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc<32>(s_tmem);
-  for (int i = tid; i < 2 * kBBytes / 16; i += 256) reinterpret_cast<uint4*>(s_b)[i] = make_uint4(0, 0, 0, 0);  // h(-1) = 0
+  if (warp == 1) tmem_alloc<32>(s_tmem);  // a warp that has not diverged: tcgen05.alloc is .sync.aligned
+  for (int i = tid; i < kBBytes / 16; i += 256) reinterpret_cast<uint4*>(s_b)[i] = make_uint4(0, 0, 0, 0);  // h(-1) = 0 in buffer 0
+  fence_proxy_async();  // generic-proxy zero fill, async-proxy (tcgen05.mma) reader
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *s_tmem;
-  if (tid == 0) {  // resident weights: 128 KB in 8 bulk copies
+  if (tid == 0) {  // resident weights: 128 KB in 8 bulk copies; and expect h(0) in buffer 1
     const uint8_t* src = reinterpret_cast<const uint8_t*>(wp) + (static_cast<size_t>(dir) * kClu + rank) * 2 * kABytes;
     mbar_expect_tx(bar_w, 2 * kABytes);
     for (int i = 0; i < 8; ++i) bulk_g2s(s_a + i * (kABytes / 4), src + static_cast<size_t>(i) * (kABytes / 4), kABytes / 4, bar_w);
+    mbar_expect_tx(&bar_h[1], kBBytes);
   }
   const float br = b_hh[dir * 3 * kH + J], bz = b_hh[dir * 3 * kH + kH + J], bn = b_hh[dir * 3 * kH + 2 * kH + J];
   float h0 = 0.f, h1 = 0.f;
-  fence_proxy_async();  // the zeroed h buffers are read by the async proxy (tcgen05.mma)
   mbar_wait(bar_w, 0);
+  // all CTAs of the cluster have initialised their barriers and buffers before anyone sends
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 
-  const uint32_t a_lo32 = smem_u32(s_a) >> 4, b_lo32 = smem_u32(s_b) >> 4, stage_addr = smem_u32(s_stage);
+  // In a cluster launch the shared-window address of a CTA carries its cluster rank above bit 24 (rank 1: 0x01000400).
+  // The descriptor's start-address field is 14 bits of (address >> 4): mask, or the rank lands in the LBO field.
+  const uint32_t a_lo32 = (smem_u32(s_a) & 0x3FFFFu) >> 4, b_lo32 = (smem_u32(s_b) & 0x3FFFFu) >> 4;
   constexpr uint64_t kHi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;  // SBO 128 B, descriptor version 1
   constexpr uint32_t kLboA = ((kRows * 16) >> 4) << 16, kLboB = ((2 * kClips * 16) >> 4) << 16;
-  const uint32_t idesc_w = umma_idesc_bf16(128, 2 * kClips), idesc_n = umma_idesc_bf16(128, kClips);
+  const uint32_t idesc_w = umma_idesc_bf16(128, 2 * kClips);
+  uint32_t h_phase[2] = {0, 0};
 
   for (int s = 0; s < T; ++s) {
     const int t = dir ? T - 1 - s : s;
     const int cur = s & 1;
-    // ---- mat-vec on the tensor core: D[row, 0:16] = W_hi.h_hi + W_lo.h_hi, D[row, 16:32] = W_hi.h_lo
+    // ---- mat-vec on the tensor core: D[row, 0:16] = (W_hi + W_lo).h_hi, D[row, 16:32] = (W_hi + W_lo).h_lo
     if (tid == 0) {
-      fence_proxy_async();  // h(t-1) arrived through generic-proxy DSMEM stores
+      if (s > 0) {  // h(t-1) from all 8 CTAs has landed in buffer `cur`
+        mbar_wait(&bar_h[cur], h_phase[cur]);
+        h_phase[cur] ^= 1;
+      }
+      if (s + 2 < T) mbar_expect_tx(&bar_h[cur], kBBytes);  // next tenant of this buffer: h(t+1), sent during step s+1
       tc_fence_after();
       const uint32_t bb = b_lo32 + cur * (kBBytes >> 4);
 #pragma unroll
@@ -95,7 +120,7 @@ gru_cluster_umma_kernel(const float* __restrict__ xp, const __nv_bfloat16* __res
         const uint32_t a_hi = a_lo32 + (2 * j) * (kRows * 16 >> 4), a_lo = a_hi + (kABytes >> 4);
         const uint32_t bj = bb + (2 * j) * (2 * kClips * 16 >> 4);
         umma_f16(tmem_d, kHi | kLboA | a_hi, kHi | kLboB | bj, idesc_w, j != 0 ? 1u : 0u);
-        umma_f16(tmem_d, kHi | kLboA | a_lo, kHi | kLboB | bj, idesc_n, 1u);
+        umma_f16(tmem_d, kHi | kLboA | a_lo, kHi | kLboB | bj, idesc_w, 1u);  // also adds the tiny W_lo.h_lo term
       }
       tc_commit(bar_mma);
     }
@@ -111,6 +136,7 @@ gru_cluster_umma_kernel(const float* __restrict__ xp, const __nv_bfloat16* __res
     }
     if (warp < 4) {  // lane of TMEM = gate row (gate * 32 + unit); rows >= 96 are padding
       mbar_wait(bar_mma, s & 1);
+      __syncwarp();  // lane 0 issued the MMAs and arrives late: tcgen05.ld is .aligned and needs the warp converged
       tc_fence_after();
       uint32_t v[32];
       tmem_ld32(tmem_d + (static_cast<uint32_t>(warp * 32) << 16), v);
@@ -128,41 +154,40 @@ gru_cluster_umma_kernel(const float* __restrict__ xp, const __nv_bfloat16* __res
         const float z = 1.f / (1.f + expf(-(gi0[1] + s_x[(1 * kUnits + lane) * kXsPitch + c0] + bz)));
         const float n = tanhf(gi0[2] + r * (s_x[(2 * kUnits + lane) * kXsPitch + c0] + bn));
         h0 = (1.f - z) * n + z * h0;
+        out[(static_cast<size_t>(b0) * T + t) * 2 * kH + dir * kH + J] = h0;
       }
       if (c1 < n_valid) {
         const float r = 1.f / (1.f + expf(-(gi1[0] + s_x[(0 * kUnits + lane) * kXsPitch + c1] + br)));
         const float z = 1.f / (1.f + expf(-(gi1[1] + s_x[(1 * kUnits + lane) * kXsPitch + c1] + bz)));
         const float n = tanhf(gi1[2] + r * (s_x[(2 * kUnits + lane) * kXsPitch + c1] + bn));
         h1 = (1.f - z) * n + z * h1;
+        out[(static_cast<size_t>(b1) * T + t) * 2 * kH + dir * kH + J] = h1;
       }
     }
-    {  // this CTA's 32 units of h(t), split hi/lo, in operand layout [chunk (4)][hi|lo][clip][8]
+    if (s + 1 < T) {
+      // this CTA's 32 units of h(t), split hi/lo, staged in operand layout [chunk (4)][hi|lo][clip][8] ...
+      uint8_t* stage = s_stage + cur * kStageBytes;
       const __nv_bfloat16 h0h = __float2bfloat16_rn(h0), h1h = __float2bfloat16_rn(h1);
-      __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(s_stage) + (lane >> 3) * (2 * kClips * 8) + (lane & 7);
+      __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(stage) + (lane >> 3) * (2 * kClips * 8) + (lane & 7);
       st[c0 * 8] = h0h;
       st[c1 * 8] = h1h;
       st[kClips * 8 + c0 * 8] = __float2bfloat16_rn(h0 - __bfloat162float(h0h));
       st[kClips * 8 + c1 * 8] = __float2bfloat16_rn(h1 - __bfloat162float(h1h));
+      fence_proxy_async();  // staged with generic stores, read by the bulk-copy engine
+      __syncthreads();
+      // ... and pushed to chunks [4 rank, 4 rank + 4) of every CTA's next buffer: one 2 KB bulk copy per CTA
+      if (tid < kClu) {
+        const uint32_t dst_off = static_cast<uint32_t>((cur ^ 1) * kBBytes + rank * kStageBytes);
+        bulk_s2c(map_to_rank(smem_u32(s_b) + dst_off, tid), stage, kStageBytes, map_to_rank(smem_u32(&bar_h[cur ^ 1]), tid));
+      }
     }
-    __syncthreads();
-    // 128 16-byte vectors to each of the 8 CTAs' next h buffer (chunks 4*rank .. 4*rank+3)
-    for (int i = tid; i < 128 * kClu; i += 256) {
-      const int vec = i & 127, dst = i >> 7;
-      const uint4 val = reinterpret_cast<const uint4*>(s_stage)[vec];
-      const uint32_t off = static_cast<uint32_t>((cur ^ 1) * kBBytes + (rank * 4) * (2 * kClips * 16) + vec * 16);
-      st_cluster_v4(smem_u32(s_b) + off, dst, val);
-    }
-    (void)stage_addr;
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    if (c0 < n_valid) {
-      out[(static_cast<size_t>(b0) * T + t) * 2 * kH + dir * kH + J] = h0;
-      if (c1 < n_valid) out[(static_cast<size_t>(b1) * T + t) * 2 * kH + dir * kH + J] = h1;
-    }
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
+  // nobody may exit while a peer could still be sending to it or reading its staging buffers
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 1) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc<32>(tmem_d);
