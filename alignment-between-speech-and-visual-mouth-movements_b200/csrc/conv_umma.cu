@@ -14,15 +14,24 @@
 //     offset, never a copy (K-major no-swizzle UMMA layout: rows 16 B apart, 8-channel chunks LBO apart);
 //   * conv rows 2r and 2r+1 are accumulated in two TMEM accumulators over the same lanes, so the
 //     2x2 max-pool is max(acc0, acc1) per thread plus one shuffle with the neighbouring lane;
+//   * the two accumulators sit in ADJACENT column blocks, and padded input row 2r+q feeds filter row q of
+//     the even conv row and filter row q-1 of the odd one: one MMA of width 2*Cout per (kd, q, kw) with
+//     B = [W[q] | W[q-1]] does both (the weight stage stores W[KH-1] .. W[0] back to back, so these pairs
+//     are plain sub-ranges of it) — KH+1 fetches of A per filter column instead of 2*KH;
 //   * a tile's halo'd input is one contiguous run per (chunk, parity): plain cp.async.bulk.
 //
 // Kernel structure: persistent CTAs (one per SM), 8 warps:
 //   warp 0  lane 0 : A producer   — bulk-copies A units (one time plane, or half its channels)
 //   warp 2  lane 0 : B producer   — bulk-copies weight stages (one filter tap each)
-//   warp 1  lane 0 : MMA issuer   — walks the per-layer K-step table, tcgen05.mma into TMEM
+//   warps 1 and 3  : MMA issuers  — take the weight stages of the schedule in turn (one elected lane each issues
+//                                   tcgen05.mma into TMEM): the tensor pipe accepts an MMA only about one
+//                                   instruction ahead of the one executing (tools/umma_rate.cu), so everything an
+//                                   issuer does between two stages — barrier waits, schedule fetch, descriptor
+//                                   arithmetic — would idle it; with two issuers one prepares while the other issues
 //   warp 2         : TMEM allocator
 //   warps 4..7     : epilogue     — tcgen05.ld, pool, bias, ReLU, bf16 (hi/lo) pack, store
-// mbarrier rings: a_full/a_empty[RING], w_full/w_empty[WSTAGES], acc_full/acc_empty[NBUF].
+// mbarrier rings: a_full/a_empty[RING], w_full/w_empty[WSTAGES], acc_full/acc_empty[NBUF]; turn[2] hands the
+// right to issue from one issuer warp to the other.
 #include <stdlib.h>
 #include <vector>
 #include "stcnn.cuh"
@@ -41,13 +50,12 @@ struct UnitDesc {
 struct ConvKernelParams {
   const __nv_bfloat16* act;
   const __nv_bfloat16* w;
-  const KStepDev* ksteps;
   const float* bias;
   EpiOut eo;
   UnitDesc units[kMaxUnits];
   int n_units;
   int N, acc_stride, NT, NBUF, ring, wstages;
-  int n_ksteps, ksteps_per_stage, stage_bytes, n_stages;
+  int stage_bytes, n_stages;
   int unit_slot_bytes, region_pos, region_full;
   int n_chunks, PP, Wt, Ho, Wo, n_tiles, n_tilesets;
   int T, n_items, split;
@@ -62,34 +70,142 @@ __device__ __forceinline__ void decode_item(const ConvKernelParams& p, int item,
   b = r / p.T;
 }
 
-template <int NT, int KPS>
+// ------------------------------------------------------------------------------------------------ MMA schedule
+// The schedule of one weight stage is generated at COMPILE time per layer kind: every descriptor is a run-time
+// uniform base (unit slot, weight slot, accumulator buffer) plus compile-time multiples of two run-time strides
+// (arr16 = positions per (chunk, parity) array, Wt = row pitch), so the issuing thread executes one or two uniform
+// adds per tcgen05.mma and nothing else.  Measured (tools/umma_rate.cu): descriptors fetched from a shared-memory
+// table cost 10-14 cycles per MMA that no amount of unrolling hides (LDS -> IADD -> R2UR feeding UTCHMMA);
+// compile-time offsets issue at the hardware rate, max((4 KB + 32 N) / 128 B, N / 2) cycles per 128 x N x 16 MMA.
+enum : int { KIND_L1 = 0, KIND_L2 = 1, KIND_L3 = 2, KIND_L1_SPLIT = 3, KIND_L2_SPLIT = 4, KIND_L3_SPLIT = 5 };
+template <int KIND>
+struct LayerKind {
+  static constexpr bool split = KIND >= KIND_L1_SPLIT;
+  static constexpr bool first = KIND == KIND_L1 || KIND == KIND_L1_SPLIT;               // Cin = 1, X8 input
+  static constexpr int N = first ? 32 : ((KIND == KIND_L2 || KIND == KIND_L2_SPLIT) ? 64 : 96);  // Cout
+  static constexpr int KH = first ? 5 : (N == 64 ? 5 : 3);
+  static constexpr int KW = KH;
+  static constexpr int NROW = first ? 3 : KH;       // bf16: row taps R[0..NROW-1] of one filter column (conv1: row pairs)
+  static constexpr int PAIRS = first ? 1 : (split ? 2 : (N == 64 ? 2 : 4));  // K = 16 steps (channel pairs) per tap in a unit
+  static constexpr int ACC = split ? (N == 96 ? 256 : 2 * N) : N;            // TMEM columns between even/odd-row accumulators
+  static constexpr int NT = KIND == KIND_L1 ? 4 : (KIND <= KIND_L1_SPLIT ? 2 : 1);  // tiles per work item
+  // stages per A unit: bf16 = one filter column per stage, bf16x3 = one filter row per stage; conv1: the unit is one stage
+  static constexpr int SPU = first ? 1 : KW;
+  // Geometry of LipNet's layer (50 x 100 frames, halved by every pool), mirrored from geom_finalize()/umma_layer_build()
+  // — which refuse anything else — so that the two strides of the activation layout are COMPILE-time constants
+  // and every descriptor of the schedule is "uniform base + immediate".
+  static constexpr int H = first ? 50 : (N == 64 ? 25 : 12), W = first ? 100 : (N == 64 ? 50 : 25);
+  static constexpr int WT = W + KW / 2;                                  // row pitch (positions)
+  static constexpr int HALO = first ? (KH / 2 + 1) * WT + 8 : (KH / 2) * WT + KW - 1;
+  static constexpr int REGION_FULL = NT * 128 + HALO;
+  static constexpr int NTILES = ((H / 2) * WT + 127) / 128, NTS = (NTILES + NT - 1) / NT;
+  static constexpr int EXTENT = ((KW / 2 + (H / 2 + KH / 2) * WT + (first ? 8 : 0)) + 7) / 8 * 8;
+  static constexpr int ARR16 = NTS == 1 ? (REGION_FULL < EXTENT ? REGION_FULL : EXTENT) : REGION_FULL;  // positions per (chunk, parity) run in a slot
+};
+
+constexpr uint64_t kDescHi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, descriptor version 1
+
+// bf16: row-parity stacking (see the header).  a_base = unit slot (+ kw) | LBO_A << 16, b_base = weight slot | LBO_B << 16.
+// TILES (tiles of this work item) is a template parameter: a predicated-off tcgen05.mma is not free — it holds the
+// issue slot ~40 cycles (tools/umma_rate.cu) — so the last, partial tile set of a plane gets its own instantiation.
+template <int KIND, int TILES>
+__device__ __forceinline__ void issue_stage_bf16(uint32_t a_base, uint32_t b_base, uint32_t d_base, bool overwrite,
+                                                 uint32_t idesc_n, uint32_t idesc_w) {
+  using K = LayerKind<KIND>;
+  constexpr int PLANES = K::first ? 3 : 1;  // conv1: the three time planes of the merged unit
+  constexpr uint32_t arr16 = K::ARR16, Wt = K::WT;
+#pragma unroll
+  for (int kd = 0; kd < PLANES; ++kd)
+#pragma unroll
+    for (int pr = 0; pr < K::PAIRS; ++pr)
+#pragma unroll
+      for (int e = 0; e <= K::NROW; ++e) {
+        // padded input row 2r+q; the wide entries go first so that an item's very first MMA covers both accumulators
+        const int q = e < K::NROW - 1 ? e + 1 : (e == K::NROW - 1 ? 0 : K::NROW);
+        const bool wide = q >= 1 && q <= K::NROW - 1;
+        const uint32_t a = a_base + (kd * 2 + pr * 4 + (q & 1)) * arr16 + (q >> 1) * Wt;
+        const uint32_t b = b_base + (kd * K::PAIRS + pr) * (2 * K::NROW * K::N) + (K::NROW - 1 - (q == K::NROW ? K::NROW - 1 : q)) * K::N;
+        const uint32_t d = d_base + (q == K::NROW ? K::N : 0);
+        const uint32_t acc = (kd == 0 && pr == 0 && e == 0) ? (overwrite ? 0u : 1u) : 1u;
+#pragma unroll
+        for (int i = 0; i < TILES; ++i) umma_f16(d + i * 2 * K::ACC, kDescHi | (a + i * 128), kDescHi | b, wide ? idesc_w : idesc_n, acc);
+      }
+}
+
+// bf16x3: per tap and channel pair, A_hi x [B_hi | B_lo] (2N wide) then A_lo x B_hi (N wide), for the even and the odd
+// conv row (A shifted by one padded row) into accumulators ACC columns apart.  kh: filter row of this stage
+// (run-time; conv1 walks its three row-pair taps at compile time).
+template <int KIND, int TILES>
+__device__ __forceinline__ void issue_stage_split(uint32_t a_base, uint32_t b_base, uint32_t d_base, bool overwrite,
+                                                  int kh, uint32_t idesc_n, uint32_t idesc_w) {
+  using K = LayerKind<KIND>;
+  constexpr int TAPS = K::first ? 3 : K::KW;
+  constexpr uint32_t arr16 = K::ARR16, Wt = K::WT;
+  uint32_t row_off[2];  // (parity array, row shift) of padded row 2r + a + kh
+#pragma unroll
+  for (int a = 0; a < 2; ++a) row_off[a] = static_cast<uint32_t>((a + kh) & 1) * arr16 + static_cast<uint32_t>((a + kh) >> 1) * Wt;
+#pragma unroll
+  for (int tap = 0; tap < TAPS; ++tap)
+#pragma unroll
+    for (int pr = 0; pr < K::PAIRS; ++pr)
+#pragma unroll
+      for (int v = 0; v < 2; ++v)
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          uint32_t ra;
+          if (K::first) {
+            const int khh = a + (tap == 2 ? 4 : tap);
+            ra = static_cast<uint32_t>(khh & 1) * arr16 + static_cast<uint32_t>(khh >> 1) * Wt;
+          } else {
+            ra = row_off[a] + tap;
+          }
+          const uint32_t aa = a_base + (pr * 8 + v * 2) * arr16 + ra;
+          const uint32_t b = b_base + (tap * K::PAIRS + pr) * (4 * K::N);
+          const uint32_t d = d_base + a * K::ACC;
+          const uint32_t acc = (tap == 0 && pr == 0 && v == 0) ? (overwrite ? 0u : 1u) : 1u;
+#pragma unroll
+          for (int i = 0; i < TILES; ++i) umma_f16(d + i * 2 * K::ACC, kDescHi | (aa + i * 128), kDescHi | b, v == 0 ? idesc_w : idesc_n, acc);
+        }
+}
+
+template <int KIND, int TILES>
+__device__ __forceinline__ void issue_stage(uint32_t a_base, uint32_t b_base, uint32_t d_base, bool overwrite, int s_in_unit,
+                                            uint32_t idesc_n, uint32_t idesc_w) {
+  using K = LayerKind<KIND>;
+  if (K::split)
+    issue_stage_split<KIND, TILES>(a_base, b_base, d_base, overwrite, s_in_unit, idesc_n, idesc_w);
+  else
+    issue_stage_bf16<KIND, TILES>(a_base + (K::first ? 0 : s_in_unit), b_base, d_base, overwrite, idesc_n, idesc_w);
+}
+
+template <int KIND>
 // 128 registers per thread so that one FFT CTA (256 x 64 registers) of the audio branch fits beside it on the SM
 __global__ void __maxnreg__(128)
 conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  // carve: [unit slots][weight stages][kstep table][barriers][tmem ptr]
+  // carve: [unit slots][weight stages][barriers][tmem ptr]
   uint8_t* s_units = smem;
   uint8_t* s_w = s_units + static_cast<size_t>(p.ring) * p.unit_slot_bytes +
                  static_cast<size_t>(p.region_full - p.region_pos) * 16;  // slack for garbage-lane over-reads
-  KStepDev* s_ks = reinterpret_cast<KStepDev*>(s_w + static_cast<size_t>(p.wstages) * p.stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(
-      reinterpret_cast<uint8_t*>(s_ks) + static_cast<size_t>(p.n_ksteps) * sizeof(KStepDev));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + static_cast<size_t>(p.wstages) * p.stage_bytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kMaxRing;
   uint64_t* w_full = a_empty + kMaxRing;
   uint64_t* w_empty = w_full + kMaxWStages;
   uint64_t* acc_full = w_empty + kMaxWStages;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* turn = acc_empty + 2;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(turn + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < p.n_ksteps * static_cast<int>(sizeof(KStepDev) / 4); i += kConvThreads)
-    reinterpret_cast<uint32_t*>(s_ks)[i] = reinterpret_cast<const uint32_t*>(p.ksteps)[i];
+  using K = LayerKind<KIND>;
+  constexpr int NT = K::NT;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.ring; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 1);
+    for (int i = 0; i < p.ring; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 2);   // both issuers commit
     for (int i = 0; i < p.wstages; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
-    for (int i = 0; i < p.NBUF; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 8);
+    for (int i = 0; i < p.NBUF; ++i) mbar_init(&acc_full[i], 2), mbar_init(&acc_empty[i], 8);
+    mbar_init(&turn[0], 1), mbar_init(&turn[1], 1);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<512>(s_tmem);
@@ -134,66 +250,99 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
                  &w_full[slot]);
       }
     }
-  } else if (warp == 1) {
-    // ============================================================ MMA issuer
-    // The whole warp walks the schedule converged; one elected lane issues tcgen05.mma / .commit.
-    // Loop nest: item -> weight stage -> KPS K-steps (unrolled) -> NT tiles x 2 accumulators.
-    // A units are made of whole stages, so unit boundaries are only checked once per stage.
-    const uint32_t idesc_n = umma_idesc_bf16(128, p.N), idesc_w = umma_idesc_bf16(128, 2 * p.N);
+  } else if (warp == 1 || warp == 3) {
+    // ============================================================ MMA issuers
+    // Both warps walk the whole schedule converged (slot and phase counters stay identical); issuer x owns every
+    // other weight stage (global stage counter g, g & 1 == x).  For an owned stage: wait for its operands, wait for
+    // the turn token of the other issuer's previous stage (its MMAs are then in the pipe, so MMAs reach the tensor
+    // core in schedule order — the overwrite of an item's first MMA comes first), issue, commit, pass the token on.
+    // Barriers that cover MMAs of both issuers (a_empty, acc_full) take a commit from each.
+    const uint32_t x = warp >> 1;
+    const uint32_t idesc_n = umma_idesc_bf16(128, K::N), idesc_w = umma_idesc_bf16(128, 2 * K::N);
     const uint32_t units_lo = (smem_u32(s_units) & 0x3FFFFu) >> 4, w_lo = (smem_u32(s_w) & 0x3FFFFu) >> 4;
     const uint32_t unit_step = static_cast<uint32_t>(p.unit_slot_bytes) >> 4, stage_step = static_cast<uint32_t>(p.stage_bytes) >> 4;
-    const uint32_t ring = p.ring, wstages = p.wstages, nbuf = p.NBUF, acc_stride = p.acc_stride;
+    const uint32_t ring = p.ring, wstages = p.wstages, nbuf = p.NBUF;
+    constexpr uint32_t arr16 = K::ARR16, Wt = K::WT;
+    // LBO fields (16-byte units, bits 16..29): A = next 8-channel chunk of the same parity (conv1: next row of the same
+    // parity, the second kh of the pair); B = the other K half of the tile
+    const uint32_t lbo_a = (K::first ? Wt : (K::split ? 4u : 2u) * arr16) << 16;
+    constexpr uint32_t lbo_b = static_cast<uint32_t>(K::split ? 2 * K::N : K::NROW * K::N) << 16;
     const int n_stages = p.n_stages, n_tilesets = p.n_tilesets, n_tiles = p.n_tiles, dbg = p.dbg;
-    constexpr uint64_t kDescHi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, version 1
     uint32_t a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0, acc_buf = 0, acc_phase = 0;
     uint32_t a_loaded = 0, w_loaded = 0;  // only used by the dbg switches
+    uint32_t g = 0, turn_phase = 0;
+    long long tk_prep = 0, tk_turn = 0, tk_issue = 0, tk_total = clock64();  // dbg 16: issuer time split
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int ts = item % n_tilesets;
       const int nt = min(NT, n_tiles - ts * NT);
-      mbar_wait(&acc_empty[acc_buf], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_base = tmem_base + acc_buf * (NT * 2 * acc_stride);
-      uint32_t unit_lo = 0;
-      for (int st = 0; st < n_stages; ++st) {
-        const KStepDev* ks = s_ks + st * KPS;
-        const uint32_t f0 = ks[0].flags, f1 = ks[KPS - 1].flags;
-        if (f0 & KS_FIRST_OF_UNIT) {
-          if (!(dbg & 2) || a_loaded < ring) mbar_wait(&a_full[a_slot], a_phase);
-          ++a_loaded;
-          unit_lo = units_lo + a_slot * unit_step;
-        }
-        if (!(dbg & 1) || w_loaded < wstages) mbar_wait(&w_full[w_slot], w_phase);
-        ++w_loaded;
-        tc_fence_after();
-        const uint32_t stage_lo = w_lo + w_slot * stage_step;
-        if (elect_one()) {
-          for (int rep = 0; rep < ((dbg & 8) ? 2 : 1); ++rep)  // dbg 8: issue every MMA twice (tensor-vs-issue bound test)
-#pragma unroll
-          for (int j = 0; j < KPS; ++j) {
-            const uint4 k4 = *reinterpret_cast<const uint4*>(ks + j);  // a_lo[0], a_lo[1], b_lo, flags
-            const uint64_t bdesc = kDescHi | (k4.z + stage_lo);
-            const uint32_t a0 = k4.x + unit_lo, a1 = k4.y + unit_lo;
-            const uint32_t acc = (st | j) != 0 ? 1u : 0u;
-            const uint32_t idesc = (k4.w & KS_WIDE) ? idesc_w : idesc_n;
-#pragma unroll
-            for (int i = 0; i < NT; ++i) {
-              if (i < nt) {
-                umma_f16(d_base + (i * 2 + 0) * acc_stride, kDescHi | (a0 + i * 128), bdesc, idesc, acc);
-                umma_f16(d_base + (i * 2 + 1) * acc_stride, kDescHi | (a1 + i * 128), bdesc, idesc, acc);
-              }
-            }
+      bool acc_ready = false;
+      const uint32_t d_base = tmem_base + acc_buf * (NT * 2 * K::ACC);
+      int s_in_unit = 0;  // stage inside the current A unit: the filter column (bf16) / filter row (bf16x3) of the stage
+      for (int st = 0; st < n_stages; ++st, ++g) {
+        const bool last_of_unit = s_in_unit == K::SPU - 1;
+        if ((g & 1) == x) {
+          const long long tk0 = (dbg & 16) ? clock64() : 0;
+          if (!acc_ready) {
+            mbar_wait(&acc_empty[acc_buf], acc_phase ^ 1);
+            acc_ready = true;
           }
-          if (!(dbg & 1)) tc_commit(&w_empty[w_slot]);
-          if ((f1 & KS_LAST_OF_UNIT) && !(dbg & 2)) tc_commit(&a_empty[a_slot]);
-          if (st == n_stages - 1) tc_commit(&acc_full[acc_buf]);
+          if (!(dbg & 2) || a_loaded < ring) mbar_wait(&a_full[a_slot], a_phase);  // a completed phase stays observable: cheap re-check
+          if (!(dbg & 1) || w_loaded < wstages) mbar_wait(&w_full[w_slot], w_phase);
+          const uint32_t unit_lo = units_lo + a_slot * unit_step, stage_lo = w_lo + w_slot * stage_step;
+          const long long tk1 = (dbg & 16) ? clock64() : 0;
+          if (g != 0) {
+            mbar_wait_poll(&turn[x], turn_phase);
+            turn_phase ^= 1;
+          }
+          tc_fence_after();
+          const long long tk2 = (dbg & 16) ? clock64() : 0;
+          if (elect_one()) {
+            for (int rep = 0; rep < ((dbg & 8) ? 2 : 1); ++rep) {  // dbg 8: issue every MMA twice (tensor-vs-issue bound test)
+              const uint32_t ab = unit_lo | lbo_a, bb = stage_lo | lbo_b;
+              const bool ow = st == 0 && rep == 0;
+              if (nt == NT) issue_stage<KIND, NT>(ab, bb, d_base, ow, s_in_unit, idesc_n, idesc_w);
+              else if (NT > 1 && nt == 1) issue_stage<KIND, 1>(ab, bb, d_base, ow, s_in_unit, idesc_n, idesc_w);
+              else if (NT > 2 && nt == 2) issue_stage<KIND, 2>(ab, bb, d_base, ow, s_in_unit, idesc_n, idesc_w);
+              else if (NT > 3 && nt == 3) issue_stage<KIND, 3>(ab, bb, d_base, ow, s_in_unit, idesc_n, idesc_w);
+            }
+            // Token right after the last MMA (the other issuer's MMAs follow these in the pipe, so the accumulation
+            // order — and with it every output bit — is the schedule's, whatever the timing); the commits are owed
+            // before this issuer's next arrival on the same barriers, which data dependencies already guarantee for
+            // multi-stage items, and for conv1's single-stage items they come first.
+            if (K::SPU > 1) mbar_arrive(&turn[x ^ 1]);
+            if (!(dbg & 1)) tc_commit(&w_empty[w_slot]);
+            if (last_of_unit && !(dbg & 2)) tc_commit(&a_empty[a_slot]);
+            if (st == n_stages - 1) tc_commit(&acc_full[acc_buf]);
+            if (K::SPU == 1) mbar_arrive(&turn[x ^ 1]);
+          }
+          __syncwarp();
+          if (dbg & 16) {
+            const long long tk3 = clock64();
+            tk_prep += tk1 - tk0; tk_turn += tk2 - tk1; tk_issue += tk3 - tk2;
+          }
+        } else if (last_of_unit || st == n_stages - 1) {
+          // barriers over MMAs of both issuers: the non-owner commits its share when the schedule passes the boundary
+          if (elect_one()) {
+            if (last_of_unit && !(dbg & 2)) tc_commit(&a_empty[a_slot]);
+            if (st == n_stages - 1) tc_commit(&acc_full[acc_buf]);
+          }
+          __syncwarp();
         }
-        __syncwarp();
+        ++w_loaded;
         if (++w_slot == wstages) w_slot = 0, w_phase ^= 1;
-        if (f1 & KS_LAST_OF_UNIT) {
+        ++s_in_unit;
+        if (last_of_unit) {
+          s_in_unit = 0;
+          ++a_loaded;
           if (++a_slot == ring) a_slot = 0, a_phase ^= 1;
         }
       }
       if (++acc_buf == nbuf) acc_buf = 0, acc_phase ^= 1;
+    }
+    if ((dbg & 16) && lane == 0 && blockIdx.x == 0) {
+      tk_total = clock64() - tk_total;
+      printf("conv issuer %u block %d (N=%d): total %lld cycles | operand waits %lld | turn wait %lld | issue+commit %lld | rest %lld\n",
+             x, blockIdx.x, p.N, tk_total, tk_prep, tk_turn, tk_issue, tk_total - tk_prep - tk_turn - tk_issue);
     }
   } else if (warp >= 4) {
     // ============================================================ epilogue
@@ -291,19 +440,38 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   }
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
 using ConvKernel = void (*)(const ConvKernelParams);
 // (tiles per item, K-steps per weight stage) of the six layer x precision configurations
-static ConvKernel conv_kernel_for(int NT, int KPS) {
-  if (NT == 4 && KPS == 3) return conv_umma_kernel<4, 3>;   // conv1 bf16
-  if (NT == 4 && KPS == 9) return conv_umma_kernel<4, 9>;   // conv1 bf16 (merged unit)
-  if (NT == 2 && KPS == 6) return conv_umma_kernel<2, 6>;   // conv1 bf16x3
-  if (NT == 1 && KPS == 20) return conv_umma_kernel<1, 20>; // conv2 bf16x3, 5 taps per stage
-  if (NT == 1 && KPS == 12) return conv_umma_kernel<1, 12>; // conv3 bf16x3, 3 taps per stage (channel halves)
-  if (NT == 2 && KPS == 2) return conv_umma_kernel<2, 2>;   // conv2 bf16, 1 tap per stage
-  if (NT == 2 && KPS == 10) return conv_umma_kernel<2, 10>; // conv2 bf16, 5 taps per stage
-  if (NT == 2 && KPS == 12) return conv_umma_kernel<2, 12>; // conv3 bf16, 3 taps per stage
-  if (NT == 2 && KPS == 4) return conv_umma_kernel<2, 4>;   // conv3 bf16
+static ConvKernel conv_kernel_for(int kind) {
+  switch (kind) {
+    case KIND_L1: return conv_umma_kernel<KIND_L1>;
+    case KIND_L2: return conv_umma_kernel<KIND_L2>;
+    case KIND_L3: return conv_umma_kernel<KIND_L3>;
+    case KIND_L1_SPLIT: return conv_umma_kernel<KIND_L1_SPLIT>;
+    case KIND_L2_SPLIT: return conv_umma_kernel<KIND_L2_SPLIT>;
+    case KIND_L3_SPLIT: return conv_umma_kernel<KIND_L3_SPLIT>;
+  }
   return nullptr;
+}
+template <int KIND>
+static void kind_traits(int* NT, int* acc, int* spu, int* pairs, int* arr16, int* wt) {
+  using K = LayerKind<KIND>;
+  *NT = K::NT; *acc = K::ACC; *spu = K::SPU; *pairs = K::PAIRS; *arr16 = K::ARR16; *wt = K::WT;
+}
+static void kind_traits_for(int kind, int* NT, int* acc, int* spu, int* pairs, int* arr16, int* wt) {
+  switch (kind) {
+    case KIND_L1: return kind_traits<KIND_L1>(NT, acc, spu, pairs, arr16, wt);
+    case KIND_L2: return kind_traits<KIND_L2>(NT, acc, spu, pairs, arr16, wt);
+    case KIND_L3: return kind_traits<KIND_L3>(NT, acc, spu, pairs, arr16, wt);
+    case KIND_L1_SPLIT: return kind_traits<KIND_L1_SPLIT>(NT, acc, spu, pairs, arr16, wt);
+    case KIND_L2_SPLIT: return kind_traits<KIND_L2_SPLIT>(NT, acc, spu, pairs, arr16, wt);
+    default: return kind_traits<KIND_L3_SPLIT>(NT, acc, spu, pairs, arr16, wt);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ layout kernels
@@ -391,26 +559,19 @@ static float bf2f(uint16_t h) {
   return x;
 }
 
-struct LayerCfg { int NT, NBUF, ring, wstages, TPS; };  // TPS = filter taps per weight stage
-
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
-}
+struct LayerCfg { int NT, NBUF, ring, wstages; };
 
 static LayerCfg pick_cfg(const LayerGeom& g, int split) {
   LayerCfg c;
   // Big weight stages amortise the issuer's per-stage cost (two mbarrier waits + descriptor setup,
   // ~330 cycles) over more MMAs: conv2 bf16 uses one kernel row (5 taps, 40 MMAs) per stage.
   // split mode doubles the accumulator width (hi*hi+lo*hi | hi*lo column blocks), so fewer tiles fit in TMEM
-  if (g.Cin == 1) c = split ? LayerCfg{2, 2, 3, 4, 1} : LayerCfg{4, 2, 2, 2, 1};
-  else if (g.Cout == 64) c = split ? LayerCfg{1, 2, 2, 2, 5} : LayerCfg{2, 2, 3, 3, 5};
-  else c = split ? LayerCfg{1, 1, 3, 2, 3} : LayerCfg{2, 1, 2, 3, 3};  // Cout = 96 (TMEM: 2 tiles x 2 accs x 128 columns)
+  if (g.Cin == 1) c = split ? LayerCfg{2, 2, 3, 4} : LayerCfg{4, 2, 2, 2};
+  else if (g.Cout == 64) c = split ? LayerCfg{1, 2, 2, 2} : LayerCfg{2, 2, 3, 3};
+  else c = split ? LayerCfg{1, 1, 3, 2} : LayerCfg{2, 1, 2, 3};  // Cout = 96 (TMEM: 2 tiles x 2 accs x 96 columns, or 1 x 2 x 256 split)
   // tuning overrides (experiments only; an over-large value fails the smem check in umma_layer_build)
   const char* tag = g.Cin == 1 ? "1" : (g.Cout == 64 ? "2" : "3");
   char name[32];
-  snprintf(name, sizeof(name), "AVS_CONV%s_TPS", tag);
-  c.TPS = env_int(name, c.TPS);
   snprintf(name, sizeof(name), "AVS_CONV%s_WSTAGES", tag);
   c.wstages = env_int(name, c.wstages);
   snprintf(name, sizeof(name), "AVS_CONV%s_RING", tag);
@@ -443,170 +604,151 @@ size_t umma_act_bytes(const LayerGeom& g, int split, int B) {
   return static_cast<size_t>(B) * (AVS_T + 2) * g.n_chunks * 2 * g.PP * 16;
 }
 
+static int layer_kind(const LayerGeom& g, int split) {
+  if (g.Cin == 1 && g.Cout == 32 && g.KH == 5 && g.KW == 5) return split ? KIND_L1_SPLIT : KIND_L1;
+  if (g.Cin == 32 && g.Cout == 64 && g.KH == 5 && g.KW == 5) return split ? KIND_L2_SPLIT : KIND_L2;
+  if (g.Cin == 64 && g.Cout == 96 && g.KH == 3 && g.KW == 3) return split ? KIND_L3_SPLIT : KIND_L3;
+  return -1;
+}
+
+// Packs the weights in the order the compile-time schedule of the layer kind walks them (issue_stage_bf16 /
+// issue_stage_split above are the readers; keep the two in step).
 int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w, const float* bias) {
   L->g = g;
   L->split = split;
+  L->kind = layer_kind(g, split);
+  if (L->kind < 0) {
+    set_error("no tcgen05 schedule for a %d->%d channel %dx%d layer (LipNet's three STCNN layers only)", g.Cin, g.Cout, g.KH, g.KW);
+    return AVS_EINVAL;
+  }
   const LayerCfg c = pick_cfg(g, split);
+  int kNT, kACC, kSPU, kPAIRS, kARR16, kWT;
+  kind_traits_for(L->kind, &kNT, &kACC, &kSPU, &kPAIRS, &kARR16, &kWT);
   L->NT = c.NT; L->NBUF = c.NBUF; L->ring = c.ring; L->wstages = c.wstages;
-  L->acc_stride = split ? (g.Cout == 96 ? 256 : 2 * g.Cout) : (g.Cout == 96 ? 128 : g.Cout);
+  L->acc_stride = kACC;
   const int halo = (g.Cin == 1) ? (g.KH / 2 + 1) * g.Wt + 8 : (g.KH / 2) * g.Wt + g.KW - 1;
   const int region_full = c.NT * 128 + halo;
   const int n_tilesets = cdiv(g.n_tiles, c.NT);
   L->region_pos = (n_tilesets == 1) ? g.PP : region_full;
-  const int N = g.Cout, taps = 3 * g.KH * g.KW;
-  std::vector<KStep> ks;
+  if (L->region_pos != kARR16 || g.Wt != kWT || c.NT != kNT) {
+    set_error("layer geometry (%dx%d input, row pitch %d, %d positions per run, %d tiles per item) is not the one the tcgen05 "
+              "schedule was compiled for (%d, %d, %d)", g.H, g.W, g.Wt, L->region_pos, c.NT, kWT, kARR16, kNT);
+    return AVS_EINVAL;
+  }
+  const int N = g.Cout;
   std::vector<uint16_t> wp;
   auto wat = [&](int n, int ci, int kd, int kh, int kw) {
     return w[(((static_cast<size_t>(n) * g.Cin + ci) * 3 + kd) * g.KH + kh) * g.KW + kw];
   };
-  // One B tile = [2 K-halves][rows][8] bf16, appended to the packed weights; returns its byte offset within
-  // the stage.  Plain bf16: rows = the N output channels.  Split: rows = N "hi" rows followed by N "lo"
-  // residual rows, so that ONE MMA of width 2N computes A_hi*B_hi and A_hi*B_lo with a single fetch of A
-  // (the two halves land in adjacent accumulator column blocks and are added in the epilogue), and the
-  // A_lo*B_hi MMA of width N reads the first N rows of the same tile.
-  auto push_tile = [&](size_t stage_begin, auto&& elem) {
-    const uint32_t off = static_cast<uint32_t>((wp.size() - stage_begin) * 2);
-    for (int half = 0; half < 2; ++half)
-      for (int kind = 0; kind < (split ? 2 : 1); ++kind)
-        for (int n = 0; n < N; ++n)
-          for (int k = 0; k < 8; ++k) {
-            const float x = elem(half, n, k);
-            const uint16_t h = f2bf(x);
-            wp.push_back(kind == 0 ? h : f2bf(x - bf2f(h)));
-          }
-    return off;
-  };
   const uint32_t arr_bytes = static_cast<uint32_t>(L->region_pos) * 16;  // one (chunk, parity) run in a unit slot
-  int n_units = 0;
-  if (g.Cin == 1) {
-    // layer 1: K index = (kh pair, kw'): pairs (0,2), (1,3), (4, zero)
-    // bf16: the three time planes form ONE unit and all nine K-steps ONE weight stage (72 MMAs per
-    // issuer iteration); split: one plane per unit, one stage per plane (shared memory is the limit)
-    const bool merged = !split;
-    L->ksteps_per_stage = split ? 6 : 9;
-    const uint32_t plane_bytes = (split ? 2 : 1) * 2 * arr_bytes;
+  const bool first = g.Cin == 1;
+  int n_units = 0, n_stages = 0;
+  if (!split) {
+    // ---- bf16: row-parity stacking.  Padded input row 2r+q is filter row q for conv row 2r and filter row
+    // q-1 for conv row 2r+1, so with the "row taps" R[0..n-1] of one filter column stored back to back in
+    // REVERSE order ([R[n-1] | ... | R[0]], Cout rows each, per K half), the B operand of A(q) is the 2*Cout
+    // rows starting at R[q]: R[q] -> even-row accumulator, R[q-1] -> odd-row accumulator right behind it.
+    // q = 0 and q = n touch one accumulator only (width Cout).
+    //   conv2/conv3: R[j] = W[kd][kh = j][kw], K = 16 input channels, A(q) = parity plane q&1 shifted q>>1 rows;
+    //                one weight stage per (kd, kw): [channel pair][K half][R[n-1] .. R[0]][Cout rows][8].
+    //   conv1 (X8 input, K = 2 rows x 8 kw'): A(q) = rows (2r+q, 2r+q+2) as the two K halves;
+    //          R[0] = (kh0, kh2), R[1] = (kh1, kh3), R[2] = (0, kh4); ONE stage: [kd][K half][R2 R1 R0][32 rows][8].
+    const int n = first ? 3 : g.KH;
+    const int pairs = first ? 1 : g.Cin / 16;
+    const int cols = first ? 1 : g.KW;
     for (int kd = 0; kd < 3; ++kd) {
-      const size_t sb = merged ? 0 : wp.size();
-      uint32_t boff[3];
-      for (int pr = 0; pr < 3; ++pr) {
-        const int kha = (pr == 2) ? 4 : pr, khb = (pr == 2) ? -1 : pr + 2;
-        auto elem = [&](int half, int n, int k) {
-          const int kh = half == 0 ? kha : khb;
-          return (kh >= 0 && k < g.KW) ? wat(n, 0, kd, kh, k) : 0.f;
-        };
-        boff[pr] = push_tile(sb, elem);
-      }
-      for (int pr = 0; pr < 3; ++pr) {
-        const int kha = (pr == 2) ? 4 : pr;
-        for (int v = 0; v < (split ? 2 : 1); ++v) {  // split: A_hi x [B_hi | B_lo] (wide), then A_lo x B_hi
-          const int akind = v;
-          KStep s;
-          s.wide = split && v == 0;
-          for (int a = 0; a < 2; ++a) {
-            const int par = (a + kha) & 1, dr = (a + kha) >> 1;
-            s.a_off[a] = (merged ? kd * plane_bytes : 0) + (akind * 2 + par) * arr_bytes + dr * g.Wt * 16;
-          }
-          s.lbo = g.Wt * 16;
-          s.b_off = boff[pr];
-          s.kd = kd;
-          ks.push_back(s);
-        }
-      }
-      if (!merged || kd == 2) n_units++;
-    }
-    L->stage_bytes = static_cast<int>(wp.size() * 2 / (merged ? 1 : 3));
-    L->unit_planes = merged ? 3 : 1;
-  } else {
-    // generic: unit = (kd, channel group); stage = (tap, channel group)
-    const int groups = (g.Cout == 96 && split) ? 2 : 1;
-    const int CG = g.Cin / groups, pairs = CG / 16;
-    const int TPS = c.TPS;
-    if ((g.KH * g.KW) % TPS != 0) {
-      set_error("taps per stage %d does not divide %d", TPS, g.KH * g.KW);
-      return AVS_EINVAL;
-    }
-    L->ksteps_per_stage = TPS * pairs * (split ? 2 : 1);
-    const int kmul = split ? 2 : 1;
-    for (int kd = 0; kd < 3; ++kd)
-      for (int cg = 0; cg < groups; ++cg) {
-        const int chunk0 = cg * (CG / 8) * kmul;  // first chunk array of this unit
-        size_t sb = 0;
-        for (int kh = 0; kh < g.KH; ++kh)
-          for (int kw = 0; kw < g.KW; ++kw) {
-            if ((kh * g.KW + kw) % TPS == 0) sb = wp.size();  // a new weight stage starts here
-            std::vector<uint32_t> bt(pairs);
-            for (int pr = 0; pr < pairs; ++pr) {
-              auto elem = [&](int half, int n, int k) { return wat(n, cg * CG + pr * 16 + half * 8 + k, kd, kh, kw); };
-              bt[pr] = push_tile(sb, elem);
-            }
-            for (int pr = 0; pr < pairs; ++pr)
-              for (int v = 0; v < (split ? 2 : 1); ++v) {  // split: A_hi x [B_hi | B_lo] (wide), then A_lo x B_hi
-                const int akind = v;
-                const int c8 = (cg * CG + pr * 16) / 8;              // global 8-channel chunk of the first K half
-                const int arr = (split ? 2 * c8 + akind : c8) - chunk0;  // chunk array index inside the unit
-                KStep s;
-                s.wide = split && v == 0;
-                for (int a = 0; a < 2; ++a) {
-                  const int par = (a + kh) & 1, dr = (a + kh) >> 1;
-                  s.a_off[a] = (arr * 2 + par) * arr_bytes + (dr * g.Wt + kw) * 16;
+      for (int kw = 0; kw < cols; ++kw) {
+        for (int pr = 0; pr < pairs; ++pr)
+          for (int half = 0; half < 2; ++half)
+            for (int j = n - 1; j >= 0; --j)
+              for (int row = 0; row < N; ++row)
+                for (int k = 0; k < 8; ++k) {
+                  float x;
+                  if (first) {
+                    const int kh = half == 0 ? (j < 2 ? j : -1) : j + 2;
+                    x = (kh >= 0 && k < g.KW) ? wat(row, 0, kd, kh, k) : 0.f;
+                  } else {
+                    x = wat(row, pr * 16 + half * 8 + k, kd, j, kw);
+                  }
+                  wp.push_back(f2bf(x));
                 }
-                s.lbo = kmul * 2 * arr_bytes;
-                s.b_off = bt[pr];
-                s.kd = kd;
-                ks.push_back(s);
-              }
-          }
-        n_units++;
+        if (!first) n_stages++;
       }
-    L->stage_bytes = static_cast<int>(wp.size() * 2 / (taps * groups / TPS));
+      if (!first) n_units++;
+    }
+    if (first) n_units = 1, n_stages = 1;
+    L->unit_planes = first ? 3 : 1;
+    if (pairs != kPAIRS) return AVS_EINVAL;
+  } else {
+    // ---- bf16x3: operands split hi/lo.  One B tile = [2 K-halves][N hi rows | N lo rows][8]: ONE MMA of width 2N
+    // computes A_hi*B_hi and A_hi*B_lo with a single fetch of A (adjacent accumulator column blocks, added in
+    // the epilogue), and the A_lo*B_hi MMA of width N reads the first N rows of the same tile.  Even and odd
+    // conv rows use separate MMAs (A shifted by one padded row) into accumulators acc_stride columns apart.
+    auto push_tile = [&](auto&& elem) {
+      for (int half = 0; half < 2; ++half)
+        for (int kind = 0; kind < 2; ++kind)
+          for (int nn = 0; nn < N; ++nn)
+            for (int k = 0; k < 8; ++k) {
+              const float x = elem(half, nn, k);
+              const uint16_t h = f2bf(x);
+              wp.push_back(kind == 0 ? h : f2bf(x - bf2f(h)));
+            }
+    };
+    if (first) {
+      // layer 1: K index = (kh pair, kw'): pairs (0,2), (1,3), (4, zero); one plane per unit, one stage per plane
+      for (int kd = 0; kd < 3; ++kd) {
+        for (int pr = 0; pr < 3; ++pr) {
+          const int kha = (pr == 2) ? 4 : pr, khb = (pr == 2) ? -1 : pr + 2;
+          push_tile([&](int half, int nn, int k) {
+            const int kh = half == 0 ? kha : khb;
+            return (kh >= 0 && k < g.KW) ? wat(nn, 0, kd, kh, k) : 0.f;
+          });
+        }
+        n_units++, n_stages++;
+      }
+    } else {
+      // unit = (kd, channel group); stage = (filter row kh, channel group): tiles in (kw, channel pair) order
+      const int groups = (g.Cout == 96) ? 2 : 1;
+      const int CG = g.Cin / groups, pairs = CG / 16;
+      if (pairs != kPAIRS) return AVS_EINVAL;
+      for (int kd = 0; kd < 3; ++kd)
+        for (int cg = 0; cg < groups; ++cg) {
+          for (int kh = 0; kh < g.KH; ++kh) {
+            for (int kw = 0; kw < g.KW; ++kw)
+              for (int pr = 0; pr < pairs; ++pr)
+                push_tile([&](int half, int nn, int k) { return wat(nn, cg * CG + pr * 16 + half * 8 + k, kd, kh, kw); });
+            n_stages++;
+          }
+          n_units++;
+        }
+    }
+    L->unit_planes = 1;
   }
-  L->n_ksteps = static_cast<int>(ks.size());
-  L->n_stages = L->n_ksteps / L->ksteps_per_stage;
-  if (g.Cin != 1) L->unit_planes = 1;
+  L->n_stages = n_stages;
+  L->stage_bytes = static_cast<int>(wp.size() * 2 / n_stages);
   L->n_units = n_units;
   L->chunks_per_unit = g.n_chunks / (n_units * L->unit_planes / 3);
   L->plane_slot_bytes = L->unit_planes * L->chunks_per_unit * 2 * static_cast<int>(arr_bytes);
   L->smem_bytes = static_cast<size_t>(L->ring) * L->plane_slot_bytes + static_cast<size_t>(region_full - L->region_pos) * 16 +
-                  static_cast<size_t>(L->wstages) * L->stage_bytes + ks.size() * sizeof(KStepDev) +
-                  (2 * kMaxRing + 2 * kMaxWStages + 4) * 8 + 16;
-  if (L->smem_bytes > 232448 || L->ring > kMaxRing || L->wstages > kMaxWStages || n_units > kMaxUnits ||
-      wp.size() * 2 != static_cast<size_t>(L->n_stages) * L->stage_bytes || L->stage_bytes % 16 != 0) {
-    set_error("umma layer config invalid: smem %zu stage_bytes %d n_stages %d packed %zu", L->smem_bytes, L->stage_bytes,
-              L->n_stages, wp.size() * 2);
+                  static_cast<size_t>(L->wstages) * L->stage_bytes + (2 * kMaxRing + 2 * kMaxWStages + 6) * 8 + 16;
+  if (L->smem_bytes > 232448 || L->ring > kMaxRing || L->wstages > kMaxWStages || n_units > kMaxUnits || L->NT != kNT ||
+      n_stages != n_units * kSPU || wp.size() * 2 != static_cast<size_t>(L->n_stages) * L->stage_bytes || L->stage_bytes % 16 != 0) {
+    set_error("umma layer config invalid: smem %zu stage_bytes %d n_stages %d units %d packed %zu", L->smem_bytes, L->stage_bytes,
+              L->n_stages, n_units, wp.size() * 2);
     return AVS_EINVAL;
   }
-  std::vector<KStepDev> kd(ks.size());
-  const int ks_per_unit = L->n_ksteps / n_units;
-  for (size_t e = 0; e < ks.size(); ++e) {
-    for (int a = 0; a < 2; ++a) kd[e].a_lo[a] = (ks[e].a_off[a] >> 4) | ((ks[e].lbo >> 4) << 16);
-    kd[e].b_lo = (ks[e].b_off >> 4) | (static_cast<uint32_t>(split ? 2 * N : N) << 16);  // LBO of B = tile rows * 16 B
-    uint32_t f = 0;
-    if (e % ks_per_unit == 0) f |= KS_FIRST_OF_UNIT;
-    if ((e + 1) % ks_per_unit == 0) f |= KS_LAST_OF_UNIT;
-    if (e % L->ksteps_per_stage == 0) f |= KS_FIRST_OF_STAGE;
-    if ((e + 1) % L->ksteps_per_stage == 0) f |= KS_LAST_OF_STAGE;
-    if (ks[e].wide) f |= KS_WIDE;
-    kd[e].flags = f;
-  }
-  AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&L->d_ksteps), kd.size() * sizeof(KStepDev)));
-  AVS_CUDA(cudaMemcpy(L->d_ksteps, kd.data(), kd.size() * sizeof(KStepDev), cudaMemcpyHostToDevice));
   AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&L->d_w), wp.size() * 2));
   AVS_CUDA(cudaMemcpy(L->d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
   AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&L->d_bias), N * sizeof(float)));
   AVS_CUDA(cudaMemcpy(L->d_bias, bias, N * sizeof(float), cudaMemcpyHostToDevice));
-  if (conv_kernel_for(L->NT, L->ksteps_per_stage) == nullptr) {
-    set_error("no conv_umma_kernel instantiation for NT=%d KPS=%d", L->NT, L->ksteps_per_stage);
-    return AVS_EINVAL;
-  }
-  AVS_CUDA(cudaFuncSetAttribute(conv_kernel_for(L->NT, L->ksteps_per_stage), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  AVS_CUDA(cudaFuncSetAttribute(conv_kernel_for(L->kind), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   return AVS_OK;
 }
 
 void umma_layer_free(UmmaLayer* L) {
-  cudaFree(L->d_ksteps);
   cudaFree(L->d_w);
   cudaFree(L->d_bias);
-  L->d_ksteps = nullptr; L->d_w = nullptr; L->d_bias = nullptr;
+  L->d_w = nullptr; L->d_bias = nullptr;
 }
 
 int umma_pack_frames(const float* frames, __nv_bfloat16* act, const LayerGeom& g, int split, int B, cudaStream_t st) {
@@ -628,14 +770,14 @@ int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const Epi
   ConvKernelParams p;
   memset(&p, 0, sizeof(p));
   const LayerGeom& g = L.g;
-  p.act = act_in; p.w = L.d_w; p.ksteps = L.d_ksteps; p.bias = L.d_bias; p.eo = eo;
+  p.act = act_in; p.w = L.d_w; p.bias = L.d_bias; p.eo = eo;
   p.n_units = L.n_units;
   const int units_per_kd = L.n_units * L.unit_planes / 3;  // 2 for conv3-split (channel halves), else 1
   for (int u = 0; u < p.n_units; ++u)
     p.units[u] = UnitDesc{L.unit_planes == 3 ? 0 : u / units_per_kd, L.unit_planes, (u % units_per_kd) * L.chunks_per_unit,
                           L.chunks_per_unit};
   p.N = g.Cout; p.acc_stride = L.acc_stride; p.NT = L.NT; p.NBUF = L.NBUF; p.ring = L.ring; p.wstages = L.wstages;
-  p.n_ksteps = L.n_ksteps; p.ksteps_per_stage = L.ksteps_per_stage; p.stage_bytes = L.stage_bytes; p.n_stages = L.n_stages;
+  p.stage_bytes = L.stage_bytes; p.n_stages = L.n_stages;
   p.unit_slot_bytes = L.plane_slot_bytes; p.region_pos = L.region_pos;
   const int halo = (g.Cin == 1) ? (g.KH / 2 + 1) * g.Wt + 8 : (g.KH / 2) * g.Wt + g.KW - 1;
   p.region_full = L.NT * 128 + halo;
@@ -651,7 +793,7 @@ int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const Epi
   p.clip_stride = p.plane_stride * (AVS_T + 2);
   const int grid = static_cast<int>(std::min<long long>(items, n_sms));
   ProfScope ps(L.g.Cin == 1 ? PROF_CONV1 : (L.g.Cout == 64 ? PROF_CONV2 : PROF_CONV3), st);
-  conv_kernel_for(L.NT, L.ksteps_per_stage)<<<grid, kConvThreads, L.smem_bytes, st>>>(p);
+  conv_kernel_for(L.kind)<<<grid, kConvThreads, L.smem_bytes, st>>>(p);
   AVS_LAUNCHED();
   return AVS_OK;
 }

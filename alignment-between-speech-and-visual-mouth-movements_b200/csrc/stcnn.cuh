@@ -24,25 +24,6 @@ struct LayerGeom {
   int n_chunks;                   // 16-byte chunk arrays per (plane, parity): Cin/8 (conv1: 1), x2 when split
 };
 
-struct KStep {                    // one tcgen05.mma (K = 16) of the per-output-step schedule
-  uint32_t a_off[2];              // byte offset of the A tile inside a plane slot, for acc 0 (even rows) / 1 (odd rows)
-  uint32_t lbo;                   // byte stride between the two 8-wide K halves of A
-  uint32_t b_off;                 // byte offset of the B tile inside its weight stage
-  int32_t kd;                     // which of the 3 time planes A comes from
-  bool wide = false;              // split mode: this MMA is 2N wide (B_hi | B_lo rows)
-};
-
-// device form of a K-step: descriptor low words with the slot-independent parts pre-folded
-//   a_lo[a] = (a_off[a] >> 4) | ((lbo >> 4) << 16),  b_lo = (b_off >> 4) | ((N * 16 >> 4) << 16)
-// the issuer only adds (slot base >> 4) (+ tile * 128) — smem addresses are < 256 KB so the 14-bit
-// address field never carries into the LBO field.
-enum : uint32_t { KS_FIRST_OF_UNIT = 1, KS_LAST_OF_UNIT = 2, KS_FIRST_OF_STAGE = 4, KS_LAST_OF_STAGE = 8, KS_WIDE = 16 };
-struct KStepDev {
-  uint32_t a_lo[2];
-  uint32_t b_lo;
-  uint32_t flags;
-};
-
 struct UmmaLayer {                // device-resident, built once by stcnn_create
   LayerGeom g;
   int split;                      // 1: hi/lo bf16 split (BF16X3)
@@ -50,12 +31,12 @@ struct UmmaLayer {                // device-resident, built once by stcnn_create
   int NBUF;                       // TMEM accumulator buffers (1 or 2)
   int ring;                       // plane slots in shared memory
   int wstages;                    // weight stages in shared memory
-  int n_ksteps, ksteps_per_stage, stage_bytes, n_stages;
+  int kind;                       // compile-time MMA schedule of the layer (conv_umma.cu: LayerKind)
+  int stage_bytes, n_stages;      // weight stages per work item
   int n_units, unit_planes, chunks_per_unit;  // A units per work item; time planes and chunk arrays per unit
   int plane_slot_bytes;           // bytes of one unit slot in shared memory
   int region_pos;                 // positions loaded per (chunk, parity) for a full NT-tile item
-  int acc_stride;                 // TMEM columns between accumulators
-  KStepDev* d_ksteps = nullptr;
+  int acc_stride;                 // TMEM columns between the even-row and odd-row accumulators of a tile
   __nv_bfloat16* d_w = nullptr;   // packed B tiles, n_stages * stage_bytes
   float* d_bias = nullptr;
   size_t smem_bytes;

@@ -39,6 +39,11 @@ def run(precision, flags, label):
     print(f"{label:44s} " + " | ".join(out), flush=True)
 
 
+QUICK = os.environ.get("MB_QUICK") == "1"
+if QUICK:
+    run("bf16", 0, "bf16 dbg=0")
+    run("bf16x3", 0, "bf16x3 dbg=0")
+    sys.exit(0)
 for prec in ("bf16",):
     for flags in (0, 7, 8, 15):
         run(prec, flags, f"{prec} dbg={flags}")
