@@ -63,12 +63,46 @@ struct ConvKernelParams {
   long long clip_stride, plane_stride;  // elements (bf16) between clips / time planes of `act`
 };
 
-__device__ __forceinline__ void decode_item(const ConvKernelParams& p, int item, int& b, int& t, int& ts) {
-  ts = item % p.n_tilesets;
-  const int r = item / p.n_tilesets;
-  t = r % p.T;
-  b = r / p.T;
-}
+// Work items in (clip, tile set, t) order: a CTA takes ONE contiguous span, so that consecutive items are consecutive
+// time steps of the same tile region and two of an item's three input planes are already in shared memory.  Spans are
+// balanced by cost (tiles per item: the last tile set of a plane may be partial), all roles of a CTA walk the same span.
+struct ItemWalk {
+  int item, first, last, b, ts, t, T, n_tilesets;
+  __device__ __forceinline__ static int item_at_cost(const ConvKernelParams& p, long long x) {  // first item starting at cost >= x
+    const int per_clip = p.T * p.n_tiles;
+    const int b = static_cast<int>(x / per_clip);
+    int rem = static_cast<int>(x % per_clip);
+    const int base = b * p.n_tilesets * p.T;
+    for (int ts = 0; ts < p.n_tilesets; ++ts) {
+      const int nt = min(p.NT, p.n_tiles - ts * p.NT), row = p.T * nt;
+      if (rem < row) return base + ts * p.T + (rem + nt - 1) / nt;
+      rem -= row;
+    }
+    return base + p.n_tilesets * p.T;
+  }
+  __device__ __forceinline__ void init(const ConvKernelParams& p) {
+    const long long total = static_cast<long long>(p.n_items / p.n_tilesets) * p.n_tiles;  // clips * T * tiles per plane
+    first = item_at_cost(p, total * blockIdx.x / gridDim.x);
+    last = item_at_cost(p, total * (blockIdx.x + 1) / gridDim.x);
+    item = first;
+    T = p.T; n_tilesets = p.n_tilesets;
+    b = item / (n_tilesets * T);
+    const int r = item % (n_tilesets * T);
+    ts = r / T;
+    t = r % T;
+  }
+  __device__ __forceinline__ bool valid() const { return item < last; }
+  __device__ __forceinline__ void next() {
+    ++item;
+    if (++t == T) {
+      t = 0;
+      if (++ts == n_tilesets) ts = 0, ++b;
+    }
+  }
+  // this item follows / is followed by the neighbouring time step of the same (clip, tile set) inside this CTA's span
+  __device__ __forceinline__ bool continues_prev() const { return item > first && t > 0; }
+  __device__ __forceinline__ bool continues_next() const { return item + 1 < last && t + 1 < T; }
+};
 
 // ------------------------------------------------------------------------------------------------ MMA schedule
 // The schedule of one weight stage is generated at COMPILE time per layer kind: every descriptor is a run-time
@@ -91,6 +125,12 @@ struct LayerKind {
   static constexpr int NT = KIND == KIND_L1 ? 4 : (KIND <= KIND_L1_SPLIT ? 2 : 1);  // tiles per work item
   // stages per A unit: bf16 = one filter column per stage, bf16x3 = one filter row per stage; conv1: the unit is one stage
   static constexpr int SPU = first ? 1 : KW;
+  // bf16 kinds keep the three input planes of an item in a ring of three plane slots (slot = padded plane index % 3)
+  // and load only the plane the previous item did not have; the split kinds (twice the bytes per plane) reload per item.
+  static constexpr bool reuse = !split;
+  // conv1's items are a single stage, so a plane is only released when the whole item is done: a fourth slot lets the
+  // next item's new plane load meanwhile (multi-stage kinds release an item's first plane after its first unit)
+  static constexpr int RING = first ? 4 : 3;
   // Geometry of LipNet's layer (50 x 100 frames, halved by every pool), mirrored from geom_finalize()/umma_layer_build()
   // — which refuse anything else — so that the two strides of the activation layout are COMPILE-time constants
   // and every descriptor of the schedule is "uniform base + immediate".
@@ -109,7 +149,7 @@ constexpr uint64_t kDescHi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 
 // TILES (tiles of this work item) is a template parameter: a predicated-off tcgen05.mma is not free — it holds the
 // issue slot ~40 cycles (tools/umma_rate.cu) — so the last, partial tile set of a plane gets its own instantiation.
 template <int KIND, int TILES>
-__device__ __forceinline__ void issue_stage_bf16(uint32_t a_base, uint32_t b_base, uint32_t d_base, bool overwrite,
+__device__ __forceinline__ void issue_stage_bf16(const uint32_t (&a_base)[3], uint32_t b_base, uint32_t d_base, bool overwrite,
                                                  uint32_t idesc_n, uint32_t idesc_w) {
   using K = LayerKind<KIND>;
   constexpr int PLANES = K::first ? 3 : 1;  // conv1: the three time planes of the merged unit
@@ -123,7 +163,7 @@ __device__ __forceinline__ void issue_stage_bf16(uint32_t a_base, uint32_t b_bas
         // padded input row 2r+q; the wide entries go first so that an item's very first MMA covers both accumulators
         const int q = e < K::NROW - 1 ? e + 1 : (e == K::NROW - 1 ? 0 : K::NROW);
         const bool wide = q >= 1 && q <= K::NROW - 1;
-        const uint32_t a = a_base + (kd * 2 + pr * 4 + (q & 1)) * arr16 + (q >> 1) * Wt;
+        const uint32_t a = a_base[kd] + (pr * 4 + (q & 1)) * arr16 + (q >> 1) * Wt;  // conv1: one plane slot per kd
         const uint32_t b = b_base + (kd * K::PAIRS + pr) * (2 * K::NROW * K::N) + (K::NROW - 1 - (q == K::NROW ? K::NROW - 1 : q)) * K::N;
         const uint32_t d = d_base + (q == K::NROW ? K::N : 0);
         const uint32_t acc = (kd == 0 && pr == 0 && e == 0) ? (overwrite ? 0u : 1u) : 1u;
@@ -169,13 +209,15 @@ __device__ __forceinline__ void issue_stage_split(uint32_t a_base, uint32_t b_ba
 }
 
 template <int KIND, int TILES>
-__device__ __forceinline__ void issue_stage(uint32_t a_base, uint32_t b_base, uint32_t d_base, bool overwrite, int s_in_unit,
+__device__ __forceinline__ void issue_stage(const uint32_t (&a_base)[3], uint32_t b_base, uint32_t d_base, bool overwrite, int s_in_unit,
                                             uint32_t idesc_n, uint32_t idesc_w) {
   using K = LayerKind<KIND>;
-  if (K::split)
-    issue_stage_split<KIND, TILES>(a_base, b_base, d_base, overwrite, s_in_unit, idesc_n, idesc_w);
-  else
-    issue_stage_bf16<KIND, TILES>(a_base + (K::first ? 0 : s_in_unit), b_base, d_base, overwrite, idesc_n, idesc_w);
+  if (K::split) {
+    issue_stage_split<KIND, TILES>(a_base[0], b_base, d_base, overwrite, s_in_unit, idesc_n, idesc_w);
+  } else {
+    const uint32_t ab[3] = {a_base[0] + (K::first ? 0 : s_in_unit), a_base[1], a_base[2]};  // generic layers: + kw
+    issue_stage_bf16<KIND, TILES>(ab, b_base, d_base, overwrite, idesc_n, idesc_w);
+  }
 }
 
 template <int KIND>
@@ -216,31 +258,56 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
 
   if (warp == 0 && lane == 0) {
     // ============================================================ A producer
-    uint32_t seq = 0, slot = 0, phase = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      int b, t, ts;
-      decode_item(p, item, b, t, ts);
-      const int q0 = ts * p.NT * 128;
-      const int len = min(p.region_pos, p.PP - q0);  // positions per (chunk, parity) run
-      for (int u = 0; u < p.n_units; ++u, ++seq, slot = (slot + 1 == static_cast<uint32_t>(p.ring)) ? 0 : slot + 1, phase ^= (slot == 0)) {
-        if ((p.dbg & 2) && seq >= static_cast<uint32_t>(p.ring)) continue;
-        mbar_wait(&a_empty[slot], phase ^ 1);
-        const UnitDesc ud = p.units[u];
-        const uint32_t bytes = static_cast<uint32_t>(len) * 16u;
-        mbar_expect_tx(&a_full[slot], bytes * 2u * ud.nchunks * ud.nplanes);
-        uint8_t* dst = s_units + static_cast<size_t>(slot) * p.unit_slot_bytes;
-        for (int pl = 0; pl < ud.nplanes; ++pl) {
-          const __nv_bfloat16* src = p.act + b * p.clip_stride + (t + ud.kd + pl) * p.plane_stride +
-                                     (static_cast<long long>(ud.chunk0) * 2 * p.PP + q0) * 8;
-          for (int c = 0; c < ud.nchunks * 2; ++c, dst += static_cast<size_t>(p.region_pos) * 16)
+    ItemWalk w;
+    w.init(p);
+    if (K::reuse) {
+      // Plane ring: padded time plane tp lives in slot tp % RING.  An item that continues its predecessor only loads
+      // its last plane (tp = t + 2) — into the slot the issuers released after the predecessor's first plane.
+      uint32_t fill_parity = 0;  // bit s: number of fills of slot s so far, mod 2
+      const uint32_t n_arrays = static_cast<uint32_t>(p.n_chunks) * 2u;
+      for (; w.valid(); w.next()) {
+        if ((p.dbg & 2) && w.item > w.first) continue;
+        const int q0 = w.ts * p.NT * 128;
+        const uint32_t bytes = static_cast<uint32_t>(min(p.region_pos, p.PP - q0)) * 16u;
+        for (int kd = w.continues_prev() ? 2 : 0; kd < 3; ++kd) {
+          const int tp = w.t + kd;
+          const uint32_t slot = static_cast<uint32_t>(tp % K::RING);
+          mbar_wait(&a_empty[slot], ((fill_parity >> slot) & 1u) ^ 1u);  // the slot's previous tenant has been released
+          fill_parity ^= 1u << slot;
+          mbar_expect_tx(&a_full[slot], bytes * n_arrays);
+          uint8_t* dst = s_units + static_cast<size_t>(slot) * p.unit_slot_bytes;
+          const __nv_bfloat16* src = p.act + w.b * p.clip_stride + tp * p.plane_stride + static_cast<long long>(q0) * 8;
+          for (uint32_t c = 0; c < n_arrays; ++c, dst += static_cast<size_t>(p.region_pos) * 16)
             bulk_g2s(dst, src + static_cast<long long>(c) * p.PP * 8, bytes, &a_full[slot]);
+        }
+      }
+    } else {
+      uint32_t seq = 0, slot = 0, phase = 0;
+      for (; w.valid(); w.next()) {
+        const int q0 = w.ts * p.NT * 128;
+        const int len = min(p.region_pos, p.PP - q0);  // positions per (chunk, parity) run
+        for (int u = 0; u < p.n_units; ++u, ++seq, slot = (slot + 1 == static_cast<uint32_t>(p.ring)) ? 0 : slot + 1, phase ^= (slot == 0)) {
+          if ((p.dbg & 2) && seq >= static_cast<uint32_t>(p.ring)) continue;
+          mbar_wait(&a_empty[slot], phase ^ 1);
+          const UnitDesc ud = p.units[u];
+          const uint32_t bytes = static_cast<uint32_t>(len) * 16u;
+          mbar_expect_tx(&a_full[slot], bytes * 2u * ud.nchunks * ud.nplanes);
+          uint8_t* dst = s_units + static_cast<size_t>(slot) * p.unit_slot_bytes;
+          for (int pl = 0; pl < ud.nplanes; ++pl) {
+            const __nv_bfloat16* src = p.act + w.b * p.clip_stride + (w.t + ud.kd + pl) * p.plane_stride +
+                                       (static_cast<long long>(ud.chunk0) * 2 * p.PP + q0) * 8;
+            for (int c = 0; c < ud.nchunks * 2; ++c, dst += static_cast<size_t>(p.region_pos) * 16)
+              bulk_g2s(dst, src + static_cast<long long>(c) * p.PP * 8, bytes, &a_full[slot]);
+          }
         }
       }
     }
   } else if (warp == 2 && lane == 0) {
     // ============================================================ B (weights) producer
     uint32_t seq = 0, slot = 0, phase = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    ItemWalk w;
+    w.init(p);
+    for (; w.valid(); w.next()) {
       for (int s = 0; s < p.n_stages; ++s, ++seq, slot = (slot + 1 == static_cast<uint32_t>(p.wstages)) ? 0 : slot + 1, phase ^= (slot == 0)) {
         if ((p.dbg & 1) && seq >= static_cast<uint32_t>(p.wstages)) continue;
         mbar_wait(&w_empty[slot], phase ^ 1);
@@ -267,38 +334,66 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     // parity, the second kh of the pair); B = the other K half of the tile
     const uint32_t lbo_a = (K::first ? Wt : (K::split ? 4u : 2u) * arr16) << 16;
     constexpr uint32_t lbo_b = static_cast<uint32_t>(K::split ? 2 * K::N : K::NROW * K::N) << 16;
-    const int n_stages = p.n_stages, n_tilesets = p.n_tilesets, n_tiles = p.n_tiles, dbg = p.dbg;
+    const int n_stages = p.n_stages, n_tiles = p.n_tiles, dbg = p.dbg;
     uint32_t a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0, acc_buf = 0, acc_phase = 0;
     uint32_t a_loaded = 0, w_loaded = 0;  // only used by the dbg switches
     uint32_t g = 0, turn_phase = 0;
+    uint32_t fill_parity = 0;             // plane ring (K::reuse): bit s = fills of slot s so far, mod 2
     long long tk_prep = 0, tk_turn = 0, tk_issue = 0, tk_total = clock64();  // dbg 16: issuer time split
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int ts = item % n_tilesets;
-      const int nt = min(NT, n_tiles - ts * NT);
+    ItemWalk w;
+    w.init(p);
+    for (; w.valid(); w.next()) {
+      const int nt = min(NT, n_tiles - w.ts * NT);
       bool acc_ready = false;
       const uint32_t d_base = tmem_base + acc_buf * (NT * 2 * K::ACC);
+      const bool cont_next = w.continues_next();
+      if (K::reuse) {  // the fills this item brings: all three planes, or only the last one
+        for (int kd = w.continues_prev() ? 2 : 0; kd < 3; ++kd) fill_parity ^= 1u << ((w.t + kd) % K::RING);
+      }
       int s_in_unit = 0;  // stage inside the current A unit: the filter column (bf16) / filter row (bf16x3) of the stage
+      int unit = 0;       // K::reuse: the unit is time plane kd = unit
       for (int st = 0; st < n_stages; ++st, ++g) {
         const bool last_of_unit = s_in_unit == K::SPU - 1;
+        // plane ring: which of this unit's planes go back to the producer when the unit is done (conv1's single
+        // stage spans all three planes); sequential ring: the unit's slot, always
+        const uint32_t slot0 = K::reuse ? static_cast<uint32_t>((w.t + unit) % K::RING) : a_slot;
         if ((g & 1) == x) {
           const long long tk0 = (dbg & 16) ? clock64() : 0;
           if (!acc_ready) {
             mbar_wait(&acc_empty[acc_buf], acc_phase ^ 1);
             acc_ready = true;
           }
-          if (!(dbg & 2) || a_loaded < ring) mbar_wait(&a_full[a_slot], a_phase);  // a completed phase stays observable: cheap re-check
+          uint32_t ab[3];
+          if (K::reuse) {
+            // a completed phase stays observable until the slot's NEXT fill completes, which needs our release: re-checks are cheap
+            const bool wait_a = !(dbg & 2) || w.item == w.first;
+            if (K::first) {
+#pragma unroll
+              for (int kd = 0; kd < 3; ++kd) {
+                const uint32_t sl = static_cast<uint32_t>((w.t + kd) % K::RING);
+                if (wait_a) mbar_wait(&a_full[sl], ((fill_parity >> sl) & 1u) ^ 1u);
+                ab[kd] = (units_lo + sl * unit_step) | lbo_a;
+              }
+            } else {
+              if (wait_a) mbar_wait(&a_full[slot0], ((fill_parity >> slot0) & 1u) ^ 1u);
+              ab[0] = ab[1] = ab[2] = (units_lo + slot0 * unit_step) | lbo_a;
+            }
+          } else {
+            if (!(dbg & 2) || a_loaded < ring) mbar_wait(&a_full[a_slot], a_phase);
+            ab[0] = ab[1] = ab[2] = (units_lo + a_slot * unit_step) | lbo_a;
+          }
           if (!(dbg & 1) || w_loaded < wstages) mbar_wait(&w_full[w_slot], w_phase);
-          const uint32_t unit_lo = units_lo + a_slot * unit_step, stage_lo = w_lo + w_slot * stage_step;
+          const uint32_t stage_lo = w_lo + w_slot * stage_step;
           const long long tk1 = (dbg & 16) ? clock64() : 0;
           if (g != 0) {
-            mbar_wait_poll(&turn[x], turn_phase);
+            mbar_wait(&turn[x], turn_phase);
             turn_phase ^= 1;
           }
           tc_fence_after();
           const long long tk2 = (dbg & 16) ? clock64() : 0;
           if (elect_one()) {
             for (int rep = 0; rep < ((dbg & 8) ? 2 : 1); ++rep) {  // dbg 8: issue every MMA twice (tensor-vs-issue bound test)
-              const uint32_t ab = unit_lo | lbo_a, bb = stage_lo | lbo_b;
+              const uint32_t bb = stage_lo | lbo_b;
               const bool ow = st == 0 && rep == 0;
               if (nt == NT) issue_stage<KIND, NT>(ab, bb, d_base, ow, s_in_unit, idesc_n, idesc_w);
               else if (NT > 1 && nt == 1) issue_stage<KIND, 1>(ab, bb, d_base, ow, s_in_unit, idesc_n, idesc_w);
@@ -311,28 +406,38 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
             // multi-stage items, and for conv1's single-stage items they come first.
             if (K::SPU > 1) mbar_arrive(&turn[x ^ 1]);
             if (!(dbg & 1)) tc_commit(&w_empty[w_slot]);
-            if (last_of_unit && !(dbg & 2)) tc_commit(&a_empty[a_slot]);
-            if (st == n_stages - 1) tc_commit(&acc_full[acc_buf]);
-            if (K::SPU == 1) mbar_arrive(&turn[x ^ 1]);
           }
           __syncwarp();
           if (dbg & 16) {
             const long long tk3 = clock64();
             tk_prep += tk1 - tk0; tk_turn += tk2 - tk1; tk_issue += tk3 - tk2;
           }
-        } else if (last_of_unit || st == n_stages - 1) {
-          // barriers over MMAs of both issuers: the non-owner commits its share when the schedule passes the boundary
-          if (elect_one()) {
-            if (last_of_unit && !(dbg & 2)) tc_commit(&a_empty[a_slot]);
-            if (st == n_stages - 1) tc_commit(&acc_full[acc_buf]);
-          }
-          __syncwarp();
         }
+        // barriers over MMAs of both issuers (A slots, accumulator): each issuer commits its share when the schedule
+        // passes the boundary — the owner right after its MMAs, the other one as it walks by
+        if ((last_of_unit || st == n_stages - 1) && elect_one()) {
+          if (last_of_unit && !(dbg & 2)) {
+            if (K::reuse) {
+              if (K::first) {
+                tc_commit(&a_empty[w.t % K::RING]);
+                if (!cont_next) tc_commit(&a_empty[(w.t + 1) % K::RING]), tc_commit(&a_empty[(w.t + 2) % K::RING]);
+              } else if (unit == 0 || !cont_next) {
+                tc_commit(&a_empty[slot0]);  // planes kd = 1, 2 stay for the next time step
+              }
+            } else {
+              tc_commit(&a_empty[a_slot]);
+            }
+          }
+          if (st == n_stages - 1) tc_commit(&acc_full[acc_buf]);
+          if (K::SPU == 1 && (g & 1) == x) mbar_arrive(&turn[x ^ 1]);
+        }
+        __syncwarp();
         ++w_loaded;
         if (++w_slot == wstages) w_slot = 0, w_phase ^= 1;
         ++s_in_unit;
         if (last_of_unit) {
           s_in_unit = 0;
+          ++unit;
           ++a_loaded;
           if (++a_slot == ring) a_slot = 0, a_phase ^= 1;
         }
@@ -350,9 +455,10 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     // (tile, 32-column block) work units of an item alternate between the groups.
     const int q = warp & 3, grp = (warp - 4) >> 2;
     uint32_t buf = 0, phase = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, buf = (buf + 1 == static_cast<uint32_t>(p.NBUF)) ? 0 : buf + 1, phase ^= (buf == 0)) {
-      int b, t, ts;
-      decode_item(p, item, b, t, ts);
+    ItemWalk w;
+    w.init(p);
+    for (; w.valid(); w.next(), buf = (buf + 1 == static_cast<uint32_t>(p.NBUF)) ? 0 : buf + 1, phase ^= (buf == 0)) {
+      const int b = w.b, t = w.t, ts = w.ts;
       const int nt = min(p.NT, p.n_tiles - ts * p.NT);
       mbar_wait(&acc_full[buf], phase);
       __syncwarp();  // tcgen05.ld below is .aligned
@@ -370,6 +476,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
           tmem_ld32(d_base + (i * 2 + 0) * p.acc_stride + cb, v0);
           tmem_ld32(d_base + (i * 2 + 1) * p.acc_stride + cb, v1);
           tmem_ld_wait();
+          if ((p.dbg & 32) && v0[0] != 0x7fc12345u) continue;  // experiment: TMEM reads only
           if (p.split) {  // second column block: A_hi * B_lo, the small term, added last
             uint32_t u0[32], u1[32];
             tmem_ld32(d_base + (i * 2 + 0) * p.acc_stride + p.N + cb, u0);
@@ -392,6 +499,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
             const float got = __shfl_xor_sync(0xffffffffu, half ? lo : hi, 1);
             o[c] = fmaxf(fmaxf(half ? hi : lo, got) + __ldg(p.bias + ch0 + c), 0.f);
           }
+          if ((p.dbg & 64) && o[0] != 12345.678f) continue;  // experiment: no stores
           if (valid && p.eo.mode == 0) {
             const int hp = r + p.eo.ph_next;
             const long long pos = p.eo.pw_next + (hp >> 1) * p.eo.Wt_next + wo;
@@ -566,16 +674,17 @@ static LayerCfg pick_cfg(const LayerGeom& g, int split) {
   // Big weight stages amortise the issuer's per-stage cost (two mbarrier waits + descriptor setup,
   // ~330 cycles) over more MMAs: conv2 bf16 uses one kernel row (5 taps, 40 MMAs) per stage.
   // split mode doubles the accumulator width (hi*hi+lo*hi | hi*lo column blocks), so fewer tiles fit in TMEM
-  if (g.Cin == 1) c = split ? LayerCfg{2, 2, 3, 4} : LayerCfg{4, 2, 2, 2};
+  // bf16 kinds: ring = LayerKind::RING plane slots (the plane ring of the kernel), not tunable
+  if (g.Cin == 1) c = split ? LayerCfg{2, 2, 3, 4} : LayerCfg{4, 2, 4, 2};
   else if (g.Cout == 64) c = split ? LayerCfg{1, 2, 2, 2} : LayerCfg{2, 2, 3, 3};
-  else c = split ? LayerCfg{1, 1, 3, 2} : LayerCfg{2, 1, 2, 3};  // Cout = 96 (TMEM: 2 tiles x 2 accs x 96 columns, or 1 x 2 x 256 split)
+  else c = split ? LayerCfg{1, 1, 3, 2} : LayerCfg{2, 1, 3, 2};  // Cout = 96 (TMEM: 2 tiles x 2 accs x 96 columns, or 1 x 2 x 256 split)
   // tuning overrides (experiments only; an over-large value fails the smem check in umma_layer_build)
   const char* tag = g.Cin == 1 ? "1" : (g.Cout == 64 ? "2" : "3");
   char name[32];
   snprintf(name, sizeof(name), "AVS_CONV%s_WSTAGES", tag);
   c.wstages = env_int(name, c.wstages);
   snprintf(name, sizeof(name), "AVS_CONV%s_RING", tag);
-  c.ring = env_int(name, c.ring);
+  if (split) c.ring = env_int(name, c.ring);
   return c;
 }
 
@@ -674,11 +783,11 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
                 }
         if (!first) n_stages++;
       }
-      if (!first) n_units++;
+      n_units++;  // one A unit per time plane (the kernel keeps them in a ring of three plane slots)
     }
-    if (first) n_units = 1, n_stages = 1;
-    L->unit_planes = first ? 3 : 1;
-    if (pairs != kPAIRS) return AVS_EINVAL;
+    if (first) n_stages = 1;
+    L->unit_planes = 1;
+    if (pairs != kPAIRS || L->ring != (first ? 4 : 3)) return AVS_EINVAL;
   } else {
     // ---- bf16x3: operands split hi/lo.  One B tile = [2 K-halves][N hi rows | N lo rows][8]: ONE MMA of width 2N
     // computes A_hi*B_hi and A_hi*B_lo with a single fetch of A (adjacent accumulator column blocks, added in
@@ -732,7 +841,7 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
   L->smem_bytes = static_cast<size_t>(L->ring) * L->plane_slot_bytes + static_cast<size_t>(region_full - L->region_pos) * 16 +
                   static_cast<size_t>(L->wstages) * L->stage_bytes + (2 * kMaxRing + 2 * kMaxWStages + 6) * 8 + 16;
   if (L->smem_bytes > 232448 || L->ring > kMaxRing || L->wstages > kMaxWStages || n_units > kMaxUnits || L->NT != kNT ||
-      n_stages != n_units * kSPU || wp.size() * 2 != static_cast<size_t>(L->n_stages) * L->stage_bytes || L->stage_bytes % 16 != 0) {
+      n_stages != (first && !split ? 1 : n_units * kSPU) || wp.size() * 2 != static_cast<size_t>(L->n_stages) * L->stage_bytes || L->stage_bytes % 16 != 0) {
     set_error("umma layer config invalid: smem %zu stage_bytes %d n_stages %d units %d packed %zu", L->smem_bytes, L->stage_bytes,
               L->n_stages, n_units, wp.size() * 2);
     return AVS_EINVAL;

@@ -39,6 +39,11 @@ def run(precision, flags, label):
     print(f"{label:44s} " + " | ".join(out), flush=True)
 
 
+FLAGS = os.environ.get("MB_FLAGS")
+if FLAGS:
+    for f in FLAGS.split(","):
+        run("bf16", int(f), f"bf16 dbg={f}")
+    sys.exit(0)
 QUICK = os.environ.get("MB_QUICK") == "1"
 if QUICK:
     run("bf16", 0, "bf16 dbg=0")
