@@ -50,7 +50,7 @@ def conv2_traffic(clips_per_launch: int, precision: str):
     scaled to the clips one bench launch processes."""
     if precision != "bf16":
         return None
-    return 11.56e6 * clips_per_launch
+    return 13.43e6 * clips_per_launch
 
 
 class ClockSampler:
