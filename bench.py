@@ -45,8 +45,8 @@ def peaks():
 
 def conv2_traffic(clips_per_launch: int, precision: str):
     """DRAM bytes per launch of the layer-2 conv kernel from the committed `ncu --set full` capture
-    (profiles/r01_conv2_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum = 740.1 MB for a
-    64-clip bf16 launch = 11.56 MB per clip; algorithmic: 8.6 MB padded input + 2.9 MB pooled output),
+    (profiles/r01_conv2_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum = 859.7 MB for a
+    64-clip bf16 launch = 13.43 MB per clip; algorithmic: 8.6 MB padded input + 2.9 MB pooled output),
     scaled to the clips one bench launch processes."""
     if precision != "bf16":
         return None
