@@ -150,7 +150,7 @@ def run_reference(args, rank: int):
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 def main():
@@ -306,10 +306,20 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches.item()), "clocks": clocks, "roofline": roof,
             "cpu_baseline": cpu, "kernel_ms": prof,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _json_only_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner at communicator
+    creation): point fd 1 at stderr for the life of the process and keep the real stdout for the JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 if __name__ == "__main__":
+    _REAL_STDOUT = _json_only_stdout()
     main()
