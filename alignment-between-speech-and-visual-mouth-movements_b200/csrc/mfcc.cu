@@ -189,37 +189,96 @@ mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const in
   }
 }
 
-// One CTA per (shift, clip).  128 threads; thread j owns frames j, j+128, ...
+// Per-frame pieces of the shift-dependent tail, computed once per UNIQUE frame so that mfcc_stats_kernel does not
+// redo them for every shift that contains the frame (6.7x on the 41-shift sweep): the frame's max and min log-mel
+// (power_to_db's top_db reference is a max over the shifted signal's frames; a frame whose min is above that floor is
+// not touched by the clamp) and the frame's DCT, valid whenever the clamp does not touch it.  Thread = frame.
 template <int NQ>
 __global__ void __launch_bounds__(128)
-mfcc_stats_kernel(const float* __restrict__ logmel, const int* __restrict__ map, int n_unique, int n_frames,
-                  int n_shifts, int n_mfcc, const float* __restrict__ dct_t, float* __restrict__ out_stats,
-                  float* __restrict__ out_mfcc) {
+mfcc_frame_dct_kernel(const float* __restrict__ logmel, int n_unique, const float* __restrict__ dct_t,
+                      float* __restrict__ frame_mfcc, float2* __restrict__ frame_range) {
+  __shared__ float s_dct[kMels * NQ];
+  const int clip = blockIdx.y, u = blockIdx.x * 128 + threadIdx.x;
+  for (int i = threadIdx.x; i < kMels * NQ; i += 128) s_dct[i] = dct_t[(i / NQ) * kMaxQ + (i % NQ)];
+  __syncthreads();
+  if (u >= n_unique) return;
+  const size_t f = static_cast<size_t>(clip) * n_unique + u;
+  const float4* row = reinterpret_cast<const float4*>(logmel + f * kMels);
+  float acc[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
+  float mx = -INFINITY, mn = INFINITY;
+  for (int c = 0; c < kMels / 4; ++c) {
+    const float4 v4 = row[c];
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      mx = fmaxf(mx, v[e]);
+      mn = fminf(mn, v[e]);
+      const float4* d = reinterpret_cast<const float4*>(s_dct + (c * 4 + e) * NQ);
+#pragma unroll
+      for (int q4 = 0; q4 < NQ / 4; ++q4) {
+        const float4 dd = d[q4];
+        acc[q4 * 4 + 0] = fmaf(dd.x, v[e], acc[q4 * 4 + 0]);
+        acc[q4 * 4 + 1] = fmaf(dd.y, v[e], acc[q4 * 4 + 1]);
+        acc[q4 * 4 + 2] = fmaf(dd.z, v[e], acc[q4 * 4 + 2]);
+        acc[q4 * 4 + 3] = fmaf(dd.w, v[e], acc[q4 * 4 + 3]);
+      }
+    }
+  }
+  float4* o = reinterpret_cast<float4*>(frame_mfcc + f * kMaxQ);
+#pragma unroll
+  for (int q4 = 0; q4 < NQ / 4; ++q4) o[q4] = make_float4(acc[q4 * 4], acc[q4 * 4 + 1], acc[q4 * 4 + 2], acc[q4 * 4 + 3]);
+  frame_range[f] = make_float2(mx, mn);
+}
+
+// One CTA per (shift, clip).  128 threads; thread j owns frames j, j+128, ...  The shift's frames are gathered through
+// the map: top_db floor from the per-frame maxima, then per frame either the precomputed DCT (the clamp does not touch
+// the frame: its min is above the floor) or, for frames the clamp does touch, DCT(max(x, floor)) recomputed here.
+template <int NQ>
+__global__ void __launch_bounds__(128)
+mfcc_stats_kernel(const float* __restrict__ logmel, const float* __restrict__ frame_mfcc, const float2* __restrict__ frame_range,
+                  const int* __restrict__ map, int n_unique, int n_frames, int n_shifts, int n_mfcc,
+                  const float* __restrict__ dct_t, float* __restrict__ out_stats, float* __restrict__ out_mfcc) {
   extern __shared__ float smem[];
-  float* s_dct = smem;                       // [128][NQ]
+  float* s_dct = smem;                       // [128][NQ], filled only when some frame needs the clamp
   float* s_mfcc = smem + kMels * NQ;         // [F][NQ]
   __shared__ float s_red[4];
   const int tid = threadIdx.x;
   const int k = blockIdx.x, clip = blockIdx.y;
   const int* mp = map + static_cast<size_t>(k) * n_frames;
-  const float* lm = logmel + static_cast<size_t>(clip) * n_unique * kMels;
+  const size_t cbase = static_cast<size_t>(clip) * n_unique;
+  const float* lm = logmel + cbase * kMels;
 
-  for (int i = tid; i < kMels * NQ; i += 128) s_dct[i] = dct_t[(i / NQ) * kMaxQ + (i % NQ)];
   // global max over this shifted signal's [n_mels, n_frames] log-mel array (power_to_db top_db reference)
   float mx = -INFINITY;
-  for (int i = tid; i < n_frames * (kMels / 4); i += 128) {
-    const int j = i / (kMels / 4), c = i % (kMels / 4);
-    const float4 v = reinterpret_cast<const float4*>(lm + static_cast<size_t>(mp[j]) * kMels)[c];
-    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-  }
+  for (int j = tid; j < n_frames; j += 128) mx = fmaxf(mx, frame_range[cbase + mp[j]].x);
   mx = warp_max(mx);
   if ((tid & 31) == 0) s_red[tid >> 5] = mx;
   __syncthreads();
   mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
   const float floor_db = mx - 80.0f;
 
+  bool any_clamped = false;
+  for (int j = tid; j < n_frames; j += 128) any_clamped |= frame_range[cbase + mp[j]].y < floor_db;
+  const bool block_clamped = __syncthreads_or(any_clamped);
+  if (block_clamped) {
+    for (int i = tid; i < kMels * NQ; i += 128) s_dct[i] = dct_t[(i / NQ) * kMaxQ + (i % NQ)];
+    __syncthreads();
+  }
   for (int j = tid; j < n_frames; j += 128) {
-    const float4* row = reinterpret_cast<const float4*>(lm + static_cast<size_t>(mp[j]) * kMels);
+    const int u = mp[j];
+    if (!(frame_range[cbase + u].y < floor_db)) {
+      const float4* row = reinterpret_cast<const float4*>(frame_mfcc + (cbase + u) * kMaxQ);
+#pragma unroll
+      for (int q4 = 0; q4 < NQ / 4; ++q4) {
+        const float4 v = row[q4];
+        s_mfcc[j * NQ + q4 * 4 + 0] = v.x; s_mfcc[j * NQ + q4 * 4 + 1] = v.y;
+        s_mfcc[j * NQ + q4 * 4 + 2] = v.z; s_mfcc[j * NQ + q4 * 4 + 3] = v.w;
+      }
+      continue;
+    }
+    const float4* row = reinterpret_cast<const float4*>(lm + static_cast<size_t>(u) * kMels);
     float acc[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
@@ -249,17 +308,19 @@ mfcc_stats_kernel(const float* __restrict__ logmel, const int* __restrict__ map,
     for (int i = tid; i < n_frames * n_mfcc; i += 128) om[i] = s_mfcc[(i / n_mfcc) * NQ + (i % n_mfcc)];
   }
   if (tid < n_mfcc) {
-    float s = 0.f;
-    for (int j = 0; j < n_frames; ++j) s += s_mfcc[j * NQ + tid];
-    const float mean = s / static_cast<float>(n_frames);
-    float ss = 0.f;
+    // double accumulators (20 threads x ~121 terms): a constant sequence (silence) must give std == 0 exactly, which
+    // an fp32 running sum only does by luck
+    double s = 0.0;
+    for (int j = 0; j < n_frames; ++j) s += static_cast<double>(s_mfcc[j * NQ + tid]);
+    const double mean = s / static_cast<double>(n_frames);
+    double ss = 0.0;
     for (int j = 0; j < n_frames; ++j) {
-      const float d = s_mfcc[j * NQ + tid] - mean;
-      ss = fmaf(d, d, ss);
+      const double d = static_cast<double>(s_mfcc[j * NQ + tid]) - mean;
+      ss = fma(d, d, ss);
     }
     float* o = out_stats + (static_cast<size_t>(clip) * n_shifts + k) * 2 * n_mfcc;
-    o[tid] = mean;
-    o[n_mfcc + tid] = sqrtf(ss / static_cast<float>(n_frames - 1));  // unbiased; NaN when n_frames == 1 (as torch.std)
+    o[tid] = static_cast<float>(mean);
+    o[n_mfcc + tid] = static_cast<float>(sqrt(ss / static_cast<double>(n_frames - 1)));  // unbiased; NaN when n_frames == 1 (as torch.std)
   }
 }
 
@@ -423,7 +484,10 @@ extern "C" int avs_mfcc_plan_unique_frames(const avs_mfcc_plan* p) { return p ? 
 extern "C" int avs_mfcc_plan_frames(const avs_mfcc_plan* p) { return p ? p->n_frames : AVS_EINVAL; }
 extern "C" size_t avs_mfcc_workspace_bytes(const avs_mfcc_plan* p, int n_clips) {
   if (!p || n_clips <= 0) return 0;
-  return align_up(static_cast<size_t>(n_clips) * p->n_unique * kMels * sizeof(float), 256);
+  // log-mel rows, per-frame DCT rows, per-frame (max, min)
+  const size_t frames = static_cast<size_t>(n_clips) * p->n_unique;
+  return align_up(frames * kMels * sizeof(float), 256) + align_up(frames * kMaxQ * sizeof(float), 256) +
+         align_up(frames * sizeof(float2), 256);
 }
 
 extern "C" int avs_mfcc_sweep_debug(const avs_mfcc_plan* p, const float* audio, int n_clips, float* out_stats,
@@ -435,7 +499,10 @@ extern "C" int avs_mfcc_sweep_debug(const avs_mfcc_plan* p, const float* audio, 
     return AVS_EWORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n_fr = static_cast<size_t>(n_clips) * p->n_unique;
   float* logmel = static_cast<float*>(workspace);
+  float* frame_mfcc = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align_up(n_fr * kMels * sizeof(float), 256));
+  float2* frame_range = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(frame_mfcc) + align_up(n_fr * kMaxQ * sizeof(float), 256));
   for (int c0 = 0; c0 < n_clips; c0 += 32768) {  // gridDim.y limit
     const int nc = std::min(32768, n_clips - c0);
     dim3 g1(cdiv(p->n_unique, kWarpFftWarps), nc);
@@ -449,16 +516,24 @@ extern "C" int avs_mfcc_sweep_debug(const avs_mfcc_plan* p, const float* audio, 
     float* os = out_stats + static_cast<size_t>(c0) * p->n_shifts * 2 * p->n_mfcc;
     float* om = out_mfcc ? out_mfcc + static_cast<size_t>(c0) * p->n_shifts * p->n_frames * p->n_mfcc : nullptr;
     const float* lm = logmel + static_cast<size_t>(c0) * p->n_unique * kMels;
+    const float* fmf = frame_mfcc + static_cast<size_t>(c0) * p->n_unique * kMaxQ;
+    const float2* frg = frame_range + static_cast<size_t>(c0) * p->n_unique;
     ProfScope ps2(PROF_MFCC_STATS, st);
+    dim3 gf(cdiv(p->n_unique, 128), nc);
+    if (p->n_mfcc <= 20)
+      mfcc_frame_dct_kernel<20><<<gf, 128, 0, st>>>(lm, p->n_unique, p->d_dct, const_cast<float*>(fmf), const_cast<float2*>(frg));
+    else
+      mfcc_frame_dct_kernel<kMaxQ><<<gf, 128, 0, st>>>(lm, p->n_unique, p->d_dct, const_cast<float*>(fmf), const_cast<float2*>(frg));
+    AVS_LAUNCHED();
     if (p->n_mfcc <= 20) {
       const size_t sm = (static_cast<size_t>(kMels) * 20 + static_cast<size_t>(p->n_frames) * 20) * sizeof(float);
       AVS_CUDA(cudaFuncSetAttribute(mfcc_stats_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)));
-      mfcc_stats_kernel<20><<<g2, 128, sm, st>>>(lm, p->d_map, p->n_unique, p->n_frames, p->n_shifts, p->n_mfcc,
+      mfcc_stats_kernel<20><<<g2, 128, sm, st>>>(lm, fmf, frg, p->d_map, p->n_unique, p->n_frames, p->n_shifts, p->n_mfcc,
                                                  p->d_dct, os, om);
     } else {
       const size_t sm = (static_cast<size_t>(kMels) * kMaxQ + static_cast<size_t>(p->n_frames) * kMaxQ) * sizeof(float);
       AVS_CUDA(cudaFuncSetAttribute(mfcc_stats_kernel<kMaxQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)));
-      mfcc_stats_kernel<kMaxQ><<<g2, 128, sm, st>>>(lm, p->d_map, p->n_unique, p->n_frames, p->n_shifts, p->n_mfcc,
+      mfcc_stats_kernel<kMaxQ><<<g2, 128, sm, st>>>(lm, fmf, frg, p->d_map, p->n_unique, p->n_frames, p->n_shifts, p->n_mfcc,
                                                     p->d_dct, os, om);
     }
     AVS_LAUNCHED();

@@ -11,12 +11,13 @@ import avsync_b200 as A
 L = A._native.lib()
 B = int(os.environ.get("MB_CLIPS", "64"))
 frames = torch.rand((B, 1, 75, 50, 100), generator=torch.Generator().manual_seed(3)).cuda()
-for prec in ("bf16", "bf16x3"):
+FLAGS = [int(f) for f in os.environ.get("SPLIT_FLAGS", "16,23").split(",")]
+for prec in os.environ.get("SPLIT_PREC", "bf16,bf16x3").split(","):
     torch.manual_seed(0)
     net = A.LipNet(39, precision=prec).cuda().eval()
     net.stcnn(frames)
     torch.cuda.synchronize()
-    for flags in (16, 16 + 7):
+    for flags in FLAGS:
         print(f"== {prec} dbg={flags}", flush=True)
         L.avs_debug_set(flags)
         net.stcnn(frames)
