@@ -106,7 +106,14 @@ static int run_chunk(avs_sweep* s, const float* frames, const float* audio, int 
   float* ast = s->astats + static_cast<size_t>(c0) * s->K * 2 * s->n_mfcc;
   // The audio branch forks AFTER layer 1: conv1 is the one layer that is CUDA-core sensitive (thin MMAs,
   // heavy epilogue), while conv2/conv3 are tensor/smem bound and leave the ALUs to the FFT kernels.
-  if ((rc = stcnn_forward_impl(s->net, frames, n, s->chunk, true, s->ev_fork, nullptr, vst, nullptr, nullptr,
+  static const int audio_mode = getenv("AVS_AUDIO_MODE") ? atoi(getenv("AVS_AUDIO_MODE")) : 0;  // experiments: 1 serial, 2 fork at chunk start
+  if (audio_mode == 1) {
+    if ((rc = stcnn_forward_impl(s->net, frames, n, s->chunk, true, nullptr, nullptr, vst, nullptr, nullptr, s->ws_stcnn, s->ws_stcnn_bytes, st)))
+      return rc;
+    return avs_mfcc_stats_sweep(s->plan, audio, n, ast, s->ws_mfcc, s->ws_mfcc_bytes, st);
+  }
+  if (audio_mode == 2) AVS_CUDA(cudaEventRecord(s->ev_fork, st));
+  if ((rc = stcnn_forward_impl(s->net, frames, n, s->chunk, true, audio_mode == 2 ? nullptr : s->ev_fork, nullptr, vst, nullptr, nullptr,
                                s->ws_stcnn, s->ws_stcnn_bytes, st)))
     return rc;
   AVS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
