@@ -148,7 +148,7 @@ constexpr uint64_t kDescHi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 
 // bf16: row-parity stacking (see the header).  a_base = unit slot (+ kw) | LBO_A << 16, b_base = weight slot | LBO_B << 16.
 // TILES (tiles of this work item) is a template parameter: a predicated-off tcgen05.mma is not free — it holds the
 // issue slot ~40 cycles (tools/umma_rate.cu) — so the last, partial tile set of a plane gets its own instantiation.
-template <int KIND, int TILES>
+template <int KIND, int LO, int HI>
 __device__ __forceinline__ void issue_stage_bf16(const uint32_t (&a_base)[3], uint32_t b_base, uint32_t d_base, bool overwrite,
                                                  uint32_t idesc_n, uint32_t idesc_w) {
   using K = LayerKind<KIND>;
@@ -168,14 +168,15 @@ __device__ __forceinline__ void issue_stage_bf16(const uint32_t (&a_base)[3], ui
         const uint32_t d = d_base + (q == K::NROW ? K::N : 0);
         const uint32_t acc = (kd == 0 && pr == 0 && e == 0) ? (overwrite ? 0u : 1u) : 1u;
 #pragma unroll
-        for (int i = 0; i < TILES; ++i) umma_f16(d + i * 2 * K::ACC, kDescHi | (a + i * 128), kDescHi | b, wide ? idesc_w : idesc_n, acc);
+        for (int i = LO; i < HI; ++i) umma_f16(d + i * 2 * K::ACC, kDescHi | (a + i * 128), kDescHi | b, wide ? idesc_w : idesc_n, acc);
       }
 }
 
 // bf16x3: per tap and channel pair, A_hi x [B_hi | B_lo] (2N wide) then A_lo x B_hi (N wide), for the even and the odd
 // conv row (A shifted by one padded row) into accumulators ACC columns apart.  kh: filter row of this stage
 // (run-time; conv1 walks its three row-pair taps at compile time).
-template <int KIND, int TILES>
+// AMASK: which conv-row parities (accumulators) to issue: 1 = even rows, 2 = odd rows, 3 = both
+template <int KIND, int LO, int HI, int AMASK>
 __device__ __forceinline__ void issue_stage_split(uint32_t a_base, uint32_t b_base, uint32_t d_base, bool overwrite,
                                                   int kh, uint32_t idesc_n, uint32_t idesc_w) {
   using K = LayerKind<KIND>;
@@ -192,6 +193,7 @@ __device__ __forceinline__ void issue_stage_split(uint32_t a_base, uint32_t b_ba
       for (int v = 0; v < 2; ++v)
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
+          if (!((AMASK >> a) & 1)) continue;
           uint32_t ra;
           if (K::first) {
             const int khh = a + (tap == 2 ? 4 : tap);
@@ -204,20 +206,34 @@ __device__ __forceinline__ void issue_stage_split(uint32_t a_base, uint32_t b_ba
           const uint32_t d = d_base + a * K::ACC;
           const uint32_t acc = (tap == 0 && pr == 0 && v == 0) ? (overwrite ? 0u : 1u) : 1u;
 #pragma unroll
-          for (int i = 0; i < TILES; ++i) umma_f16(d + i * 2 * K::ACC, kDescHi | (aa + i * 128), kDescHi | b, v == 0 ? idesc_w : idesc_n, acc);
+          for (int i = LO; i < HI; ++i) umma_f16(d + i * 2 * K::ACC, kDescHi | (aa + i * 128), kDescHi | b, v == 0 ? idesc_w : idesc_n, acc);
         }
 }
 
-template <int KIND, int TILES>
+// the schedule of one weight stage for tiles [LO, HI) of the item
+template <int KIND, int LO, int HI, int AMASK = 3>
 __device__ __forceinline__ void issue_stage(const uint32_t (&a_base)[3], uint32_t b_base, uint32_t d_base, bool overwrite, int s_in_unit,
                                             uint32_t idesc_n, uint32_t idesc_w) {
   using K = LayerKind<KIND>;
+  if (LO >= HI) return;
   if (K::split) {
-    issue_stage_split<KIND, TILES>(a_base[0], b_base, d_base, overwrite, s_in_unit, idesc_n, idesc_w);
+    issue_stage_split<KIND, LO, HI, AMASK>(a_base[0], b_base, d_base, overwrite, s_in_unit, idesc_n, idesc_w);
   } else {
     const uint32_t ab[3] = {a_base[0] + (K::first ? 0 : s_in_unit), a_base[1], a_base[2]};  // generic layers: + kw
-    issue_stage_bf16<KIND, TILES>(ab, b_base, d_base, overwrite, idesc_n, idesc_w);
+    issue_stage_bf16<KIND, LO, HI>(ab, b_base, d_base, overwrite, idesc_n, idesc_w);
   }
+}
+// first (HALF = 0) or second (HALF = 1) half of the stage: halves of the item's `nt` tiles, or — single-tile split
+// kinds — the even-row / odd-row accumulator.  What matters is that the halves write disjoint accumulators.
+template <int KIND, int HALF>
+__device__ __forceinline__ void issue_half(int nt, const uint32_t (&ab)[3], uint32_t bb, uint32_t d_base, bool ow, int s_in_unit,
+                                           uint32_t idesc_n, uint32_t idesc_w) {
+  constexpr int NT = LayerKind<KIND>::NT;
+  if (LayerKind<KIND>::split && nt == 1) issue_stage<KIND, 0, 1, HALF == 0 ? 1 : 2>(ab, bb, d_base, ow, s_in_unit, idesc_n, idesc_w);
+  else if (nt == 1) issue_stage<KIND, 0, HALF == 0 ? 1 : 0>(ab, bb, d_base, ow, s_in_unit, idesc_n, idesc_w);
+  else if (NT >= 2 && nt == 2) issue_stage<KIND, HALF == 0 ? 0 : 1, HALF == 0 ? 1 : 2>(ab, bb, d_base, ow, s_in_unit, idesc_n, idesc_w);
+  else if (NT >= 3 && nt == 3) issue_stage<KIND, HALF == 0 ? 0 : 2, HALF == 0 ? 2 : 3>(ab, bb, d_base, ow, s_in_unit, idesc_n, idesc_w);
+  else if (NT >= 4 && nt == 4) issue_stage<KIND, HALF == 0 ? 0 : 2, HALF == 0 ? 2 : 4>(ab, bb, d_base, ow, s_in_unit, idesc_n, idesc_w);
 }
 
 template <int KIND>
@@ -237,7 +253,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   uint64_t* acc_full = w_empty + kMaxWStages;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* turn = acc_empty + 2;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(turn + 2);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(turn + 4);  // turn[x]: early token for issuer x, turn[2 + x]: final token
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -247,7 +263,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     for (int i = 0; i < p.ring; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 2);   // both issuers commit
     for (int i = 0; i < p.wstages; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
     for (int i = 0; i < p.NBUF; ++i) mbar_init(&acc_full[i], 2), mbar_init(&acc_empty[i], 8);
-    mbar_init(&turn[0], 1), mbar_init(&turn[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&turn[i], 1);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<512>(s_tmem);
@@ -320,10 +336,9 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   } else if (warp == 1 || warp == 3) {
     // ============================================================ MMA issuers
     // Both warps walk the whole schedule converged (slot and phase counters stay identical); issuer x owns every
-    // other weight stage (global stage counter g, g & 1 == x).  For an owned stage: wait for its operands, wait for
-    // the turn token of the other issuer's previous stage (its MMAs are then in the pipe, so MMAs reach the tensor
-    // core in schedule order — the overwrite of an item's first MMA comes first), issue, commit, pass the token on.
-    // Barriers that cover MMAs of both issuers (a_empty, acc_full) take a commit from each.
+    // other weight stage (global stage counter g, g & 1 == x).  For an owned stage: wait for its operands, then issue
+    // it in two halves under the token protocol below.  Barriers that cover MMAs of both issuers (a_empty, acc_full)
+    // take a commit from each.
     const uint32_t x = warp >> 1;
     const uint32_t idesc_n = umma_idesc_bf16(128, K::N), idesc_w = umma_idesc_bf16(128, 2 * K::N);
     const uint32_t units_lo = (smem_u32(s_units) & 0x3FFFFu) >> 4, w_lo = (smem_u32(s_w) & 0x3FFFFu) >> 4;
@@ -385,51 +400,64 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
           if (!(dbg & 1) || w_loaded < wstages) mbar_wait(&w_full[w_slot], w_phase);
           const uint32_t stage_lo = w_lo + w_slot * stage_step;
           const long long tk1 = (dbg & 16) ? clock64() : 0;
-          if (g != 0) {
-            mbar_wait(&turn[x], turn_phase);
-            turn_phase ^= 1;
-          }
+          if (g != 0) mbar_wait(&turn[x], turn_phase);  // "early" token: the first half of the other issuer's stage has completed
           tc_fence_after();
           const long long tk2 = (dbg & 16) ? clock64() : 0;
           if (elect_one()) {
-            for (int rep = 0; rep < ((dbg & 8) ? 2 : 1); ++rep) {  // dbg 8: issue every MMA twice (tensor-vs-issue bound test)
-              const uint32_t bb = stage_lo | lbo_b;
-              const bool ow = st == 0 && rep == 0;
-              if (nt == NT) issue_stage<KIND, NT>(ab, bb, d_base, ow, s_in_unit, idesc_n, idesc_w);
-              else if (NT > 1 && nt == 1) issue_stage<KIND, 1>(ab, bb, d_base, ow, s_in_unit, idesc_n, idesc_w);
-              else if (NT > 2 && nt == 2) issue_stage<KIND, 2>(ab, bb, d_base, ow, s_in_unit, idesc_n, idesc_w);
-              else if (NT > 3 && nt == 3) issue_stage<KIND, 3>(ab, bb, d_base, ow, s_in_unit, idesc_n, idesc_w);
-            }
-            // Token right after the last MMA (the other issuer's MMAs follow these in the pipe, so the accumulation
-            // order — and with it every output bit — is the schedule's, whatever the timing); the commits are owed
-            // before this issuer's next arrival on the same barriers, which data dependencies already guarantee for
-            // multi-stage items, and for conv1's single-stage items they come first.
-            if (K::SPU > 1) mbar_arrive(&turn[x ^ 1]);
+            // Two-phase hand-over.  A stage is issued as [first half of the item's tiles] [second half]; the other
+            // issuer may start the first half of ITS stage once ours has COMPLETED, and its second half once our
+            // second half has (the tokens are tcgen05.commit arrivals: MMAs of two warps reach the tensor core
+            // through separate queues, so "issued" does not order them — an mbarrier.arrive token gave run-to-run
+            // different bits).  Every accumulator thus sees the stages in schedule order, bit-identical whatever the
+            // timing, while the two instruction streams overlap by half a stage, which hides each issuer's
+            // per-stage work (barrier waits, address set-up, commits) behind the other one's MMAs.
+            const uint32_t bb = stage_lo | lbo_b;
+            for (int rep = 0; rep < ((dbg & 8) ? 2 : 1); ++rep)  // dbg 8: issue every MMA twice (tensor-vs-issue bound test)
+              issue_half<KIND, 0>(nt, ab, bb, d_base, st == 0 && rep == 0, s_in_unit, idesc_n, idesc_w);
+            tc_commit(&turn[x ^ 1]);
+            if (g != 0) mbar_wait_poll(&turn[2 + x], turn_phase);  // "final" token: its second half has completed
+            for (int rep = 0; rep < ((dbg & 8) ? 2 : 1); ++rep)
+              issue_half<KIND, 1>(nt, ab, bb, d_base, st == 0 && rep == 0, s_in_unit, idesc_n, idesc_w);
+            // commits before the final token: when the other issuer may pass this point of the schedule, every
+            // arrival this one owes up to here has been made (no barrier can see two arrivals of one issuer in a phase)
             if (!(dbg & 1)) tc_commit(&w_empty[w_slot]);
+            if (last_of_unit && !(dbg & 2)) {
+              if (K::reuse) {
+                if (K::first) {
+                  tc_commit(&a_empty[w.t % K::RING]);
+                  if (!cont_next) tc_commit(&a_empty[(w.t + 1) % K::RING]), tc_commit(&a_empty[(w.t + 2) % K::RING]);
+                } else if (unit == 0 || !cont_next) {
+                  tc_commit(&a_empty[slot0]);  // planes kd = 1, 2 stay for the next time step
+                }
+              } else {
+                tc_commit(&a_empty[a_slot]);
+              }
+            }
+            if (st == n_stages - 1) tc_commit(&acc_full[acc_buf]);
+            tc_commit(&turn[2 + (x ^ 1)]);
           }
           __syncwarp();
+          if (g != 0) turn_phase ^= 1;
           if (dbg & 16) {
             const long long tk3 = clock64();
             tk_prep += tk1 - tk0; tk_turn += tk2 - tk1; tk_issue += tk3 - tk2;
           }
-        }
-        // barriers over MMAs of both issuers (A slots, accumulator): each issuer commits its share when the schedule
-        // passes the boundary — the owner right after its MMAs, the other one as it walks by
-        if ((last_of_unit || st == n_stages - 1) && elect_one()) {
+        } else if ((last_of_unit || st == n_stages - 1) && elect_one()) {
+          // barriers over MMAs of both issuers (A slots, accumulator): the issuer that does not own the boundary stage
+          // commits its share as it walks by
           if (last_of_unit && !(dbg & 2)) {
             if (K::reuse) {
               if (K::first) {
                 tc_commit(&a_empty[w.t % K::RING]);
                 if (!cont_next) tc_commit(&a_empty[(w.t + 1) % K::RING]), tc_commit(&a_empty[(w.t + 2) % K::RING]);
               } else if (unit == 0 || !cont_next) {
-                tc_commit(&a_empty[slot0]);  // planes kd = 1, 2 stay for the next time step
+                tc_commit(&a_empty[slot0]);
               }
             } else {
               tc_commit(&a_empty[a_slot]);
             }
           }
           if (st == n_stages - 1) tc_commit(&acc_full[acc_buf]);
-          if (K::SPU == 1 && (g & 1) == x) mbar_arrive(&turn[x ^ 1]);
         }
         __syncwarp();
         ++w_loaded;
@@ -839,7 +867,7 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
   L->chunks_per_unit = g.n_chunks / (n_units * L->unit_planes / 3);
   L->plane_slot_bytes = L->unit_planes * L->chunks_per_unit * 2 * static_cast<int>(arr_bytes);
   L->smem_bytes = static_cast<size_t>(L->ring) * L->plane_slot_bytes + static_cast<size_t>(region_full - L->region_pos) * 16 +
-                  static_cast<size_t>(L->wstages) * L->stage_bytes + (2 * kMaxRing + 2 * kMaxWStages + 6) * 8 + 16;
+                  static_cast<size_t>(L->wstages) * L->stage_bytes + (2 * kMaxRing + 2 * kMaxWStages + 8) * 8 + 16;
   if (L->smem_bytes > 232448 || L->ring > kMaxRing || L->wstages > kMaxWStages || n_units > kMaxUnits || L->NT != kNT ||
       n_stages != (first && !split ? 1 : n_units * kSPU) || wp.size() * 2 != static_cast<size_t>(L->n_stages) * L->stage_bytes || L->stage_bytes % 16 != 0) {
     set_error("umma layer config invalid: smem %zu stage_bytes %d n_stages %d units %d packed %zu", L->smem_bytes, L->stage_bytes,
