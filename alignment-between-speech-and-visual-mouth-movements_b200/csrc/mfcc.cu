@@ -55,8 +55,9 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 // in registers (N = 32 x 32 Cooley-Tukey, compile-time twiddles inside the 32-point FFTs) with one transpose
 // through shared memory in between — no block barriers and no per-pass index arithmetic (a first version
 // with a radix-4 Stockham FFT per 256-thread CTA issued ~2x the instructions and was 1.7x slower).  8.4 KB of
-// shared memory per warp, 2 warps per CTA, so these CTAs co-reside with the persistent conv kernels.
-constexpr int kWarpFftWarps = 2;
+// shared memory per warp, ONE warp per CTA: the persistent conv kernels leave ~25 KB of shared memory per SM, and
+// three one-warp CTAs beside them beat one two-warp CTA (whole sweep step 43.7 -> 42.7 ms).
+constexpr int kWarpFftWarps = 1;
 
 template <int IDX>  // exp(-2 pi i IDX / 32)
 __device__ __forceinline__ float2 tw32() {
