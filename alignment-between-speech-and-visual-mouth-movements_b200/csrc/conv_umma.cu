@@ -141,6 +141,9 @@ struct LayerKind {
   static constexpr int NTILES = ((H / 2) * WT + 127) / 128, NTS = (NTILES + NT - 1) / NT;
   static constexpr int EXTENT = ((KW / 2 + (H / 2 + KH / 2) * WT + (first ? 8 : 0)) + 7) / 8 * 8;
   static constexpr int ARR16 = NTS == 1 ? (REGION_FULL < EXTENT ? REGION_FULL : EXTENT) : REGION_FULL;  // positions per (chunk, parity) run in a slot
+  static constexpr int PP = NTS == 1 ? ARR16 : (NTS - 1) * NT * 128 + REGION_FULL;                      // positions per (plane, chunk, parity) array in HBM
+  static constexpr int N_CHUNKS = (first ? 1 : (N == 64 ? 32 : 64) / 8) * (split ? 2 : 1);              // chunk arrays of this layer's INPUT
+  static constexpr int NEXT = (N == 96) ? KIND : KIND + 1;                                              // kind of the layer that reads our output
 };
 
 constexpr uint64_t kDescHi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, descriptor version 1
@@ -482,33 +485,44 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     // Two groups of four warps (warps 4-7 and 8-11); warp w may read TMEM lanes 32*(w%4)..+31.  The
     // (tile, 32-column block) work units of an item alternate between the groups.
     const int q = warp & 3, grp = (warp - 4) >> 2;
+    using KN = LayerKind<K::NEXT>;             // the layer that reads our output (conv3: unused)
+    constexpr bool kToEmb = K::N == 96;        // conv3 writes the f32 embedding
+    constexpr int kHo = K::H / 2, kWo = K::W / 2, kPlane = kHo * kWo;
+    const int half = lane & 1;                 // even lane: channels 0..15 of a 32-column block, odd: 16..31
     uint32_t buf = 0, phase = 0;
     ItemWalk w;
     w.init(p);
     for (; w.valid(); w.next(), buf = (buf + 1 == static_cast<uint32_t>(p.NBUF)) ? 0 : buf + 1, phase ^= (buf == 0)) {
       const int b = w.b, t = w.t, ts = w.ts;
-      const int nt = min(p.NT, p.n_tiles - ts * p.NT);
+      const int nt = min(NT, p.n_tiles - ts * NT);
       mbar_wait(&acc_full[buf], phase);
       __syncwarp();  // tcgen05.ld below is .aligned
       tc_fence_after();
-      const uint32_t d_base = tmem_base + buf * (p.NT * 2 * p.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t d_base = tmem_base + buf * (NT * 2 * K::ACC) + (static_cast<uint32_t>(q * 32) << 16);
       for (int i = 0; i < ((p.dbg & 4) ? 0 : nt); ++i) {
-        const int Q = (ts * p.NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
-        const int r = Q / p.Wt, wc = Q % p.Wt;                // pooled row, conv column
+        const int Q = (ts * NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
+        const int r = Q / K::WT, wc = Q % K::WT;            // pooled row, conv column
         const int wo = wc >> 1;
-        const bool valid = (r < p.Ho) && (wo < p.Wo);
-        const int half = lane & 1;                            // even lane: channels 0..15 of the block, odd: 16..31
-        for (int cb = 0; cb < p.N; cb += 32) {
-          if ((((i * p.N) >> 5) + (cb >> 5) & 1) != grp) continue;  // warp-uniform
+        const bool valid = (r < kHo) && (wo < kWo);
+#pragma unroll
+        for (int cb = 0; cb < K::N; cb += 32) {
+          if (((((i * K::N) >> 5) + (cb >> 5)) & 1) != grp) continue;  // warp-uniform
           uint32_t v0[32], v1[32];
-          tmem_ld32(d_base + (i * 2 + 0) * p.acc_stride + cb, v0);
-          tmem_ld32(d_base + (i * 2 + 1) * p.acc_stride + cb, v1);
+          tmem_ld32(d_base + (i * 2 + 0) * K::ACC + cb, v0);
+          tmem_ld32(d_base + (i * 2 + 1) * K::ACC + cb, v1);
+          const int ch0 = cb + half * 16;
+          float bias[16];  // fetched while the TMEM loads are in flight
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + c4);
+            bias[c4 * 4 + 0] = bv.x; bias[c4 * 4 + 1] = bv.y; bias[c4 * 4 + 2] = bv.z; bias[c4 * 4 + 3] = bv.w;
+          }
           tmem_ld_wait();
           if ((p.dbg & 32) && v0[0] != 0x7fc12345u) continue;  // experiment: TMEM reads only
-          if (p.split) {  // second column block: A_hi * B_lo, the small term, added last
+          if (K::split) {  // second column block: A_hi * B_lo, the small term, added last
             uint32_t u0[32], u1[32];
-            tmem_ld32(d_base + (i * 2 + 0) * p.acc_stride + p.N + cb, u0);
-            tmem_ld32(d_base + (i * 2 + 1) * p.acc_stride + p.N + cb, u1);
+            tmem_ld32(d_base + (i * 2 + 0) * K::ACC + K::N + cb, u0);
+            tmem_ld32(d_base + (i * 2 + 1) * K::ACC + K::N + cb, u1);
             tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
@@ -517,7 +531,6 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
             }
           }
           float o[16];
-          const int ch0 = cb + half * 16;
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             // rows 2r, 2r+1: max of the two accumulators; columns 2wo, 2wo+1: exchange with the
@@ -525,14 +538,14 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
             const float lo = fmaxf(__uint_as_float(v0[c]), __uint_as_float(v1[c]));
             const float hi = fmaxf(__uint_as_float(v0[c + 16]), __uint_as_float(v1[c + 16]));
             const float got = __shfl_xor_sync(0xffffffffu, half ? lo : hi, 1);
-            o[c] = fmaxf(fmaxf(half ? hi : lo, got) + __ldg(p.bias + ch0 + c), 0.f);
+            o[c] = fmaxf(fmaxf(half ? hi : lo, got) + bias[c], 0.f);
           }
           if ((p.dbg & 64) && o[0] != 12345.678f) continue;  // experiment: no stores
-          if (valid && p.eo.mode == 0) {
-            const int hp = r + p.eo.ph_next;
-            const long long pos = p.eo.pw_next + (hp >> 1) * p.eo.Wt_next + wo;
-            __nv_bfloat16* base = p.eo.act +
-                                  ((static_cast<long long>(b) * (p.T + 2) + t + 1) * p.eo.n_chunks_next) * 2 * p.eo.PP_next * 8;
+          if (valid && !kToEmb) {
+            // the NEXT layer's parity-plane layout (its geometry is a compile-time property of the kind)
+            const int hp = r + KN::KH / 2;
+            const int pos = KN::KW / 2 + (hp >> 1) * KN::WT + wo;
+            __nv_bfloat16* base = p.eo.act + ((static_cast<long long>(b) * (p.T + 2) + t + 1) * KN::N_CHUNKS) * 2 * KN::PP * 8;
 #pragma unroll
             for (int c8 = 0; c8 < 2; ++c8) {
               const int chunk = (ch0 >> 3) + c8;
@@ -542,22 +555,20 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
                 const float x0 = o[c8 * 8 + 2 * e], x1 = o[c8 * 8 + 2 * e + 1];
                 const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
                 hi[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-                lo[e] = pack_bf16x2(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+                if (K::split) lo[e] = pack_bf16x2(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
               }
-              const int idx = p.eo.split_next ? 2 * chunk : chunk;
-              uint4* dst = reinterpret_cast<uint4*>(base + ((static_cast<long long>(idx) * 2 + (hp & 1)) * p.eo.PP_next + pos) * 8);
+              const int idx = K::split ? 2 * chunk : chunk;
+              uint4* dst = reinterpret_cast<uint4*>(base + (static_cast<long long>(idx * 2 + (hp & 1)) * KN::PP + pos) * 8);
               *dst = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              if (p.eo.split_next) {
-                uint4* dl = reinterpret_cast<uint4*>(base + ((static_cast<long long>(idx + 1) * 2 + (hp & 1)) * p.eo.PP_next + pos) * 8);
+              if (K::split) {
+                uint4* dl = reinterpret_cast<uint4*>(base + (static_cast<long long>((idx + 1) * 2 + (hp & 1)) * KN::PP + pos) * 8);
                 *dl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
               }
             }
           } else if (valid) {
-            const int plane = p.Ho * p.Wo;
-            float* dst = p.eo.emb + (static_cast<long long>(b) * p.T + t) * (static_cast<long long>(p.N) * plane) +
-                         static_cast<long long>(ch0) * plane + r * p.Wo + wo;
+            float* dst = p.eo.emb + (static_cast<long long>(b) * p.T + t) * (K::N * kPlane) + ch0 * kPlane + r * kWo + wo;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) dst[static_cast<long long>(c) * plane] = o[c];
+            for (int c = 0; c < 16; ++c) dst[c * kPlane] = o[c];
           }
           __syncwarp();
         }
@@ -595,18 +606,18 @@ static ConvKernel conv_kernel_for(int kind) {
   return nullptr;
 }
 template <int KIND>
-static void kind_traits(int* NT, int* acc, int* spu, int* pairs, int* arr16, int* wt) {
+static void kind_traits(int* NT, int* acc, int* spu, int* pairs, int* arr16, int* wt, int* pp, int* nch) {
   using K = LayerKind<KIND>;
-  *NT = K::NT; *acc = K::ACC; *spu = K::SPU; *pairs = K::PAIRS; *arr16 = K::ARR16; *wt = K::WT;
+  *NT = K::NT; *acc = K::ACC; *spu = K::SPU; *pairs = K::PAIRS; *arr16 = K::ARR16; *wt = K::WT; *pp = K::PP; *nch = K::N_CHUNKS;
 }
-static void kind_traits_for(int kind, int* NT, int* acc, int* spu, int* pairs, int* arr16, int* wt) {
+static void kind_traits_for(int kind, int* NT, int* acc, int* spu, int* pairs, int* arr16, int* wt, int* pp, int* nch) {
   switch (kind) {
-    case KIND_L1: return kind_traits<KIND_L1>(NT, acc, spu, pairs, arr16, wt);
-    case KIND_L2: return kind_traits<KIND_L2>(NT, acc, spu, pairs, arr16, wt);
-    case KIND_L3: return kind_traits<KIND_L3>(NT, acc, spu, pairs, arr16, wt);
-    case KIND_L1_SPLIT: return kind_traits<KIND_L1_SPLIT>(NT, acc, spu, pairs, arr16, wt);
-    case KIND_L2_SPLIT: return kind_traits<KIND_L2_SPLIT>(NT, acc, spu, pairs, arr16, wt);
-    default: return kind_traits<KIND_L3_SPLIT>(NT, acc, spu, pairs, arr16, wt);
+    case KIND_L1: return kind_traits<KIND_L1>(NT, acc, spu, pairs, arr16, wt, pp, nch);
+    case KIND_L2: return kind_traits<KIND_L2>(NT, acc, spu, pairs, arr16, wt, pp, nch);
+    case KIND_L3: return kind_traits<KIND_L3>(NT, acc, spu, pairs, arr16, wt, pp, nch);
+    case KIND_L1_SPLIT: return kind_traits<KIND_L1_SPLIT>(NT, acc, spu, pairs, arr16, wt, pp, nch);
+    case KIND_L2_SPLIT: return kind_traits<KIND_L2_SPLIT>(NT, acc, spu, pairs, arr16, wt, pp, nch);
+    default: return kind_traits<KIND_L3_SPLIT>(NT, acc, spu, pairs, arr16, wt, pp, nch);
   }
 }
 
@@ -759,15 +770,15 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
     return AVS_EINVAL;
   }
   const LayerCfg c = pick_cfg(g, split);
-  int kNT, kACC, kSPU, kPAIRS, kARR16, kWT;
-  kind_traits_for(L->kind, &kNT, &kACC, &kSPU, &kPAIRS, &kARR16, &kWT);
+  int kNT, kACC, kSPU, kPAIRS, kARR16, kWT, kPP, kNCH;
+  kind_traits_for(L->kind, &kNT, &kACC, &kSPU, &kPAIRS, &kARR16, &kWT, &kPP, &kNCH);
   L->NT = c.NT; L->NBUF = c.NBUF; L->ring = c.ring; L->wstages = c.wstages;
   L->acc_stride = kACC;
   const int halo = (g.Cin == 1) ? (g.KH / 2 + 1) * g.Wt + 8 : (g.KH / 2) * g.Wt + g.KW - 1;
   const int region_full = c.NT * 128 + halo;
   const int n_tilesets = cdiv(g.n_tiles, c.NT);
   L->region_pos = (n_tilesets == 1) ? g.PP : region_full;
-  if (L->region_pos != kARR16 || g.Wt != kWT || c.NT != kNT) {
+  if (L->region_pos != kARR16 || g.Wt != kWT || c.NT != kNT || g.PP != kPP || g.n_chunks != kNCH) {
     set_error("layer geometry (%dx%d input, row pitch %d, %d positions per run, %d tiles per item) is not the one the tcgen05 "
               "schedule was compiled for (%d, %d, %d)", g.H, g.W, g.Wt, L->region_pos, c.NT, kWT, kARR16, kNT);
     return AVS_EINVAL;
