@@ -504,6 +504,8 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         const int r = Q / K::WT, wc = Q % K::WT;            // pooled row, conv column
         const int wo = wc >> 1;
         const bool valid = (r < kHo) && (wo < kWo);
+        // positions grow with the lane: if the warp's first lane is already past the last pooled row, nobody has work
+        if (((ts * NT + i) * 128 + q * 32) / K::WT >= kHo) continue;
 #pragma unroll
         for (int cb = 0; cb < K::N; cb += 32) {
           if (((((i * K::N) >> 5) + (cb >> 5)) & 1) != grp) continue;  // warp-uniform
