@@ -286,7 +286,10 @@ def main():
                 "peak_source": f"{pk_src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "algorithmic_flop_per_launch": CONV_FLOP[2] * clips_per_launch,
                 "issued_mma_multiplier": mult, "avg_launch_ms": avg_ms, "launches_timed": conv2["launches"],
-                "share_of_step": conv2["ms_total"] / ms_total if ms_total else None}
+                "share_of_step": conv2["ms_total"] / ms_total if ms_total else None,
+                # the sustained peak is a measured cuBLAS bf16 GEMM rate, not a hardware bound: a frac near (or a
+                # little above) 1 says "as fast as cuBLAS keeps this GPU busy under its power cap"
+                "frac_of_burst_peak": achieved / pk["bf16_tflops"] if pk.get("bf16_tflops") else None}
         cpu = None
         if args.cpu_clips > 0:
             v, dt = cpu_sweep_clips_per_s(args.cpu_clips, warm=1)
