@@ -45,12 +45,12 @@ def peaks():
 
 def conv2_traffic(clips_per_launch: int, precision: str):
     """DRAM bytes per launch of the layer-2 conv kernel from the committed `ncu --set full` capture
-    (profiles/r01_conv2_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum = 859.7 MB for a
-    64-clip bf16 launch = 13.43 MB per clip; algorithmic: 8.6 MB padded input + 2.9 MB pooled output),
+    (profiles/r01_conv2_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum = 864.9 MB for a
+    64-clip bf16 launch = 13.51 MB per clip; algorithmic: 8.6 MB padded input + 2.9 MB pooled output),
     scaled to the clips one bench launch processes."""
     if precision != "bf16":
         return None
-    return 13.43e6 * clips_per_launch
+    return 13.51e6 * clips_per_launch
 
 
 class ClockSampler:
