@@ -20,18 +20,19 @@
 //     are plain sub-ranges of it) — KH+1 fetches of A per filter column instead of 2*KH;
 //   * a tile's halo'd input is one contiguous run per (chunk, parity): plain cp.async.bulk.
 //
-// Kernel structure: persistent CTAs (one per SM), 8 warps:
-//   warp 0  lane 0 : A producer   — bulk-copies A units (one time plane, or half its channels)
-//   warp 2  lane 0 : B producer   — bulk-copies weight stages (one filter tap each)
+// Kernel structure: persistent CTAs (one per SM, each walking one contiguous span of work items), 12 warps:
+//   warp 0  lane 0 : A producer   — bulk-copies input planes into a ring of plane slots (bf16 kinds: only the plane the
+//                                   previous item did not have; split kinds: the item's three units)
+//   warp 2  lane 0 : B producer   — bulk-copies weight stages (bf16: one filter column, split: one filter row)
 //   warps 1 and 3  : MMA issuers  — take the weight stages of the schedule in turn (one elected lane each issues
 //                                   tcgen05.mma into TMEM): the tensor pipe accepts an MMA only about one
 //                                   instruction ahead of the one executing (tools/umma_rate.cu), so everything an
-//                                   issuer does between two stages — barrier waits, schedule fetch, descriptor
-//                                   arithmetic — would idle it; with two issuers one prepares while the other issues
+//                                   issuer does between two stages — barrier waits, address set-up, commits —
+//                                   would idle it; with two issuers one prepares while the other issues
 //   warp 2         : TMEM allocator
-//   warps 4..7     : epilogue     — tcgen05.ld, pool, bias, ReLU, bf16 (hi/lo) pack, store
-// mbarrier rings: a_full/a_empty[RING], w_full/w_empty[WSTAGES], acc_full/acc_empty[NBUF]; turn[2] hands the
-// right to issue from one issuer warp to the other.
+//   warps 4..11    : epilogue     — two groups of four warps: tcgen05.ld, pool, bias, ReLU, bf16 (hi/lo) pack, store
+// mbarrier rings: a_full/a_empty[RING], w_full/w_empty[WSTAGES], acc_full/acc_empty[NBUF]; turn[4] are the early and
+// final hand-over tokens between the two issuer warps.
 #include <stdlib.h>
 #include <vector>
 #include "stcnn.cuh"
@@ -59,7 +60,9 @@ struct ConvKernelParams {
   int unit_slot_bytes, region_pos, region_full;
   int n_chunks, PP, Wt, Ho, Wo, n_tiles, n_tilesets;
   int T, n_items, split;
-  int dbg;  // experiment switches (avs_debug_set): 1 = weights loaded once, 2 = A units loaded once, 4 = epilogue skips math/stores
+  // experiment switches (avs_debug_set): 1 = weights loaded once, 2 = A planes loaded once, 4 = epilogue off, 8 = every
+  // MMA issued twice, 16 = clock64 split of the issuer warps (printf), 32 = epilogue reads TMEM only, 64 = epilogue without stores
+  int dbg;
   long long clip_stride, plane_stride;  // elements (bf16) between clips / time planes of `act`
 };
 

@@ -204,8 +204,10 @@ AVS_API void avs_prof_enable(int on);
 AVS_API void avs_prof_reset(void);
 AVS_API int avs_prof_read(int slot, double* total_ms, int* count);
 /* Experiment switches for the tcgen05 conv kernel (results become garbage; used only by
- * tools/conv_microbench.py to attribute time): 1 = weight stages loaded once, 2 = activation units
- * loaded once, 4 = epilogue skips its math and stores.  0 = normal operation. */
+ * tools/conv_microbench.py and tools/conv_issuer_split.py to attribute time): 1 = weight stages loaded once,
+ * 2 = activation planes loaded once, 4 = epilogue off, 8 = every MMA issued twice, 16 = clock64 split of the
+ * issuer warps (printed by block 0), 32 = epilogue reads TMEM only, 64 = epilogue without stores.
+ * 0 = normal operation. */
 AVS_API void avs_debug_set(int flags);
 /* number of kernel launches this library has enqueued since load (all handles, this process) */
 AVS_API long long avs_launch_count(void);
