@@ -27,6 +27,7 @@ SIGNATURES = {
     "avs_device_check": (c_int, [c_int]),
     "avs_launch_count": (c_longlong, []),
     "avs_debug_set": (None, [c_int]),
+    "avs_conv_item_span": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     "avs_prof_enable": (None, [c_int]),
     "avs_prof_reset": (None, []),
     "avs_prof_read": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(c_int)]),

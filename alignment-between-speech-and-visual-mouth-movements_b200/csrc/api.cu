@@ -1,6 +1,7 @@
 // Library-wide pieces of the C-ABI: version, error string, device check, launch counter.
 #include <stdarg.h>
 #include "common.cuh"
+#include "stcnn.cuh"
 
 namespace avs {
 static thread_local char g_err[512] = "";
@@ -60,6 +61,14 @@ extern "C" int avs_prof_read(int slot, double* total_ms, int* count) {
 
 namespace avs { extern int g_conv_dbg; }
 extern "C" void avs_debug_set(int flags) { avs::g_conv_dbg = flags; }
+
+extern "C" int avs_conv_item_span(int n_clips, int n_steps, int n_tiles, int tiles_per_item, int n_ctas, int cta, int* first,
+                                  int* last) {
+  AVS_REQUIRE(first && last, "null argument");
+  AVS_REQUIRE(n_clips >= 0 && n_steps > 0 && n_tiles > 0 && tiles_per_item > 0 && n_ctas > 0 && cta >= 0 && cta < n_ctas, "bad argument");
+  avs::conv_item_span(n_clips, n_steps, n_tiles, tiles_per_item, n_ctas, cta, first, last);
+  return AVS_OK;
+}
 
 extern "C" int avs_version(void) { return AVS_VERSION; }
 extern "C" const char* avs_last_error_string(void) { return avs::g_err; }

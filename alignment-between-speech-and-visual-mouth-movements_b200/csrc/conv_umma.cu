@@ -69,19 +69,24 @@ struct ConvKernelParams {
 // Work items in (clip, tile set, t) order: a CTA takes ONE contiguous span, so that consecutive items are consecutive
 // time steps of the same tile region and two of an item's three input planes are already in shared memory.  Spans are
 // balanced by cost (tiles per item: the last tile set of a plane may be partial), all roles of a CTA walk the same span.
+// first item (in (clip, tile set, t) order) whose cost prefix is >= x; cost of an item = its tile count
+__host__ __device__ inline int span_item_at_cost(int T, int n_tiles, int n_tilesets, int NT, long long x) {
+  const int per_clip = T * n_tiles;
+  const int b = static_cast<int>(x / per_clip);
+  int rem = static_cast<int>(x % per_clip);
+  const int base = b * n_tilesets * T;
+  for (int ts = 0; ts < n_tilesets; ++ts) {
+    const int nt = (NT < n_tiles - ts * NT) ? NT : n_tiles - ts * NT, row = T * nt;
+    if (rem < row) return base + ts * T + (rem + nt - 1) / nt;
+    rem -= row;
+  }
+  return base + n_tilesets * T;
+}
+
 struct ItemWalk {
   int item, first, last, b, ts, t, T, n_tilesets;
-  __device__ __forceinline__ static int item_at_cost(const ConvKernelParams& p, long long x) {  // first item starting at cost >= x
-    const int per_clip = p.T * p.n_tiles;
-    const int b = static_cast<int>(x / per_clip);
-    int rem = static_cast<int>(x % per_clip);
-    const int base = b * p.n_tilesets * p.T;
-    for (int ts = 0; ts < p.n_tilesets; ++ts) {
-      const int nt = min(p.NT, p.n_tiles - ts * p.NT), row = p.T * nt;
-      if (rem < row) return base + ts * p.T + (rem + nt - 1) / nt;
-      rem -= row;
-    }
-    return base + p.n_tilesets * p.T;
+  __device__ __forceinline__ static int item_at_cost(const ConvKernelParams& p, long long x) {
+    return span_item_at_cost(p.T, p.n_tiles, p.n_tilesets, p.NT, x);
   }
   __device__ __forceinline__ void init(const ConvKernelParams& p) {
     const long long total = static_cast<long long>(p.n_items / p.n_tilesets) * p.n_tiles;  // clips * T * tiles per plane
@@ -896,6 +901,14 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
   AVS_CUDA(cudaMemcpy(L->d_bias, bias, N * sizeof(float), cudaMemcpyHostToDevice));
   AVS_CUDA(cudaFuncSetAttribute(conv_kernel_for(L->kind), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   return AVS_OK;
+}
+
+// host mirror of ItemWalk::init, for the CPU test of the partition (tests/test_host.py)
+void conv_item_span(int n_clips, int T, int n_tiles, int NT, int grid, int cta, int* first, int* last) {
+  const int n_tilesets = cdiv(n_tiles, NT);
+  const long long total = static_cast<long long>(n_clips) * T * n_tiles;
+  *first = span_item_at_cost(T, n_tiles, n_tilesets, NT, total * cta / grid);
+  *last = span_item_at_cost(T, n_tiles, n_tilesets, NT, total * (cta + 1) / grid);
 }
 
 void umma_layer_free(UmmaLayer* L) {

@@ -53,6 +53,7 @@ extern int g_conv_dbg;
 void geom_finalize(LayerGeom& g, int split);  // fills the derived fields from Cin, Cout, H, W, KH, KW
 int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w_host, const float* b_host);
 void umma_layer_free(UmmaLayer* L);
+void conv_item_span(int n_clips, int T, int n_tiles, int NT, int grid, int cta, int* first, int* last);
 size_t umma_act_bytes(const LayerGeom& g, int split, int B);   // bytes of the input activation buffer of a layer
 int umma_pack_frames(const float* frames, __nv_bfloat16* act, const LayerGeom& g1, int split, int B, cudaStream_t st);
 int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const EpiOut& eo, int B, int n_sms, cudaStream_t st);

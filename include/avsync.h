@@ -209,6 +209,12 @@ AVS_API int avs_prof_read(int slot, double* total_ms, int* count);
  * issuer warps (printed by block 0), 32 = epilogue reads TMEM only, 64 = epilogue without stores.
  * 0 = normal operation. */
 AVS_API void avs_debug_set(int flags);
+/* How the persistent conv kernels split their work (host mirror of the device code, no GPU needed): the items of a
+ * launch, in (clip, tile set, time step) order, are cut into n_ctas contiguous spans of near-equal cost (cost of an item =
+ * its tile count; the last tile set of a plane may be partial).  Returns the half-open item range [first, last) of `cta`.
+ * n_tiles = 128-position tiles per plane, tiles_per_item = tiles one work item covers. */
+AVS_API int avs_conv_item_span(int n_clips, int n_steps, int n_tiles, int tiles_per_item, int n_ctas, int cta, int* first,
+                               int* last);
 /* number of kernel launches this library has enqueued since load (all handles, this process) */
 AVS_API long long avs_launch_count(void);
 

@@ -209,3 +209,30 @@ def test_run_epoch_matches_reference_semantics():
             assert torch.allclose(p, q, atol=1e-7)
     one = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, torch.ones(40)), batch_size=8)
     assert np.isnan(A.run_epoch(model, one, crit, torch.device("cpu"))["auc"])
+
+
+def test_conv_work_partition_covers_every_item_once_and_is_balanced():
+    """The persistent conv kernels cut their work items into contiguous, cost-balanced spans (one per CTA).  The host
+    mirror of that device code needs no GPU: every item in exactly one span, spans in order, cost within one item."""
+    import ctypes
+    L = A._native.lib()
+    # (tiles per plane, tiles per item) of the six layer kinds, plus awkward sizes
+    for n_tiles, nt in ((20, 4), (5, 2), (2, 2), (20, 2), (5, 1), (2, 1), (7, 3)):
+        n_ts = -(-n_tiles // nt)
+        for n_clips, steps, ctas in ((1, 75, 148), (3, 75, 148), (64, 75, 148), (5, 75, 7), (2, 4, 148), (1, 1, 1)):
+            n_items = n_clips * steps * n_ts
+            grid = min(n_items, ctas)
+            cost = lambda it: min(nt, n_tiles - ((it // steps) % n_ts) * nt)
+            prev_last, costs = 0, []
+            for c in range(grid):
+                f, l = ctypes.c_int(), ctypes.c_int()
+                assert L.avs_conv_item_span(n_clips, steps, n_tiles, nt, grid, c, ctypes.byref(f), ctypes.byref(l)) == 0
+                assert f.value == prev_last and l.value >= f.value, (n_tiles, nt, n_clips, steps, c)
+                prev_last = l.value
+                costs.append(sum(cost(i) for i in range(f.value, l.value)))
+            assert prev_last == n_items
+            total = n_clips * steps * n_tiles
+            assert sum(costs) == total
+            assert max(costs) - min(costs) <= 2 * nt, (n_tiles, nt, n_clips, steps, ctas, max(costs), min(costs))
+    f, l = ctypes.c_int(), ctypes.c_int()
+    assert L.avs_conv_item_span(1, 75, 5, 2, 4, 4, ctypes.byref(f), ctypes.byref(l)) != 0      # cta out of range
