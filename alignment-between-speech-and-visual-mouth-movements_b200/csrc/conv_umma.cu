@@ -59,7 +59,8 @@ struct ConvKernelParams {
   int stage_bytes, n_stages;
   int unit_slot_bytes, region_pos, region_full;
   int n_chunks, PP, Wt, Ho, Wo, n_tiles, n_tilesets;
-  int T, n_items, split;
+  int T, n_items, split;        // T: steps per (clip, tile set) of the item walk (time steps; conv3 bf16: items per clip)
+  int T_out;                    // time steps of the clip (75)
   // experiment switches (avs_debug_set): 1 = weights loaded once, 2 = A planes loaded once, 4 = epilogue off, 8 = every
   // MMA issued twice, 16 = clock64 split of the issuer warps (printf), 32 = epilogue reads TMEM only, 64 = epilogue without stores
   int dbg;
@@ -135,7 +136,12 @@ struct LayerKind {
   static constexpr int SPU = first ? 1 : KW;
   // bf16 kinds keep the three input planes of an item in a ring of three plane slots (slot = padded plane index % 3)
   // and load only the plane the previous item did not have; the split kinds (twice the bytes per plane) reload per item.
-  static constexpr bool reuse = !split;
+  // conv3 (bf16) tiles the TIME-CONCATENATED position space: its input is stored [clip][chunk][parity][time plane][PITCH]
+  // positions, so a filter's time tap kd is one more position offset (kd * PITCH) and 128-position tiles run across plane
+  // boundaries: 1.44 tiles per 156-position plane instead of 2 (-28 % MMAs).  An item = NT consecutive tiles; its three A
+  // units are the kd-shifted regions of NT * 128 + HALO positions (sequential ring, no plane reuse).
+  static constexpr bool tcat = KIND == KIND_L3;
+  static constexpr bool reuse = !split && !tcat;
   // conv1's items are a single stage, so a plane is only released when the whole item is done: a fourth slot lets the
   // next item's new plane load meanwhile (multi-stage kinds release an item's first plane after its first unit)
   static constexpr int RING = first ? 4 : 3;
@@ -148,8 +154,11 @@ struct LayerKind {
   static constexpr int REGION_FULL = NT * 128 + HALO;
   static constexpr int NTILES = ((H / 2) * WT + 127) / 128, NTS = (NTILES + NT - 1) / NT;
   static constexpr int EXTENT = ((KW / 2 + (H / 2 + KH / 2) * WT + (first ? 8 : 0)) + 7) / 8 * 8;
-  static constexpr int ARR16 = NTS == 1 ? (REGION_FULL < EXTENT ? REGION_FULL : EXTENT) : REGION_FULL;  // positions per (chunk, parity) run in a slot
-  static constexpr int PP = NTS == 1 ? ARR16 : (NTS - 1) * NT * 128 + REGION_FULL;                      // positions per (plane, chunk, parity) array in HBM
+  static constexpr int ARR16 = (NTS == 1 && !tcat) ? (REGION_FULL < EXTENT ? REGION_FULL : EXTENT) : REGION_FULL;  // positions per (chunk, parity) run in a slot
+  static constexpr int PITCH = EXTENT;                                       // tcat: positions per time plane
+  static constexpr int TCAT_ITEMS = (AVS_T * PITCH + NT * 128 - 1) / (NT * 128);                       // items per clip
+  static constexpr int TCAT_LEN = ((TCAT_ITEMS - 1) * NT * 128 + 2 * PITCH + REGION_FULL + 7) / 8 * 8;  // positions per (clip, chunk, parity) array
+  static constexpr int PP = tcat ? PITCH : NTS == 1 ? ARR16 : (NTS - 1) * NT * 128 + REGION_FULL;                      // positions per (plane, chunk, parity) array in HBM
   static constexpr int N_CHUNKS = (first ? 1 : (N == 64 ? 32 : 64) / 8) * (split ? 2 : 1);              // chunk arrays of this layer's INPUT
   static constexpr int NEXT = (N == 96) ? KIND : KIND + 1;                                              // kind of the layer that reads our output
 };
@@ -287,7 +296,21 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     // ============================================================ A producer
     ItemWalk w;
     w.init(p);
-    if (K::reuse) {
+    if (K::tcat) {
+      // time-concatenated input: unit kd of item `it` is the region [it * NT*128 + kd * PITCH, + ARR16) of every (chunk, parity) array
+      uint32_t seq = 0, slot = 0, phase = 0;
+      constexpr uint32_t bytes = K::ARR16 * 16u, n_arrays = K::N_CHUNKS * 2u;
+      for (; w.valid(); w.next()) {
+        for (int kd = 0; kd < 3; ++kd, ++seq, slot = (slot + 1 == static_cast<uint32_t>(p.ring)) ? 0 : slot + 1, phase ^= (slot == 0)) {
+          if ((p.dbg & 2) && seq >= static_cast<uint32_t>(p.ring)) continue;
+          mbar_wait(&a_empty[slot], phase ^ 1);
+          mbar_expect_tx(&a_full[slot], bytes * n_arrays);
+          uint8_t* dst = s_units + static_cast<size_t>(slot) * p.unit_slot_bytes;
+          const __nv_bfloat16* src = p.act + w.b * p.clip_stride + static_cast<long long>(w.t * NT * 128 + kd * K::PITCH) * 8;
+          for (uint32_t c = 0; c < n_arrays; ++c, dst += bytes) bulk_g2s(dst, src + static_cast<long long>(c) * K::TCAT_LEN * 8, bytes, &a_full[slot]);
+        }
+      }
+    } else if (K::reuse) {
       // Plane ring: padded time plane tp lives in slot tp % RING.  An item that continues its predecessor only loads
       // its last plane (tp = t + 2) — into the slot the issuers released after the predecessor's first plane.
       uint32_t fill_parity = 0;  // bit s: number of fills of slot s so far, mod 2
@@ -508,12 +531,19 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       tc_fence_after();
       const uint32_t d_base = tmem_base + buf * (NT * 2 * K::ACC) + (static_cast<uint32_t>(q * 32) << 16);
       for (int i = 0; i < ((p.dbg & 4) ? 0 : nt); ++i) {
-        const int Q = (ts * NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
+        int Q = (ts * NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
+        int t_out = t;
+        if (K::tcat) {  // time-concatenated position space: item index -> (time step, position in its plane)
+          const int S = (t * NT + i) * 128 + q * 32 + lane;
+          t_out = S / K::PITCH;
+          Q = S - t_out * K::PITCH;
+          if (((t * NT + i) * 128 + q * 32) / K::PITCH >= p.T_out) continue;  // the whole warp is past the last time step
+        }
         const int r = Q / K::WT, wc = Q % K::WT;            // pooled row, conv column
         const int wo = wc >> 1;
-        const bool valid = (r < kHo) && (wo < kWo);
+        const bool valid = (r < kHo) && (wo < kWo) && (t_out < p.T_out);
         // positions grow with the lane: if the warp's first lane is already past the last pooled row, nobody has work
-        if (((ts * NT + i) * 128 + q * 32) / K::WT >= kHo) continue;
+        if (!K::tcat && ((ts * NT + i) * 128 + q * 32) / K::WT >= kHo) continue;
 #pragma unroll
         for (int cb = 0; cb < K::N; cb += 32) {
           if (((((i * K::N) >> 5) + (cb >> 5)) & 1) != grp) continue;  // warp-uniform
@@ -555,7 +585,12 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
             // the NEXT layer's parity-plane layout (its geometry is a compile-time property of the kind)
             const int hp = r + KN::KH / 2;
             const int pos = KN::KW / 2 + (hp >> 1) * KN::WT + wo;
-            __nv_bfloat16* base = p.eo.act + ((static_cast<long long>(b) * (p.T + 2) + t + 1) * KN::N_CHUNKS) * 2 * KN::PP * 8;
+            // element offset of array `a` (= chunk array * 2 + parity), position `pos` of time plane t + 1
+            auto out_ptr = [&](int a) {
+              if (KN::tcat)
+                return p.eo.act + ((static_cast<long long>(b) * (KN::N_CHUNKS * 2) + a) * KN::TCAT_LEN + (t + 1) * KN::PITCH + pos) * 8;
+              return p.eo.act + ((((static_cast<long long>(b) * (p.T_out + 2) + t + 1) * KN::N_CHUNKS) * 2 + a) * KN::PP + pos) * 8;
+            };
 #pragma unroll
             for (int c8 = 0; c8 < 2; ++c8) {
               const int chunk = (ch0 >> 3) + c8;
@@ -568,15 +603,11 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
                 if (K::split) lo[e] = pack_bf16x2(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
               }
               const int idx = K::split ? 2 * chunk : chunk;
-              uint4* dst = reinterpret_cast<uint4*>(base + (static_cast<long long>(idx * 2 + (hp & 1)) * KN::PP + pos) * 8);
-              *dst = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              if (K::split) {
-                uint4* dl = reinterpret_cast<uint4*>(base + (static_cast<long long>((idx + 1) * 2 + (hp & 1)) * KN::PP + pos) * 8);
-                *dl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              }
+              *reinterpret_cast<uint4*>(out_ptr(idx * 2 + (hp & 1))) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              if (K::split) *reinterpret_cast<uint4*>(out_ptr((idx + 1) * 2 + (hp & 1))) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
           } else if (valid) {
-            float* dst = p.eo.emb + (static_cast<long long>(b) * p.T + t) * (K::N * kPlane) + ch0 * kPlane + r * kWo + wo;
+            float* dst = p.eo.emb + (static_cast<long long>(b) * p.T_out + t_out) * (K::N * kPlane) + ch0 * kPlane + r * kWo + wo;
 #pragma unroll
             for (int c = 0; c < 16; ++c) dst[c * kPlane] = o[c];
           }
@@ -616,18 +647,19 @@ static ConvKernel conv_kernel_for(int kind) {
   return nullptr;
 }
 template <int KIND>
-static void kind_traits(int* NT, int* acc, int* spu, int* pairs, int* arr16, int* wt, int* pp, int* nch) {
+static void kind_traits(int* NT, int* acc, int* spu, int* pairs, int* arr16, int* wt, int* pp, int* nch, int* tlen, int* titems) {
   using K = LayerKind<KIND>;
   *NT = K::NT; *acc = K::ACC; *spu = K::SPU; *pairs = K::PAIRS; *arr16 = K::ARR16; *wt = K::WT; *pp = K::PP; *nch = K::N_CHUNKS;
+  *tlen = K::tcat ? K::TCAT_LEN : 0; *titems = K::tcat ? K::TCAT_ITEMS : 0;
 }
-static void kind_traits_for(int kind, int* NT, int* acc, int* spu, int* pairs, int* arr16, int* wt, int* pp, int* nch) {
+static void kind_traits_for(int kind, int* NT, int* acc, int* spu, int* pairs, int* arr16, int* wt, int* pp, int* nch, int* tlen, int* titems) {
   switch (kind) {
-    case KIND_L1: return kind_traits<KIND_L1>(NT, acc, spu, pairs, arr16, wt, pp, nch);
-    case KIND_L2: return kind_traits<KIND_L2>(NT, acc, spu, pairs, arr16, wt, pp, nch);
-    case KIND_L3: return kind_traits<KIND_L3>(NT, acc, spu, pairs, arr16, wt, pp, nch);
-    case KIND_L1_SPLIT: return kind_traits<KIND_L1_SPLIT>(NT, acc, spu, pairs, arr16, wt, pp, nch);
-    case KIND_L2_SPLIT: return kind_traits<KIND_L2_SPLIT>(NT, acc, spu, pairs, arr16, wt, pp, nch);
-    default: return kind_traits<KIND_L3_SPLIT>(NT, acc, spu, pairs, arr16, wt, pp, nch);
+    case KIND_L1: return kind_traits<KIND_L1>(NT, acc, spu, pairs, arr16, wt, pp, nch, tlen, titems);
+    case KIND_L2: return kind_traits<KIND_L2>(NT, acc, spu, pairs, arr16, wt, pp, nch, tlen, titems);
+    case KIND_L3: return kind_traits<KIND_L3>(NT, acc, spu, pairs, arr16, wt, pp, nch, tlen, titems);
+    case KIND_L1_SPLIT: return kind_traits<KIND_L1_SPLIT>(NT, acc, spu, pairs, arr16, wt, pp, nch, tlen, titems);
+    case KIND_L2_SPLIT: return kind_traits<KIND_L2_SPLIT>(NT, acc, spu, pairs, arr16, wt, pp, nch, tlen, titems);
+    default: return kind_traits<KIND_L3_SPLIT>(NT, acc, spu, pairs, arr16, wt, pp, nch, tlen, titems);
   }
 }
 
@@ -695,8 +727,12 @@ unpack_act_kernel(const __nv_bfloat16* __restrict__ act, float* __restrict__ out
   const int hp = h + g.ph;
   const long long pos = g.pw + (hp >> 1) * g.Wt + w;
   const int chunk = c >> 3, nch = g.n_chunks;
-  const __nv_bfloat16* base = act + ((b * (T + 2) + t + 1) * nch) * 2 * static_cast<long long>(g.PP) * 8;
   const int i0 = split ? 2 * chunk : chunk;
+  if (g.tcat_len > 0) {  // [clip][chunk][parity][time-concatenated positions]
+    out[idx] = __bfloat162float(act[((b * nch * 2 + i0 * 2 + (hp & 1)) * g.tcat_len + static_cast<long long>(t + 1) * g.PP + pos) * 8 + (c & 7)]);
+    return;
+  }
+  const __nv_bfloat16* base = act + ((b * (T + 2) + t + 1) * nch) * 2 * static_cast<long long>(g.PP) * 8;
   float v = __bfloat162float(base[((static_cast<long long>(i0) * 2 + (hp & 1)) * g.PP + pos) * 8 + (c & 7)]);
   if (split) v += __bfloat162float(base[((static_cast<long long>(i0 + 1) * 2 + (hp & 1)) * g.PP + pos) * 8 + (c & 7)]);
   out[idx] = v;
@@ -726,7 +762,7 @@ static LayerCfg pick_cfg(const LayerGeom& g, int split) {
   // bf16 kinds: ring = LayerKind::RING plane slots (the plane ring of the kernel), not tunable
   if (g.Cin == 1) c = split ? LayerCfg{2, 2, 3, 4} : LayerCfg{4, 2, 4, 2};
   else if (g.Cout == 64) c = split ? LayerCfg{1, 2, 2, 2} : LayerCfg{2, 2, 3, 3};
-  else c = split ? LayerCfg{1, 1, 3, 2} : LayerCfg{2, 1, 3, 2};  // Cout = 96 (TMEM: 2 tiles x 2 accs x 96 columns, or 1 x 2 x 256 split)
+  else c = split ? LayerCfg{1, 1, 3, 2} : LayerCfg{2, 1, 2, 2};  // bf16: two unit slots of NT*128 + halo positions (time-concatenated tiling)  // Cout = 96 (TMEM: 2 tiles x 2 accs x 96 columns, or 1 x 2 x 256 split)
   // tuning overrides (experiments only; an over-large value fails the smem check in umma_layer_build)
   const char* tag = g.Cin == 1 ? "1" : (g.Cout == 64 ? "2" : "3");
   char name[32];
@@ -738,6 +774,13 @@ static LayerCfg pick_cfg(const LayerGeom& g, int split) {
 }
 
 int g_conv_dbg = 0;
+
+static int layer_kind(const LayerGeom& g, int split) {
+  if (g.Cin == 1 && g.Cout == 32 && g.KH == 5 && g.KW == 5) return split ? KIND_L1_SPLIT : KIND_L1;
+  if (g.Cin == 32 && g.Cout == 64 && g.KH == 5 && g.KW == 5) return split ? KIND_L2_SPLIT : KIND_L2;
+  if (g.Cin == 64 && g.Cout == 96 && g.KH == 3 && g.KW == 3) return split ? KIND_L3_SPLIT : KIND_L3;
+  return -1;
+}
 
 void geom_finalize(LayerGeom& g, int split) {
   g.ph = g.KH / 2;
@@ -755,19 +798,20 @@ void geom_finalize(LayerGeom& g, int split) {
   const int n_tilesets = cdiv(g.n_tiles, c.NT);
   const int extent = static_cast<int>(align_up(static_cast<size_t>(g.pw + g.Hh * g.Wt + (g.Cin == 1 ? 8 : 0)), 8));
   g.PP = (n_tilesets == 1) ? std::min(region_full, extent) : (n_tilesets - 1) * c.NT * 128 + region_full;
+  g.tcat_len = g.tcat_items = 0;
+  const int kind = layer_kind(g, split);
+  if (kind >= 0) {
+    int a, b2, c2, d, e, f, pp, nch;
+    kind_traits_for(kind, &a, &b2, &c2, &d, &e, &f, &pp, &nch, &g.tcat_len, &g.tcat_items);
+  }
 }
 
 size_t umma_act_bytes(const LayerGeom& g, int split, int B) {
   (void)split;
+  if (g.tcat_len > 0) return static_cast<size_t>(B) * g.n_chunks * 2 * g.tcat_len * 16;
   return static_cast<size_t>(B) * (AVS_T + 2) * g.n_chunks * 2 * g.PP * 16;
 }
 
-static int layer_kind(const LayerGeom& g, int split) {
-  if (g.Cin == 1 && g.Cout == 32 && g.KH == 5 && g.KW == 5) return split ? KIND_L1_SPLIT : KIND_L1;
-  if (g.Cin == 32 && g.Cout == 64 && g.KH == 5 && g.KW == 5) return split ? KIND_L2_SPLIT : KIND_L2;
-  if (g.Cin == 64 && g.Cout == 96 && g.KH == 3 && g.KW == 3) return split ? KIND_L3_SPLIT : KIND_L3;
-  return -1;
-}
 
 // Packs the weights in the order the compile-time schedule of the layer kind walks them (issue_stage_bf16 /
 // issue_stage_split above are the readers; keep the two in step).
@@ -780,14 +824,14 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
     return AVS_EINVAL;
   }
   const LayerCfg c = pick_cfg(g, split);
-  int kNT, kACC, kSPU, kPAIRS, kARR16, kWT, kPP, kNCH;
-  kind_traits_for(L->kind, &kNT, &kACC, &kSPU, &kPAIRS, &kARR16, &kWT, &kPP, &kNCH);
+  int kNT, kACC, kSPU, kPAIRS, kARR16, kWT, kPP, kNCH, kTLEN, kTITEMS;
+  kind_traits_for(L->kind, &kNT, &kACC, &kSPU, &kPAIRS, &kARR16, &kWT, &kPP, &kNCH, &kTLEN, &kTITEMS);
   L->NT = c.NT; L->NBUF = c.NBUF; L->ring = c.ring; L->wstages = c.wstages;
   L->acc_stride = kACC;
   const int halo = (g.Cin == 1) ? (g.KH / 2 + 1) * g.Wt + 8 : (g.KH / 2) * g.Wt + g.KW - 1;
   const int region_full = c.NT * 128 + halo;
   const int n_tilesets = cdiv(g.n_tiles, c.NT);
-  L->region_pos = (n_tilesets == 1) ? g.PP : region_full;
+  L->region_pos = (n_tilesets == 1 && kTLEN == 0) ? g.PP : region_full;
   if (L->region_pos != kARR16 || g.Wt != kWT || c.NT != kNT || g.PP != kPP || g.n_chunks != kNCH) {
     set_error("layer geometry (%dx%d input, row pitch %d, %d positions per run, %d tiles per item) is not the one the tcgen05 "
               "schedule was compiled for (%d, %d, %d)", g.H, g.W, g.Wt, L->region_pos, c.NT, kWT, kARR16, kNT);
@@ -836,7 +880,7 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
     }
     if (first) n_stages = 1;
     L->unit_planes = 1;
-    if (pairs != kPAIRS || L->ring != (first ? 4 : 3)) return AVS_EINVAL;
+    if (pairs != kPAIRS || L->ring != (first ? 4 : (kTLEN ? 2 : 3))) return AVS_EINVAL;
   } else {
     // ---- bf16x3: operands split hi/lo.  One B tile = [2 K-halves][N hi rows | N lo rows][8]: ONE MMA of width 2N
     // computes A_hi*B_hi and A_hi*B_lo with a single fetch of A (adjacent accumulator column blocks, added in
@@ -950,13 +994,19 @@ int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const Epi
   p.n_chunks = g.n_chunks; p.PP = g.PP; p.Wt = g.Wt; p.Ho = g.Ho; p.Wo = g.Wo; p.n_tiles = g.n_tiles;
   p.n_tilesets = cdiv(g.n_tiles, L.NT);
   p.T = AVS_T;
+  p.T_out = AVS_T;
   p.split = L.split;
   p.dbg = g_conv_dbg;
-  const long long items = static_cast<long long>(B) * AVS_T * p.n_tilesets;
+  if (g.tcat_len > 0) {  // items = consecutive NT-tile groups of the clip's time-concatenated position space
+    p.T = g.tcat_items;
+    p.n_tiles = L.NT;
+    p.n_tilesets = 1;
+  }
+  const long long items = static_cast<long long>(B) * p.T * p.n_tilesets;
   AVS_REQUIRE(items < (1LL << 31), "too many work items for one launch");
   p.n_items = static_cast<int>(items);
   p.plane_stride = static_cast<long long>(g.n_chunks) * 2 * g.PP * 8;
-  p.clip_stride = p.plane_stride * (AVS_T + 2);
+  p.clip_stride = g.tcat_len > 0 ? static_cast<long long>(g.n_chunks) * 2 * g.tcat_len * 8 : p.plane_stride * (AVS_T + 2);
   const int grid = static_cast<int>(std::min<long long>(items, n_sms));
   ProfScope ps(L.g.Cin == 1 ? PROF_CONV1 : (L.g.Cout == 64 ? PROF_CONV2 : PROF_CONV3), st);
   conv_kernel_for(L.kind)<<<grid, kConvThreads, L.smem_bytes, st>>>(p);

@@ -22,6 +22,8 @@ struct LayerGeom {
   int n_tiles;                    // ceil(n_q / 128)
   int PP;                         // positions per (plane, chunk, parity) array in HBM
   int n_chunks;                   // 16-byte chunk arrays per (plane, parity): Cin/8 (conv1: 1), x2 when split
+  int tcat_len;                   // > 0: time-concatenated layout [clip][chunk][parity][tcat_len positions] (conv3, bf16); PP = plane pitch
+  int tcat_items;                 // work items per clip in that layout
 };
 
 struct UmmaLayer {                // device-resident, built once by stcnn_create
