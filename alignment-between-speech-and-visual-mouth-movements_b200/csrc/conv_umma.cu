@@ -136,11 +136,11 @@ struct LayerKind {
   static constexpr int SPU = first ? 1 : KW;
   // bf16 kinds keep the three input planes of an item in a ring of three plane slots (slot = padded plane index % 3)
   // and load only the plane the previous item did not have; the split kinds (twice the bytes per plane) reload per item.
-  // conv3 (bf16) tiles the TIME-CONCATENATED position space: its input is stored [clip][chunk][parity][time plane][PITCH]
+  // conv3 tiles the TIME-CONCATENATED position space: its input is stored [clip][chunk][parity][time plane][PITCH]
   // positions, so a filter's time tap kd is one more position offset (kd * PITCH) and 128-position tiles run across plane
-  // boundaries: 1.44 tiles per 156-position plane instead of 2 (-28 % MMAs).  An item = NT consecutive tiles; its three A
-  // units are the kd-shifted regions of NT * 128 + HALO positions (sequential ring, no plane reuse).
-  static constexpr bool tcat = KIND == KIND_L3;
+  // boundaries: 1.44 tiles per 156-position plane instead of 2 (-28 % MMAs).  An item = NT consecutive tiles; its A units
+  // are the kd-shifted regions of NT * 128 + HALO positions (bf16x3: per channel half), sequential ring, no plane reuse.
+  static constexpr bool tcat = KIND == KIND_L3 || KIND == KIND_L3_SPLIT;
   static constexpr bool reuse = !split && !tcat;
   // conv1's items are a single stage, so a plane is only released when the whole item is done: a fourth slot lets the
   // next item's new plane load meanwhile (multi-stage kinds release an item's first plane after its first unit)
@@ -297,16 +297,21 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     ItemWalk w;
     w.init(p);
     if (K::tcat) {
-      // time-concatenated input: unit kd of item `it` is the region [it * NT*128 + kd * PITCH, + ARR16) of every (chunk, parity) array
+      // time-concatenated input: the unit (kd, channel group) of item `it` is the region [it * NT*128 + kd * PITCH, + ARR16)
+      // of the group's (chunk, parity) arrays
       uint32_t seq = 0, slot = 0, phase = 0;
-      constexpr uint32_t bytes = K::ARR16 * 16u, n_arrays = K::N_CHUNKS * 2u;
+      constexpr uint32_t bytes = K::ARR16 * 16u;
+      constexpr int UPK = K::split ? 2 : 1;                       // units per time tap: channel halves in the split kind
+      constexpr uint32_t n_arrays = K::N_CHUNKS * 2u / UPK;
       for (; w.valid(); w.next()) {
-        for (int kd = 0; kd < 3; ++kd, ++seq, slot = (slot + 1 == static_cast<uint32_t>(p.ring)) ? 0 : slot + 1, phase ^= (slot == 0)) {
+        for (int u = 0; u < 3 * UPK; ++u, ++seq, slot = (slot + 1 == static_cast<uint32_t>(p.ring)) ? 0 : slot + 1, phase ^= (slot == 0)) {
           if ((p.dbg & 2) && seq >= static_cast<uint32_t>(p.ring)) continue;
+          const int kd = u / UPK, cg = u % UPK;
           mbar_wait(&a_empty[slot], phase ^ 1);
           mbar_expect_tx(&a_full[slot], bytes * n_arrays);
           uint8_t* dst = s_units + static_cast<size_t>(slot) * p.unit_slot_bytes;
-          const __nv_bfloat16* src = p.act + w.b * p.clip_stride + static_cast<long long>(w.t * NT * 128 + kd * K::PITCH) * 8;
+          const __nv_bfloat16* src = p.act + w.b * p.clip_stride +
+                                     (static_cast<long long>(cg * n_arrays) * K::TCAT_LEN + w.t * NT * 128 + kd * K::PITCH) * 8;
           for (uint32_t c = 0; c < n_arrays; ++c, dst += bytes) bulk_g2s(dst, src + static_cast<long long>(c) * K::TCAT_LEN * 8, bytes, &a_full[slot]);
         }
       }
@@ -729,7 +734,10 @@ unpack_act_kernel(const __nv_bfloat16* __restrict__ act, float* __restrict__ out
   const int chunk = c >> 3, nch = g.n_chunks;
   const int i0 = split ? 2 * chunk : chunk;
   if (g.tcat_len > 0) {  // [clip][chunk][parity][time-concatenated positions]
-    out[idx] = __bfloat162float(act[((b * nch * 2 + i0 * 2 + (hp & 1)) * g.tcat_len + static_cast<long long>(t + 1) * g.PP + pos) * 8 + (c & 7)]);
+    const long long e0 = static_cast<long long>(t + 1) * g.PP + pos;
+    float v = __bfloat162float(act[((b * nch * 2 + i0 * 2 + (hp & 1)) * g.tcat_len + e0) * 8 + (c & 7)]);
+    if (split) v += __bfloat162float(act[((b * nch * 2 + (i0 + 1) * 2 + (hp & 1)) * g.tcat_len + e0) * 8 + (c & 7)]);
+    out[idx] = v;
     return;
   }
   const __nv_bfloat16* base = act + ((b * (T + 2) + t + 1) * nch) * 2 * static_cast<long long>(g.PP) * 8;
@@ -803,6 +811,7 @@ void geom_finalize(LayerGeom& g, int split) {
   if (kind >= 0) {
     int a, b2, c2, d, e, f, pp, nch;
     kind_traits_for(kind, &a, &b2, &c2, &d, &e, &f, &pp, &nch, &g.tcat_len, &g.tcat_items);
+    if (g.tcat_len > 0) g.PP = extent;  // plane pitch inside the time-concatenated arrays
   }
 }
 
