@@ -197,6 +197,19 @@ def test_stcnn_batch_independence(A, lipnet_sd, precision):
         assert torch.equal(net.stcnn(frames[i:i + 1])[0], full[i]), i
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_stcnn_run_to_run_and_batch_split_bit_identical(A, lipnet_sd, precision):
+    """Two MMA-issuing warps share the tensor core: the accumulation order must not depend on timing.  Same input twice,
+    and one batch against its halves (different work partition over the CTAs), bit for bit."""
+    frames = sweep_ref.synth_frames(24, seed=7).cuda()
+    net = make_lipnet(A, lipnet_sd, precision)
+    first = net.stcnn(frames)
+    for _ in range(3):
+        assert torch.equal(net.stcnn(frames), first)
+    halves = torch.cat([net.stcnn(frames[:11]), net.stcnn(frames[11:])])
+    assert torch.equal(halves, first)
+
+
 # ------------------------------------------------------------------------------------------ K3
 @pytest.mark.parametrize("precision,n_clips", [("fp32", 3), ("bf16x3", 3), ("bf16x3", 19)])
 def test_bigru_head_vs_oracle(A, lipnet_sd, precision, n_clips):
