@@ -1,5 +1,5 @@
 // K3 recurrence on the tensor cores (hidden = 256): the per-step mat-vec  gh[rows, clips] = W_hh[rows, :] . h[clips, :]^T
-// of one cluster CTA (96 gate rows of 32 hidden units, 16 clips) is 32 tcgen05.mma per step.
+// of one cluster CTA (96 gate rows of 32 hidden units, 16 or 32 clips) is 32 tcgen05.mma per step.
 //
 //   * W_hh slice resident in shared memory for the whole sequence, split hi/lo in bf16, in the K-major
 //     no-swizzle UMMA layout [k chunk][128 rows][8] (rows 96..127 are zero padding): the A operand.
@@ -11,17 +11,24 @@
 //     the CTA's 32 new hidden values go to all 8 CTAs' B operands as 16-byte DSMEM stores.
 // Cluster of 8 CTAs per (16 clips, direction), as in gru.cu's CUDA-core kernel (which remains the fp32 path).
 #include <stdlib.h>
+#include <algorithm>
 #include "common.cuh"
 #include "gru_umma.cuh"
 
 namespace avs {
 
-constexpr int kH = 256, kClu = 8, kClips = 16, kUnits = 32, kRows = 128, kChunks = kH / 8;
+constexpr int kH = 256, kClu = 8, kUnits = 32, kRows = 128, kChunks = kH / 8;
 constexpr int kABytes = kChunks * kRows * 16;             // one kind (hi or lo): 64 KB
-constexpr int kBBytes = kChunks * 2 * kClips * 16;        // one h buffer (hi + lo): 16 KB
-constexpr int kXsPitch = kClips + 1;
-constexpr int kStageBytes = 4 * 2 * kClips * 16;          // this CTA's 32 units (4 chunks) of h, hi + lo: 2 KB
-constexpr size_t kSmem = 2ull * kABytes + 2ull * kBBytes + kRows * kXsPitch * 4 + 2 * kStageBytes + 64;
+// CLIPS = clips per cluster (16 is what runs; the kernel also works with 32)
+template <int CLIPS>
+struct GruCfg {
+  static constexpr int kBBytes = kChunks * 2 * CLIPS * 16;      // one h buffer (hi + lo): 16 / 32 KB
+  static constexpr int kXsPitch = CLIPS + 1;
+  static constexpr int kStageBytes = 4 * 2 * CLIPS * 16;        // this CTA's 32 units (4 chunks) of h, hi + lo: 2 / 4 KB
+  static constexpr int kCpt = CLIPS / 8;                        // clips per thread (thread = (unit, warp's clips))
+  static constexpr int kTmemCols = 2 * CLIPS;                   // D = [W.h_hi | W.h_lo]
+  static constexpr size_t kSmem = 2ull * kABytes + 2ull * kBBytes + kRows * kXsPitch * 4 + 2 * kStageBytes + 64;
+};
 
 __device__ __forceinline__ uint32_t cta_rank() {
   uint32_t r;
@@ -47,13 +54,16 @@ __device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster_addr, const void* 
 // complete on the RECEIVER's mbarrier bar_h[buffer] (8 x 2 KB per step), so the tensor core only ever reads
 // operand bytes written through the async proxy.  Buffer reuse is safe by data dependence: a CTA can start
 // step s+1 only after every peer delivered h(s), which each peer sends after its own step-s MMAs finished.
+template <int CLIPS>
 __global__ void __launch_bounds__(256, 1)
 gru_cluster_umma_kernel(const float* __restrict__ xp, const __nv_bfloat16* __restrict__ wp, const float* __restrict__ b_hh,
                         float* __restrict__ out, int B, int T) {
+  using C = GruCfg<CLIPS>;
+  constexpr int kBBytes = C::kBBytes, kXsPitch = C::kXsPitch, kStageBytes = C::kStageBytes, kCpt = C::kCpt;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_a = smem;                                               // [hi|lo][chunk][row][16 B]
   uint8_t* s_b = s_a + 2 * kABytes;                                  // [2 buffers][chunk][hi|lo][clip][16 B]
-  float* s_x = reinterpret_cast<float*>(s_b + 2 * kBBytes);          // [128 rows][17]
+  float* s_x = reinterpret_cast<float*>(s_b + 2 * kBBytes);          // [128 rows][CLIPS + 1]
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_x + kRows * kXsPitch);  // [2][this CTA's 4 chunks: chunk][hi|lo][clip][16 B]
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_stage + 2 * kStageBytes);
   uint64_t* bar_mma = bar_w + 1;
@@ -64,9 +74,9 @@ gru_cluster_umma_kernel(const float* __restrict__ xp, const __nv_bfloat16* __res
   const uint32_t rank = cta_rank();
   const int dir = blockIdx.y, group = blockIdx.x / kClu;
   const int J = rank * kUnits + lane;
-  const int n_valid = min(kClips, B - group * kClips);
-  const int c0 = 2 * warp, c1 = c0 + 1;
-  const int b0 = group * kClips + c0, b1 = b0 + 1;
+  const int n_valid = min(CLIPS, B - group * CLIPS);
+  const int c0 = kCpt * warp;                 // this thread's clips inside the group: c0 .. c0 + kCpt - 1
+  const int b0 = group * CLIPS + c0;
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
@@ -75,7 +85,7 @@ gru_cluster_umma_kernel(const float* __restrict__ xp, const __nv_bfloat16* __res
     mbar_init(&bar_h[1], 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<32>(s_tmem);  // a warp that has not diverged: tcgen05.alloc is .sync.aligned
+  if (warp == 1) tmem_alloc<C::kTmemCols>(s_tmem);  // a warp that has not diverged: tcgen05.alloc is .sync.aligned
   for (int i = tid; i < kBBytes / 16; i += 256) reinterpret_cast<uint4*>(s_b)[i] = make_uint4(0, 0, 0, 0);  // h(-1) = 0 in buffer 0
   fence_proxy_async();  // generic-proxy zero fill, async-proxy (tcgen05.mma) reader
   tc_fence_before();
@@ -89,7 +99,9 @@ gru_cluster_umma_kernel(const float* __restrict__ xp, const __nv_bfloat16* __res
     mbar_expect_tx(&bar_h[1], kBBytes);
   }
   const float br = b_hh[dir * 3 * kH + J], bz = b_hh[dir * 3 * kH + kH + J], bn = b_hh[dir * 3 * kH + 2 * kH + J];
-  float h0 = 0.f, h1 = 0.f;
+  float h[kCpt];
+#pragma unroll
+  for (int k = 0; k < kCpt; ++k) h[k] = 0.f;
   mbar_wait(bar_w, 0);
   // all CTAs of the cluster have initialised their barriers and buffers before anyone sends
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -99,83 +111,92 @@ gru_cluster_umma_kernel(const float* __restrict__ xp, const __nv_bfloat16* __res
   // The descriptor's start-address field is 14 bits of (address >> 4): mask, or the rank lands in the LBO field.
   const uint32_t a_lo32 = (smem_u32(s_a) & 0x3FFFFu) >> 4, b_lo32 = (smem_u32(s_b) & 0x3FFFFu) >> 4;
   constexpr uint64_t kHi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;  // SBO 128 B, descriptor version 1
-  constexpr uint32_t kLboA = ((kRows * 16) >> 4) << 16, kLboB = ((2 * kClips * 16) >> 4) << 16;
-  const uint32_t idesc_w = umma_idesc_bf16(128, 2 * kClips);
+  constexpr uint32_t kLboA = ((kRows * 16) >> 4) << 16, kLboB = ((2 * CLIPS * 16) >> 4) << 16;
+  const uint32_t idesc_w = umma_idesc_bf16(128, 2 * CLIPS);
   uint32_t h_phase[2] = {0, 0};
 
   for (int s = 0; s < T; ++s) {
     const int t = dir ? T - 1 - s : s;
     const int cur = s & 1;
-    // ---- mat-vec on the tensor core: D[row, 0:16] = (W_hi + W_lo).h_hi, D[row, 16:32] = (W_hi + W_lo).h_lo
-    if (tid == 0) {
+    // ---- mat-vec on the tensor core: D[row, 0:CLIPS] = (W_hi + W_lo).h_hi, D[row, CLIPS:2 CLIPS] = (W_hi + W_lo).h_lo
+    if (warp == 0) {  // converged warp, one elected lane issues: a tcgen05.mma inside a divergent branch costs ~49 instead of 40 cycles
       if (s > 0) {  // h(t-1) from all 8 CTAs has landed in buffer `cur`
         mbar_wait(&bar_h[cur], h_phase[cur]);
         h_phase[cur] ^= 1;
       }
-      if (s + 2 < T) mbar_expect_tx(&bar_h[cur], kBBytes);  // next tenant of this buffer: h(t+1), sent during step s+1
       tc_fence_after();
-      const uint32_t bb = b_lo32 + cur * (kBBytes >> 4);
+      if (elect_one()) {
+        if (s + 2 < T) mbar_expect_tx(&bar_h[cur], kBBytes);  // next tenant of this buffer: h(t+1), sent during step s+1
+        const uint32_t bb = b_lo32 + cur * (kBBytes >> 4);
 #pragma unroll
-      for (int j = 0; j < kChunks / 2; ++j) {
-        const uint32_t a_hi = a_lo32 + (2 * j) * (kRows * 16 >> 4), a_lo = a_hi + (kABytes >> 4);
-        const uint32_t bj = bb + (2 * j) * (2 * kClips * 16 >> 4);
-        umma_f16(tmem_d, kHi | kLboA | a_hi, kHi | kLboB | bj, idesc_w, j != 0 ? 1u : 0u);
-        umma_f16(tmem_d, kHi | kLboA | a_lo, kHi | kLboB | bj, idesc_w, 1u);  // also adds the tiny W_lo.h_lo term
+        for (int j = 0; j < kChunks / 2; ++j) {
+          const uint32_t a_hi = a_lo32 + (2 * j) * (kRows * 16 >> 4), a_lo = a_hi + (kABytes >> 4);
+          const uint32_t bj = bb + (2 * j) * (2 * CLIPS * 16 >> 4);
+          umma_f16(tmem_d, kHi | kLboA | a_hi, kHi | kLboB | bj, idesc_w, j != 0 ? 1u : 0u);
+          umma_f16(tmem_d, kHi | kLboA | a_lo, kHi | kLboB | bj, idesc_w, 1u);  // also adds the tiny W_lo.h_lo term
+        }
+        tc_commit(bar_mma);
       }
-      tc_commit(bar_mma);
+      __syncwarp();
     }
     // input-projection terms: their latency hides behind the MMAs
-    float gi0[3] = {0.f, 0.f, 0.f}, gi1[3] = {0.f, 0.f, 0.f};
-    if (b0 < B) {
-      const float* g = xp + (static_cast<size_t>(b0) * T + t) * 6 * kH + dir * 3 * kH + J;
-      gi0[0] = g[0]; gi0[1] = g[kH]; gi0[2] = g[2 * kH];
-    }
-    if (b1 < B) {
-      const float* g = xp + (static_cast<size_t>(b1) * T + t) * 6 * kH + dir * 3 * kH + J;
-      gi1[0] = g[0]; gi1[1] = g[kH]; gi1[2] = g[2 * kH];
+    float gi[kCpt][3];
+#pragma unroll
+    for (int k = 0; k < kCpt; ++k) {
+      gi[k][0] = gi[k][1] = gi[k][2] = 0.f;
+      if (b0 + k < B) {
+        const float* g = xp + (static_cast<size_t>(b0 + k) * T + t) * 6 * kH + dir * 3 * kH + J;
+        gi[k][0] = g[0]; gi[k][1] = g[kH]; gi[k][2] = g[2 * kH];
+      }
     }
     if (warp < 4) {  // lane of TMEM = gate row (gate * 32 + unit); rows >= 96 are padding
       mbar_wait(bar_mma, s & 1);
       __syncwarp();  // lane 0 issued the MMAs and arrives late: tcgen05.ld is .aligned and needs the warp converged
       tc_fence_after();
-      uint32_t v[32];
-      tmem_ld32(tmem_d + (static_cast<uint32_t>(warp * 32) << 16), v);
-      tmem_ld_wait();
       float* xr = s_x + (warp * 32 + lane) * kXsPitch;
+      const uint32_t trow = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
+      if (CLIPS == 16) {
+        uint32_t v[32];
+        tmem_ld32(trow, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < kClips; ++c) xr[c] = __uint_as_float(v[c]) + __uint_as_float(v[kClips + c]);
+        for (int c = 0; c < 16; ++c) xr[c] = __uint_as_float(v[c]) + __uint_as_float(v[16 + c]);
+      } else {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(trow, v0);
+        tmem_ld32(trow + 32, v1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) xr[c] = __uint_as_float(v0[c]) + __uint_as_float(v1[c]);
+      }
       tc_fence_before();
     }
     __syncthreads();
-    // ---- gates: thread = (unit, clips c0 / c1)
-    if (c0 < n_valid) {
-      {
-        const float r = 1.f / (1.f + expf(-(gi0[0] + s_x[(0 * kUnits + lane) * kXsPitch + c0] + br)));
-        const float z = 1.f / (1.f + expf(-(gi0[1] + s_x[(1 * kUnits + lane) * kXsPitch + c0] + bz)));
-        const float n = tanhf(gi0[2] + r * (s_x[(2 * kUnits + lane) * kXsPitch + c0] + bn));
-        h0 = (1.f - z) * n + z * h0;
-        out[(static_cast<size_t>(b0) * T + t) * 2 * kH + dir * kH + J] = h0;
-      }
-      if (c1 < n_valid) {
-        const float r = 1.f / (1.f + expf(-(gi1[0] + s_x[(0 * kUnits + lane) * kXsPitch + c1] + br)));
-        const float z = 1.f / (1.f + expf(-(gi1[1] + s_x[(1 * kUnits + lane) * kXsPitch + c1] + bz)));
-        const float n = tanhf(gi1[2] + r * (s_x[(2 * kUnits + lane) * kXsPitch + c1] + bn));
-        h1 = (1.f - z) * n + z * h1;
-        out[(static_cast<size_t>(b1) * T + t) * 2 * kH + dir * kH + J] = h1;
+    // ---- gates: thread = (unit, the warp's kCpt clips)
+#pragma unroll
+    for (int k = 0; k < kCpt; ++k) {
+      if (c0 + k < n_valid) {
+        const int c = c0 + k;
+        const float r = 1.f / (1.f + expf(-(gi[k][0] + s_x[(0 * kUnits + lane) * kXsPitch + c] + br)));
+        const float z = 1.f / (1.f + expf(-(gi[k][1] + s_x[(1 * kUnits + lane) * kXsPitch + c] + bz)));
+        const float n = tanhf(gi[k][2] + r * (s_x[(2 * kUnits + lane) * kXsPitch + c] + bn));
+        h[k] = (1.f - z) * n + z * h[k];
+        out[(static_cast<size_t>(b0 + k) * T + t) * 2 * kH + dir * kH + J] = h[k];
       }
     }
     if (s + 1 < T) {
       // this CTA's 32 units of h(t), split hi/lo, staged in operand layout [chunk (4)][hi|lo][clip][8] ...
       uint8_t* stage = s_stage + cur * kStageBytes;
-      const __nv_bfloat16 h0h = __float2bfloat16_rn(h0), h1h = __float2bfloat16_rn(h1);
-      __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(stage) + (lane >> 3) * (2 * kClips * 8) + (lane & 7);
-      st[c0 * 8] = h0h;
-      st[c1 * 8] = h1h;
-      st[kClips * 8 + c0 * 8] = __float2bfloat16_rn(h0 - __bfloat162float(h0h));
-      st[kClips * 8 + c1 * 8] = __float2bfloat16_rn(h1 - __bfloat162float(h1h));
+      __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(stage) + (lane >> 3) * (2 * CLIPS * 8) + (lane & 7);
+#pragma unroll
+      for (int k = 0; k < kCpt; ++k) {
+        const __nv_bfloat16 hh = __float2bfloat16_rn(h[k]);
+        st[(c0 + k) * 8] = hh;
+        st[CLIPS * 8 + (c0 + k) * 8] = __float2bfloat16_rn(h[k] - __bfloat162float(hh));
+      }
       fence_proxy_async();  // staged with generic stores, read by the bulk-copy engine
       __syncthreads();
-      // ... and pushed to chunks [4 rank, 4 rank + 4) of every CTA's next buffer: one 2 KB bulk copy per CTA
+      // ... and pushed to chunks [4 rank, 4 rank + 4) of every CTA's next buffer: one bulk copy per CTA
       if (tid < kClu) {
         const uint32_t dst_off = static_cast<uint32_t>((cur ^ 1) * kBBytes + rank * kStageBytes);
         bulk_s2c(map_to_rank(smem_u32(s_b) + dst_off, tid), stage, kStageBytes, map_to_rank(smem_u32(&bar_h[cur ^ 1]), tid));
@@ -190,7 +211,7 @@ gru_cluster_umma_kernel(const float* __restrict__ xp, const __nv_bfloat16* __res
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc<32>(tmem_d);
+    tmem_dealloc<C::kTmemCols>(tmem_d);
   }
 }
 
@@ -226,21 +247,30 @@ int gru_pack_whh(const float* w_hh, __nv_bfloat16* out, cudaStream_t st) {
   return AVS_OK;
 }
 
-int gru_recurrence_umma(const float* xp, const __nv_bfloat16* w_packed, const float* b_hh, float* out, int B, int T,
-                        cudaStream_t st) {
+template <int CLIPS>
+static int launch_recurrence(const float* xp, const __nv_bfloat16* w_packed, const float* b_hh, float* out, int B, int T,
+                             cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(kClu * cdiv(B, kClips), 2, 1);
+  cfg.gridDim = dim3(kClu * cdiv(B, CLIPS), 2, 1);
   cfg.blockDim = dim3(256, 1, 1);
-  cfg.dynamicSmemBytes = kSmem;
+  cfg.dynamicSmemBytes = GruCfg<CLIPS>::kSmem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kClu; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  AVS_CUDA(cudaFuncSetAttribute(gru_cluster_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem)));
-  AVS_CUDA(cudaLaunchKernelEx(&cfg, gru_cluster_umma_kernel, xp, w_packed, b_hh, out, B, T));
+  AVS_CUDA(cudaFuncSetAttribute(gru_cluster_umma_kernel<CLIPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(GruCfg<CLIPS>::kSmem)));
+  AVS_CUDA(cudaLaunchKernelEx(&cfg, gru_cluster_umma_kernel<CLIPS>, xp, w_packed, b_hh, out, B, T));
   AVS_LAUNCHED();
   return AVS_OK;
+}
+
+int gru_recurrence_umma(const float* xp, const __nv_bfloat16* w_packed, const float* b_hh, float* out, int B, int T,
+                        cudaStream_t st) {
+  // 16 clips per cluster.  32 (half the clusters: one wave instead of two at 256 clips) was measured too: its step takes
+  // 7.6 us against 4.2, so it only breaks even — the step is gate- and exchange-bound, not MMA-bound.
+  return launch_recurrence<16>(xp, w_packed, b_hh, out, B, T, st);
 }
 
 }  // namespace avs
