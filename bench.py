@@ -89,31 +89,6 @@ class ClockSampler:
                 "power_w_max": max(float(r[3]) for r in rows), "reasons": reasons}
 
 
-def bind_to_gpu_numa_node(local_rank: int):
-    """One process per GPU: keep this rank's threads — and with them the first-touch placement of its pinned host
-    buffers — on the NUMA node the GPU's PCIe root hangs off, so that eight ranks streaming frames do not all pull
-    through one socket's memory controllers and the inter-socket link.  Best effort: any failure leaves the default."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
-        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
-        if len(bus.split(":")[0]) == 8:      # nvml pads the PCI domain to 8 hex digits, sysfs uses 4
-            bus = bus[4:]
-        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
-            cpus = set()
-            for part in f.read().strip().split(","):
-                lo, _, hi = part.partition("-")
-                cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return len(cpus)
-    except Exception:
-        pass
-    return 0
-
-
 def synth_inputs(n: int, seed: int):
     """Pinned host tensors: frames [n,1,75,50,100] ~ U[0,1), audio [n,48000] ~ N(0,0.1^2) clipped, with a
     per-clip random amplitude envelope so shifted versions differ."""
@@ -207,8 +182,6 @@ def main():
     import avsync_b200 as A
 
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        bind_to_gpu_numa_node(local_rank)
     A._native.device_check()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
