@@ -59,8 +59,10 @@ extern "C" int avs_prof_read(int slot, double* total_ms, int* count) {
   return AVS_OK;
 }
 
+#ifdef AVS_EXPERIMENTS
 namespace avs { extern int g_conv_dbg; }
 extern "C" void avs_debug_set(int flags) { avs::g_conv_dbg = flags; }
+#endif
 
 extern "C" int avs_conv_item_span(int n_clips, int n_steps, int n_tiles, int tiles_per_item, int n_ctas, int cta, int* first,
                                   int* last) {
@@ -71,13 +73,17 @@ extern "C" int avs_conv_item_span(int n_clips, int n_steps, int n_tiles, int til
 }
 
 extern "C" int avs_version(void) { return AVS_VERSION; }
+static const char kSourceHash[] =
+#include "build_src_hash.inc"
+    ;
+extern "C" const char* avs_source_hash(void) { return kSourceHash; }
 extern "C" const char* avs_last_error_string(void) { return avs::g_err; }
 extern "C" long long avs_launch_count(void) { return avs::g_launches; }
 
 extern "C" int avs_device_check(int device) {
-  cudaDeviceProp prop;
+  cudaDeviceProp prop;  // (callers cache the verdict per device: cudaGetDeviceProperties is slow)
   AVS_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) {
+  if (prop.major != 10 || prop.minor != 0) {  // the cubin is sm_100a: no other 10.x part can run it
     avs::set_error("device %d is sm_%d%d; libavsync_b200 is built for sm_100a only and has no fallback", device,
                    prop.major, prop.minor);
     return AVS_EARCH;

@@ -39,6 +39,14 @@
 
 namespace avs {
 
+// Experiment switches exist only in the tools build (make EXPERIMENTS=1 -> libavsync_b200_exp.so): in the product
+// library AVS_DBG is the literal 0 and every switch below is dead code the compiler removes.
+#ifdef AVS_EXPERIMENTS
+#define AVS_DBG(p) ((p).dbg)
+#else
+#define AVS_DBG(p) 0
+#endif
+
 constexpr int kConvThreads = 384;  // 4 control warps + 2 epilogue groups of 4 warps
 constexpr int kMaxUnits = 6;
 constexpr int kMaxRing = 4;
@@ -63,7 +71,7 @@ struct ConvKernelParams {
   int T_out;                    // time steps of the clip (75)
   // experiment switches (avs_debug_set): 1 = weights loaded once, 2 = A planes loaded once, 4 = epilogue off, 8 = every
   // MMA issued twice, 16 = clock64 split of the issuer warps (printf), 32 = epilogue reads TMEM only, 64 = epilogue without stores
-  int dbg;
+  int dbg;                      // only read when built with -DAVS_EXPERIMENTS (tools/); the product build folds it to 0
   long long clip_stride, plane_stride;  // elements (bf16) between clips / time planes of `act`
 };
 
@@ -305,7 +313,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       constexpr uint32_t n_arrays = K::N_CHUNKS * 2u / UPK;
       for (; w.valid(); w.next()) {
         for (int u = 0; u < 3 * UPK; ++u, ++seq, slot = (slot + 1 == static_cast<uint32_t>(p.ring)) ? 0 : slot + 1, phase ^= (slot == 0)) {
-          if ((p.dbg & 2) && seq >= static_cast<uint32_t>(p.ring)) continue;
+          if ((AVS_DBG(p) & 2) && seq >= static_cast<uint32_t>(p.ring)) continue;
           const int kd = u / UPK, cg = u % UPK;
           mbar_wait(&a_empty[slot], phase ^ 1);
           mbar_expect_tx(&a_full[slot], bytes * n_arrays);
@@ -321,7 +329,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       uint32_t fill_parity = 0;  // bit s: number of fills of slot s so far, mod 2
       const uint32_t n_arrays = static_cast<uint32_t>(p.n_chunks) * 2u;
       for (; w.valid(); w.next()) {
-        if ((p.dbg & 2) && w.item > w.first) continue;
+        if ((AVS_DBG(p) & 2) && w.item > w.first) continue;
         const int q0 = w.ts * p.NT * 128;
         const uint32_t bytes = static_cast<uint32_t>(min(p.region_pos, p.PP - q0)) * 16u;
         for (int kd = w.continues_prev() ? 2 : 0; kd < 3; ++kd) {
@@ -342,7 +350,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         const int q0 = w.ts * p.NT * 128;
         const int len = min(p.region_pos, p.PP - q0);  // positions per (chunk, parity) run
         for (int u = 0; u < p.n_units; ++u, ++seq, slot = (slot + 1 == static_cast<uint32_t>(p.ring)) ? 0 : slot + 1, phase ^= (slot == 0)) {
-          if ((p.dbg & 2) && seq >= static_cast<uint32_t>(p.ring)) continue;
+          if ((AVS_DBG(p) & 2) && seq >= static_cast<uint32_t>(p.ring)) continue;
           mbar_wait(&a_empty[slot], phase ^ 1);
           const UnitDesc ud = p.units[u];
           const uint32_t bytes = static_cast<uint32_t>(len) * 16u;
@@ -364,7 +372,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     w.init(p);
     for (; w.valid(); w.next()) {
       for (int s = 0; s < p.n_stages; ++s, ++seq, slot = (slot + 1 == static_cast<uint32_t>(p.wstages)) ? 0 : slot + 1, phase ^= (slot == 0)) {
-        if ((p.dbg & 1) && seq >= static_cast<uint32_t>(p.wstages)) continue;
+        if ((AVS_DBG(p) & 1) && seq >= static_cast<uint32_t>(p.wstages)) continue;
         mbar_wait(&w_empty[slot], phase ^ 1);
         mbar_expect_tx(&w_full[slot], p.stage_bytes);
         bulk_g2s(s_w + static_cast<size_t>(slot) * p.stage_bytes,
@@ -388,7 +396,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     // parity, the second kh of the pair); B = the other K half of the tile
     const uint32_t lbo_a = (K::first ? Wt : (K::split ? 4u : 2u) * arr16) << 16;
     constexpr uint32_t lbo_b = static_cast<uint32_t>(K::split ? 2 * K::N : K::NROW * K::N) << 16;
-    const int n_stages = p.n_stages, n_tiles = p.n_tiles, dbg = p.dbg;
+    const int n_stages = p.n_stages, n_tiles = p.n_tiles, dbg = AVS_DBG(p);
     uint32_t a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0, acc_buf = 0, acc_phase = 0;
     uint32_t a_loaded = 0, w_loaded = 0;  // only used by the dbg switches
     uint32_t g = 0, turn_phase = 0;
@@ -535,7 +543,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       __syncwarp();  // tcgen05.ld below is .aligned
       tc_fence_after();
       const uint32_t d_base = tmem_base + buf * (NT * 2 * K::ACC) + (static_cast<uint32_t>(q * 32) << 16);
-      for (int i = 0; i < ((p.dbg & 4) ? 0 : nt); ++i) {
+      for (int i = 0; i < ((AVS_DBG(p) & 4) ? 0 : nt); ++i) {
         int Q = (ts * NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
         int t_out = t;
         if (K::tcat) {  // time-concatenated position space: item index -> (time step, position in its plane)
@@ -563,7 +571,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
             bias[c4 * 4 + 0] = bv.x; bias[c4 * 4 + 1] = bv.y; bias[c4 * 4 + 2] = bv.z; bias[c4 * 4 + 3] = bv.w;
           }
           tmem_ld_wait();
-          if ((p.dbg & 32) && v0[0] != 0x7fc12345u) continue;  // experiment: TMEM reads only
+          if ((AVS_DBG(p) & 32) && v0[0] != 0x7fc12345u) continue;  // experiment: TMEM reads only
           if (K::split) {  // second column block: A_hi * B_lo, the small term, added last
             uint32_t u0[32], u1[32];
             tmem_ld32(d_base + (i * 2 + 0) * K::ACC + K::N + cb, u0);
@@ -585,7 +593,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
             const float got = __shfl_xor_sync(0xffffffffu, half ? lo : hi, 1);
             o[c] = fmaxf(fmaxf(half ? hi : lo, got) + bias[c], 0.f);
           }
-          if ((p.dbg & 64) && o[0] != 12345.678f) continue;  // experiment: no stores
+          if ((AVS_DBG(p) & 64) && o[0] != 12345.678f) continue;  // experiment: no stores
           if (valid && !kToEmb) {
             // the NEXT layer's parity-plane layout (its geometry is a compile-time property of the kind)
             const int hp = r + KN::KH / 2;
@@ -633,10 +641,12 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   }
 }
 
+#ifdef AVS_EXPERIMENTS
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v && *v ? atoi(v) : dflt;
 }
+#endif
 
 using ConvKernel = void (*)(const ConvKernelParams);
 // (tiles per item, K-steps per weight stage) of the six layer x precision configurations
@@ -669,31 +679,49 @@ static void kind_traits_for(int kind, int* NT, int* acc, int* spu, int* pairs, i
 }
 
 // ------------------------------------------------------------------------------------------------ layout kernels
-// frames f32 [B,1,T,H,W] -> layer-1 input: X8 layout, position p holds the 8 consecutive padded-row values
+// frames [B,1,T,H,W] (f32 as the reference passes them, or the u8 pixels they were made from: dataset.py:226-231,
+// value = float32(u8 / 255.0)) -> layer-1 input: X8 layout, position p holds the 8 consecutive padded-row values
 // val(p) .. val(p+7) (so the kw taps are the K index of the MMA).  One CTA per (clip, tp, parity): the
 // flattened padded parity array is staged in shared memory as bf16 (hi and lo residual) with coalesced
-// row loads, then every thread emits 16-byte X8 entries for consecutive positions.
+// row loads, then every thread emits 16-byte X8 entries for consecutive positions.  The u8 variant converts through
+// a 256-entry table of (bf16 hi, bf16 lo) built from the same double division, so both variants write the same bits
+// for frames that came from 8-bit pixels.
+template <typename TIn>
 __global__ void __launch_bounds__(256)
-pack_frames_kernel(const float* __restrict__ frames, __nv_bfloat16* __restrict__ act, LayerGeom g, int split, int T) {
+pack_frames_kernel(const TIn* __restrict__ frames, __nv_bfloat16* __restrict__ act, LayerGeom g, int split, int T) {
   extern __shared__ uint16_t s_val[];           // [2][PP + 8]: hi, lo
+  __shared__ uint32_t s_lut[256];               // u8 variant: bf16 hi | bf16 lo << 16 of float32(v / 255.0)
+  constexpr bool kU8 = sizeof(TIn) == 1;
   const int n = g.PP + 8;
   uint16_t* s_hi = s_val;
   uint16_t* s_lo = s_val + n;
   const int par = blockIdx.x & 1, tp = (blockIdx.x >> 1) % (T + 2);
   const long long b = (blockIdx.x >> 1) / (T + 2);
   for (int i = threadIdx.x; i < 2 * n; i += 256) s_val[i] = 0;
+  if (kU8) {
+    const float v = static_cast<float>(static_cast<double>(threadIdx.x) / 255.0);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    s_lut[threadIdx.x] = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) |
+                         (static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hi)))) << 16);
+  }
   __syncthreads();
   if (tp >= 1 && tp <= T) {
-    const float* f = frames + (b * T + (tp - 1)) * static_cast<long long>(g.H) * g.W;
+    const TIn* f = frames + (b * T + (tp - 1)) * static_cast<long long>(g.H) * g.W;
     for (int i = threadIdx.x; i < g.Hh * g.W; i += 256) {
       const int row = i / g.W, wq = i - row * g.W;
       const int h = 2 * row + par - g.ph;
       if (h >= 0 && h < g.H) {
-        const float v = f[h * g.W + wq];
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const int pos = g.pw + row * g.Wt + wq;
-        s_hi[pos] = __bfloat16_as_ushort(hi);
-        s_lo[pos] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hi)));
+        if constexpr (kU8) {
+          const uint32_t e = s_lut[f[h * g.W + wq]];
+          s_hi[pos] = static_cast<uint16_t>(e);
+          s_lo[pos] = static_cast<uint16_t>(e >> 16);
+        } else {
+          const float v = f[h * g.W + wq];
+          const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+          s_hi[pos] = __bfloat16_as_ushort(hi);
+          s_lo[pos] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hi)));
+        }
       }
     }
   }
@@ -771,17 +799,21 @@ static LayerCfg pick_cfg(const LayerGeom& g, int split) {
   if (g.Cin == 1) c = split ? LayerCfg{2, 2, 3, 4} : LayerCfg{4, 2, 4, 2};
   else if (g.Cout == 64) c = split ? LayerCfg{1, 2, 2, 2} : LayerCfg{2, 2, 3, 3};
   else c = split ? LayerCfg{1, 1, 3, 2} : LayerCfg{2, 1, 2, 2};  // bf16: two unit slots of NT*128 + halo positions (time-concatenated tiling)  // Cout = 96 (TMEM: 2 tiles x 2 accs x 96 columns, or 1 x 2 x 256 split)
-  // tuning overrides (experiments only; an over-large value fails the smem check in umma_layer_build)
+#ifdef AVS_EXPERIMENTS
+  // tuning overrides (tools build only; an over-large value fails the smem check in umma_layer_build)
   const char* tag = g.Cin == 1 ? "1" : (g.Cout == 64 ? "2" : "3");
   char name[32];
   snprintf(name, sizeof(name), "AVS_CONV%s_WSTAGES", tag);
   c.wstages = env_int(name, c.wstages);
   snprintf(name, sizeof(name), "AVS_CONV%s_RING", tag);
   if (split) c.ring = env_int(name, c.ring);
+#endif
   return c;
 }
 
+#ifdef AVS_EXPERIMENTS
 int g_conv_dbg = 0;
+#endif
 
 static int layer_kind(const LayerGeom& g, int split) {
   if (g.Cin == 1 && g.Cout == 32 && g.KH == 5 && g.KW == 5) return split ? KIND_L1_SPLIT : KIND_L1;
@@ -970,10 +1002,12 @@ void umma_layer_free(UmmaLayer* L) {
   L->d_w = nullptr; L->d_bias = nullptr;
 }
 
-int umma_pack_frames(const float* frames, __nv_bfloat16* act, const LayerGeom& g, int split, int B, cudaStream_t st) {
+int umma_pack_frames(const void* frames, bool frames_u8, __nv_bfloat16* act, const LayerGeom& g, int split, int B, cudaStream_t st) {
   ProfScope ps(PROF_PACK, st);
   const size_t sm = static_cast<size_t>(2) * (g.PP + 8) * sizeof(uint16_t);
-  pack_frames_kernel<<<static_cast<unsigned>(B) * (AVS_T + 2) * 2, 256, sm, st>>>(frames, act, g, split, AVS_T);
+  const unsigned grid = static_cast<unsigned>(B) * (AVS_T + 2) * 2;
+  if (frames_u8) pack_frames_kernel<uint8_t><<<grid, 256, sm, st>>>(static_cast<const uint8_t*>(frames), act, g, split, AVS_T);
+  else pack_frames_kernel<float><<<grid, 256, sm, st>>>(static_cast<const float*>(frames), act, g, split, AVS_T);
   AVS_LAUNCHED();
   return AVS_OK;
 }
@@ -1005,7 +1039,9 @@ int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const Epi
   p.T = AVS_T;
   p.T_out = AVS_T;
   p.split = L.split;
+#ifdef AVS_EXPERIMENTS
   p.dbg = g_conv_dbg;
+#endif
   if (g.tcat_len > 0) {  // items = consecutive NT-tile groups of the clip's time-concatenated position space
     p.T = g.tcat_items;
     p.n_tiles = L.NT;

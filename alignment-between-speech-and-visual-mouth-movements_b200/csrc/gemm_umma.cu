@@ -196,11 +196,8 @@ int gemm_pack(const float* x, int ld, int rows, int K, int tile, __nv_bfloat16* 
 int gemm_umma_nt(const __nv_bfloat16* a_packed, const __nv_bfloat16* w_packed, const float* bias, float* c, int ldc, int M,
                  int N, int K, int n_sms, cudaStream_t st) {
   AVS_REQUIRE(K % kGK == 0 && ldc % 4 == 0 && N % 4 == 0, "gemm_umma_nt shape");
-  static bool attr_set = false;
-  if (!attr_set) {
-    AVS_CUDA(cudaFuncSetAttribute(gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem)));
-    attr_set = true;
-  }
+  // per-device attribute: set on every call (cheap), a process may drive several GPUs
+  AVS_CUDA(cudaFuncSetAttribute(gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem)));
   GemmParams p;
   p.a = a_packed; p.w = w_packed; p.bias = bias; p.c = c;
   p.M = M; p.N = N; p.K8 = K / 8; p.ldc = ldc;

@@ -391,7 +391,12 @@ extern "C" int avs_bigru_forward(const avs_bigru* g, const float* emb, int B, in
       if ((rc = gemm_umma_nt(w.ap, g->w_ih_packed[l], g->b_ih[l], w.xp, 6 * H, rows, 6 * H, ins[l], g->n_sms, st))) return rc;
     }
     ProfScope psr(PROF_GRU_REC, st);
-    if (g->w_hh_packed[l] != nullptr && !getenv("AVS_GRU_FMA")) {
+#ifdef AVS_EXPERIMENTS
+    const bool force_fma = getenv("AVS_GRU_FMA") != nullptr;  // tools build: CUDA-core recurrence instead of the tcgen05 one
+#else
+    constexpr bool force_fma = false;
+#endif
+    if (g->w_hh_packed[l] != nullptr && !force_fma) {
       if ((rc = gru_recurrence_umma(w.xp, g->w_hh_packed[l], g->b_hh[l], outs[l], B, T, st))) return rc;
     } else if (H == kCluH) {
       cudaLaunchConfig_t cfg{};

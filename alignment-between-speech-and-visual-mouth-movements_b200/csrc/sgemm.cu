@@ -3,6 +3,14 @@ namespace avs {
 
 constexpr int BM = 128, BN = 128, BK = 8;
 
+// BVEC: rows of B are 16-byte aligned (ldb % 4 == 0) and are staged with float4 loads; otherwise four scalar loads
+// (the detector's W1 has ldb = 13824 + 2*n_mfcc: odd n_mfcc, e.g. the common 13, is not a multiple of 4).
+__device__ __forceinline__ float4 ld4(const float* p, bool vec) {
+  if (vec) return *reinterpret_cast<const float4*>(p);
+  return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+}
+
+template <bool BVEC>
 __global__ void __launch_bounds__(256)
 sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                 const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N, int K) {
@@ -26,7 +34,7 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
   const float* ap = A + static_cast<size_t>(m0 + lr) * lda + lk;
   const float* bp = B + static_cast<size_t>(n0 + lr) * ldb + lk;
   float4 ra = a_ok ? *reinterpret_cast<const float4*>(ap) : make_float4(0, 0, 0, 0);
-  float4 rb = b_ok ? *reinterpret_cast<const float4*>(bp) : make_float4(0, 0, 0, 0);
+  float4 rb = b_ok ? ld4(bp, BVEC) : make_float4(0, 0, 0, 0);
   const int nk = K / BK;  // K % 8 == 0 is enforced by the host wrapper via padding check
   int buf = 0;
   As[0][lk + 0][lr] = ra.x; As[0][lk + 1][lr] = ra.y; As[0][lk + 2][lr] = ra.z; As[0][lk + 3][lr] = ra.w;
@@ -35,7 +43,7 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
   for (int kt = 0; kt < nk; ++kt) {
     if (kt + 1 < nk) {
       ra = a_ok ? *reinterpret_cast<const float4*>(ap + (kt + 1) * BK) : make_float4(0, 0, 0, 0);
-      rb = b_ok ? *reinterpret_cast<const float4*>(bp + (kt + 1) * BK) : make_float4(0, 0, 0, 0);
+      rb = b_ok ? ld4(bp + (kt + 1) * BK, BVEC) : make_float4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
@@ -84,11 +92,12 @@ splitk_reduce_kernel(const float* __restrict__ part, const float* __restrict__ b
 // which must hold splits * M * N floats); C is dense [M, N].
 int sgemm_nt_splitk(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int M, int N, int K,
                     int splits, float* partial, cudaStream_t st) {
-  AVS_REQUIRE(splits >= 1 && K % (splits * BK) == 0 && lda % 4 == 0 && ldb % 4 == 0, "bad split-K configuration");
+  AVS_REQUIRE(splits >= 1 && K % (splits * BK) == 0 && lda % 4 == 0, "bad split-K configuration");
   if (M <= 0 || N <= 0) return AVS_OK;
   if (splits == 1) return sgemm_nt(A, lda, B, ldb, bias, C, N, M, N, K, st);
   dim3 grid(cdiv(N, BN), cdiv(M, BM), splits);
-  sgemm_nt_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, nullptr, partial, N, M, N, K / splits);
+  if (ldb % 4 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0) sgemm_nt_kernel<true><<<grid, 256, 0, st>>>(A, lda, B, ldb, nullptr, partial, N, M, N, K / splits);
+  else sgemm_nt_kernel<false><<<grid, 256, 0, st>>>(A, lda, B, ldb, nullptr, partial, N, M, N, K / splits);
   AVS_LAUNCHED();
   splitk_reduce_kernel<<<cdiv(M * N, 1024), 256, 0, st>>>(partial, bias, C, M, N, splits);
   AVS_LAUNCHED();
@@ -97,10 +106,11 @@ int sgemm_nt_splitk(const float* A, int lda, const float* B, int ldb, const floa
 
 int sgemm_nt(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N,
              int K, cudaStream_t st) {
-  AVS_REQUIRE(K % BK == 0 && lda % 4 == 0 && ldb % 4 == 0, "sgemm_nt needs K % 8 == 0 and 16-byte aligned rows");
+  AVS_REQUIRE(K % BK == 0 && lda % 4 == 0, "sgemm_nt needs K % 8 == 0 and 16-byte aligned rows of A");
   if (M <= 0 || N <= 0) return AVS_OK;
   dim3 grid(cdiv(N, BN), cdiv(M, BM));
-  sgemm_nt_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+  if (ldb % 4 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0) sgemm_nt_kernel<true><<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+  else sgemm_nt_kernel<false><<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
   AVS_LAUNCHED();
   return AVS_OK;
 }

@@ -4,7 +4,7 @@
 #include "common.cuh"
 namespace avs {
 // A row-major with leading dimension lda, B row-major [N, K] with ldb (torch Linear weight), C with ldc.
-// Requires K % 4 == 0, lda % 4 == 0, ldb % 4 == 0 and 16-byte aligned A / B.
+// Requires K % 8 == 0, lda % 4 == 0 and 16-byte aligned A; B rows of any alignment (scalar loads when ldb % 4 != 0).
 int sgemm_nt(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N,
              int K, cudaStream_t st);
 int sgemm_nt_splitk(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int M, int N, int K,

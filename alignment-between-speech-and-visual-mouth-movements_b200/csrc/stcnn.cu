@@ -21,6 +21,7 @@ static const int kHin[3] = {AVS_H, AVS_H / 2, AVS_H / 4}, kWin[3] = {AVS_W, AVS_
 static size_t wcount(int l) { return static_cast<size_t>(kCout[l]) * kCin[l] * 3 * kKH[l] * kKW[l]; }
 
 struct StcnnWs {  // workspace carve, shared by size query and forward
+  float* f32frames;                                  // fp32 path fed with u8 pixels: the f32 frames it convolves
   float* p1; float* p2; float* emb;                  // fp32 path: pooled NCDHW activations; emb when caller passes none
   __nv_bfloat16* act[3];                             // tensor-core path: parity-plane inputs of the three layers
   size_t act_bytes[3];
@@ -34,6 +35,7 @@ static StcnnWs carve(const avs_stcnn* net, int B, void* ws, bool need_emb) {
   Carver c(ws);
   StcnnWs r{};
   if (net->precision == AVS_PREC_FP32) {
+    r.f32frames = c.take<float>(static_cast<size_t>(B) * AVS_T * AVS_H * AVS_W);
     r.p1 = c.take<float>(static_cast<size_t>(B) * 32 * AVS_T * 25 * 50);
     r.p2 = c.take<float>(static_cast<size_t>(B) * 64 * AVS_T * 12 * 25);
   } else {
@@ -46,6 +48,12 @@ static StcnnWs carve(const avs_stcnn* net, int B, void* ws, bool need_emb) {
   if (need_emb) r.emb = c.take<float>(static_cast<size_t>(B) * AVS_T * AVS_EMB);
   r.total = align_up(c.off, 256);
   return r;
+}
+
+// u8 pixels -> float32(v / 255.0), the frames tensor the reference builds (dataset.py:226-231)
+__global__ void __launch_bounds__(256) u8_to_unit_f32_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i < n) out[i] = static_cast<float>(static_cast<double>(in[i]) / 255.0);
 }
 
 }  // namespace avs
@@ -119,10 +127,10 @@ extern "C" size_t avs_stcnn_workspace_bytes(const avs_stcnn* net, int n_clips) {
 // cap_clips: the workspace is carved for this many clips (>= B), so that repeated calls with different
 // B see the same buffer placement; pads_clean: the caller guarantees that the padding positions of the
 // parity-plane buffers are still zero (zeroed once, and kernels only ever write data positions).
-int avs::stcnn_forward_impl(const avs_stcnn* net, const float* frames, int B, int cap_clips, bool pads_clean,
+int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool frames_u8, int B, int cap_clips, bool pads_clean,
                             cudaEvent_t after_layer1, float* out_emb, float* out_vstats, float* out_pool1, float* out_pool2, void* workspace,
                             size_t workspace_bytes, void* stream) {
-  AVS_REQUIRE(net && frames && workspace, "null argument");
+  AVS_REQUIRE(net && frames_any && workspace, "null argument");
   AVS_REQUIRE(out_emb || out_vstats, "nothing to compute");
   AVS_REQUIRE(cap_clips >= B, "workspace capacity below batch");
   if (B <= 0) return AVS_OK;
@@ -135,6 +143,13 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const float* frames, int B, in
   float* emb = out_emb ? out_emb : w.emb;
   int rc;
   if (net->precision == AVS_PREC_FP32) {
+    const float* frames = static_cast<const float*>(frames_any);
+    if (frames_u8) {
+      const long long n = static_cast<long long>(B) * AVS_T * AVS_H * AVS_W;
+      u8_to_unit_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(static_cast<const uint8_t*>(frames_any), w.f32frames, n);
+      AVS_LAUNCHED();
+      frames = w.f32frames;
+    }
     // gridDim.y = clips * T is capped at 65535: run in slabs of 512 clips
     for (int b0 = 0; b0 < B; b0 += 512) {
       const int nb = std::min(512, B - b0);
@@ -162,7 +177,7 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const float* frames, int B, in
       AVS_CUDA(cudaMemsetAsync(w.act[1], 0, umma_act_bytes(net->L[1].g, split, B), st));
       AVS_CUDA(cudaMemsetAsync(w.act[2], 0, umma_act_bytes(net->L[2].g, split, B), st));
     }
-    if ((rc = umma_pack_frames(frames, w.act[0], net->L[0].g, split, B, st))) return rc;
+    if ((rc = umma_pack_frames(frames_any, frames_u8, w.act[0], net->L[0].g, split, B, st))) return rc;
     for (int l = 0; l < 3; ++l) {
       EpiOut eo{};
       if (l < 2) {
@@ -188,7 +203,13 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const float* frames, int B, in
 extern "C" int avs_stcnn_forward_debug(const avs_stcnn* net, const float* frames, int B, float* out_emb,
                                        float* out_vstats, float* out_pool1, float* out_pool2, void* workspace,
                                        size_t workspace_bytes, void* stream) {
-  return stcnn_forward_impl(net, frames, B, B, false, nullptr, out_emb, out_vstats, out_pool1, out_pool2, workspace,
+  return stcnn_forward_impl(net, frames, false, B, B, false, nullptr, out_emb, out_vstats, out_pool1, out_pool2, workspace,
+                            workspace_bytes, stream);
+}
+
+extern "C" int avs_stcnn_forward_u8(const avs_stcnn* net, const uint8_t* frames, int n_clips, float* out_emb, float* out_vstats,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  return stcnn_forward_impl(net, frames, true, n_clips, n_clips, false, nullptr, out_emb, out_vstats, nullptr, nullptr, workspace,
                             workspace_bytes, stream);
 }
 

@@ -177,6 +177,8 @@ class SyncSweeper:
     ``run(frames, audio)`` takes device tensors; ``run_host(frames, audio)`` takes host arrays and
     pipelines the H2D/D2H copies against compute chunk by chunk.  Both return
     ``(scores [B, 2S+1], best_shift_frames [B])`` where ``best_shift_frames = argmax_k - S``.
+    ``frames`` is the reference's f32 tensor ``[B,1,75,50,100]`` or the uint8 pixels it is made from
+    (``float32(u8 / 255.0)``, dataset.py:226-231): same scores bit for bit, a quarter of the bytes.
     """
 
     def __init__(self, lipnet: LipNet, detector: MisalignmentDetector, max_shift_frames: int,
@@ -213,22 +215,22 @@ class SyncSweeper:
             raise RuntimeError(f"audio must be [{B}, {self.n_samples}], got {tuple(audio.shape)}")
         scores = torch.empty((B, self.K), dtype=torch.float32, device=frames.device)
         best = torch.empty((B,), dtype=torch.int32, device=frames.device)
-        N.check(N.lib().avs_sweep_run(self.handle.h, N.ptr(frames), N.ptr(audio), B, N.ptr(scores), N.ptr(best),
-                                      N.stream_ptr()), "sweep_run")
+        fn = N.lib().avs_sweep_run_u8 if frames.dtype == torch.uint8 else N.lib().avs_sweep_run
+        N.check(fn(self.handle.h, N.ptr(frames), N.ptr(audio), B, N.ptr(scores), N.ptr(best), N.stream_ptr()), "sweep_run")
         return scores, best - self.S
 
     def run_host(self, frames: np.ndarray, audio: np.ndarray):
-        frames = np.ascontiguousarray(frames, dtype=np.float32)
+        u8 = frames.dtype == np.uint8
+        frames = np.ascontiguousarray(frames, dtype=np.uint8 if u8 else np.float32)
         audio = np.ascontiguousarray(audio, dtype=np.float32)
         B = frames.shape[0]
         if frames.shape[1:] != (1, 75, 50, 100) or audio.shape != (B, self.n_samples):
             raise RuntimeError("frames must be [B,1,75,50,100] and audio [B, n_samples]")
         scores = np.empty((B, self.K), dtype=np.float32)
         best = np.empty((B,), dtype=np.int32)
-        N.check(N.lib().avs_sweep_run_host(self.handle.h, frames.ctypes.data_as(N.c_void_p),
-                                           audio.ctypes.data_as(N.c_void_p), B,
-                                           scores.ctypes.data_as(N.c_void_p), best.ctypes.data_as(N.c_void_p)),
-                "sweep_run_host")
+        fn = N.lib().avs_sweep_run_host_u8 if u8 else N.lib().avs_sweep_run_host
+        N.check(fn(self.handle.h, frames.ctypes.data_as(N.c_void_p), audio.ctypes.data_as(N.c_void_p), B,
+                   scores.ctypes.data_as(N.c_void_p), best.ctypes.data_as(N.c_void_p)), "sweep_run_host")
         return scores, best - self.S
 
 

@@ -93,11 +93,15 @@ class LipNet(nn.Module):
         if x.dim() != 5 or tuple(x.shape[1:]) != (1, 75, 50, 100):
             # same failure class as the reference's conv1/view on a wrong shape (model.py:22,52)
             raise RuntimeError(f"expected frames of shape (B, 1, 75, 50, 100), got {tuple(x.shape)}")
+        if x.dtype == torch.uint8:         # the 8-bit pixels the reference divides by 255 (dataset.py:226-231)
+            return x.detach().contiguous()
         return N.f32c(x)
 
     def stcnn(self, x: torch.Tensor, want_vstats: bool = False, debug: bool = False):
         """Conv half of ``forward`` (model.py:67-82): [B,1,75,50,100] -> emb [B,75,6912]
-        (and, optionally, the time-pooled statistics of misalignment_detection_train.py:165)."""
+        (and, optionally, the time-pooled statistics of misalignment_detection_train.py:165).
+        ``x`` may also be the uint8 pixels (same shape) the reference's f32 frames are made from
+        (``float32(u8 / 255.0)``): same bits out, a quarter of the bytes in."""
         if self.training:
             raise RuntimeError("the B200 LipNet implements eval-mode forward only; call .eval()")
         x = self._check_frames(x)
@@ -108,11 +112,17 @@ class LipNet(nn.Module):
         vst = torch.empty((B, 2 * self.conv_output_dim), dtype=torch.float32, device=x.device) if want_vstats else None
         ws = N.workspace(L.avs_stcnn_workspace_bytes(net.h, B), x.device)
         if debug:
+            if x.dtype == torch.uint8:
+                raise RuntimeError("debug=True takes f32 frames")
             p1 = torch.empty((B, 32, 75, 25, 50), dtype=torch.float32, device=x.device)
             p2 = torch.empty((B, 64, 75, 12, 25), dtype=torch.float32, device=x.device)
             N.check(L.avs_stcnn_forward_debug(net.h, N.ptr(x), B, N.ptr(emb), N.ptr(vst), N.ptr(p1), N.ptr(p2),
                                               N.ptr(ws), ws.numel(), N.stream_ptr()), "stcnn_forward_debug")
             return emb, vst, p1, p2
+        if x.dtype == torch.uint8:
+            N.check(L.avs_stcnn_forward_u8(net.h, N.ptr(x), B, N.ptr(emb), N.ptr(vst), N.ptr(ws), ws.numel(),
+                                           N.stream_ptr()), "stcnn_forward_u8")
+            return (emb, vst) if want_vstats else emb
         N.check(L.avs_stcnn_forward(net.h, N.ptr(x), B, N.ptr(emb), N.ptr(vst), N.ptr(ws), ws.numel(),
                                     N.stream_ptr()), "stcnn_forward")
         return (emb, vst) if want_vstats else emb

@@ -2,21 +2,38 @@
 """bench.py — clips/s of the 41-offset (+-20 frame) AV sync sweep (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
-                    [--precision bf16|bf16x3|fp32] [--clips-per-gpu C] [--chunk M]
+                    [--precision bf16|bf16x3|fp32] [--clips-per-gpu C] [--chunk M] [--no-configs]
 
 A "step" is one pass of the hot path (K2 STCNN + visual stats | K1 MFCC stats for 41 shifts -> K4
 scores + arg-max, plus the cross-rank score gather when N > 1) over one batch of synthetic clips:
 C clips per GPU, fixed as N grows (weak scaling; N = 8, C = 1024 is BASELINE config 3's 8192 clips).
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` goes through the
-host-buffer entry point (pinned host inputs, H2D/D2H inside the timed region).
+Prints ONE JSON line (rank 0).
+
+  value      device-resident throughput (inputs already in HBM), CUDA events, max over ranks
+  e2e        the same sweep through the host-buffer entry point: pinned host inputs, H2D / D2H inside the timed
+             region.  Frames cross PCIe as the uint8 pixels GRID frames are made of (dataset.py:226-231:
+             frames = float32(u8 / 255.0)); `e2e_f32_frames` is the same call fed with the f32 tensor instead.
+  parity     bf16 (headline dtype) against the fp32-grade bf16x3 path on this very batch, outside the timed region
+  configs    the other BASELINE configs (1, 2, 4, 5, the fp32-grade sweep, the drop-in per-shift loop), measured
+             after the headline; config 5 (DDP detector step) runs on all N ranks
+  roofline   the dominant kernel (conv2) against the measured sustained bf16 rate
+  cpu_baseline  the reference's CPU path (oracle port) on this box's host cores, BASELINE.md section 2 protocol
 """
 from __future__ import annotations
 
+import os
+import sys
+
+if "reference" in sys.argv:
+    # The reference arm uses every host core.  torchrun exports OMP_NUM_THREADS=1 to its workers, which would pin the
+    # BLAS / OpenMP pools of numpy, scipy and torch to one thread before they initialise (round 1: 3.7 vs 7.4 clips/s
+    # between torchrun and plain launches): set the pools explicitly, before those libraries load.
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import argparse
 import json
-import os
 import subprocess
-import sys
 import tempfile
 import time
 
@@ -44,10 +61,10 @@ def peaks():
 
 
 def conv2_traffic(clips_per_launch: int, precision: str):
-    """DRAM bytes per launch of the layer-2 conv kernel from the committed `ncu --set full` capture
-    (profiles/r01_conv2_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum = 864.9 MB for a
-    64-clip bf16 launch = 13.51 MB per clip; algorithmic: 8.6 MB padded input + 2.9 MB pooled output),
-    scaled to the clips one bench launch processes."""
+    """DRAM bytes per launch of the layer-2 conv kernel: a CONSTANT taken from the committed `ncu --set full` capture
+    (profiles/r01_conv2_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum = 864.9 MB for a 64-clip bf16
+    launch = 13.51 MB per clip; algorithmic: 8.6 MB padded input + 2.9 MB pooled output), scaled to the clips one
+    bench launch processes — not measured by this run."""
     if precision != "bf16":
         return None
     return 13.51e6 * clips_per_launch
@@ -89,68 +106,254 @@ class ClockSampler:
                 "power_w_max": max(float(r[3]) for r in rows), "reasons": reasons}
 
 
-def synth_inputs(n: int, seed: int):
-    """Pinned host tensors: frames [n,1,75,50,100] ~ U[0,1), audio [n,48000] ~ N(0,0.1^2) clipped, with a
-    per-clip random amplitude envelope so shifted versions differ."""
+def synth_inputs(n: int, seed: int, pin: bool = True):
+    """Host tensors (pinned when a GPU is present): frames u8 [n,1,75,50,100] uniform over 0..255 — the 8-bit mouth crops
+    GRID frames are made of; the reference's f32 tensor is float32(u8 / 255.0) (dataset.py:226-231), see frames_f32() —
+    and audio [n,48000] ~ N(0,0.1^2) clipped, with a per-clip random amplitude envelope so shifted versions differ
+    (SURVEY.md section 8d)."""
     g = torch.Generator().manual_seed(seed)
-    frames = torch.empty((n, 1, 75, 50, 100), dtype=torch.float32).pin_memory()
-    audio = torch.empty((n, N_SAMPLES), dtype=torch.float32).pin_memory()
+    pin = pin and torch.cuda.is_available()
+    frames = torch.empty((n, 1, 75, 50, 100), dtype=torch.uint8)
+    audio = torch.empty((n, N_SAMPLES), dtype=torch.float32)
+    if pin:
+        frames, audio = frames.pin_memory(), audio.pin_memory()
     for i in range(0, n, 64):
         m = min(64, n - i)
-        frames[i:i + m] = torch.rand((m, 1, 75, 50, 100), generator=g)
+        frames[i:i + m] = torch.randint(0, 256, (m, 1, 75, 50, 100), generator=g, dtype=torch.uint8)
         env = torch.nn.functional.interpolate(torch.rand((m, 1, 13), generator=g), size=N_SAMPLES, mode="linear",
                                               align_corners=True)[:, 0]
         audio[i:i + m] = (torch.randn((m, N_SAMPLES), generator=g) * 0.1).clamp_(-1, 1) * env * env
     return frames, audio
 
 
-def cpu_sweep_clips_per_s(n_clips: int, warm: int = 1):
-    """The reference's CPU path (oracle port: reference-style loop, B=1 STCNN, one MFCC + one detector call
-    per shift) on this box's host cores."""
+def frames_f32(frames_u8: torch.Tensor, pin: bool = True) -> torch.Tensor:
+    """The reference's frames tensor for these pixels: u8 / 255.0 in float64, stored as float32."""
+    out = torch.empty(frames_u8.shape, dtype=torch.float32)
+    if pin and torch.cuda.is_available():
+        out = out.pin_memory()
+    for i in range(0, frames_u8.shape[0], 64):
+        out[i:i + 64] = (frames_u8[i:i + 64].to(torch.float64) / 255.0).to(torch.float32)
+    return out
+
+
+def parity_stats(scores, best, scores_ref, best_ref):
+    """Headline-dtype scores / best offsets against the fp32-grade path on the same clips.  A clip is *resolvable*
+    when the reference's top-2 score margin exceeds 10x the largest score difference seen; on those the best offset
+    must be identical (north_star: arg-max bit-exact)."""
+    scores, scores_ref = np.asarray(scores, dtype=np.float64), np.asarray(scores_ref, dtype=np.float64)
+    d = float(np.abs(scores - scores_ref).max())
+    srt = np.sort(scores_ref, axis=1)
+    margin = srt[:, -1] - srt[:, -2]
+    res = margin > 10 * d
+    agree = np.asarray(best) == np.asarray(best_ref)
+    return {"clips": int(scores.shape[0]), "max_abs_dscore": d, "argmax_agree": float(agree.mean()),
+            "resolvable_frac": float(res.mean()),
+            "argmax_agree_resolvable": float(agree[res].mean()) if res.any() else None,
+            "unresolvable_disagreements": int((~agree & ~res).sum()),
+            "median_top2_margin": float(np.median(margin))}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_clip_times(n_clips: int, warm: int, batched: bool, S: int = S_FRAMES):
+    """Per-clip wall times of the reference's CPU path (oracle port: B=1 STCNN once per clip, then per shift
+    shift_audio -> MFCC stats -> cat -> sigmoid(detector); batched=True is the "best-effort CPU" variant with one
+    detector call for all shifts) on this box's host cores."""
     from oracle import lipnet_ref, sweep_ref
     torch.set_num_threads(os.cpu_count() or 1)
     sd = lipnet_ref.init_lipnet_state(39, 256, seed=0)
     det = sweep_ref.init_detector_state(13864, 512, seed=1)
     frames = sweep_ref.synth_frames(n_clips + warm, seed=4321)
     audio = sweep_ref.synth_audio(n_clips + warm, seed=4321, kind="speechlike")
-    shifts = list(range(-S_FRAMES, S_FRAMES + 1))
-    for i in range(warm):
-        sweep_ref.sweep_clip(sd, det, frames[i], audio[i], shifts)
-    t0 = time.perf_counter()
-    for i in range(warm, warm + n_clips):
-        sweep_ref.sweep_clip(sd, det, frames[i], audio[i], shifts)
-    dt = time.perf_counter() - t0
-    return n_clips / dt, dt
+    shifts = list(range(-S, S + 1))
+    times = []
+    for i in range(warm + n_clips):
+        t0 = time.perf_counter()
+        sweep_ref.sweep_clip(sd, det, frames[i], audio[i], shifts, batched=batched)
+        if i >= warm:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def cpu_stage_split(n_clips: int = 3):
+    """Seconds per clip of the three stages of the reference-style loop (STCNN B=1, 41 MFCC-stats calls, 41 detector calls)."""
+    from oracle import lipnet_ref, sweep_ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = lipnet_ref.init_lipnet_state(39, 256, seed=0)
+    det = sweep_ref.init_detector_state(13864, 512, seed=1)
+    frames = sweep_ref.synth_frames(n_clips, seed=99)
+    audio = sweep_ref.synth_audio(n_clips, seed=99, kind="speechlike")
+    t = {"stcnn_b1": 0.0, "mfcc_x41": 0.0, "detector_x41": 0.0}
+    with torch.no_grad():
+        for i in range(n_clips):
+            t0 = time.perf_counter()
+            v = sweep_ref.visual_stats(lipnet_ref.stcnn(sd, frames[i].unsqueeze(0))[0])
+            t1 = time.perf_counter()
+            a = [sweep_ref.compute_audio_stats(sweep_ref.shift_audio(audio[i], k, 25.0, 16000), 16000, 20)
+                 for k in range(-S_FRAMES, S_FRAMES + 1)]
+            t2 = time.perf_counter()
+            for ak in a:
+                torch.sigmoid(sweep_ref.detector_logits(det, torch.cat([v, ak]).unsqueeze(0)))
+            t3 = time.perf_counter()
+            t["stcnn_b1"] += (t1 - t0) / n_clips
+            t["mfcc_x41"] += (t2 - t1) / n_clips
+            t["detector_x41"] += (t3 - t2) / n_clips
+    return t
 
 
 def run_reference(args, rank: int):
-    """--impl reference: the reference's CPU implementation (oracle port; /root/reference is Python and does
-    not exist on the GPU box) timed on the host cores.  Rank 0 only."""
+    """--impl reference: the reference's CPU implementation (oracle port; /root/reference is Python and does not exist
+    on the GPU box) timed on the host cores with all the threads it can use.  Rank 0 only.  Protocol of BASELINE.md
+    section 2: warm-up clips, then >= 16 timed clips (steps x ref-clips), median s/clip -> clips/s; the best-effort
+    (batched detector) variant and a per-stage split are reported beside it."""
     if rank != 0:
         return
     per_step = args.ref_clips
-    for _ in range(args.warmup):
-        cpu_sweep_clips_per_s(1, warm=0)
+    n_timed = max(16, args.steps * per_step)
     t0 = time.perf_counter()
-    tot = 0
-    for _ in range(args.steps):
-        cpu_sweep_clips_per_s(per_step, warm=0)
-        tot += per_step
-    dt = time.perf_counter() - t0
-    v = tot / dt
+    times = cpu_clip_times(n_timed, warm=max(2, args.warmup), batched=False)
+    wall = time.perf_counter() - t0
+    med = float(np.median(times))
+    v = 1.0 / med
+    best_effort = cpu_clip_times(16, warm=2, batched=True)
+    s15 = cpu_clip_times(8, warm=1, batched=False, S=15)
     cores = os.cpu_count() or 1
+    cpu = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+           "sample": f"{n_timed} timed clips after {max(2, args.warmup)} warm-up clips, median s/clip, reference-style loop "
+                     f"(oracle port), torch {torch.get_num_threads()} threads, OMP_NUM_THREADS={os.environ.get('OMP_NUM_THREADS')}",
+           "mean_value": len(times) / sum(times), "median_s_per_clip": med,
+           "best_effort_value": 1.0 / float(np.median(best_effort)),
+           "best_effort": "same loop with one batched detector call for the 41 shifts (16 clips, median)",
+           "s15_value": 1.0 / float(np.median(s15)),
+           "stage_s_per_clip": cpu_stage_split(3)}
     line = {
         "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * med * per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
         "config": {"workload": f"+-{S_FRAMES}-frame (41-offset) sync sweep, reference-style CPU loop, "
-                               f"{per_step} clips per step (bounded sample)", "l2": "n/a (CPU)"},
-        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
-                         "sample": f"{tot} clips, torch {torch.get_num_threads()} threads"},
+                               f"{per_step} clips per step (bounded sample of the 1024-clip step)", "l2": "n/a (CPU)",
+                   "wall_s": wall},
+        "cpu_baseline": cpu,
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
+
+
+def cpu_baseline_subprocess(n_clips: int):
+    """The cpu_baseline leg of the native arm runs the reference arm in a fresh process (same code, same thread pools:
+    this process may have been started with OMP_NUM_THREADS=1) and returns its cpu_baseline object."""
+    steps = max(1, (n_clips + 3) // 4)
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", "2"],
+                       capture_output=True, text=True, env=env, timeout=900)
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    return {"value": None, "error": r.stderr[-400:]}
+
+
+# ------------------------------------------------------------------------------------------------ other configs
+def cuda_time(fn, iters: int, warm: int = 2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def other_configs(A, dev, det, frames_u8_h, audio_h, world: int):
+    """BASELINE configs 1, 2, 4 and the fp32-grade sweep on this GPU (rank 0, N = 1), device-resident, CUDA events."""
+    out = {}
+    f32_64 = frames_f32(frames_u8_h[:256], pin=False).to(dev)
+    au = audio_h[:256].to(dev)
+    nets = {}
+    for prec in ("bf16x3", "bf16"):
+        torch.manual_seed(0)
+        nets[prec] = A.LipNet(39, precision=prec).to(dev).eval()
+    # config 1: ONE clip end to end (STCNN + Bi-GRU head + greedy decode + +-15 sweep), fp32-grade
+    sw1 = A.SyncSweeper(nets["bf16x3"], det, 15, N_SAMPLES, chunk_clips=1)
+
+    def cfg1():
+        lp = nets["bf16x3"](f32_64[:1])
+        A.ctc_greedy_decode(lp)
+        sw1.run(f32_64[:1], au[:1])
+    out["config1_one_clip_ms"] = {"value": cuda_time(cfg1, 20), "unit": "ms/clip", "precision": "bf16x3",
+                                  "what": "1 clip: LipNet forward + greedy CTC + +-15 sweep, device-resident"}
+    # config 2: 64 clips, +-15, fp32-grade (and bf16 beside it)
+    for prec in ("bf16x3", "bf16"):
+        sw = A.SyncSweeper(nets[prec], det, 15, N_SAMPLES, chunk_clips=64)
+        ms = cuda_time(lambda: sw.run(f32_64[:64], au[:64]), 10)
+        out[f"config2_batch64_s15_{prec}"] = {"value": 64 / (ms / 1e3), "unit": "clips/s", "ms_per_step": ms}
+    # config 4: 256 clips LipNet.forward + greedy decode
+    for prec in ("bf16x3", "bf16"):
+        def cfg4(p=prec):
+            A.ctc_greedy_decode(nets[p](f32_64))
+        ms = cuda_time(cfg4, 5)
+        out[f"config4_batch256_decode_{prec}"] = {"value": 256 / (ms / 1e3), "unit": "clips/s", "ms_per_step": ms}
+    del f32_64
+    return out, nets
+
+
+def dropin_loop(A, dev, det, net, frames_u8_h, audio_h, n_clips: int = 6):
+    """What INTEGRATION.md's two-line import swap buys a maintainer who keeps the reference's per-(clip, shift) loop:
+    FeatureExtractor.build_feature(path, k) + sigmoid(detector(feature[None])) for every k (B = 1 STCNN once per clip,
+    one K1 launch + one H2D + one D2H per shift), wall clock."""
+    class Grid:
+        def process_video(self, path):
+            return frames_f32(frames_u8_h[int(path):int(path) + 1], pin=False)[0]
+
+    def loader(path):
+        return audio_h[int(path)].numpy(), 16000
+    fx = A.FeatureExtractor(Grid(), net, dev, A.DetectorConfig(max_shift_frames=S_FRAMES), audio_loader=loader)
+
+    def clip(i):
+        with torch.no_grad():
+            sc = [float(torch.sigmoid(det(fx.build_feature(str(i), k)[0].to(dev).unsqueeze(0)))[0])
+                  for k in range(-S_FRAMES, S_FRAMES + 1)]
+        return int(np.argmax(sc))
+    clip(0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(1, 1 + n_clips):
+        clip(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": n_clips / dt, "unit": "clips/s", "clips": n_clips, "precision": net.precision,
+            "what": "per-(clip, shift) loop through the reference-named shims (build_feature + detector), wall clock"}
+
+
+def ddp_config5(A, dev, world: int, rank: int, steps: int = 20):
+    """Config 5: one data-parallel training step of the detector (hidden 512, batch 64 per rank, BCE-with-logits,
+    Adam lr 1e-3 / L2 1e-5; run_train_misalignment.sh:32-42, misalignment_detection_train.py:260-266) with ONE
+    all-reduce of the flat 28.4 MB gradient bucket; CUDA events, max over ranks.  Also times the bare all-reduce of the
+    same bucket to report its share of the step."""
+    import torch.distributed as dist
+    torch.manual_seed(1)
+    det = A.MisalignmentDetector(13864, 512).to(dev)
+    opt = torch.optim.Adam(det.parameters(), lr=1e-3, weight_decay=1e-5)
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randn((64, 13864), generator=g).to(dev)
+    y = (torch.rand((64,), generator=g) > 0.5).float().to(dev)
+    ms_step = cuda_time(lambda: A.distributed.ddp_detector_step(det, x, y, opt), steps, warm=3)
+    n_grad = sum(p.numel() for p in det.parameters())
+    ms_ar = 0.0
+    if world > 1:
+        flat = torch.zeros(n_grad, device=dev)
+        ms_ar = cuda_time(lambda: dist.all_reduce(flat), steps, warm=3)
+    t = torch.tensor([ms_step, ms_ar], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, ms_ar = float(t[0]), float(t[1])
+    return {"value": ms_step, "unit": "ms/step", "global_batch": 64 * world, "grad_floats": n_grad,
+            "allreduce_ms": ms_ar, "allreduce_share": (ms_ar / ms_step) if ms_step else None,
+            "allreduce_busbw_gbs": (2 * (world - 1) / world * n_grad * 4 / (ms_ar / 1e3) / 1e9) if ms_ar else None,
+            "samples_per_s": 64 * world / (ms_step / 1e3)}
 
 
 def main():
@@ -163,8 +366,9 @@ def main():
     ap.add_argument("--clips-per-gpu", type=int, default=1024)
     ap.add_argument("--chunk", type=int, default=128)
     ap.add_argument("--ref-clips", type=int, default=4, help="clips per step of the reference arm")
-    ap.add_argument("--cpu-clips", type=int, default=12, help="clips of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--cpu-clips", type=int, default=16, help="timed clips of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs and the parity pass")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -198,7 +402,7 @@ def main():
     C = args.clips_per_gpu
     n_total = C * world
     sw = A.SyncSweeper(net, det, S_FRAMES, N_SAMPLES, chunk_clips=min(args.chunk, C))
-    frames_h, audio_h = synth_inputs(C, seed=1000 + rank)
+    frames_h, audio_h = synth_inputs(C, seed=1000 + rank)         # u8 pixels + f32 audio, pinned
     frames_d, audio_d = frames_h.to(dev), audio_h.to(dev)
 
     def step_device():
@@ -243,11 +447,29 @@ def main():
         L.avs_prof_read(i, ctypes.byref(t), ctypes.byref(c))
         prof[nme] = {"ms_total": t.value, "launches": c.value}
 
-    # ---------------- end-to-end through the host-buffer entry point
-    e2e = None
-    if not args.no_e2e:
-        fh, ah = frames_h.numpy(), audio_h.numpy()
+    # ---------------- the same step fed with the reference's f32 frames tensor (device-resident)
+    f32_h = frames_f32(frames_h)
+    f32_d = f32_h.to(dev)
 
+    def step_device_f32():
+        s, b = sw.run(f32_d, audio_d)
+        return A.distributed.gather_scores(s, b, n_total)
+    step_device_f32()
+    barrier()
+    ev0.record()
+    for _ in range(max(2, args.steps // 2)):
+        s32, b32 = step_device_f32()
+    ev1.record()
+    barrier()
+    ms32 = torch.tensor([ev0.elapsed_time(ev1) / max(2, args.steps // 2)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms32, op=dist.ReduceOp.MAX)
+    value_f32 = n_total / (float(ms32.item()) / 1e3)
+    f32_matches = bool(torch.equal(s32, scores) and torch.equal(b32, best))
+    del f32_d
+
+    # ---------------- end-to-end through the host-buffer entry points
+    def time_host(fh, ah):
         def step_host():
             s, b = sw.run_host(fh, ah)
             if world > 1:
@@ -263,12 +485,47 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": n_total * args.steps / float(dt.item()), "unit": "clips/s",
-               "h2d_bytes_per_step": n_total * (FRAME_ELEMS + N_SAMPLES) * 4,
-               "d2h_bytes_per_step": n_total * (N_SHIFTS + 1) * 4,
-               "timer": "host wall clock around the synchronous host-buffer call, barrier + cuda sync both sides, max over ranks"}
         same = np.array_equal(np.asarray(s_h if world == 1 else s_h.cpu().numpy()), scores.cpu().numpy())
-        e2e["matches_device_path"] = bool(same)
+        return n_total * args.steps / float(dt.item()), bool(same)
+
+    e2e = e2e_f32 = None
+    if not args.no_e2e:
+        v, same = time_host(frames_h.numpy(), audio_h.numpy())
+        e2e = {"value": v, "unit": "clips/s",
+               "h2d_bytes_per_step": n_total * (FRAME_ELEMS * 1 + N_SAMPLES * 4),
+               "d2h_bytes_per_step": n_total * (N_SHIFTS + 1) * 4, "frames": "uint8 pixels (avs_sweep_run_host_u8)",
+               "timer": "host wall clock around the synchronous host-buffer call, barrier + cuda sync both sides, max over ranks",
+               "matches_device_path": same}
+        v, same = time_host(f32_h.numpy(), audio_h.numpy())
+        e2e_f32 = {"value": v, "unit": "clips/s",
+                   "h2d_bytes_per_step": n_total * (FRAME_ELEMS + N_SAMPLES) * 4,
+                   "d2h_bytes_per_step": n_total * (N_SHIFTS + 1) * 4, "frames": "float32 tensor (avs_sweep_run_host)",
+                   "matches_device_path": same}
+    del f32_h
+
+    # ---------------- parity of the headline dtype on this batch, and the other BASELINE configs (outside the timed region)
+    parity = None
+    configs = {}
+    if not args.no_configs:
+        if rank == 0 and args.precision == "bf16":
+            torch.manual_seed(0)
+            net3 = A.LipNet(39, precision="bf16x3").to(dev).eval()
+            sw3 = A.SyncSweeper(net3, det, S_FRAMES, N_SAMPLES, chunk_clips=min(args.chunk, C))
+            s3, b3 = sw3.run(frames_d, audio_d)
+            loc_s, loc_b = sw.run(frames_d, audio_d)
+            parity = parity_stats(loc_s.cpu().numpy(), loc_b.cpu().numpy(), s3.cpu().numpy(), b3.cpu().numpy())
+            parity["reference"] = "bf16x3 (fp32-grade) path of this library on the same clips; that path is pinned to the " \
+                                  "reference's golden scores to 3.6e-7 in tests/test_gpu_parity.py"
+            ms3 = cuda_time(lambda: sw3.run(frames_d, audio_d), 3, warm=1)
+            configs["sweep_s20_bf16x3"] = {"value": C / (ms3 / 1e3), "unit": "clips/s", "ms_per_step": ms3,
+                                           "what": f"the headline step ({C} clips, +-20) in fp32-grade arithmetic, 1 GPU"}
+            del sw3, net3, s3, b3
+        if world == 1:
+            oc, nets = other_configs(A, dev, det, frames_h, audio_h, world)
+            configs.update(oc)
+            configs["dropin_per_shift_loop"] = dropin_loop(A, dev, det, nets["bf16x3"], frames_h, audio_h)
+            del nets
+        configs["config5_ddp_detector_step"] = ddp_config5(A, dev, world, rank)
 
     if rank == 0:
         pk, pk_src = peaks()
@@ -283,31 +540,36 @@ def main():
                 else "conv_pool_ffma_kernel[layer 2]",
                 "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": achieved / tensor_peak, "traffic": conv2_traffic(clips_per_launch, args.precision),
+                "traffic_source": "constant from the committed ncu --set full capture (13.51 MB per clip) x clips per launch; "
+                                  "not measured by this run",
                 "peak_source": f"{pk_src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "algorithmic_flop_per_launch": CONV_FLOP[2] * clips_per_launch,
                 "issued_mma_multiplier": mult, "avg_launch_ms": avg_ms, "launches_timed": conv2["launches"],
                 "share_of_step": conv2["ms_total"] / ms_total if ms_total else None,
                 # the sustained peak is a measured cuBLAS bf16 GEMM rate, not a hardware bound: a frac near (or a
                 # little above) 1 says "as fast as cuBLAS keeps this GPU busy under its power cap"
-                "frac_of_burst_peak": achieved / pk["bf16_tflops"] if pk.get("bf16_tflops") else None}
+                "frac_of_burst_peak": achieved / pk["bf16_tflops"] if pk.get("bf16_tflops") else None,
+                "whole_step_tflops": sum(CONV_FLOP.values()) * n_total / world / (ms_total / args.steps / 1e3) / 1e12}
         cpu = None
-        if args.cpu_clips > 0:
-            v, dt = cpu_sweep_clips_per_s(args.cpu_clips, warm=1)
-            cpu = {"value": v, "unit": "clips/s", "cores": os.cpu_count() or 1, "kind": "port",
-                   "sample": f"{args.cpu_clips} clips of the same 41-offset sweep, reference-style loop "
-                             f"(oracle port, torch {torch.get_num_threads()} threads), {dt:.1f} s"}
+        if args.cpu_clips > 0 and world == 1:
+            cpu = cpu_baseline_subprocess(args.cpu_clips)
         line = {
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"+-{S_FRAMES}-frame (41-offset) sync sweep, {C} clips per GPU per step "
-                                   f"({n_total} clips/step), GRID-shaped 1x75x50x100 f32 frames + 3 s 16 kHz audio, "
+                                   f"({n_total} clips/step), GRID-shaped 1x75x50x100 mouth crops as uint8 pixels "
+                                   f"(the reference's f32 frames are float32(u8/255)) + 3 s 16 kHz f32 audio, "
                                    f"random-init LipNet STCNN + detector(hidden 512), chunks of {min(args.chunk, C)} clips",
                        "clips_per_gpu": C, "n_shifts": N_SHIFTS, "precision": args.precision,
                        "parallelism": f"clip-sharded x{world}, NCCL all_gather of [{n_total},41] scores" if world > 1 else "1 GPU",
-                       "l2": f"inputs per step {C * (FRAME_ELEMS + N_SAMPLES) * 4 / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)"},
-            "e2e": e2e, "gpu_launches": int(launches.item()), "clocks": clocks, "roofline": roof,
-            "cpu_baseline": cpu, "kernel_ms": prof,
+                       "l2": f"inputs per step {C * (FRAME_ELEMS + N_SAMPLES * 4) / 1e6:.0f} MB per GPU and "
+                             f"{C * 19.3:.0f} MB of inter-layer activations > 126 MB L2 (no flush needed)"},
+            "e2e": e2e, "e2e_f32_frames": e2e_f32,
+            "value_f32_frames": {"value": value_f32, "unit": "clips/s", "scores_identical_to_u8_path": f32_matches,
+                                 "what": "device-resident step fed with the reference's f32 frames tensor"},
+            "gpu_launches": int(launches.item()), "clocks": clocks, "roofline": roof, "parity": parity,
+            "configs": configs, "cpu_baseline": cpu, "kernel_ms": prof,
         }
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:

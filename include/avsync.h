@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AVS_VERSION 100 /* 0.1.0 */
+#define AVS_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define AVS_API __attribute__((visibility("default")))
@@ -62,8 +62,11 @@ enum {
 #define AVS_NMELS 128
 
 AVS_API int avs_version(void);
+/* sha256 (hex) of the sources this binary was compiled from (csrc/*.cu, *.cuh, Makefile, include/avsync.h, in sorted
+ * file-name order): lets a loader prove that a prebuilt .so matches the tree it sits in. */
+AVS_API const char* avs_source_hash(void);
 AVS_API const char* avs_last_error_string(void);
-/* 0 iff `device` is compute capability 10.x. */
+/* 0 iff `device` is compute capability 10.0 (the library is compiled for sm_100a only). */
 AVS_API int avs_device_check(int device);
 
 /* ---------------------------------------------------------------- K1: MFCC statistics sweep
@@ -107,6 +110,10 @@ AVS_API size_t avs_stcnn_workspace_bytes(const avs_stcnn* net, int n_clips);
  * c*72+h*12+w) and out_vstats (f32 [n_clips,13824] = [mean_t, unbiased std_t]) may each be NULL. */
 AVS_API int avs_stcnn_forward(const avs_stcnn* net, const float* frames, int n_clips, float* out_emb,
                       float* out_vstats, void* workspace, size_t workspace_bytes, void* stream);
+/* Same, from the 8-bit pixels the reference's frames tensor is made of (dataset.py:226-231: frames = float32(u8 / 255.0)):
+ * frames device u8 [n_clips,1,75,50,100].  Bit-identical outputs to avs_stcnn_forward on the f32 tensor of those pixels. */
+AVS_API int avs_stcnn_forward_u8(const avs_stcnn* net, const uint8_t* frames, int n_clips, float* out_emb,
+                         float* out_vstats, void* workspace, size_t workspace_bytes, void* stream);
 /* debug/parity: copy the pooled activations of layer 1/2 out as f32 NCDHW
  * ([n,32,75,25,50] / [n,64,75,12,25]); either pointer may be NULL. */
 AVS_API int avs_stcnn_forward_debug(const avs_stcnn* net, const float* frames, int n_clips, float* out_emb,
@@ -165,13 +172,23 @@ AVS_API int avs_sweep_create(const avs_stcnn* net, const avs_mfcc_plan* plan, co
                      const float* b1, const float* w2, const float* b2, int hidden,
                      int chunk_clips, avs_sweep** out);
 AVS_API void avs_sweep_destroy(avs_sweep* sw);
-/* frames/audio/out_* are DEVICE buffers; enqueues on `stream`, no sync. */
+/* frames/audio/out_* are DEVICE buffers; enqueues on `stream`, no host or device synchronisation (per-call buffers grow
+ * with stream-ordered allocations).  Calls on one handle are serialised on the device in issue order, whatever streams
+ * they are issued on (each call waits for the handle's previous one), so run / run_host may be mixed freely; calls on one
+ * handle must not be issued concurrently from several host threads. */
 AVS_API int avs_sweep_run(avs_sweep* sw, const float* frames, const float* audio, int n_clips,
                   float* out_scores, int32_t* out_best, void* stream);
 /* frames/audio/out_* are HOST buffers (pageable or pinned); copies are pipelined against
- * compute chunk by chunk; returns after the results are in the host buffers. */
+ * compute chunk by chunk on the handle's own streams; returns after the results are in the host buffers.  The detector
+ * and STCNN weights the handle points to must be complete (their producing streams synchronised) before the call. */
 AVS_API int avs_sweep_run_host(avs_sweep* sw, const float* frames_host, const float* audio_host,
                        int n_clips, float* out_scores_host, int32_t* out_best_host);
+/* u8-pixel variants (frames u8 [n_clips,1,75,50,100], 375 KB per clip instead of 1.5 MB): scores bit-identical to the f32
+ * entry points on float32(u8 / 255.0) frames. */
+AVS_API int avs_sweep_run_u8(avs_sweep* sw, const uint8_t* frames, const float* audio, int n_clips,
+                     float* out_scores, int32_t* out_best, void* stream);
+AVS_API int avs_sweep_run_host_u8(avs_sweep* sw, const uint8_t* frames_host, const float* audio_host,
+                          int n_clips, float* out_scores_host, int32_t* out_best_host);
 /* ---------------------------------------------------------------- decode metrics
  * Edit distances behind calculate_cer / calculate_wer (train.py:945-993) and the positional character
  * matches of evaluate_model (utils.py:83-86) for a batch of id sequences that are already on the device
@@ -203,12 +220,15 @@ AVS_API int avs_preproc_run(const avs_preproc* p, const uint8_t* frames, int n_c
 AVS_API void avs_prof_enable(int on);
 AVS_API void avs_prof_reset(void);
 AVS_API int avs_prof_read(int slot, double* total_ms, int* count);
-/* Experiment switches for the tcgen05 conv kernel (results become garbage; used only by
- * tools/conv_microbench.py and tools/conv_issuer_split.py to attribute time): 1 = weight stages loaded once,
- * 2 = activation planes loaded once, 4 = epilogue off, 8 = every MMA issued twice, 16 = clock64 split of the
- * issuer warps (printed by block 0), 32 = epilogue reads TMEM only, 64 = epilogue without stores.
- * 0 = normal operation. */
+#ifdef AVS_EXPERIMENTS
+/* Tools build only (make -C csrc EXPERIMENTS=1 -> libavsync_b200_exp.so; never part of the product library).
+ * Experiment switches for the tcgen05 conv kernel (results become garbage; used by tools/conv_microbench.py and
+ * tools/conv_issuer_split.py to attribute time): 1 = weight stages loaded once, 2 = activation planes loaded once,
+ * 4 = epilogue off, 8 = every MMA issued twice, 16 = clock64 split of the issuer warps (printed by block 0),
+ * 32 = epilogue reads TMEM only, 64 = epilogue without stores.  0 = normal operation.  The same build reads the
+ * environment knobs AVS_CONV{1,2,3}_WSTAGES / _RING, AVS_AUDIO_MODE, AVS_HOST_FIRST_CHUNK, AVS_GRU_FMA. */
 AVS_API void avs_debug_set(int flags);
+#endif
 /* How the persistent conv kernels split their work (host mirror of the device code, no GPU needed): the items of a
  * launch, in (clip, tile set, time step) order, are cut into n_ctas contiguous spans of near-equal cost (cost of an item =
  * its tile count; the last tile set of a plane may be partial).  Returns the half-open item range [first, last) of `cta`.

@@ -9,8 +9,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "avsync.h")
 
 
-def declared_symbols():
+def declared_symbols(experiments: bool = False):
     src = open(HEADER).read()
+    exp_blocks = re.findall(r"#ifdef AVS_EXPERIMENTS(.*?)#endif", src, flags=re.S)
+    if experiments:
+        src = "\n".join(exp_blocks)
+    else:
+        src = re.sub(r"#ifdef AVS_EXPERIMENTS.*?#endif", "", src, flags=re.S)
     return sorted(set(re.findall(r"AVS_API\s+[\w\s\*]+?\b(avs_\w+)\s*\(", src)))
 
 
@@ -26,7 +31,8 @@ def native():
 def test_header_declares_the_expected_surface():
     syms = declared_symbols()
     for must in ("avs_mfcc_stats_sweep", "avs_stcnn_forward", "avs_bigru_forward", "avs_sweep_score",
-                 "avs_ctc_greedy", "avs_sweep_run", "avs_sweep_run_host", "avs_version", "avs_last_error_string"):
+                 "avs_ctc_greedy", "avs_sweep_run", "avs_sweep_run_host", "avs_sweep_run_u8", "avs_sweep_run_host_u8",
+                 "avs_stcnn_forward_u8", "avs_source_hash", "avs_version", "avs_last_error_string"):
         assert must in syms
     assert len(syms) >= 27
 
@@ -39,7 +45,21 @@ def test_library_exports_every_declared_symbol(native):
 
 def test_binding_covers_every_declared_symbol(native):
     assert sorted(native.SIGNATURES) == declared_symbols()
-    assert native.lib().avs_version() == 100
+    assert sorted(native.EXPERIMENT_SIGNATURES) == declared_symbols(experiments=True)
+    assert native.lib().avs_version() == 200
+
+
+def test_product_library_carries_no_experiment_switches(native):
+    """The experiment switches (avs_debug_set, AVS_* environment knobs) live in the tools build only
+    (make EXPERIMENTS=1 -> libavsync_b200_exp.so): the product binary neither exports the switch nor reads the
+    environment, and its baked-in source hash matches the tree it was loaded from."""
+    import subprocess
+    L = ctypes.CDLL(native.LIB_PATH)
+    for s in declared_symbols(experiments=True):
+        assert not hasattr(L, s), f"{s} must not be exported by the product library"
+    undefined = subprocess.run(["nm", "-D", "--undefined-only", native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "getenv" not in undefined
+    assert native.lib().avs_source_hash().decode() == native.source_hash()
 
 
 def test_no_cpu_fallback_without_cuda(native):

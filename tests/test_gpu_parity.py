@@ -151,7 +151,11 @@ def test_mfcc_edge_cases(A):
 
 
 # ------------------------------------------------------------------------------------------ K2
-TOL = {"fp32": dict(rtol=1e-3, atol=1e-5), "bf16x3": dict(rtol=1e-3, atol=1e-4), "bf16": dict(rtol=3e-2, atol=6e-3)}
+TOL = {"fp32": dict(rtol=1e-3, atol=1e-5), "bf16x3": dict(rtol=1e-3, atol=1e-4)}
+# Single-pass bf16 (operands rounded to 8 mantissa bits, fp32 accumulation): absolute bounds pinned at ~2x the
+# error measured on the B200 (pool1 5.0e-3 on values <= 1.2, pool2 3.2e-3 on <= 0.67, emb 1.85e-3 on <= 0.28,
+# vstats 8.4e-4 on <= 0.23), so that a regression in the K split or the accumulation order cannot hide.
+TOL_BF16 = {"pool1": 1.0e-2, "pool2": 6.5e-3, "emb": 3.7e-3, "vstats": 1.7e-3}
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
@@ -162,18 +166,19 @@ def test_stcnn_vs_oracle_and_golden(A, golden, lipnet_sd, precision):
     net = make_lipnet(A, lipnet_sd, precision)
     emb, vst, p1, p2 = net.stcnn(frames.cuda(), want_vstats=True, debug=True)
     torch.cuda.synchronize()
-    tol = TOL[precision]
+    def tol(name):
+        return dict(rtol=0, atol=TOL_BF16[name]) if precision == "bf16" else TOL[precision]
     report(f"pool1[{precision}]", p1.cpu().numpy(), p1_ref.numpy())
     report(f"pool2[{precision}]", p2.cpu().numpy(), p2_ref.numpy())
     report(f"emb[{precision}]", emb.cpu().numpy(), emb_ref.numpy())
-    np.testing.assert_allclose(p1.cpu().numpy(), p1_ref.numpy(), **tol)
-    np.testing.assert_allclose(p2.cpu().numpy(), p2_ref.numpy(), **tol)
-    np.testing.assert_allclose(emb.cpu().numpy(), emb_ref.numpy(), **tol)
+    np.testing.assert_allclose(p1.cpu().numpy(), p1_ref.numpy(), **tol("pool1"))
+    np.testing.assert_allclose(p2.cpu().numpy(), p2_ref.numpy(), **tol("pool2"))
+    np.testing.assert_allclose(emb.cpu().numpy(), emb_ref.numpy(), **tol("emb"))
     g = golden("stcnn")
     flat = emb.reshape(2, -1).cpu().numpy()
-    np.testing.assert_allclose(flat[:, ::int(g["emb_stride"])], g["emb_sample"], **tol)
+    np.testing.assert_allclose(flat[:, ::int(g["emb_stride"])], g["emb_sample"], **tol("emb"))
     report(f"vstats[{precision}]", vst.cpu().numpy(), g["vstats"])
-    np.testing.assert_allclose(vst.cpu().numpy(), g["vstats"], **tol)
+    np.testing.assert_allclose(vst.cpu().numpy(), g["vstats"], **tol("vstats"))
     # drop-in entry point
     e2 = A.extract_visual_embeddings(net, frames.cuda())
     assert e2.is_cuda and torch.equal(e2, emb)
@@ -226,7 +231,19 @@ def test_bigru_head_vs_oracle(A, lipnet_sd, precision, n_clips):
     np.testing.assert_allclose(np.exp(got).sum(-1), 1.0, atol=1e-4)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def argmax_agreement(logp, logp_ref):
+    """Per-step arg-max agreement of two [B,T,V] log-prob arrays: (all steps agree where resolvable, fraction agreeing,
+    max |delta|, resolvable fraction).  A step is resolvable when the reference's top-2 margin exceeds 10x the largest
+    difference between the two arrays — below that the arg-max is not a property of the model but of rounding."""
+    d = float(np.abs(logp - logp_ref).max())
+    srt = np.sort(logp_ref, axis=-1)
+    margin = srt[..., -1] - srt[..., -2]
+    agree = logp.argmax(-1) == logp_ref.argmax(-1)
+    resolvable = margin > 10 * d
+    return bool(agree[resolvable].all()), float(agree.mean()), d, float(resolvable.mean())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
 def test_lipnet_forward_and_decode_vs_golden(A, golden, lipnet_sd, precision):
     g = golden("lipnet")
     frames = sweep_ref.synth_frames(2, seed=1234).cuda()
@@ -234,13 +251,23 @@ def test_lipnet_forward_and_decode_vs_golden(A, golden, lipnet_sd, precision):
     logp = net(frames)
     assert logp.shape == (2, 75, 39)
     report(f"logp[{precision}]", logp.cpu().numpy(), g["logp"])
-    np.testing.assert_allclose(logp.cpu().numpy(), g["logp"], rtol=1e-3, atol=2e-4)
 
     class DS:
         idx_to_char = lipnet_ref.make_vocab()
     texts = A.decode_batch(logp, DS)
-    assert texts == [str(t) for t in g["texts"]]
     assert [A.decode_prediction(logp[i], DS) for i in range(2)] == texts
+    if precision == "bf16":
+        # bf16 STCNN in front of the fp32-grade head: log-probs within 2e-3 of the reference's (measured: see the
+        # report line); CTC ids are compared step by step and must agree wherever the reference's own top-2 margin
+        # resolves the arg-max (random-init log-probs are near-uniform, so not every step does)
+        np.testing.assert_allclose(logp.cpu().numpy(), g["logp"], rtol=0, atol=2e-3)
+        ok, frac, d, res = argmax_agreement(logp.cpu().numpy(), g["logp"])
+        print(f"[parity] bf16 LipNet vs golden: arg-max agreement {frac:.4f} of steps, {res:.4f} resolvable, max|dlogp| {d:.2e}; "
+              f"texts {texts} vs {[str(t) for t in g['texts']]}")
+        assert ok
+        return
+    np.testing.assert_allclose(logp.cpu().numpy(), g["logp"], rtol=1e-3, atol=2e-4)
+    assert texts == [str(t) for t in g["texts"]]
 
 
 def test_config4_batch256_forward_and_decode(A, lipnet_sd):
@@ -263,6 +290,27 @@ def test_config4_batch256_forward_and_decode(A, lipnet_sd):
     np.testing.assert_allclose(lp[[5, 200]], want, rtol=1e-3, atol=2e-4)
 
 
+def test_config4_bf16_decode_agreement_with_fp32_grade(A, lipnet_sd):
+    """Config 4 in the headline dtype: 256 clips through the bf16 STCNN against the fp32-grade (bf16x3) path.
+    Greedy-CTC ids must be identical for every clip whose steps are all resolvable, and per step wherever the
+    fp32-grade top-2 margin is above 10x the measured log-prob difference; the unresolvable rest is counted and printed."""
+    n = 256
+    frames = sweep_ref.synth_frames(n, seed=77).cuda()
+    lp_ref = make_lipnet(A, lipnet_sd, "bf16x3")(frames)
+    lp = make_lipnet(A, lipnet_sd, "bf16")(frames)
+    ok, frac, d, res = argmax_agreement(lp.cpu().numpy(), lp_ref.cpu().numpy())
+    ids, lens = A.ctc_greedy_decode(lp)
+    ids_r, lens_r = A.ctc_greedy_decode(lp_ref)
+    same_clip = [(int(lens[i]) == int(lens_r[i]) and torch.equal(ids[i], ids_r[i])) for i in range(n)]
+    print(f"[parity] config 4 bf16 vs bf16x3: per-step arg-max agreement {frac:.5f}, resolvable steps {res:.5f}, "
+          f"max|dlogp| {d:.2e}, clips with identical decoded ids {sum(same_clip)}/{n}")
+    assert d < 2e-3 and ok
+    srt = np.sort(lp_ref.cpu().numpy(), axis=-1)
+    clip_resolvable = ((srt[..., -1] - srt[..., -2]) > 10 * d).all(axis=1)
+    for i in np.nonzero(clip_resolvable)[0]:
+        assert same_clip[i], i
+
+
 # ------------------------------------------------------------------------------------------ K4 + sweep
 def test_sweep_score_kernel_vs_oracle(A, det_sd):
     g = torch.Generator().manual_seed(4)
@@ -283,7 +331,9 @@ def test_sweep_score_kernel_vs_oracle(A, det_sd):
     assert (sc0 == 0.5).all() and (best0 == 0).all()
 
 
-@pytest.mark.parametrize("precision,atol", [("fp32", 2e-5), ("bf16x3", 2e-5), ("bf16", 3e-3)])
+# bf16: measured max |score - golden| = 7.5e-6 (the STCNN's bf16 error is common-mode across shifts and averaged over
+# 13 824 features); 5e-5 keeps the arg-max assertion live for both golden clips (top-2 margins 2.1e-3 and 4.6e-3)
+@pytest.mark.parametrize("precision,atol", [("fp32", 2e-5), ("bf16x3", 2e-5), ("bf16", 5e-5)])
 def test_sync_sweep_vs_golden(A, golden, lipnet_sd, det_sd, precision, atol):
     g = golden("sweep")
     frames = sweep_ref.synth_frames(2, seed=1234).cuda()
@@ -295,10 +345,104 @@ def test_sync_sweep_vs_golden(A, golden, lipnet_sd, det_sd, precision, atol):
     report(f"sweep scores[{precision}]", got, g["scores"])
     print("[parity] golden top-2 margins", g["margin"], "best", g["best"] - 20, "got", best.cpu().numpy())
     np.testing.assert_allclose(got, g["scores"], rtol=1e-3, atol=atol)
-    for i in range(2):
-        if g["margin"][i] > 2 * atol:              # best-offset arg-max must be exact when the margin is resolvable
-            assert int(best[i]) == int(g["best"][i]) - 20
+    assert (g["margin"] > 2 * atol).all(), "golden margins must be resolvable at this tolerance: the check below is live"
+    for i in range(2):                             # best-offset arg-max: bit-exact against the reference
+        assert int(best[i]) == int(g["best"][i]) - 20
     assert best.cpu().tolist() == (got.argmax(1) - 20).tolist()
+
+
+def test_bench_batch_bf16_vs_fp32_grade_best_offset(A, lipnet_sd, det_sd):
+    """The headline workload (1024 clips, +-20 frames) in the headline dtype against the fp32-grade path: best offsets
+    must agree for every clip whose fp32-grade top-2 margin exceeds 10x the largest score difference (north_star:
+    best-offset arg-max bit-exact); the rest is counted and printed.  Same inputs as bench.py (u8 pixels)."""
+    import bench
+    n = 1024
+    fr, au = bench.synth_inputs(n, seed=1000)
+    fr, au = fr.cuda(), au.cuda()
+    det = make_detector(A, det_sd)
+    out = {}
+    for prec in ("bf16x3", "bf16"):
+        sw = A.SyncSweeper(make_lipnet(A, lipnet_sd, prec), det, 20, chunk_clips=128)
+        s, b = sw.run(fr, au)
+        out[prec] = (s.cpu().numpy(), b.cpu().numpy())
+    p = bench.parity_stats(out["bf16"][0], out["bf16"][1], out["bf16x3"][0], out["bf16x3"][1])
+    print(f"[parity] bench batch bf16 vs bf16x3: {p}")
+    assert p["max_abs_dscore"] < 5e-5
+    assert p["argmax_agree_resolvable"] == 1.0
+    assert p["resolvable_frac"] > 0.5, "the agreement check must cover most of the batch"
+
+
+def test_u8_frames_bit_identical_to_f32(A, lipnet_sd, det_sd):
+    """GRID frames are uint8 / 255 (dataset.py:226-231): the u8 entry points must give the bits of the f32 ones."""
+    g = torch.Generator().manual_seed(11)
+    u8 = torch.randint(0, 256, (6, 1, 75, 50, 100), generator=g, dtype=torch.uint8)
+    f32 = torch.from_numpy((u8.numpy() / 255.0).astype(np.float32))          # the reference's arithmetic (float64 / then f32)
+    audio = sweep_ref.synth_audio(6, seed=3, kind="speechlike")
+    det = make_detector(A, det_sd)
+    for prec in ("bf16", "bf16x3", "fp32"):
+        net = make_lipnet(A, lipnet_sd, prec)
+        e_u8, v_u8 = net.stcnn(u8[:2].cuda(), want_vstats=True)
+        e_f, v_f = net.stcnn(f32[:2].cuda(), want_vstats=True)
+        assert torch.equal(e_u8, e_f) and torch.equal(v_u8, v_f), prec
+        if prec == "fp32":
+            continue
+        sw = A.SyncSweeper(net, det, 20, chunk_clips=4)
+        s_f, b_f = sw.run(f32.cuda(), torch.from_numpy(audio).cuda())
+        s_u, b_u = sw.run(u8.cuda(), torch.from_numpy(audio).cuda())
+        s_h, b_h = sw.run_host(u8.numpy(), audio)
+        assert torch.equal(s_f, s_u) and torch.equal(b_f, b_u), prec
+        assert np.array_equal(s_h, s_f.cpu().numpy()) and np.array_equal(b_h, b_f.cpu().numpy()), prec
+
+
+def test_sweeper_calls_interleave_without_syncs(A, lipnet_sd, det_sd):
+    """One handle, device and host entry points back to back on different streams and with growing batches (buffer
+    growth is stream-ordered), no synchronisation in between: every call must see its own inputs only."""
+    net, det = make_lipnet(A, lipnet_sd, "bf16"), make_detector(A, det_sd)
+    sw = A.SyncSweeper(net, det, 10, chunk_clips=4)
+    sets = []
+    for i, n in enumerate((3, 9, 5, 17)):
+        fr = sweep_ref.synth_frames(n, seed=50 + i)
+        au = sweep_ref.synth_audio(n, seed=50 + i, kind="speechlike")
+        sets.append((fr, au, fr.cuda(), torch.from_numpy(au).cuda()))
+    torch.cuda.synchronize()
+    ref = []
+    for fr, au, frd, aud in sets:                                    # reference results, one synchronised call each
+        s, b = A.SyncSweeper(net, det, 10, chunk_clips=4).run(frd, aud)
+        torch.cuda.synchronize()
+        ref.append((s.cpu().numpy(), b.cpu().numpy()))
+    side = torch.cuda.Stream()
+    got = []
+    for rep_ in range(3):
+        for j, (fr, au, frd, aud) in enumerate(sets):
+            if (j + rep_) % 3 == 0:
+                got.append((j, sw.run_host(fr.numpy(), au)))
+            elif (j + rep_) % 3 == 1:
+                with torch.cuda.stream(side):
+                    got.append((j, sw.run(frd, aud)))
+            else:
+                got.append((j, sw.run(frd, aud)))
+    torch.cuda.synchronize()
+    for j, (s, b) in got:
+        s = s.cpu().numpy() if torch.is_tensor(s) else s
+        b = b.cpu().numpy() if torch.is_tensor(b) else b
+        assert np.array_equal(s, ref[j][0]) and np.array_equal(b, ref[j][1]), j
+
+
+def test_sweep_with_odd_n_mfcc(A, lipnet_sd):
+    """n_mfcc = 13 (the common choice) makes the detector's row stride 13850, not a multiple of 4 floats."""
+    net = make_lipnet(A, lipnet_sd, "bf16x3")
+    torch.manual_seed(5)
+    det = A.MisalignmentDetector(13824 + 26, 64).cuda().eval()
+    frames = sweep_ref.synth_frames(2, seed=8).cuda()
+    audio = torch.from_numpy(sweep_ref.synth_audio(2, seed=8, kind="speechlike")).cuda()
+    scores, best = A.sync_sweep(net, det, frames, audio, 5, n_mfcc=13)
+    vst = A.visual_stats(net, frames)
+    ast = A.audio_stats_sweep(audio, [640 * k for k in range(-5, 6)], 16000, 13)
+    with torch.no_grad():
+        x = torch.cat([vst[:, None, :].expand(-1, 11, -1), ast], dim=-1)
+        want = torch.sigmoid(det(x))
+    np.testing.assert_allclose(scores.cpu().numpy(), want.cpu().numpy(), rtol=1e-3, atol=2e-5)
+    assert (best + 5).cpu().tolist() == scores.argmax(1).cpu().tolist()
 
 
 def test_sweeper_host_entry_and_chunking(A, lipnet_sd, det_sd):

@@ -8,6 +8,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import avsync_b200 as A
 
+A._native.use_experiments_build()   # libavsync_b200_exp.so: avs_debug_set + AVS_* knobs (make -C csrc EXPERIMENTS=1)
 L = A._native.lib()
 B = int(os.environ.get("MB_CLIPS", "64"))
 frames = torch.rand((B, 1, 75, 50, 100), generator=torch.Generator().manual_seed(3)).cuda()
