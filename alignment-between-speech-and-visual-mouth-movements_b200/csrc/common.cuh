@@ -236,6 +236,11 @@ __device__ __host__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
          | (static_cast<uint32_t>(M >> 4) << 24); // m_dim
 }
 
+// fire-and-forget f64 add to global memory (no return value: the L2 performs it)
+__device__ __forceinline__ void red_add_f64(double* addr, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

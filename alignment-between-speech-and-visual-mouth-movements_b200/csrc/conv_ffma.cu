@@ -130,6 +130,59 @@ vstats_kernel(const float* __restrict__ emb, float* __restrict__ out, int F) {
   out[static_cast<size_t>(b) * 2 * F + F + f] = sqrtf(ss / (T - 1));
 }
 
+// Fused-statistics path (conv3 epilogue mode 2): fold the per-(clip, part) f64 partial sums into
+// [mean_t, unbiased std_t] (misalignment_detection_train.py:165) and leave the scratch zeroed for the next launch.
+// Parts are added in part order, so the result does not depend on which CTA finished first.
+__global__ void __launch_bounds__(128)
+vstats_finish_kernel(double* __restrict__ stat, int parts, float* __restrict__ out, int F, int T) {
+  const int f = blockIdx.x * 128 + threadIdx.x, b = blockIdx.y;
+  if (f >= F) return;
+  double* base = stat + static_cast<size_t>(b) * parts * 2 * F;
+  double s = 0.0, ss = 0.0;
+  for (int p = 0; p < parts; ++p) {
+    double* q = base + static_cast<size_t>(p) * 2 * F;
+    s += q[f];
+    ss += q[F + f];
+    q[f] = 0.0;
+    q[F + f] = 0.0;
+  }
+  const double mean = s / T;
+  const double var = fmax(ss - s * mean, 0.0) / (T - 1);   // sum (x - mean)^2 = sum x^2 - (sum x)^2 / T, exact to ~1e-16 relative in f64
+  out[static_cast<size_t>(b) * 2 * F + f] = static_cast<float>(mean);
+  out[static_cast<size_t>(b) * 2 * F + F + f] = static_cast<float>(sqrt(var));
+}
+
+int vstat_parts(int n_clips, int items_per_clip, int n_sms) {
+  if (n_clips <= 0 || items_per_clip <= 0) return 1;
+  const long long items = static_cast<long long>(n_clips) * items_per_clip;
+  const long long grid = items < n_sms ? items : n_sms;
+  const long long span_min = items / grid;                       // spans are floor or ceil of items / grid
+  long long parts = (items_per_clip + span_min - 1) / span_min + 1;
+  if (parts > items_per_clip) parts = items_per_clip;
+  if (parts > grid) parts = grid;
+  return static_cast<int>(parts);
+}
+
+size_t vstat_scratch_bytes(int cap_clips, int items_per_clip, int n_sms) {
+  size_t worst = 0;  // a call may bring any number of clips up to the capacity: clips x parts peaks for small batches
+  for (int b = 1; b <= cap_clips; ++b) {
+    const size_t n = static_cast<size_t>(b) * vstat_parts(b, items_per_clip, n_sms);
+    if (n > worst) worst = n;
+  }
+  return worst * 2 * AVS_EMB * sizeof(double);
+}
+
+int vstats_finish(double* stat, int parts, float* out, int B, cudaStream_t st) {
+  ProfScope ps(PROF_VSTATS, st);
+  for (int b0 = 0; b0 < B; b0 += 32768) {
+    const int nb = B - b0 < 32768 ? B - b0 : 32768;
+    vstats_finish_kernel<<<dim3(cdiv(AVS_EMB, 128), nb), 128, 0, st>>>(stat + static_cast<size_t>(b0) * parts * 2 * AVS_EMB, parts,
+                                                                      out + static_cast<size_t>(b0) * 2 * AVS_EMB, AVS_EMB, AVS_T);
+    AVS_LAUNCHED();
+  }
+  return AVS_OK;
+}
+
 int vstats(const float* emb, float* out, int B, int F, cudaStream_t st) {
   if (B <= 0) return AVS_OK;
   ProfScope ps(PROF_VSTATS, st);

@@ -534,6 +534,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     constexpr int kHo = K::H / 2, kWo = K::W / 2, kPlane = kHo * kWo;
     const int half = lane & 1;                 // even lane: channels 0..15 of a 32-column block, odd: 16..31
     uint32_t buf = 0, phase = 0;
+    int stat_clip = -1, stat_part = 0;
     ItemWalk w;
     w.init(p);
     for (; w.valid(); w.next(), buf = (buf + 1 == static_cast<uint32_t>(p.NBUF)) ? 0 : buf + 1, phase ^= (buf == 0)) {
@@ -543,22 +544,37 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       __syncwarp();  // tcgen05.ld below is .aligned
       tc_fence_after();
       const uint32_t d_base = tmem_base + buf * (NT * 2 * K::ACC) + (static_cast<uint32_t>(q * 32) << 16);
+      // mode 2 (conv3, visual statistics only): which (clip, part) slab of the scratch this CTA adds into.  part = this
+      // CTA's rank among the CTAs whose span touches the clip; the first of them is found by walking the span starts down.
+      double* stat_base = nullptr;
+      if (kToEmb && p.eo.mode == 2) {
+        if (b != stat_clip) {
+          stat_clip = b;
+          const long long total = static_cast<long long>(p.n_items / p.n_tilesets) * p.n_tiles;
+          int c = blockIdx.x;
+          while (c > 0 && ItemWalk::item_at_cost(p, total * c / gridDim.x) > b * p.T) --c;
+          stat_part = static_cast<int>(blockIdx.x) - c;
+        }
+        stat_base = p.eo.stat + (static_cast<long long>(b) * p.eo.stat_parts + stat_part) * (2 * K::N * kPlane);
+      }
       for (int i = 0; i < ((AVS_DBG(p) & 4) ? 0 : nt); ++i) {
         int Q = (ts * NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
         int t_out = t;
+        bool warp_has_work = true;
         if (K::tcat) {  // time-concatenated position space: item index -> (time step, position in its plane)
           const int S = (t * NT + i) * 128 + q * 32 + lane;
           t_out = S / K::PITCH;
           Q = S - t_out * K::PITCH;
-          if (((t * NT + i) * 128 + q * 32) / K::PITCH >= p.T_out) continue;  // the whole warp is past the last time step
+          if (((t * NT + i) * 128 + q * 32) / K::PITCH >= p.T_out) warp_has_work = false;  // the whole warp is past the last time step
         }
         const int r = Q / K::WT, wc = Q % K::WT;            // pooled row, conv column
         const int wo = wc >> 1;
         const bool valid = (r < kHo) && (wo < kWo) && (t_out < p.T_out);
         // positions grow with the lane: if the warp's first lane is already past the last pooled row, nobody has work
-        if (!K::tcat && ((ts * NT + i) * 128 + q * 32) / K::WT >= kHo) continue;
+        if (!K::tcat && ((ts * NT + i) * 128 + q * 32) / K::WT >= kHo) warp_has_work = false;
 #pragma unroll
         for (int cb = 0; cb < K::N; cb += 32) {
+          if (!warp_has_work) break;
           if (((((i * K::N) >> 5) + (cb >> 5)) & 1) != grp) continue;  // warp-uniform
           uint32_t v0[32], v1[32];
           tmem_ld32(d_base + (i * 2 + 0) * K::ACC + cb, v0);
@@ -619,6 +635,17 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
               *reinterpret_cast<uint4*>(out_ptr(idx * 2 + (hp & 1))) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               if (K::split) *reinterpret_cast<uint4*>(out_ptr((idx + 1) * 2 + (hp & 1))) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
+          } else if (valid && kToEmb && stat_base != nullptr) {
+            // time sums of the feature (c, r, wo) in f64 (x and x*x of an fp32 value are exact in f64): fire-and-forget
+            // reductions into this CTA's private slab.  The order in which one accumulator receives its addends is fixed by
+            // the barriers below, so the sums do not depend on timing.
+            double* acc = stat_base + ch0 * kPlane + r * kWo + wo;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const double x = static_cast<double>(o[c]);
+              red_add_f64(acc + c * kPlane, x);
+              red_add_f64(acc + K::N * kPlane + c * kPlane, x * x);
+            }
           } else if (valid) {
             float* dst = p.eo.emb + (static_cast<long long>(b) * p.T_out + t_out) * (K::N * kPlane) + ch0 * kPlane + r * kWo + wo;
 #pragma unroll
@@ -626,6 +653,10 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
           }
           __syncwarp();
         }
+        // mode 2: a feature occurs at most once per 128-position tile (128 < PITCH), but the tiles of an item — and
+        // consecutive items — hold the same feature at different time steps, handled by different warps: all eight
+        // epilogue warps finish tile i before any of them adds tile i+1, which fixes the order of every accumulator's addends
+        if (kToEmb && stat_base != nullptr) asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       tc_fence_before();
       __syncwarp();
