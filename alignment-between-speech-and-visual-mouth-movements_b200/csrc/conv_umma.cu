@@ -34,6 +34,7 @@
 // mbarrier rings: a_full/a_empty[RING], w_full/w_empty[WSTAGES], acc_full/acc_empty[NBUF]; turn[4] are the early and
 // final hand-over tokens between the two issuer warps.
 #include <stdlib.h>
+#include <type_traits>
 #include <vector>
 #include "stcnn.cuh"
 
@@ -546,7 +547,11 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       const uint32_t d_base = tmem_base + buf * (NT * 2 * K::ACC) + (static_cast<uint32_t>(q * 32) << 16);
       // mode 2 (conv3, visual statistics only): which (clip, part) slab of the scratch this CTA adds into.  part = this
       // CTA's rank among the CTAs whose span touches the clip; the first of them is found by walking the span starts down.
-      double* stat_base = nullptr;
+      // Slab layout [feature][2] = (sum_t x, sum_t x^2): f32 pairs in the bf16 kind (one red.v2.f32 per value), f64 pairs in
+      // the fp32-grade kind (two red.f64 per value).
+      using StatT = typename std::conditional<K::split, double, float>::type;
+      StatT* stat_base = nullptr;
+      bool acc_released = false;
       if (kToEmb && p.eo.mode == 2) {
         if (b != stat_clip) {
           stat_clip = b;
@@ -555,8 +560,12 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
           while (c > 0 && ItemWalk::item_at_cost(p, total * c / gridDim.x) > b * p.T) --c;
           stat_part = static_cast<int>(blockIdx.x) - c;
         }
-        stat_base = p.eo.stat + (static_cast<long long>(b) * p.eo.stat_parts + stat_part) * (2 * K::N * kPlane);
+        stat_base = static_cast<StatT*>(p.eo.stat) + (static_cast<long long>(b) * p.eo.stat_parts + stat_part) * (2 * K::N * kPlane);
       }
+      // last (tile, column block) unit of the item that this epilogue group reads: after its TMEM loads have landed in
+      // registers the accumulator buffer goes back to the issuers, before the arithmetic and the stores
+      const int n_units_item = nt * (K::N / 32);
+      const int last_unit = ((n_units_item - 1) & 1) == grp ? n_units_item - 1 : n_units_item - 2;
       for (int i = 0; i < ((AVS_DBG(p) & 4) ? 0 : nt); ++i) {
         int Q = (ts * NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
         int t_out = t;
@@ -599,6 +608,12 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
               v1[c] = __float_as_uint(__uint_as_float(v1[c]) + __uint_as_float(u1[c]));
             }
           }
+          if (i * (K::N / 32) + (cb >> 5) == last_unit) {  // warp-uniform: this warp's TMEM reads of the item are done
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            acc_released = true;
+          }
           float o[16];
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
@@ -639,12 +654,16 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
             // time sums of the feature (c, r, wo) in f64 (x and x*x of an fp32 value are exact in f64): fire-and-forget
             // reductions into this CTA's private slab.  The order in which one accumulator receives its addends is fixed by
             // the barriers below, so the sums do not depend on timing.
-            double* acc = stat_base + ch0 * kPlane + r * kWo + wo;
+            StatT* acc = stat_base + 2 * (ch0 * kPlane + r * kWo + wo);
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-              const double x = static_cast<double>(o[c]);
-              red_add_f64(acc + c * kPlane, x);
-              red_add_f64(acc + K::N * kPlane + c * kPlane, x * x);
+              if constexpr (K::split) {
+                const double x = static_cast<double>(o[c]);
+                red_add_f64(acc + 2 * c * kPlane, x);
+                red_add_f64(acc + 2 * c * kPlane + 1, x * x);
+              } else {
+                red_add_v2f32(acc + 2 * c * kPlane, o[c], o[c] * o[c]);
+              }
             }
           } else if (valid) {
             float* dst = p.eo.emb + (static_cast<long long>(b) * p.T_out + t_out) * (K::N * kPlane) + ch0 * kPlane + r * kWo + wo;
@@ -658,9 +677,11 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         // epilogue warps finish tile i before any of them adds tile i+1, which fixes the order of every accumulator's addends
         if (kToEmb && stat_base != nullptr) asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (!acc_released) {  // no unit of this item's last tile was ours (or the experiment switches skipped it)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
     }
   }
   tc_fence_before();

@@ -25,7 +25,7 @@ struct StcnnWs {  // workspace carve, shared by size query and forward
   float* p1; float* p2; float* emb;                  // fp32 path: pooled NCDHW activations; emb when caller passes none
   __nv_bfloat16* act[3];                             // tensor-core path: parity-plane inputs of the three layers
   size_t act_bytes[3];
-  double* stat; size_t stat_bytes;                   // tensor-core path, statistics only: f64 time sums (conv3 epilogue mode 2)
+  void* stat; size_t stat_bytes;                   // tensor-core path, statistics only: f64 time sums (conv3 epilogue mode 2)
   size_t total;
 };
 
@@ -45,8 +45,8 @@ static StcnnWs carve(const avs_stcnn* net, int B, void* ws, bool need_emb) {
       r.act_bytes[l] = umma_act_bytes(net->L[l].g, split, B);
       r.act[l] = reinterpret_cast<__nv_bfloat16*>(c.take<uint8_t>(r.act_bytes[l]));
     }
-    r.stat_bytes = vstat_scratch_bytes(B, net->L[2].g.tcat_items, net->n_sms);
-    r.stat = reinterpret_cast<double*>(c.take<uint8_t>(r.stat_bytes));
+    r.stat_bytes = vstat_scratch_bytes(B, net->L[2].g.tcat_items, net->n_sms, split != 0);
+    r.stat = c.take<uint8_t>(r.stat_bytes);
   }
   if (need_emb) r.emb = c.take<float>(static_cast<size_t>(B) * AVS_T * AVS_EMB);
   r.total = align_up(c.off, 256);
@@ -207,7 +207,8 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
     if (out_pool1 && (rc = umma_unpack_act(w.act[1], out_pool1, net->L[1].g, split, 32, B, st))) return rc;
     if (out_pool2 && (rc = umma_unpack_act(w.act[2], out_pool2, net->L[2].g, split, 64, B, st))) return rc;
   }
-  if (fused_stats) return vstats_finish(w.stat, vstat_parts(B, net->L[2].g.tcat_items, net->n_sms), out_vstats, B, st);
+  if (fused_stats)
+    return vstats_finish(w.stat, net->precision == AVS_PREC_BF16X3, vstat_parts(B, net->L[2].g.tcat_items, net->n_sms), out_vstats, B, st);
   if (out_vstats && (rc = vstats(emb, out_vstats, B, AVS_EMB, st))) return rc;
   return AVS_OK;
 }

@@ -187,7 +187,7 @@ def test_stcnn_vs_oracle_and_golden(A, golden, lipnet_sd, precision):
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
 def test_fused_visual_stats_match_embedding_path(A, golden, lipnet_sd, precision):
     """Statistics-only calls (the sweep) never write the embedding: the conv3 epilogue accumulates sum_t x and sum_t x^2
-    in f64 and a finishing kernel forms [mean_t, unbiased std_t] (misalignment_detection_train.py:165).  Same values as
+    (f64 in the fp32-grade kind, f32 pairs in the bf16 kind) and a finishing kernel forms [mean_t, unbiased std_t] (misalignment_detection_train.py:165).  Same values as
     the statistics of the written embedding (both are within rounding of the exact ones), golden parity unchanged,
     run-to-run and batch-split bit-identical (the accumulation order is fixed by barriers, not by timing)."""
     net = make_lipnet(A, lipnet_sd, precision)
@@ -196,7 +196,9 @@ def test_fused_visual_stats_match_embedding_path(A, golden, lipnet_sd, precision
     none, v_fused = net.stcnn(frames, want_vstats=True, want_emb=False)
     assert none is None
     report(f"vstats fused vs emb path[{precision}]", v_fused.cpu().numpy(), v_emb.cpu().numpy())
-    np.testing.assert_allclose(v_fused.cpu().numpy(), v_emb.cpu().numpy(), rtol=2e-5, atol=2e-7)
+    # fp32-grade kind: f64 partial sums; bf16 kind: f32 partial sums (relative variance error ~1e-7 * (1 + mean^2 / var))
+    np.testing.assert_allclose(v_fused.cpu().numpy(), v_emb.cpu().numpy(), **(dict(rtol=2e-5, atol=2e-7) if precision == "bf16x3"
+                                                                               else dict(rtol=2e-4, atol=1e-6)))
     g = golden("stcnn")
     tol = dict(rtol=0, atol=TOL_BF16["vstats"]) if precision == "bf16" else TOL[precision]
     np.testing.assert_allclose(v_fused.cpu().numpy(), g["vstats"], **tol)
