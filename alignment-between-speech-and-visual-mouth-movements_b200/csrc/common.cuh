@@ -236,16 +236,6 @@ __device__ __host__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
          | (static_cast<uint32_t>(M >> 4) << 24); // m_dim
 }
 
-// fire-and-forget f64 add to global memory (no return value: the L2 performs it)
-__device__ __forceinline__ void red_add_f64(double* addr, double v) {
-  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
-}
-
-// one 8-byte reduction for an adjacent f32 pair (sm_90+)
-__device__ __forceinline__ void red_add_v2f32(float* addr, float a, float b) {
-  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
-}
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

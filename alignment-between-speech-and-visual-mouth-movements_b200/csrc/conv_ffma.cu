@@ -6,7 +6,6 @@
 // CO_T = 8 output channels: each thread owns one pooled position = a 2 x 2 conv quad x 8 channels.
 // Input patches (3 time planes x (32 + KH - 1) x (32 + KW - 1)) and the weights of the current input
 // channel are staged in shared memory.
-#include <type_traits>
 #include "stcnn.cuh"
 
 namespace avs {
@@ -129,75 +128,6 @@ vstats_kernel(const float* __restrict__ emb, float* __restrict__ out, int F) {
   }
   out[static_cast<size_t>(b) * 2 * F + f] = mean;
   out[static_cast<size_t>(b) * 2 * F + F + f] = sqrtf(ss / (T - 1));
-}
-
-// Fused-statistics path (conv3 epilogue mode 2): fold the per-(clip, part) partial sums (sum_t x, sum_t x^2) into
-// [mean_t, unbiased std_t] (misalignment_detection_train.py:165) and leave the scratch zeroed for the next launch.
-// Parts are added in part order, so the result does not depend on which CTA finished first.  The final arithmetic is
-// f64: sum (x - mean)^2 = sum x^2 - (sum x)^2 / T.  With f64 partials (fp32-grade kind) that is exact to ~1e-16 of
-// sum x^2; with f32 partials (bf16 kind) the partial sums carry ~1e-7 relative rounding, i.e. a relative error of about
-// 1e-7 * (1 + mean^2 / var) on the variance — below the bf16 kind's own error (2^-9 per operand) for mean / std < 100.
-template <typename StatT>
-__global__ void __launch_bounds__(256)
-vstats_finish_kernel(StatT* __restrict__ stat, int parts, float* __restrict__ out, int F, int T) {
-  const int f = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
-  if (f >= F) return;
-  using Pair = typename std::conditional<sizeof(StatT) == 8, double2, float2>::type;
-  Pair* base = reinterpret_cast<Pair*>(stat) + static_cast<size_t>(b) * parts * F + f;
-  Pair v[4];
-  double s = 0.0, ss = 0.0;
-  for (int p0 = 0; p0 < parts; p0 += 4) {  // loads of four parts in flight, then their zeroing stores
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (p0 + j < parts) v[j] = base[static_cast<size_t>(p0 + j) * F];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (p0 + j < parts) {
-        s += static_cast<double>(v[j].x);
-        ss += static_cast<double>(v[j].y);
-        Pair z; z.x = 0; z.y = 0;
-        base[static_cast<size_t>(p0 + j) * F] = z;
-      }
-  }
-  const double mean = s / T;
-  const double var = fmax(ss - s * mean, 0.0) / (T - 1);
-  out[static_cast<size_t>(b) * 2 * F + f] = static_cast<float>(mean);
-  out[static_cast<size_t>(b) * 2 * F + F + f] = static_cast<float>(sqrt(var));
-}
-
-int vstat_parts(int n_clips, int items_per_clip, int n_sms) {
-  if (n_clips <= 0 || items_per_clip <= 0) return 1;
-  const long long items = static_cast<long long>(n_clips) * items_per_clip;
-  const long long grid = items < n_sms ? items : n_sms;
-  const long long span_min = items / grid;                       // spans are floor or ceil of items / grid
-  long long parts = (items_per_clip + span_min - 1) / span_min + 1;
-  if (parts > items_per_clip) parts = items_per_clip;
-  if (parts > grid) parts = grid;
-  return static_cast<int>(parts);
-}
-
-size_t vstat_scratch_bytes(int cap_clips, int items_per_clip, int n_sms, bool f64) {
-  size_t worst = 0;  // a call may bring any number of clips up to the capacity: clips x parts peaks for small batches
-  for (int b = 1; b <= cap_clips; ++b) {
-    const size_t n = static_cast<size_t>(b) * vstat_parts(b, items_per_clip, n_sms);
-    if (n > worst) worst = n;
-  }
-  return worst * 2 * AVS_EMB * (f64 ? sizeof(double) : sizeof(float));
-}
-
-int vstats_finish(void* stat, bool f64, int parts, float* out, int B, cudaStream_t st) {
-  ProfScope ps(PROF_VSTATS, st);
-  const size_t clip_bytes = static_cast<size_t>(parts) * 2 * AVS_EMB * (f64 ? sizeof(double) : sizeof(float));
-  for (int b0 = 0; b0 < B; b0 += 32768) {
-    const int nb = B - b0 < 32768 ? B - b0 : 32768;
-    const dim3 grid(cdiv(AVS_EMB, 256), nb);
-    void* sp = static_cast<uint8_t*>(stat) + b0 * clip_bytes;
-    float* op = out + static_cast<size_t>(b0) * 2 * AVS_EMB;
-    if (f64) vstats_finish_kernel<double><<<grid, 256, 0, st>>>(static_cast<double*>(sp), parts, op, AVS_EMB, AVS_T);
-    else vstats_finish_kernel<float><<<grid, 256, 0, st>>>(static_cast<float*>(sp), parts, op, AVS_EMB, AVS_T);
-    AVS_LAUNCHED();
-  }
-  return AVS_OK;
 }
 
 int vstats(const float* emb, float* out, int B, int F, cudaStream_t st) {

@@ -34,7 +34,6 @@
 // mbarrier rings: a_full/a_empty[RING], w_full/w_empty[WSTAGES], acc_full/acc_empty[NBUF]; turn[4] are the early and
 // final hand-over tokens between the two issuer warps.
 #include <stdlib.h>
-#include <type_traits>
 #include <vector>
 #include "stcnn.cuh"
 
@@ -522,8 +521,10 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     }
     if ((dbg & 16) && lane == 0 && blockIdx.x == 0) {
       tk_total = clock64() - tk_total;
-      printf("conv issuer %u block %d (N=%d): total %lld cycles | operand waits %lld | turn wait %lld | issue+commit %lld | rest %lld\n",
-             x, blockIdx.x, p.N, tk_total, tk_prep, tk_turn, tk_issue, tk_total - tk_prep - tk_turn - tk_issue);
+      uint32_t hw_warp;
+      asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw_warp));
+      printf("conv issuer %u (hw warp slot %u) block %d (N=%d): total %lld cycles | operand waits %lld | turn wait %lld | issue+commit %lld | rest %lld\n",
+             x, hw_warp, blockIdx.x, p.N, tk_total, tk_prep, tk_turn, tk_issue, tk_total - tk_prep - tk_turn - tk_issue);
     }
   } else if (warp >= 4) {
     // ============================================================ epilogue
@@ -535,7 +536,6 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     constexpr int kHo = K::H / 2, kWo = K::W / 2, kPlane = kHo * kWo;
     const int half = lane & 1;                 // even lane: channels 0..15 of a 32-column block, odd: 16..31
     uint32_t buf = 0, phase = 0;
-    int stat_clip = -1, stat_part = 0;
     ItemWalk w;
     w.init(p);
     for (; w.valid(); w.next(), buf = (buf + 1 == static_cast<uint32_t>(p.NBUF)) ? 0 : buf + 1, phase ^= (buf == 0)) {
@@ -545,45 +545,27 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       __syncwarp();  // tcgen05.ld below is .aligned
       tc_fence_after();
       const uint32_t d_base = tmem_base + buf * (NT * 2 * K::ACC) + (static_cast<uint32_t>(q * 32) << 16);
-      // mode 2 (conv3, visual statistics only): which (clip, part) slab of the scratch this CTA adds into.  part = this
-      // CTA's rank among the CTAs whose span touches the clip; the first of them is found by walking the span starts down.
-      // Slab layout [feature][2] = (sum_t x, sum_t x^2): f32 pairs in the bf16 kind (one red.v2.f32 per value), f64 pairs in
-      // the fp32-grade kind (two red.f64 per value).
-      using StatT = typename std::conditional<K::split, double, float>::type;
-      StatT* stat_base = nullptr;
-      bool acc_released = false;
-      if (kToEmb && p.eo.mode == 2) {
-        if (b != stat_clip) {
-          stat_clip = b;
-          const long long total = static_cast<long long>(p.n_items / p.n_tilesets) * p.n_tiles;
-          int c = blockIdx.x;
-          while (c > 0 && ItemWalk::item_at_cost(p, total * c / gridDim.x) > b * p.T) --c;
-          stat_part = static_cast<int>(blockIdx.x) - c;
-        }
-        stat_base = static_cast<StatT*>(p.eo.stat) + (static_cast<long long>(b) * p.eo.stat_parts + stat_part) * (2 * K::N * kPlane);
-      }
-      // last (tile, column block) unit of the item that this epilogue group reads: after its TMEM loads have landed in
+      // last (tile, column block) unit of the item that this epilogue group reads: once its TMEM loads have landed in
       // registers the accumulator buffer goes back to the issuers, before the arithmetic and the stores
       const int n_units_item = nt * (K::N / 32);
       const int last_unit = ((n_units_item - 1) & 1) == grp ? n_units_item - 1 : n_units_item - 2;
+      bool acc_released = false;
       for (int i = 0; i < ((AVS_DBG(p) & 4) ? 0 : nt); ++i) {
         int Q = (ts * NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
         int t_out = t;
-        bool warp_has_work = true;
         if (K::tcat) {  // time-concatenated position space: item index -> (time step, position in its plane)
           const int S = (t * NT + i) * 128 + q * 32 + lane;
           t_out = S / K::PITCH;
           Q = S - t_out * K::PITCH;
-          if (((t * NT + i) * 128 + q * 32) / K::PITCH >= p.T_out) warp_has_work = false;  // the whole warp is past the last time step
+          if (((t * NT + i) * 128 + q * 32) / K::PITCH >= p.T_out) continue;  // the whole warp is past the last time step
         }
         const int r = Q / K::WT, wc = Q % K::WT;            // pooled row, conv column
         const int wo = wc >> 1;
         const bool valid = (r < kHo) && (wo < kWo) && (t_out < p.T_out);
         // positions grow with the lane: if the warp's first lane is already past the last pooled row, nobody has work
-        if (!K::tcat && ((ts * NT + i) * 128 + q * 32) / K::WT >= kHo) warp_has_work = false;
+        if (!K::tcat && ((ts * NT + i) * 128 + q * 32) / K::WT >= kHo) continue;
 #pragma unroll
         for (int cb = 0; cb < K::N; cb += 32) {
-          if (!warp_has_work) break;
           if (((((i * K::N) >> 5) + (cb >> 5)) & 1) != grp) continue;  // warp-uniform
           uint32_t v0[32], v1[32];
           tmem_ld32(d_base + (i * 2 + 0) * K::ACC + cb, v0);
@@ -650,21 +632,6 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
               *reinterpret_cast<uint4*>(out_ptr(idx * 2 + (hp & 1))) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               if (K::split) *reinterpret_cast<uint4*>(out_ptr((idx + 1) * 2 + (hp & 1))) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-          } else if (valid && kToEmb && stat_base != nullptr) {
-            // time sums of the feature (c, r, wo) in f64 (x and x*x of an fp32 value are exact in f64): fire-and-forget
-            // reductions into this CTA's private slab.  The order in which one accumulator receives its addends is fixed by
-            // the barriers below, so the sums do not depend on timing.
-            StatT* acc = stat_base + 2 * (ch0 * kPlane + r * kWo + wo);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              if constexpr (K::split) {
-                const double x = static_cast<double>(o[c]);
-                red_add_f64(acc + 2 * c * kPlane, x);
-                red_add_f64(acc + 2 * c * kPlane + 1, x * x);
-              } else {
-                red_add_v2f32(acc + 2 * c * kPlane, o[c], o[c] * o[c]);
-              }
-            }
           } else if (valid) {
             float* dst = p.eo.emb + (static_cast<long long>(b) * p.T_out + t_out) * (K::N * kPlane) + ch0 * kPlane + r * kWo + wo;
 #pragma unroll
@@ -672,12 +639,8 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
           }
           __syncwarp();
         }
-        // mode 2: a feature occurs at most once per 128-position tile (128 < PITCH), but the tiles of an item — and
-        // consecutive items — hold the same feature at different time steps, handled by different warps: all eight
-        // epilogue warps finish tile i before any of them adds tile i+1, which fixes the order of every accumulator's addends
-        if (kToEmb && stat_base != nullptr) asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      if (!acc_released) {  // no unit of this item's last tile was ours (or the experiment switches skipped it)
+      if (!acc_released) {  // the warp skipped the item's last tile (positions past the plane) or the experiment switches did
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);

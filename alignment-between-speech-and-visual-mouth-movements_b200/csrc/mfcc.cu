@@ -58,6 +58,12 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 // shared memory per warp, ONE warp per CTA: the persistent conv kernels leave ~25 KB of shared memory per SM, and
 // three one-warp CTAs beside them beat one two-warp CTA (whole sweep step 43.7 -> 42.7 ms).
 constexpr int kWarpFftWarps = 1;
+// Scheduler-aware variant (kFftCtaWarps warps per CTA, kFftCtaFrames of them work): the persistent conv kernels issue
+// their tcgen05.mma from warps 1 and 3, and the tensor pipe accepts an MMA only about one instruction ahead
+// (tools/umma_rate.cu) — every issue slot an FFT warp wins on those warps' schedulers delays the tensor core.  A warp's
+// scheduler is its hardware warp slot modulo 4 (%warpid & 3): a four-warp CTA has one warp per scheduler, and only the two
+// on schedulers 0 and 2 take frames; the other two exit at once.
+constexpr int kFftCtaWarps = 4, kFftCtaFrames = 2;
 
 template <int IDX>  // exp(-2 pi i IDX / 32)
 __device__ __forceinline__ float2 tw32() {
@@ -111,16 +117,45 @@ __host__ __device__ constexpr int bitrev5(int i) {
   return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
 }
 
-__global__ void __launch_bounds__(32 * kWarpFftWarps)
+// SCHED = false: one-warp CTAs, frame = blockIdx.x.  SCHED = true: four-warp CTAs, two frames per CTA, taken by the warps
+// that sit on schedulers 0 and 2 (see kFftCtaWarps).  NQ: padded n_mfcc (20 or 40) of the fused per-frame DCT.
+template <bool SCHED, int NQ>
+__global__ void __launch_bounds__(SCHED ? 32 * kFftCtaWarps : 32 * kWarpFftWarps)
 mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const int4* __restrict__ frames, int n_unique,
                         const float* __restrict__ window, const float2* __restrict__ tw, const float2* __restrict__ tw2,
-                        const int4* __restrict__ mel_tab, const float* __restrict__ mel_w, float* __restrict__ logmel) {
-  __shared__ float2 s_z[kWarpFftWarps][32 * 33];
+                        const int4* __restrict__ mel_tab, const float* __restrict__ mel_w, const float* __restrict__ dct_t,
+                        float* __restrict__ logmel, float* __restrict__ frame_mfcc, float2* __restrict__ frame_range) {
+  __shared__ float2 s_z[SCHED ? kFftCtaFrames : kWarpFftWarps][32 * 33];
+  __shared__ int s_take;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int clip = blockIdx.y;
-  const int u = blockIdx.x * kWarpFftWarps + warp;
+  int u, zslot;
+  if (SCHED) {
+    // work slots go first to the warps on schedulers 0 and 2; if the hardware placed the CTA's warps differently than
+    // one per scheduler, the leftover slots are taken by whoever comes second (correct either way)
+    uint32_t hw_warp;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw_warp));
+    if (threadIdx.x == 0) s_take = 0;
+    __syncthreads();
+    int slot = -1;
+    if ((hw_warp & 1u) == 0) {
+      if (lane == 0) slot = atomicAdd(&s_take, 1);
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+    }
+    __syncthreads();
+    if ((hw_warp & 1u) != 0) {
+      if (lane == 0) slot = atomicAdd(&s_take, 1);
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+    }
+    if (slot < 0 || slot >= kFftCtaFrames) return;
+    zslot = slot;
+    u = blockIdx.x * kFftCtaFrames + slot;
+  } else {
+    zslot = warp;
+    u = blockIdx.x * kWarpFftWarps + warp;
+  }
   if (u >= n_unique) return;  // warp-uniform; no block barriers below
-  float2* z = s_z[warp];
+  float2* z = s_z[zslot];
   const float* x = audio + static_cast<size_t>(clip) * n_samples;
   const int4 fr = frames[u];
   float2 v[32];
@@ -174,6 +209,7 @@ mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const in
   __syncwarp();
   // sparse mel: lane takes one band of each quartile (bands lane, lane+32, lane+64, lane+96)
   float* out = logmel + (static_cast<size_t>(clip) * n_unique + u) * kMels;
+  float lm[kMels / 32];
 #pragma unroll
   for (int r = 0; r < kMels / 32; ++r) {
     const int m = lane + 32 * r;
@@ -186,51 +222,34 @@ mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const in
       acc1 = fmaf(__ldg(w + i + 1), s_pow[rg.x + i + 1], acc1);
     }
     if (i < rg.y) acc0 = fmaf(__ldg(w + i), s_pow[rg.x + i], acc0);
-    out[m] = 10.0f * log10f(fmaxf(acc0 + acc1, 1e-10f));
+    lm[r] = 10.0f * log10f(fmaxf(acc0 + acc1, 1e-10f));
+    out[m] = lm[r];
   }
-}
-
-// Per-frame pieces of the shift-dependent tail, computed once per UNIQUE frame so that mfcc_stats_kernel does not
-// redo them for every shift that contains the frame (6.7x on the 41-shift sweep): the frame's max and min log-mel
-// (power_to_db's top_db reference is a max over the shifted signal's frames; a frame whose min is above that floor is
-// not touched by the clamp) and the frame's DCT, valid whenever the clamp does not touch it.  Thread = frame.
-template <int NQ>
-__global__ void __launch_bounds__(128)
-mfcc_frame_dct_kernel(const float* __restrict__ logmel, int n_unique, const float* __restrict__ dct_t,
-                      float* __restrict__ frame_mfcc, float2* __restrict__ frame_range) {
-  __shared__ float s_dct[kMels * NQ];
-  const int clip = blockIdx.y, u = blockIdx.x * 128 + threadIdx.x;
-  for (int i = threadIdx.x; i < kMels * NQ; i += 128) s_dct[i] = dct_t[(i / NQ) * kMaxQ + (i % NQ)];
-  __syncthreads();
-  if (u >= n_unique) return;
+  // Per-frame pieces of the shift-dependent tail, computed here once per UNIQUE frame so that mfcc_stats_kernel does not
+  // redo them for every shift that contains the frame (6.7x on the 41-shift sweep): the frame's max and min log-mel
+  // (power_to_db's top_db reference is a max over the shifted signal's frames; a frame whose min is above that floor is
+  // not touched by the clamp) and the frame's DCT-II, valid whenever the clamp does not touch it.  Lane q sums
+  // coefficient q over the mel bands in band order (the order mfcc_stats_kernel uses when it has to redo a clamped frame).
+  float mx = fmaxf(fmaxf(lm[0], lm[1]), fmaxf(lm[2], lm[3])), mn = fminf(fminf(lm[0], lm[1]), fminf(lm[2], lm[3]));
+  mx = warp_max(mx);
+  mn = -warp_max(-mn);
+  __syncwarp();
+  float* s_lm = reinterpret_cast<float*>(z);  // the power spectrum has been consumed
+#pragma unroll
+  for (int r = 0; r < kMels / 32; ++r) s_lm[lane + 32 * r] = lm[r];
+  __syncwarp();
   const size_t f = static_cast<size_t>(clip) * n_unique + u;
-  const float4* row = reinterpret_cast<const float4*>(logmel + f * kMels);
-  float acc[NQ];
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
-  float mx = -INFINITY, mn = INFINITY;
-  for (int c = 0; c < kMels / 4; ++c) {
-    const float4 v4 = row[c];
-    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      mx = fmaxf(mx, v[e]);
-      mn = fminf(mn, v[e]);
-      const float4* d = reinterpret_cast<const float4*>(s_dct + (c * 4 + e) * NQ);
-#pragma unroll
-      for (int q4 = 0; q4 < NQ / 4; ++q4) {
-        const float4 dd = d[q4];
-        acc[q4 * 4 + 0] = fmaf(dd.x, v[e], acc[q4 * 4 + 0]);
-        acc[q4 * 4 + 1] = fmaf(dd.y, v[e], acc[q4 * 4 + 1]);
-        acc[q4 * 4 + 2] = fmaf(dd.z, v[e], acc[q4 * 4 + 2]);
-        acc[q4 * 4 + 3] = fmaf(dd.w, v[e], acc[q4 * 4 + 3]);
-      }
+  for (int q0 = 0; q0 < NQ; q0 += 32) {
+    const int q = q0 + lane;
+    if (q < NQ) {
+      float acc = 0.f;
+#pragma unroll 8
+      for (int m = 0; m < kMels; ++m) acc = fmaf(__ldg(dct_t + m * kMaxQ + q), s_lm[m], acc);
+      frame_mfcc[f * kMaxQ + q] = acc;
     }
   }
-  float4* o = reinterpret_cast<float4*>(frame_mfcc + f * kMaxQ);
-#pragma unroll
-  for (int q4 = 0; q4 < NQ / 4; ++q4) o[q4] = make_float4(acc[q4 * 4], acc[q4 * 4 + 1], acc[q4 * 4 + 2], acc[q4 * 4 + 3]);
-  frame_range[f] = make_float2(mx, mn);
+  if (lane == 0) frame_range[f] = make_float2(mx, mn);
 }
 
 // One CTA per (shift, clip).  128 threads; thread j owns frames j, j+128, ...  The shift's frames are gathered through
@@ -387,6 +406,16 @@ static void build_frame_plan(int n_samples, int hop, const int32_t* shift_sample
 
 using namespace avs;
 
+// which log-mel kernel variant runs: the scheduler-aware four-warp CTAs (default) or the one-warp CTAs
+static bool fft_sched_mode() {
+#ifdef AVS_EXPERIMENTS
+  static const int mode = getenv("AVS_K1_SCHED") ? atoi(getenv("AVS_K1_SCHED")) : 1;
+  return mode != 0;
+#else
+  return true;
+#endif
+}
+
 extern "C" int avs_mfcc_plan_describe(int n_samples, int sample_rate, const int32_t* shift_samples, int n_shifts,
                                       int* n_frames_out, int* n_unique_out, int32_t* frames_out, int32_t* map_out) {
   AVS_REQUIRE(shift_samples && n_frames_out && n_unique_out, "null argument");
@@ -506,26 +535,29 @@ extern "C" int avs_mfcc_sweep_debug(const avs_mfcc_plan* p, const float* audio, 
   float2* frame_range = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(frame_mfcc) + align_up(n_fr * kMaxQ * sizeof(float), 256));
   for (int c0 = 0; c0 < n_clips; c0 += 32768) {  // gridDim.y limit
     const int nc = std::min(32768, n_clips - c0);
-    dim3 g1(cdiv(p->n_unique, kWarpFftWarps), nc);
-    { ProfScope ps(PROF_LOGMEL, st);
-    mfcc_logmel_warp_kernel<<<g1, 32 * kWarpFftWarps, 0, st>>>(audio + static_cast<size_t>(c0) * p->n_samples, p->n_samples,
-                                                   p->d_frames, p->n_unique, p->d_window, p->d_tw, p->d_tw2,
-                                                   p->d_mel_tab, p->d_mel_w,
-                                                   logmel + static_cast<size_t>(c0) * p->n_unique * kMels); }
-    AVS_LAUNCHED();
-    dim3 g2(p->n_shifts, nc);
     float* os = out_stats + static_cast<size_t>(c0) * p->n_shifts * 2 * p->n_mfcc;
     float* om = out_mfcc ? out_mfcc + static_cast<size_t>(c0) * p->n_shifts * p->n_frames * p->n_mfcc : nullptr;
-    const float* lm = logmel + static_cast<size_t>(c0) * p->n_unique * kMels;
-    const float* fmf = frame_mfcc + static_cast<size_t>(c0) * p->n_unique * kMaxQ;
-    const float2* frg = frame_range + static_cast<size_t>(c0) * p->n_unique;
-    ProfScope ps2(PROF_MFCC_STATS, st);
-    dim3 gf(cdiv(p->n_unique, 128), nc);
-    if (p->n_mfcc <= 20)
-      mfcc_frame_dct_kernel<20><<<gf, 128, 0, st>>>(lm, p->n_unique, p->d_dct, const_cast<float*>(fmf), const_cast<float2*>(frg));
-    else
-      mfcc_frame_dct_kernel<kMaxQ><<<gf, 128, 0, st>>>(lm, p->n_unique, p->d_dct, const_cast<float*>(fmf), const_cast<float2*>(frg));
+    float* lm = logmel + static_cast<size_t>(c0) * p->n_unique * kMels;
+    float* fmf = frame_mfcc + static_cast<size_t>(c0) * p->n_unique * kMaxQ;
+    float2* frg = frame_range + static_cast<size_t>(c0) * p->n_unique;
+    const float* au = audio + static_cast<size_t>(c0) * p->n_samples;
+    {
+      ProfScope ps(PROF_LOGMEL, st);
+#define AVS_LOGMEL_ARGS au, p->n_samples, p->d_frames, p->n_unique, p->d_window, p->d_tw, p->d_tw2, p->d_mel_tab, p->d_mel_w, p->d_dct, lm, fmf, frg
+      if (fft_sched_mode()) {
+        const dim3 g1(cdiv(p->n_unique, kFftCtaFrames), nc);
+        if (p->n_mfcc <= 20) mfcc_logmel_warp_kernel<true, 20><<<g1, 32 * kFftCtaWarps, 0, st>>>(AVS_LOGMEL_ARGS);
+        else mfcc_logmel_warp_kernel<true, kMaxQ><<<g1, 32 * kFftCtaWarps, 0, st>>>(AVS_LOGMEL_ARGS);
+      } else {
+        const dim3 g1(cdiv(p->n_unique, kWarpFftWarps), nc);
+        if (p->n_mfcc <= 20) mfcc_logmel_warp_kernel<false, 20><<<g1, 32 * kWarpFftWarps, 0, st>>>(AVS_LOGMEL_ARGS);
+        else mfcc_logmel_warp_kernel<false, kMaxQ><<<g1, 32 * kWarpFftWarps, 0, st>>>(AVS_LOGMEL_ARGS);
+      }
+#undef AVS_LOGMEL_ARGS
+    }
     AVS_LAUNCHED();
+    dim3 g2(p->n_shifts, nc);
+    ProfScope ps2(PROF_MFCC_STATS, st);
     if (p->n_mfcc <= 20) {
       const size_t sm = (static_cast<size_t>(kMels) * 20 + static_cast<size_t>(p->n_frames) * 20) * sizeof(float);
       AVS_CUDA(cudaFuncSetAttribute(mfcc_stats_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)));

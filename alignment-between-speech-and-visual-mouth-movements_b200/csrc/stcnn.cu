@@ -25,7 +25,6 @@ struct StcnnWs {  // workspace carve, shared by size query and forward
   float* p1; float* p2; float* emb;                  // fp32 path: pooled NCDHW activations; emb when caller passes none
   __nv_bfloat16* act[3];                             // tensor-core path: parity-plane inputs of the three layers
   size_t act_bytes[3];
-  void* stat; size_t stat_bytes;                   // tensor-core path, statistics only: f64 time sums (conv3 epilogue mode 2)
   size_t total;
 };
 
@@ -45,8 +44,6 @@ static StcnnWs carve(const avs_stcnn* net, int B, void* ws, bool need_emb) {
       r.act_bytes[l] = umma_act_bytes(net->L[l].g, split, B);
       r.act[l] = reinterpret_cast<__nv_bfloat16*>(c.take<uint8_t>(r.act_bytes[l]));
     }
-    r.stat_bytes = vstat_scratch_bytes(B, net->L[2].g.tcat_items, net->n_sms, split != 0);
-    r.stat = c.take<uint8_t>(r.stat_bytes);
   }
   if (need_emb) r.emb = c.take<float>(static_cast<size_t>(B) * AVS_T * AVS_EMB);
   r.total = align_up(c.off, 256);
@@ -138,9 +135,7 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
   AVS_REQUIRE(cap_clips >= B, "workspace capacity below batch");
   if (B <= 0) return AVS_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // only the statistics are wanted (the sweep): the conv3 epilogue accumulates them and no embedding is written
-  const bool fused_stats = net->precision != AVS_PREC_FP32 && out_emb == nullptr && net->L[2].g.tcat_items > 0;
-  StcnnWs w = carve(net, cap_clips, workspace, out_emb == nullptr && !fused_stats);
+  StcnnWs w = carve(net, cap_clips, workspace, out_emb == nullptr);
   if (workspace_bytes < w.total) {
     set_error("stcnn workspace too small: %zu < %zu", workspace_bytes, w.total);
     return AVS_EWORKSPACE;
@@ -181,9 +176,7 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
     if (!pads_clean) {
       AVS_CUDA(cudaMemsetAsync(w.act[1], 0, umma_act_bytes(net->L[1].g, split, B), st));
       AVS_CUDA(cudaMemsetAsync(w.act[2], 0, umma_act_bytes(net->L[2].g, split, B), st));
-      if (fused_stats) AVS_CUDA(cudaMemsetAsync(w.stat, 0, w.stat_bytes, st));
     }
-    const int stat_parts = vstat_parts(B, net->L[2].g.tcat_items, net->n_sms);
     if ((rc = umma_pack_frames(frames_any, frames_u8, w.act[0], net->L[0].g, split, B, st))) return rc;
     for (int l = 0; l < 3; ++l) {
       EpiOut eo{};
@@ -193,10 +186,6 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
         eo.act = w.act[l + 1];
         eo.n_chunks_next = gn.n_chunks; eo.PP_next = gn.PP; eo.Wt_next = gn.Wt; eo.ph_next = gn.ph; eo.pw_next = gn.pw;
         eo.split_next = split;
-      } else if (fused_stats) {
-        eo.mode = 2;
-        eo.stat = w.stat;
-        eo.stat_parts = stat_parts;
       } else {
         eo.mode = 1;
         eo.emb = emb;
@@ -207,8 +196,6 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
     if (out_pool1 && (rc = umma_unpack_act(w.act[1], out_pool1, net->L[1].g, split, 32, B, st))) return rc;
     if (out_pool2 && (rc = umma_unpack_act(w.act[2], out_pool2, net->L[2].g, split, 64, B, st))) return rc;
   }
-  if (fused_stats)
-    return vstats_finish(w.stat, net->precision == AVS_PREC_BF16X3, vstat_parts(B, net->L[2].g.tcat_items, net->n_sms), out_vstats, B, st);
   if (out_vstats && (rc = vstats(emb, out_vstats, B, AVS_EMB, st))) return rc;
   return AVS_OK;
 }

@@ -9,11 +9,6 @@ namespace avs {
 int conv_pool_ffma(const float* in, const float* w, const float* bias, float* out, int B, int Cin, int Cout, int T,
                    int H, int W, int KH, int KW, long long o_sb, long long o_sc, long long o_st, cudaStream_t st);
 int vstats(const float* emb, float* out, int B, int F, cudaStream_t st);
-// conv3 epilogue mode 2: CTAs per clip (upper bound over the span partition of `n_clips` clips on `n_sms` CTAs), the
-// scratch it needs, and the kernel that folds the partials into [mean_t, unbiased std_t] and re-zeroes them
-int vstat_parts(int n_clips, int items_per_clip, int n_sms);
-size_t vstat_scratch_bytes(int cap_clips, int items_per_clip, int n_sms, bool f64);
-int vstats_finish(void* stat, bool f64, int parts, float* out, int B, cudaStream_t st);
 
 // ---- tcgen05 path ------------------------------------------------------------------------------
 // Geometry of one layer in the "parity-plane" activation layout.
@@ -50,14 +45,10 @@ struct UmmaLayer {                // device-resident, built once by stcnn_create
 };
 
 struct EpiOut {                   // where the fused bias+ReLU+pool epilogue writes
-  int mode;                       // 0: next layer's parity-plane bf16 layout, 1: emb f32 [B, T, C*Ho*Wo],
-                                  // 2 (conv3 only): no embedding at all — per-(clip, feature) time sums for the visual statistics
+  int mode;                       // 0: next layer's parity-plane bf16 layout, 1: emb f32 [B, T, C*Ho*Wo]
   __nv_bfloat16* act;             // mode 0
   int n_chunks_next, PP_next, Wt_next, ph_next, pw_next, split_next;
   float* emb;                     // mode 1
-  void* stat;                     // mode 2: [clip][part][AVS_EMB][2] partial (sum_t x, sum_t x^2), f32 pairs (bf16 kind) or f64 pairs
-                                  // (fp32-grade kind); must be zero on entry
-  int stat_parts;                 // mode 2: parts per clip = most CTAs whose item span touches one clip (vstat_parts())
 };
 
 extern int g_conv_dbg;

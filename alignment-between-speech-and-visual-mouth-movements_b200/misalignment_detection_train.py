@@ -127,7 +127,7 @@ def extract_visual_embeddings(lipnet: LipNet, frames: torch.Tensor) -> torch.Ten
 def visual_stats(lipnet: LipNet, frames: torch.Tensor) -> torch.Tensor:
     """[B,1,75,50,100] -> [B,13824] = cat(emb.mean(t), emb.std(t)) per clip (:165), on device."""
     with torch.no_grad():
-        return lipnet.stcnn(frames, want_vstats=True, want_emb=False)[1]
+        return lipnet.stcnn(frames, want_vstats=True)[1]
 
 
 # ---------------------------------------------------------------------------------- detector

@@ -97,22 +97,18 @@ class LipNet(nn.Module):
             return x.detach().contiguous()
         return N.f32c(x)
 
-    def stcnn(self, x: torch.Tensor, want_vstats: bool = False, debug: bool = False, want_emb: bool = True):
+    def stcnn(self, x: torch.Tensor, want_vstats: bool = False, debug: bool = False):
         """Conv half of ``forward`` (model.py:67-82): [B,1,75,50,100] -> emb [B,75,6912]
         (and, optionally, the time-pooled statistics of misalignment_detection_train.py:165).
         ``x`` may also be the uint8 pixels (same shape) the reference's f32 frames are made from
-        (``float32(u8 / 255.0)``): same bits out, a quarter of the bytes in.  ``want_emb=False`` (with
-        ``want_vstats``) returns ``(None, vstats)``: the last conv layer then accumulates the time statistics in its
-        epilogue and no embedding is written."""
+        (``float32(u8 / 255.0)``): same bits out, a quarter of the bytes in."""
         if self.training:
             raise RuntimeError("the B200 LipNet implements eval-mode forward only; call .eval()")
         x = self._check_frames(x)
         B = x.shape[0]
         net = self._stcnn()
         L = N.lib()
-        if not want_emb and not (want_vstats and not debug):
-            raise RuntimeError("want_emb=False needs want_vstats=True (and no debug outputs)")
-        emb = torch.empty((B, 75, self.conv_output_dim), dtype=torch.float32, device=x.device) if want_emb else None
+        emb = torch.empty((B, 75, self.conv_output_dim), dtype=torch.float32, device=x.device)
         vst = torch.empty((B, 2 * self.conv_output_dim), dtype=torch.float32, device=x.device) if want_vstats else None
         ws = N.workspace(L.avs_stcnn_workspace_bytes(net.h, B), x.device)
         if debug:

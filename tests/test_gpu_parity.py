@@ -184,38 +184,6 @@ def test_stcnn_vs_oracle_and_golden(A, golden, lipnet_sd, precision):
     assert e2.is_cuda and torch.equal(e2, emb)
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
-def test_fused_visual_stats_match_embedding_path(A, golden, lipnet_sd, precision):
-    """Statistics-only calls (the sweep) never write the embedding: the conv3 epilogue accumulates sum_t x and sum_t x^2
-    (f64 in the fp32-grade kind, f32 pairs in the bf16 kind) and a finishing kernel forms [mean_t, unbiased std_t] (misalignment_detection_train.py:165).  Same values as
-    the statistics of the written embedding (both are within rounding of the exact ones), golden parity unchanged,
-    run-to-run and batch-split bit-identical (the accumulation order is fixed by barriers, not by timing)."""
-    net = make_lipnet(A, lipnet_sd, precision)
-    frames = sweep_ref.synth_frames(2, seed=1234).cuda()
-    _, v_emb = net.stcnn(frames, want_vstats=True)
-    none, v_fused = net.stcnn(frames, want_vstats=True, want_emb=False)
-    assert none is None
-    report(f"vstats fused vs emb path[{precision}]", v_fused.cpu().numpy(), v_emb.cpu().numpy())
-    # fp32-grade kind: f64 partial sums; bf16 kind: f32 partial sums (relative variance error ~1e-7 * (1 + mean^2 / var))
-    np.testing.assert_allclose(v_fused.cpu().numpy(), v_emb.cpu().numpy(), **(dict(rtol=2e-5, atol=2e-7) if precision == "bf16x3"
-                                                                               else dict(rtol=2e-4, atol=1e-6)))
-    g = golden("stcnn")
-    tol = dict(rtol=0, atol=TOL_BF16["vstats"]) if precision == "bf16" else TOL[precision]
-    np.testing.assert_allclose(v_fused.cpu().numpy(), g["vstats"], **tol)
-    big = sweep_ref.synth_frames(37, seed=3).cuda()          # 37 clips: spans of 13.5 items, up to 5 CTAs per clip
-    first = A.visual_stats(net, big)
-    for _ in range(3):
-        assert torch.equal(A.visual_stats(net, big), first)
-    halves = torch.cat([A.visual_stats(net, big[:9]), A.visual_stats(net, big[9:])])
-    assert torch.equal(halves, first)
-    one = A.visual_stats(net, big[20:21])                      # one clip: every CTA holds a single item (54 parts)
-    assert torch.equal(one[0], first[20])
-    # an all-zero clip: every feature is relu(bias) at every interior time step; dead features must give exactly (0, 0)
-    v = A.visual_stats(net, torch.zeros((1, 1, 75, 50, 100), device="cuda"))[0]
-    dead = v[:6912] == 0
-    assert dead.any() and torch.all(v[6912:][dead] == 0)
-
-
 def test_stcnn_wrong_shape_raises(A, lipnet_sd):
     net = make_lipnet(A, lipnet_sd, "bf16")
     with pytest.raises(RuntimeError):
