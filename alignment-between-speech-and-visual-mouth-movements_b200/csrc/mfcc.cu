@@ -406,13 +406,17 @@ static void build_frame_plan(int n_samples, int hop, const int32_t* shift_sample
 
 using namespace avs;
 
-// which log-mel kernel variant runs: the scheduler-aware four-warp CTAs (default) or the one-warp CTAs
+// which log-mel kernel variant runs: one-warp CTAs (product), or — tools build, AVS_K1_SCHED=1 — the four-warp CTAs whose
+// working warps sit on hardware warp slots 0 and 2.  Measured inside the sweep step (profiles/r02_k1_sched_ab.txt): the
+// variant is slower, 39.8 against 38.1 ms per 1024 clips (conv2 -1.1 ms, conv3 +3.1 ms): with four-warp CTAs only one
+// CTA (two working warps) fits beside a conv CTA instead of three one-warp CTAs, the audio branch stretches past conv2
+// and lands on conv3, whose epilogue sits on its critical path.
 static bool fft_sched_mode() {
 #ifdef AVS_EXPERIMENTS
-  static const int mode = getenv("AVS_K1_SCHED") ? atoi(getenv("AVS_K1_SCHED")) : 1;
+  static const int mode = getenv("AVS_K1_SCHED") ? atoi(getenv("AVS_K1_SCHED")) : 0;
   return mode != 0;
 #else
-  return true;
+  return false;
 #endif
 }
 
