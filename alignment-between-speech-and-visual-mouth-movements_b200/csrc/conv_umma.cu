@@ -31,8 +31,12 @@
 //                                   would idle it; with two issuers one prepares while the other issues
 //   warp 2         : TMEM allocator
 //   warps 4..11    : epilogue     — two groups of four warps: tcgen05.ld, pool, bias, ReLU, bf16 (hi/lo) pack, store
-// mbarrier rings: a_full/a_empty[RING], w_full/w_empty[WSTAGES], acc_full/acc_empty[NBUF]; turn[4] are the early and
-// final hand-over tokens between the two issuer warps.
+// mbarrier rings: a_full/a_empty[RING], w_full/w_empty[WSTAGES], acc_full/acc_empty[NBUF][2 halves]; turn[4] are the early
+// and final hand-over tokens between the two issuer warps.  An accumulator buffer is handed over in the two HALVES the
+// issuers write separately (first / second half of the item's tiles): the epilogue starts on the first tiles while the
+// last stage still runs on the others, and the issuers restart on the first tiles while the epilogue drains the rest —
+// this is what overlaps the TMEM read-out (64 B/cycle per SM: 1536 cycles per conv3 tile) with tensor work for the
+// layer whose two tiles fill TMEM and cannot be double-buffered.
 #include <stdlib.h>
 #include <vector>
 #include "stcnn.cuh"
@@ -278,9 +282,9 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   uint64_t* a_empty = a_full + kMaxRing;
   uint64_t* w_full = a_empty + kMaxRing;
   uint64_t* w_empty = w_full + kMaxWStages;
-  uint64_t* acc_full = w_empty + kMaxWStages;
-  uint64_t* acc_empty = acc_full + 2;
-  uint64_t* turn = acc_empty + 2;
+  uint64_t* acc_full = w_empty + kMaxWStages;   // [buffer * 2 + half]
+  uint64_t* acc_empty = acc_full + 4;
+  uint64_t* turn = acc_empty + 4;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(turn + 4);  // turn[x]: early token for issuer x, turn[2 + x]: final token
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -290,7 +294,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.ring; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 2);   // both issuers commit
     for (int i = 0; i < p.wstages; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
-    for (int i = 0; i < p.NBUF; ++i) mbar_init(&acc_full[i], 2), mbar_init(&acc_empty[i], 8);
+    for (int i = 0; i < 2 * p.NBUF; ++i) mbar_init(&acc_full[i], 2), mbar_init(&acc_empty[i], 8);
     for (int i = 0; i < 4; ++i) mbar_init(&turn[i], 1);
     mbar_fence_init();
   }
@@ -406,7 +410,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     w.init(p);
     for (; w.valid(); w.next()) {
       const int nt = min(NT, n_tiles - w.ts * NT);
-      bool acc_ready = false;
+      bool acc_ready0 = false, acc_ready1 = false;  // this issuer has seen the accumulator halves released by the epilogue
       const uint32_t d_base = tmem_base + acc_buf * (NT * 2 * K::ACC);
       const bool cont_next = w.continues_next();
       if (K::reuse) {  // the fills this item brings: all three planes, or only the last one
@@ -421,9 +425,9 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         const uint32_t slot0 = K::reuse ? static_cast<uint32_t>((w.t + unit) % K::RING) : a_slot;
         if ((g & 1) == x) {
           const long long tk0 = (dbg & 16) ? clock64() : 0;
-          if (!acc_ready) {
-            mbar_wait(&acc_empty[acc_buf], acc_phase ^ 1);
-            acc_ready = true;
+          if (!acc_ready0) {
+            mbar_wait(&acc_empty[acc_buf * 2], acc_phase ^ 1);
+            acc_ready0 = true;
           }
           uint32_t ab[3];
           if (K::reuse) {
@@ -461,7 +465,12 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
             const uint32_t bb = stage_lo | lbo_b;
             for (int rep = 0; rep < ((dbg & 8) ? 2 : 1); ++rep)  // dbg 8: issue every MMA twice (tensor-vs-issue bound test)
               issue_half<KIND, 0>(nt, ab, bb, d_base, st == 0 && rep == 0, s_in_unit, idesc_n, idesc_w);
+            if (st == n_stages - 1) tc_commit(&acc_full[acc_buf * 2]);  // the item's first tiles are complete: the epilogue may start on them
             tc_commit(&turn[x ^ 1]);
+            if (!acc_ready1) {  // the second half of the accumulator buffer is drained later than the first
+              mbar_wait(&acc_empty[acc_buf * 2 + 1], acc_phase ^ 1);
+              tc_fence_after();
+            }
             if (g != 0) mbar_wait_poll(&turn[2 + x], turn_phase);  // "final" token: its second half has completed
             for (int rep = 0; rep < ((dbg & 8) ? 2 : 1); ++rep)
               issue_half<KIND, 1>(nt, ab, bb, d_base, st == 0 && rep == 0, s_in_unit, idesc_n, idesc_w);
@@ -480,10 +489,11 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
                 tc_commit(&a_empty[a_slot]);
               }
             }
-            if (st == n_stages - 1) tc_commit(&acc_full[acc_buf]);
+            if (st == n_stages - 1) tc_commit(&acc_full[acc_buf * 2 + 1]);
             tc_commit(&turn[2 + (x ^ 1)]);
           }
           __syncwarp();
+          acc_ready1 = true;
           if (g != 0) turn_phase ^= 1;
           if (dbg & 16) {
             const long long tk3 = clock64();
@@ -504,7 +514,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
               tc_commit(&a_empty[a_slot]);
             }
           }
-          if (st == n_stages - 1) tc_commit(&acc_full[acc_buf]);
+          if (st == n_stages - 1) tc_commit(&acc_full[acc_buf * 2]), tc_commit(&acc_full[acc_buf * 2 + 1]);
         }
         __syncwarp();
         ++w_loaded;
@@ -528,122 +538,172 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     }
   } else if (warp >= 4) {
     // ============================================================ epilogue
-    // Two groups of four warps (warps 4-7 and 8-11); warp w may read TMEM lanes 32*(w%4)..+31.  The
-    // (tile, 32-column block) work units of an item alternate between the groups.
+    // Two groups of four warps (warps 4-7 and 8-11); warp w may read TMEM lanes 32*(w%4)..+31.  The work unit is a
+    // 16-column block of one tile (both row accumulators): group 0 takes the even blocks of every tile, group 1 the odd
+    // ones, so both groups drain the same tile and a tile (and with it an accumulator half) is free after
+    // N/32 units per warp.  TMEM reads run at 64 B/cycle per SM — 512 cycles for a conv1 tile, about what its MMAs
+    // take — so the loads of unit k+1 are issued before the arithmetic of unit k (two register buffers), which keeps the
+    // TMEM pipe busy instead of alternating between loading and computing.
     const int q = warp & 3, grp = (warp - 4) >> 2;
     using KN = LayerKind<K::NEXT>;             // the layer that reads our output (conv3: unused)
     constexpr bool kToEmb = K::N == 96;        // conv3 writes the f32 embedding
     constexpr int kHo = K::H / 2, kWo = K::W / 2, kPlane = kHo * kWo;
-    const int half = lane & 1;                 // even lane: channels 0..15 of a 32-column block, odd: 16..31
+    constexpr int UPT = K::N / 32;             // units per tile for one group
+    constexpr int UMAX = NT * UPT;             // units per item for one warp
+    constexpr bool kPipe = !K::split;          // the split kinds need four loads per unit: no room for a second buffer
+    const int half = lane & 1;                 // even lane keeps channels 0..7 of a 16-column block, odd lane 8..15
     uint32_t buf = 0, phase = 0;
     ItemWalk w;
     w.init(p);
     for (; w.valid(); w.next(), buf = (buf + 1 == static_cast<uint32_t>(p.NBUF)) ? 0 : buf + 1, phase ^= (buf == 0)) {
       const int b = w.b, t = w.t, ts = w.ts;
       const int nt = min(NT, p.n_tiles - ts * NT);
-      mbar_wait(&acc_full[buf], phase);
+      const int n_units = (AVS_DBG(p) & 4) ? 0 : nt * UPT;
+      // tiles [0, h0) are the first half of the accumulator buffer; the single-tile split kinds halve it by row
+      // accumulator instead, and need both halves for the first unit already
+      const int h0 = (nt + 1) >> 1;
+      mbar_wait(&acc_full[buf * 2], phase);
+      bool full1 = false;
+      if (K::split && nt == 1) {
+        mbar_wait(&acc_full[buf * 2 + 1], phase);
+        full1 = true;
+      }
       __syncwarp();  // tcgen05.ld below is .aligned
       tc_fence_after();
       const uint32_t d_base = tmem_base + buf * (NT * 2 * K::ACC) + (static_cast<uint32_t>(q * 32) << 16);
-      // last (tile, column block) unit of the item that this epilogue group reads: once its TMEM loads have landed in
-      // registers the accumulator buffer goes back to the issuers, before the arithmetic and the stores
-      const int n_units_item = nt * (K::N / 32);
-      const int last_unit = ((n_units_item - 1) & 1) == grp ? n_units_item - 1 : n_units_item - 2;
-      bool acc_released = false;
-      for (int i = 0; i < ((AVS_DBG(p) & 4) ? 0 : nt); ++i) {
+      // does tile i hold any position of this warp's 32 lanes?  (positions grow with the lane and with i)
+      auto tile_has_work = [&](int i) {
+        if (K::tcat) return ((t * NT + i) * 128 + q * 32) / K::PITCH < p.T_out;
+        return ((ts * NT + i) * 128 + q * 32) / K::WT < kHo;
+      };
+      // tiles from h0 on belong to the second accumulator half, which completes a little later than the first
+      auto need_half1 = [&](int i) {
+        if (i >= h0 && !full1) {
+          mbar_wait(&acc_full[buf * 2 + 1], phase);
+          __syncwarp();
+          tc_fence_after();
+          full1 = true;
+        }
+      };
+      uint32_t va[2][16], vb[2][16];
+      auto issue_loads = [&](int k, uint32_t (&x0)[16], uint32_t (&x1)[16]) {
+        const int i = k / UPT, cb = (2 * (k % UPT) + grp) * 16;
+        tmem_ld16(d_base + (i * 2 + 0) * K::ACC + cb, x0);
+        tmem_ld16(d_base + (i * 2 + 1) * K::ACC + cb, x1);
+      };
+      if (kPipe && n_units > 0 && tile_has_work(0)) issue_loads(0, va[0], vb[0]);
+      bool released0 = false, released1 = false;
+#pragma unroll
+      for (int k = 0; k < UMAX; ++k) {
+        if (k >= n_units) break;
+        const int i = k / UPT, cb = (2 * (k % UPT) + grp) * 16;
+        const bool work = tile_has_work(i);
+        uint32_t (&v0)[16] = va[kPipe ? (k & 1) : 0];
+        uint32_t (&v1)[16] = vb[kPipe ? (k & 1) : 0];
+        if (!kPipe && work) {
+          need_half1(i);
+          issue_loads(k, v0, v1);
+          tmem_ld_wait();
+          if (K::split) {  // second column block: A_hi * B_lo, the small term, added last
+            uint32_t u0[16], u1[16];
+            tmem_ld16(d_base + (i * 2 + 0) * K::ACC + K::N + cb, u0);
+            tmem_ld16(d_base + (i * 2 + 1) * K::ACC + K::N + cb, u1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              v0[c] = __float_as_uint(__uint_as_float(v0[c]) + __uint_as_float(u0[c]));
+              v1[c] = __float_as_uint(__uint_as_float(v1[c]) + __uint_as_float(u1[c]));
+            }
+          }
+        }
+        const int ch0 = cb + half * 8;
+        float bias[8];  // fetched while the TMEM loads are in flight
+        {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + 1);
+          bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w; bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+        }
+        if (kPipe) tmem_ld_wait();  // unit k's loads (nothing else is outstanding)
+        // hand the accumulator halves back as soon as their last loads have landed in registers
+        if (k == h0 * UPT - 1 && !(K::split && nt == 1)) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf * 2]);
+          released0 = true;
+        }
+        if (k == n_units - 1) {
+          need_half1(NT);  // (an item without second-half tiles: do not hand the half back before the issuers are done with it)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (!released0) mbar_arrive(&acc_empty[buf * 2]);
+            mbar_arrive(&acc_empty[buf * 2 + 1]);
+          }
+          released0 = released1 = true;
+        }
+        if (kPipe && k + 1 < n_units) {  // loads of the next unit, under the arithmetic of this one
+          const int i1 = (k + 1) / UPT;
+          need_half1(i1);
+          if (tile_has_work(i1)) issue_loads(k + 1, va[(k + 1) & 1], vb[(k + 1) & 1]);
+        }
+        if (!work) continue;
+        if ((AVS_DBG(p) & 32) && v0[0] != 0x7fc12345u) continue;  // experiment: TMEM reads only
         int Q = (ts * NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
         int t_out = t;
         if (K::tcat) {  // time-concatenated position space: item index -> (time step, position in its plane)
           const int S = (t * NT + i) * 128 + q * 32 + lane;
           t_out = S / K::PITCH;
           Q = S - t_out * K::PITCH;
-          if (((t * NT + i) * 128 + q * 32) / K::PITCH >= p.T_out) continue;  // the whole warp is past the last time step
         }
         const int r = Q / K::WT, wc = Q % K::WT;            // pooled row, conv column
         const int wo = wc >> 1;
         const bool valid = (r < kHo) && (wo < kWo) && (t_out < p.T_out);
-        // positions grow with the lane: if the warp's first lane is already past the last pooled row, nobody has work
-        if (!K::tcat && ((ts * NT + i) * 128 + q * 32) / K::WT >= kHo) continue;
+        float o[8];
 #pragma unroll
-        for (int cb = 0; cb < K::N; cb += 32) {
-          if (((((i * K::N) >> 5) + (cb >> 5)) & 1) != grp) continue;  // warp-uniform
-          uint32_t v0[32], v1[32];
-          tmem_ld32(d_base + (i * 2 + 0) * K::ACC + cb, v0);
-          tmem_ld32(d_base + (i * 2 + 1) * K::ACC + cb, v1);
-          const int ch0 = cb + half * 16;
-          float bias[16];  // fetched while the TMEM loads are in flight
+        for (int c = 0; c < 8; ++c) {
+          // rows 2r, 2r+1: max of the two accumulators; columns 2wo, 2wo+1: exchange with the
+          // neighbouring lane — each lane keeps 8 of the 16 channels and ships the other 8
+          const float lo = fmaxf(__uint_as_float(v0[c]), __uint_as_float(v1[c]));
+          const float hi = fmaxf(__uint_as_float(v0[c + 8]), __uint_as_float(v1[c + 8]));
+          const float got = __shfl_xor_sync(0xffffffffu, half ? lo : hi, 1);
+          o[c] = fmaxf(fmaxf(half ? hi : lo, got) + bias[c], 0.f);
+        }
+        if ((AVS_DBG(p) & 64) && o[0] != 12345.678f) continue;  // experiment: no stores
+        if (valid && !kToEmb) {
+          // the NEXT layer's parity-plane layout (its geometry is a compile-time property of the kind)
+          const int hp = r + KN::KH / 2;
+          const int pos = KN::KW / 2 + (hp >> 1) * KN::WT + wo;
+          // element offset of array `a` (= chunk array * 2 + parity), position `pos` of time plane t + 1
+          auto out_ptr = [&](int a) {
+            if (KN::tcat)
+              return p.eo.act + ((static_cast<long long>(b) * (KN::N_CHUNKS * 2) + a) * KN::TCAT_LEN + (t + 1) * KN::PITCH + pos) * 8;
+            return p.eo.act + ((((static_cast<long long>(b) * (p.T_out + 2) + t + 1) * KN::N_CHUNKS) * 2 + a) * KN::PP + pos) * 8;
+          };
+          const int chunk = ch0 >> 3;
+          uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + c4);
-            bias[c4 * 4 + 0] = bv.x; bias[c4 * 4 + 1] = bv.y; bias[c4 * 4 + 2] = bv.z; bias[c4 * 4 + 3] = bv.w;
+          for (int e = 0; e < 4; ++e) {
+            const float x0 = o[2 * e], x1 = o[2 * e + 1];
+            const __nv_bfloat16 h0b = __float2bfloat16_rn(x0), h1b = __float2bfloat16_rn(x1);
+            hi[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
+            if (K::split) lo[e] = pack_bf16x2(x0 - __bfloat162float(h0b), x1 - __bfloat162float(h1b));
           }
-          tmem_ld_wait();
-          if ((AVS_DBG(p) & 32) && v0[0] != 0x7fc12345u) continue;  // experiment: TMEM reads only
-          if (K::split) {  // second column block: A_hi * B_lo, the small term, added last
-            uint32_t u0[32], u1[32];
-            tmem_ld32(d_base + (i * 2 + 0) * K::ACC + K::N + cb, u0);
-            tmem_ld32(d_base + (i * 2 + 1) * K::ACC + K::N + cb, u1);
-            tmem_ld_wait();
+          const int idx = K::split ? 2 * chunk : chunk;
+          *reinterpret_cast<uint4*>(out_ptr(idx * 2 + (hp & 1))) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (K::split) *reinterpret_cast<uint4*>(out_ptr((idx + 1) * 2 + (hp & 1))) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        } else if (valid) {
+          float* dst = p.eo.emb + (static_cast<long long>(b) * p.T_out + t_out) * (K::N * kPlane) + ch0 * kPlane + r * kWo + wo;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              v0[c] = __float_as_uint(__uint_as_float(v0[c]) + __uint_as_float(u0[c]));
-              v1[c] = __float_as_uint(__uint_as_float(v1[c]) + __uint_as_float(u1[c]));
-            }
-          }
-          if (i * (K::N / 32) + (cb >> 5) == last_unit) {  // warp-uniform: this warp's TMEM reads of the item are done
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            acc_released = true;
-          }
-          float o[16];
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            // rows 2r, 2r+1: max of the two accumulators; columns 2wo, 2wo+1: exchange with the
-            // neighbouring lane — each lane keeps 16 of the 32 channels and ships the other 16
-            const float lo = fmaxf(__uint_as_float(v0[c]), __uint_as_float(v1[c]));
-            const float hi = fmaxf(__uint_as_float(v0[c + 16]), __uint_as_float(v1[c + 16]));
-            const float got = __shfl_xor_sync(0xffffffffu, half ? lo : hi, 1);
-            o[c] = fmaxf(fmaxf(half ? hi : lo, got) + bias[c], 0.f);
-          }
-          if ((AVS_DBG(p) & 64) && o[0] != 12345.678f) continue;  // experiment: no stores
-          if (valid && !kToEmb) {
-            // the NEXT layer's parity-plane layout (its geometry is a compile-time property of the kind)
-            const int hp = r + KN::KH / 2;
-            const int pos = KN::KW / 2 + (hp >> 1) * KN::WT + wo;
-            // element offset of array `a` (= chunk array * 2 + parity), position `pos` of time plane t + 1
-            auto out_ptr = [&](int a) {
-              if (KN::tcat)
-                return p.eo.act + ((static_cast<long long>(b) * (KN::N_CHUNKS * 2) + a) * KN::TCAT_LEN + (t + 1) * KN::PITCH + pos) * 8;
-              return p.eo.act + ((((static_cast<long long>(b) * (p.T_out + 2) + t + 1) * KN::N_CHUNKS) * 2 + a) * KN::PP + pos) * 8;
-            };
-#pragma unroll
-            for (int c8 = 0; c8 < 2; ++c8) {
-              const int chunk = (ch0 >> 3) + c8;
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float x0 = o[c8 * 8 + 2 * e], x1 = o[c8 * 8 + 2 * e + 1];
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                hi[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-                if (K::split) lo[e] = pack_bf16x2(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
-              }
-              const int idx = K::split ? 2 * chunk : chunk;
-              *reinterpret_cast<uint4*>(out_ptr(idx * 2 + (hp & 1))) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              if (K::split) *reinterpret_cast<uint4*>(out_ptr((idx + 1) * 2 + (hp & 1))) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-          } else if (valid) {
-            float* dst = p.eo.emb + (static_cast<long long>(b) * p.T_out + t_out) * (K::N * kPlane) + ch0 * kPlane + r * kWo + wo;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) dst[c * kPlane] = o[c];
-          }
-          __syncwarp();
+          for (int c = 0; c < 8; ++c) dst[c * kPlane] = o[c];
         }
       }
-      if (!acc_released) {  // the warp skipped the item's last tile (positions past the plane) or the experiment switches did
+      if (!released1) {  // experiment switch 4 (no units): still hand the buffer back
+        need_half1(NT);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (lane == 0) {
+          if (!released0) mbar_arrive(&acc_empty[buf * 2]);
+          mbar_arrive(&acc_empty[buf * 2 + 1]);
+        }
       }
     }
   }
@@ -988,7 +1048,7 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
   L->chunks_per_unit = g.n_chunks / (n_units * L->unit_planes / 3);
   L->plane_slot_bytes = L->unit_planes * L->chunks_per_unit * 2 * static_cast<int>(arr_bytes);
   L->smem_bytes = static_cast<size_t>(L->ring) * L->plane_slot_bytes + static_cast<size_t>(region_full - L->region_pos) * 16 +
-                  static_cast<size_t>(L->wstages) * L->stage_bytes + (2 * kMaxRing + 2 * kMaxWStages + 8) * 8 + 16;
+                  static_cast<size_t>(L->wstages) * L->stage_bytes + (2 * kMaxRing + 2 * kMaxWStages + 12) * 8 + 16;
   if (L->smem_bytes > 232448 || L->ring > kMaxRing || L->wstages > kMaxWStages || n_units > kMaxUnits || L->NT != kNT ||
       n_stages != (first && !split ? 1 : n_units * kSPU) || wp.size() * 2 != static_cast<size_t>(L->n_stages) * L->stage_bytes || L->stage_bytes % 16 != 0) {
     set_error("umma layer config invalid: smem %zu stage_bytes %d n_stages %d units %d packed %zu", L->smem_bytes, L->stage_bytes,

@@ -233,21 +233,43 @@ mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const in
   float mx = fmaxf(fmaxf(lm[0], lm[1]), fmaxf(lm[2], lm[3])), mn = fminf(fminf(lm[0], lm[1]), fminf(lm[2], lm[3]));
   mx = warp_max(mx);
   mn = -warp_max(-mn);
-  __syncwarp();
-  float* s_lm = reinterpret_cast<float*>(z);  // the power spectrum has been consumed
-#pragma unroll
-  for (int r = 0; r < kMels / 32; ++r) s_lm[lane + 32 * r] = lm[r];
-  __syncwarp();
   const size_t f = static_cast<size_t>(clip) * n_unique + u;
+  // DCT: every lane forms the partial sums of its four bands for all NQ coefficients (the basis row of a band is NQ
+  // consecutive floats), then the 32 partial vectors are summed with a halving exchange: in the round for lane bit b a
+  // lane keeps one half of its remaining coefficients and ships the other half to lane ^ (1 << b), so the reduction
+  // costs NP - NP/32 shuffles instead of 5 NQ.  Afterwards lane l holds coefficient l (NP = 32) or 2l, 2l + 1 (NP = 64).
+  constexpr int NP = NQ <= 32 ? 32 : 64;  // coefficients padded to a power of two for the exchange
+  float part[NP];
 #pragma unroll
-  for (int q0 = 0; q0 < NQ; q0 += 32) {
-    const int q = q0 + lane;
-    if (q < NQ) {
-      float acc = 0.f;
-#pragma unroll 8
-      for (int m = 0; m < kMels; ++m) acc = fmaf(__ldg(dct_t + m * kMaxQ + q), s_lm[m], acc);
-      frame_mfcc[f * kMaxQ + q] = acc;
+  for (int q = 0; q < NP; ++q) part[q] = 0.f;
+#pragma unroll
+  for (int r = 0; r < kMels / 32; ++r) {
+    const float4* d = reinterpret_cast<const float4*>(dct_t + (lane + 32 * r) * kMaxQ);
+#pragma unroll
+    for (int q4 = 0; q4 < NQ / 4; ++q4) {
+      const float4 dd = __ldg(d + q4);
+      part[q4 * 4 + 0] = fmaf(dd.x, lm[r], part[q4 * 4 + 0]);
+      part[q4 * 4 + 1] = fmaf(dd.y, lm[r], part[q4 * 4 + 1]);
+      part[q4 * 4 + 2] = fmaf(dd.z, lm[r], part[q4 * 4 + 2]);
+      part[q4 * 4 + 3] = fmaf(dd.w, lm[r], part[q4 * 4 + 3]);
     }
+  }
+#pragma unroll
+  for (int b = 4; b >= 0; --b) {
+    const int len = NP >> (5 - b);  // coefficients a lane still holds after this round
+    const bool up = (lane >> b) & 1;  // lanes with the bit set keep the upper half
+#pragma unroll
+    for (int q = 0; q < len; ++q) {
+      const float keep = up ? part[q + len] : part[q];
+      const float send = up ? part[q] : part[q + len];
+      part[q] = keep + __shfl_xor_sync(0xffffffffu, send, 1 << b);
+    }
+  }
+  if (NP == 32) {
+    if (lane < NQ) frame_mfcc[f * kMaxQ + lane] = part[0];
+  } else {
+    if (2 * lane < NQ) frame_mfcc[f * kMaxQ + 2 * lane] = part[0];
+    if (2 * lane + 1 < NQ) frame_mfcc[f * kMaxQ + 2 * lane + 1] = part[1];
   }
   if (lane == 0) frame_range[f] = make_float2(mx, mn);
 }
