@@ -539,19 +539,19 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   } else if (warp >= 4) {
     // ============================================================ epilogue
     // Two groups of four warps (warps 4-7 and 8-11); warp w may read TMEM lanes 32*(w%4)..+31.  The work unit is a
-    // 16-column block of one tile (both row accumulators): group 0 takes the even blocks of every tile, group 1 the odd
-    // ones, so both groups drain the same tile and a tile (and with it an accumulator half) is free after
-    // N/32 units per warp.  TMEM reads run at 64 B/cycle per SM — 512 cycles for a conv1 tile, about what its MMAs
-    // take — so the loads of unit k+1 are issued before the arithmetic of unit k (two register buffers), which keeps the
-    // TMEM pipe busy instead of alternating between loading and computing.
+    // 32-column block of one tile (both row accumulators); the units of an item, in (tile, block) order, alternate between
+    // the groups.  An accumulator half goes back to the issuers as soon as this warp's last unit of the half has been
+    // loaded into registers — before the arithmetic and the stores.
+    // (Measured and dropped, profiles/r02_bench_d_epilogue16_pipelined.json: 16-column units with the next unit's TMEM
+    // loads in flight under the arithmetic of the current one.  conv3 7.45 -> 7.2 ms per 1024 clips, but conv1 4.9 -> 6.6:
+    // twice the position decodes and address computations per tile, and every instruction the epilogue warps issue
+    // competes with the MMA-issuing warps for issue slots — conv1's MMAs are the shortest, so it is the most sensitive.)
     const int q = warp & 3, grp = (warp - 4) >> 2;
     using KN = LayerKind<K::NEXT>;             // the layer that reads our output (conv3: unused)
     constexpr bool kToEmb = K::N == 96;        // conv3 writes the f32 embedding
     constexpr int kHo = K::H / 2, kWo = K::W / 2, kPlane = kHo * kWo;
-    constexpr int UPT = K::N / 32;             // units per tile for one group
-    constexpr int UMAX = NT * UPT;             // units per item for one warp
-    constexpr bool kPipe = !K::split;          // the split kinds need four loads per unit: no room for a second buffer
-    const int half = lane & 1;                 // even lane keeps channels 0..7 of a 16-column block, odd lane 8..15
+    constexpr int UPT = K::N / 32;             // units per tile
+    const int half = lane & 1;                 // even lane: channels 0..15 of a 32-column block, odd: 16..31
     uint32_t buf = 0, phase = 0;
     ItemWalk w;
     w.init(p);
@@ -560,110 +560,101 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       const int nt = min(NT, p.n_tiles - ts * NT);
       const int n_units = (AVS_DBG(p) & 4) ? 0 : nt * UPT;
       // tiles [0, h0) are the first half of the accumulator buffer; the single-tile split kinds halve it by row
-      // accumulator instead, and need both halves for the first unit already
+      // accumulator instead, and need both halves from the first unit on
+      const bool by_rows = K::split && nt == 1;
       const int h0 = (nt + 1) >> 1;
+      // this warp's last unit (units u with (u & 1) == grp are ours) overall and inside the first half; -1: none
+      const int own_last = ((n_units - 1) & 1) == grp ? n_units - 1 : n_units - 2;
+      const int n_units0 = by_rows ? 0 : h0 * UPT;
+      const int own_last0 = ((n_units0 - 1) & 1) == grp ? n_units0 - 1 : n_units0 - 2;
       mbar_wait(&acc_full[buf * 2], phase);
       bool full1 = false;
-      if (K::split && nt == 1) {
-        mbar_wait(&acc_full[buf * 2 + 1], phase);
-        full1 = true;
-      }
-      __syncwarp();  // tcgen05.ld below is .aligned
-      tc_fence_after();
-      const uint32_t d_base = tmem_base + buf * (NT * 2 * K::ACC) + (static_cast<uint32_t>(q * 32) << 16);
-      // does tile i hold any position of this warp's 32 lanes?  (positions grow with the lane and with i)
-      auto tile_has_work = [&](int i) {
-        if (K::tcat) return ((t * NT + i) * 128 + q * 32) / K::PITCH < p.T_out;
-        return ((ts * NT + i) * 128 + q * 32) / K::WT < kHo;
-      };
-      // tiles from h0 on belong to the second accumulator half, which completes a little later than the first
-      auto need_half1 = [&](int i) {
-        if (i >= h0 && !full1) {
+      auto need_half1 = [&]() {  // the second accumulator half completes a little later than the first
+        if (!full1) {
           mbar_wait(&acc_full[buf * 2 + 1], phase);
           __syncwarp();
           tc_fence_after();
           full1 = true;
         }
       };
-      uint32_t va[2][16], vb[2][16];
-      auto issue_loads = [&](int k, uint32_t (&x0)[16], uint32_t (&x1)[16]) {
-        const int i = k / UPT, cb = (2 * (k % UPT) + grp) * 16;
-        tmem_ld16(d_base + (i * 2 + 0) * K::ACC + cb, x0);
-        tmem_ld16(d_base + (i * 2 + 1) * K::ACC + cb, x1);
+      auto release = [&](int h) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf * 2 + h]);
       };
-      if (kPipe && n_units > 0 && tile_has_work(0)) issue_loads(0, va[0], vb[0]);
-      bool released0 = false, released1 = false;
+      __syncwarp();  // tcgen05.ld below is .aligned
+      tc_fence_after();
+      if (by_rows) need_half1();
+      bool released0 = false;
+      if (own_last0 < 0 && !by_rows) {  // none of the first half's units is ours: nothing to wait for
+        release(0);
+        released0 = true;
+      }
+      const uint32_t d_base = tmem_base + buf * (NT * 2 * K::ACC) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
-      for (int k = 0; k < UMAX; ++k) {
-        if (k >= n_units) break;
-        const int i = k / UPT, cb = (2 * (k % UPT) + grp) * 16;
-        const bool work = tile_has_work(i);
-        uint32_t (&v0)[16] = va[kPipe ? (k & 1) : 0];
-        uint32_t (&v1)[16] = vb[kPipe ? (k & 1) : 0];
-        if (!kPipe && work) {
-          need_half1(i);
-          issue_loads(k, v0, v1);
+      for (int u = 0; u < NT * UPT; ++u) {
+        if (u >= n_units) break;
+        if ((u & 1) != grp) continue;  // warp-uniform
+        const int i = u / UPT, cb = (u % UPT) * 32;
+        int Q = (ts * NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
+        int t_out = t;
+        bool warp_has_work = true;  // positions grow with the lane: if the warp's first lane is past the end, nobody has work
+        if (K::tcat) {  // time-concatenated position space: item index -> (time step, position in its plane)
+          const int S = (t * NT + i) * 128 + q * 32 + lane;
+          t_out = S / K::PITCH;
+          Q = S - t_out * K::PITCH;
+          warp_has_work = ((t * NT + i) * 128 + q * 32) / K::PITCH < p.T_out;
+        } else {
+          warp_has_work = ((ts * NT + i) * 128 + q * 32) / K::WT < kHo;
+        }
+        const int r = Q / K::WT, wc = Q % K::WT;            // pooled row, conv column
+        const int wo = wc >> 1;
+        const bool valid = (r < kHo) && (wo < kWo) && (t_out < p.T_out);
+        if (i >= h0) need_half1();
+        uint32_t v0[32], v1[32];
+        const int ch0 = cb + half * 16;
+        float bias[16];
+        if (warp_has_work) {
+          tmem_ld32(d_base + (i * 2 + 0) * K::ACC + cb, v0);
+          tmem_ld32(d_base + (i * 2 + 1) * K::ACC + cb, v1);
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {  // fetched while the TMEM loads are in flight
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + c4);
+            bias[c4 * 4 + 0] = bv.x; bias[c4 * 4 + 1] = bv.y; bias[c4 * 4 + 2] = bv.z; bias[c4 * 4 + 3] = bv.w;
+          }
           tmem_ld_wait();
           if (K::split) {  // second column block: A_hi * B_lo, the small term, added last
-            uint32_t u0[16], u1[16];
-            tmem_ld16(d_base + (i * 2 + 0) * K::ACC + K::N + cb, u0);
-            tmem_ld16(d_base + (i * 2 + 1) * K::ACC + K::N + cb, u1);
+            uint32_t u0[32], u1[32];
+            tmem_ld32(d_base + (i * 2 + 0) * K::ACC + K::N + cb, u0);
+            tmem_ld32(d_base + (i * 2 + 1) * K::ACC + K::N + cb, u1);
             tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
+            for (int c = 0; c < 32; ++c) {
               v0[c] = __float_as_uint(__uint_as_float(v0[c]) + __uint_as_float(u0[c]));
               v1[c] = __float_as_uint(__uint_as_float(v1[c]) + __uint_as_float(u1[c]));
             }
           }
         }
-        const int ch0 = cb + half * 8;
-        float bias[8];  // fetched while the TMEM loads are in flight
-        {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + 1);
-          bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w; bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
-        }
-        if (kPipe) tmem_ld_wait();  // unit k's loads (nothing else is outstanding)
-        // hand the accumulator halves back as soon as their last loads have landed in registers
-        if (k == h0 * UPT - 1 && !(K::split && nt == 1)) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf * 2]);
+        // hand the accumulator halves back: this warp's TMEM reads of them are in registers
+        if (u == own_last0) {
+          release(0);
           released0 = true;
         }
-        if (k == n_units - 1) {
-          need_half1(NT);  // (an item without second-half tiles: do not hand the half back before the issuers are done with it)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (!released0) mbar_arrive(&acc_empty[buf * 2]);
-            mbar_arrive(&acc_empty[buf * 2 + 1]);
-          }
-          released0 = released1 = true;
+        if (u == own_last) {
+          need_half1();  // (an item without second-half tiles: the issuers must be done with the half before it goes back)
+          if (!released0) release(0);
+          release(1);
+          released0 = true;
         }
-        if (kPipe && k + 1 < n_units) {  // loads of the next unit, under the arithmetic of this one
-          const int i1 = (k + 1) / UPT;
-          need_half1(i1);
-          if (tile_has_work(i1)) issue_loads(k + 1, va[(k + 1) & 1], vb[(k + 1) & 1]);
-        }
-        if (!work) continue;
+        if (!warp_has_work) continue;
         if ((AVS_DBG(p) & 32) && v0[0] != 0x7fc12345u) continue;  // experiment: TMEM reads only
-        int Q = (ts * NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
-        int t_out = t;
-        if (K::tcat) {  // time-concatenated position space: item index -> (time step, position in its plane)
-          const int S = (t * NT + i) * 128 + q * 32 + lane;
-          t_out = S / K::PITCH;
-          Q = S - t_out * K::PITCH;
-        }
-        const int r = Q / K::WT, wc = Q % K::WT;            // pooled row, conv column
-        const int wo = wc >> 1;
-        const bool valid = (r < kHo) && (wo < kWo) && (t_out < p.T_out);
-        float o[8];
+        float o[16];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 16; ++c) {
           // rows 2r, 2r+1: max of the two accumulators; columns 2wo, 2wo+1: exchange with the
-          // neighbouring lane — each lane keeps 8 of the 16 channels and ships the other 8
+          // neighbouring lane — each lane keeps 16 of the 32 channels and ships the other 16
           const float lo = fmaxf(__uint_as_float(v0[c]), __uint_as_float(v1[c]));
-          const float hi = fmaxf(__uint_as_float(v0[c + 8]), __uint_as_float(v1[c + 8]));
+          const float hi = fmaxf(__uint_as_float(v0[c + 16]), __uint_as_float(v1[c + 16]));
           const float got = __shfl_xor_sync(0xffffffffu, half ? lo : hi, 1);
           o[c] = fmaxf(fmaxf(half ? hi : lo, got) + bias[c], 0.f);
         }
@@ -678,32 +669,32 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
               return p.eo.act + ((static_cast<long long>(b) * (KN::N_CHUNKS * 2) + a) * KN::TCAT_LEN + (t + 1) * KN::PITCH + pos) * 8;
             return p.eo.act + ((((static_cast<long long>(b) * (p.T_out + 2) + t + 1) * KN::N_CHUNKS) * 2 + a) * KN::PP + pos) * 8;
           };
-          const int chunk = ch0 >> 3;
-          uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float x0 = o[2 * e], x1 = o[2 * e + 1];
-            const __nv_bfloat16 h0b = __float2bfloat16_rn(x0), h1b = __float2bfloat16_rn(x1);
-            hi[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
-            if (K::split) lo[e] = pack_bf16x2(x0 - __bfloat162float(h0b), x1 - __bfloat162float(h1b));
+          for (int c8 = 0; c8 < 2; ++c8) {
+            const int chunk = (ch0 >> 3) + c8;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = o[c8 * 8 + 2 * e], x1 = o[c8 * 8 + 2 * e + 1];
+              const __nv_bfloat16 h0b = __float2bfloat16_rn(x0), h1b = __float2bfloat16_rn(x1);
+              hi[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
+              if (K::split) lo[e] = pack_bf16x2(x0 - __bfloat162float(h0b), x1 - __bfloat162float(h1b));
+            }
+            const int idx = K::split ? 2 * chunk : chunk;
+            *reinterpret_cast<uint4*>(out_ptr(idx * 2 + (hp & 1))) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (K::split) *reinterpret_cast<uint4*>(out_ptr((idx + 1) * 2 + (hp & 1))) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
-          const int idx = K::split ? 2 * chunk : chunk;
-          *reinterpret_cast<uint4*>(out_ptr(idx * 2 + (hp & 1))) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (K::split) *reinterpret_cast<uint4*>(out_ptr((idx + 1) * 2 + (hp & 1))) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         } else if (valid) {
           float* dst = p.eo.emb + (static_cast<long long>(b) * p.T_out + t_out) * (K::N * kPlane) + ch0 * kPlane + r * kWo + wo;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) dst[c * kPlane] = o[c];
+          for (int c = 0; c < 16; ++c) dst[c * kPlane] = o[c];
         }
-      }
-      if (!released1) {  // experiment switch 4 (no units): still hand the buffer back
-        need_half1(NT);
-        tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          if (!released0) mbar_arrive(&acc_empty[buf * 2]);
-          mbar_arrive(&acc_empty[buf * 2 + 1]);
-        }
+      }
+      if (own_last < 0) {  // no unit of this item was ours (or the experiment switches skipped them all)
+        need_half1();
+        if (!released0) release(0);
+        release(1);
       }
     }
   }
