@@ -20,7 +20,8 @@ from .utils import ctc_greedy_decode, decode_batch, decode_metrics, decode_predi
 from .misalignment_detection_train import (DetectorConfig, FeatureExtractor, MisalignmentDataset, MisalignmentDetector,
                                            SyncSweeper, run_epoch,
                                            audio_stats_sweep, compute_audio_stats, extract_visual_embeddings,
-                                           load_detector, load_lipnet, save_detector, shift_audio, shift_samples,
+                                           load_detector, load_lipnet, save_detector, shift_audio, shift_samples, get_video_fps,
+                                           resample_audio, default_audio_loader,
                                            sweep_score, sync_sweep, visual_stats)
 from .dataset import GridPreprocessor
 from . import distributed
@@ -28,4 +29,4 @@ from . import distributed
 __all__ = ["LipNet", "ctc_greedy_decode", "decode_batch", "decode_prediction", "DetectorConfig", "FeatureExtractor",
            "MisalignmentDataset", "MisalignmentDetector", "SyncSweeper", "run_epoch", "evaluate_model", "decode_metrics", "audio_stats_sweep", "compute_audio_stats",
            "extract_visual_embeddings", "load_detector", "load_lipnet", "save_detector", "shift_audio",
-           "shift_samples", "sweep_score", "sync_sweep", "visual_stats", "GridPreprocessor", "distributed"]
+           "shift_samples", "get_video_fps", "resample_audio", "default_audio_loader", "sweep_score", "sync_sweep", "visual_stats", "GridPreprocessor", "distributed"]

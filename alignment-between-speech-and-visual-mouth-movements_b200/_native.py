@@ -62,6 +62,10 @@ SIGNATURES = {
     "avs_preproc_destroy": (None, [_P]),
     "avs_preproc_crop": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "avs_preproc_run": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
+    "avs_resample_plan_create": (c_int, [c_int, c_int, POINTER(_P)]),
+    "avs_resample_plan_destroy": (None, [_P]),
+    "avs_resample_out_len": (c_longlong, [_P, c_longlong]),
+    "avs_resample": (c_int, [_P, _P, c_longlong, c_int, _P, _P]),
     "avs_sweep_create": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, POINTER(_P)]),
     "avs_sweep_destroy": (None, [_P]),
     "avs_sweep_run": (c_int, [_P, _P, _P, c_int, _P, _P, _P]),

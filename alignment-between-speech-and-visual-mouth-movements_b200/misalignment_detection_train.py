@@ -1,7 +1,7 @@
 """Drop-in for the feature pipeline + detector of ``misalignment_detection_train.py`` (reference
 lines 79-250, 299-318) and the batched +-S sync sweep built from it.
 
-Kept names / signatures: ``DetectorConfig``, ``shift_audio``, ``compute_audio_stats``,
+Kept names / signatures: ``DetectorConfig``, ``get_video_fps``, ``shift_audio``, ``compute_audio_stats``,
 ``extract_visual_embeddings``, ``FeatureExtractor`` (``build_feature``), ``MisalignmentDetector``,
 ``load_lipnet``, ``save_detector``, ``load_detector``.  New batched entry points: ``SyncSweeper`` /
 ``sync_sweep`` (all clips x all shifts in three kernels).
@@ -31,6 +31,20 @@ class DetectorConfig:                      # reference :79-88
     max_shift_frames: int = 10
     num_negative_samples: int = 1
     default_fps: float = 25.0
+
+
+def get_video_fps(video_path: str, fallback: float = 25.0) -> float:
+    """Reference :91-97: frame rate of a video file through OpenCV; ``.npy`` clips and unreadable files fall back."""
+    if video_path.endswith(".npy"):
+        return fallback
+    try:
+        import cv2
+    except ImportError:
+        return fallback
+    cap = cv2.VideoCapture(video_path)
+    fps = cap.get(cv2.CAP_PROP_FPS)
+    cap.release()
+    return fps if fps and fps > 1e-3 else fallback
 
 
 def shift_samples(shift_frames: int, fps: float, sample_rate: int) -> int:
@@ -115,6 +129,37 @@ def compute_audio_stats(audio: np.ndarray, sample_rate: int, n_mfcc: int) -> tor
     N.device_check()
     a = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32)).cuda().unsqueeze(0)
     return audio_stats_sweep(a, [0], sample_rate, n_mfcc)[0, 0].cpu()
+
+
+# ---------------------------------------------------------------------------------- resampling
+_resample_plans: Dict[tuple, N.Handle] = {}
+
+
+def resample_audio(audio, orig_sr: int, target_sr: int) -> torch.Tensor:
+    """``librosa.resample(audio, orig_sr=orig_sr, target_sr=target_sr)`` of the reference (:202-204) on the GPU:
+    audio [n] or [B, n] (numpy or tensor) -> CUDA f32 tensor of ceil(n * target / orig) samples per signal.
+    Kaiser-windowed-sinc polyphase filter (resampy ``kaiser_best``); librosa's current default filter, soxr_hq, is an
+    un-vendored C library and is not reproduced bit for bit (include/avsync.h, oracle/resample_ref.py)."""
+    N.device_check()
+    x = torch.as_tensor(np.ascontiguousarray(audio) if isinstance(audio, np.ndarray) else audio)
+    x = N.f32c(x.cuda() if not x.is_cuda else x)
+    one = x.dim() == 1
+    if one:
+        x = x.unsqueeze(0)
+    if int(orig_sr) == int(target_sr):
+        return x[0] if one else x
+    key = (torch.cuda.current_device(), int(orig_sr), int(target_sr))
+    plan = _resample_plans.get(key)
+    if plan is None:
+        h = N.c_void_p()
+        N.check(N.lib().avs_resample_plan_create(int(orig_sr), int(target_sr), ctypes.byref(h)), "resample_plan_create")
+        plan = _resample_plans[key] = N.Handle(h, N.lib().avs_resample_plan_destroy)
+    B, n = x.shape
+    n_out = int(N.lib().avs_resample_out_len(plan.h, n))
+    out = torch.empty((B, n_out), dtype=torch.float32, device=x.device)
+    if B and n_out:
+        N.check(N.lib().avs_resample(plan.h, N.ptr(x), n, B, N.ptr(out), N.stream_ptr()), "resample")
+    return out[0] if one else out
 
 
 # ---------------------------------------------------------------------------------- K2
@@ -243,10 +288,46 @@ def sync_sweep(lipnet: LipNet, detector: MisalignmentDetector, frames: torch.Ten
 
 
 # ---------------------------------------------------------------------------------- FeatureExtractor
+def default_audio_loader(video_path: str):
+    """The reference's audio loading (:174-191): ``librosa.load(path, sr=None)``, then moviepy's ``VideoFileClip`` for
+    containers librosa cannot open.  Neither package is part of this path (file / codec IO); when both are missing,
+    ``.wav`` files are still read through scipy.  Raises like the reference when nothing can open the file."""
+    try:
+        import librosa
+        return librosa.load(video_path, sr=None)
+    except Exception as first:
+        try:
+            from moviepy.editor import VideoFileClip
+            clip = VideoFileClip(video_path)
+            if clip.audio is None:
+                clip.close()
+                raise RuntimeError(f"No audio in {video_path}")
+            sr = clip.audio.fps
+            audio = clip.audio.to_soundarray(fps=sr)
+            clip.close()
+            if audio.ndim == 2:
+                audio = audio.mean(axis=1)
+            return audio, sr
+        except Exception as second:
+            if video_path.lower().endswith(".wav"):
+                try:
+                    from scipy.io import wavfile
+                    sr, data = wavfile.read(video_path)
+                    if np.issubdtype(data.dtype, np.integer):          # PCM -> [-1, 1) like librosa / soundfile
+                        data = data.astype(np.float32) / float(1 << (8 * data.dtype.itemsize - 1))
+                    if data.ndim == 2:
+                        data = data.mean(axis=1)
+                    return data.astype(np.float32), int(sr)
+                except Exception as third:
+                    second = third
+            raise RuntimeError(f"{second} (librosa: {first})")
+
+
 class FeatureExtractor:
-    """Reference :147-208.  ``grid_dataset`` must provide ``process_video(path) -> Tensor[1,T,H,W]``;
-    audio comes from ``audio_loader(path) -> (np.ndarray, sr)`` (the reference's librosa/moviepy
-    loaders are file IO and out of scope; pass a loader, or pre-fill ``audio_cache``)."""
+    """Reference :147-208, same four constructor arguments.  ``grid_dataset`` must provide
+    ``process_video(path) -> Tensor[1,T,H,W]``; audio comes from ``audio_loader(path) -> (np.ndarray, sr)`` —
+    by default the reference's own librosa -> moviepy chain (``default_audio_loader``).  Audio that is not at
+    ``cfg.sample_rate`` is resampled on the GPU (:202-204), once per clip (the reference redoes it on every call)."""
 
     def __init__(self, grid_dataset, lipnet: LipNet, device: torch.device, cfg: DetectorConfig,
                  audio_loader=None):
@@ -254,19 +335,18 @@ class FeatureExtractor:
         self.lipnet = lipnet.to(device)
         self.device = device
         self.cfg = cfg
-        self.audio_loader = audio_loader
+        self.audio_loader = audio_loader or default_audio_loader
         self.visual_cache: dict = {}
         self.audio_cache: dict = {}
         self.fps_cache: dict = {}
+        self._audio_dev: dict = {}            # path -> CUDA f32 [1, n] at cfg.sample_rate
 
     def _load_visual_stats(self, video_path: str) -> Tuple[torch.Tensor, float]:
         if video_path in self.visual_cache:
             return self.visual_cache[video_path], self.fps_cache[video_path]
         frames = self.grid.process_video(video_path)
-        fps = self.cfg.default_fps                       # .npy / synthetic clips (:91-93)
-        getter = getattr(self.grid, "get_video_fps", None)
-        if getter is not None:
-            fps = getter(video_path) or fps
+        getter = getattr(self.grid, "get_video_fps", None)     # a dataset may know better (synthetic clips)
+        fps = (getter(video_path) if getter is not None else None) or get_video_fps(video_path, self.cfg.default_fps)
         stats = visual_stats(self.lipnet, frames.unsqueeze(0).to(self.device))[0].cpu()
         self.visual_cache[video_path] = stats
         self.fps_cache[video_path] = fps
@@ -275,11 +355,9 @@ class FeatureExtractor:
     def _load_audio(self, video_path: str) -> Tuple[np.ndarray, int]:
         if video_path in self.audio_cache:
             return self.audio_cache[video_path]
-        if self.audio_loader is None:
-            raise RuntimeError(f"Failed to load audio from {video_path}: no audio_loader configured")
         try:
             audio, sr = self.audio_loader(video_path)
-        except Exception as e:                            # same error class as the reference (:191)
+        except Exception as e:                            # same error class and message as the reference (:191)
             raise RuntimeError(f"Failed to load audio from {video_path}: {e}")
         if audio.ndim > 1:
             audio = np.mean(audio, axis=0)
@@ -287,24 +365,30 @@ class FeatureExtractor:
         self.audio_cache[video_path] = (audio, sr)
         return audio, sr
 
+    def _audio_on_device(self, video_path: str) -> torch.Tensor:
+        """The clip's audio at ``cfg.sample_rate`` as a CUDA tensor [1, n]: loaded (and, if needed, resampled) once."""
+        a = self._audio_dev.get(video_path)
+        if a is None:
+            audio, sr = self._load_audio(video_path)
+            a = resample_audio(torch.from_numpy(np.ascontiguousarray(audio)).to(self.device), sr, self.cfg.sample_rate)
+            a = self._audio_dev[video_path] = a.unsqueeze(0)
+        return a
+
     def build_feature(self, video_path: str, shift_frames: int) -> Tuple[torch.Tensor, dict]:
         visual_stats_, fps = self._load_visual_stats(video_path)
-        audio, sr = self._load_audio(video_path)
-        if sr != self.cfg.sample_rate:
-            raise RuntimeError("resampling (librosa.resample, :202-204) is outside the B200 path: "
-                               f"provide {self.cfg.sample_rate} Hz audio")
+        a = self._audio_on_device(video_path)
+        sr = self.cfg.sample_rate
         s = shift_samples(shift_frames, fps, sr)
-        a = torch.from_numpy(np.ascontiguousarray(audio)).to(self.device).unsqueeze(0)
         audio_stats = audio_stats_sweep(a, [s], sr, self.cfg.n_mfcc)[0, 0].cpu()
         feature = torch.cat([visual_stats_, audio_stats], dim=0)
         return feature, {"video_path": video_path, "shift_frames": shift_frames, "fps": fps}
 
     def build_features_sweep(self, video_path: str, max_shift_frames: int) -> torch.Tensor:
-        """All 2S+1 features of one clip at once: [2S+1, 13864]."""
+        """All 2S+1 features of one clip at once: [2S+1, 13864] (same resampling and fps as ``build_feature``)."""
         visual_stats_, fps = self._load_visual_stats(video_path)
-        audio, sr = self._load_audio(video_path)
+        a = self._audio_on_device(video_path)
+        sr = self.cfg.sample_rate
         shifts = [shift_samples(k, fps, sr) for k in range(-max_shift_frames, max_shift_frames + 1)]
-        a = torch.from_numpy(np.ascontiguousarray(audio)).to(self.device).unsqueeze(0)
         ast = audio_stats_sweep(a, shifts, sr, self.cfg.n_mfcc)[0].cpu()
         return torch.cat([visual_stats_.unsqueeze(0).expand(len(shifts), -1), ast], dim=1)
 

@@ -213,6 +213,20 @@ AVS_API int avs_preproc_crop(const avs_preproc* p, int* y0, int* x0, int* crop_h
 AVS_API int avs_preproc_run(const avs_preproc* p, const uint8_t* frames, int n_clips, int n_frames_in,
                     const int32_t* lengths, float* out, void* stream);
 
+/* ---------------------------------------------------------------- sample-rate conversion (second half)
+ * Replaces librosa.resample(audio, orig_sr, target_sr) in FeatureExtractor.build_feature
+ * (misalignment_detection_train.py:202-204) for clips whose audio is not at cfg.sample_rate.  Band-limited polyphase
+ * interpolation with a Kaiser-windowed sinc (64 zero crossings, roll-off 0.9476, beta 14.77: resampy's "kaiser_best", the
+ * filter librosa shipped before soxr), in the formulation of torchaudio.functional.resample; librosa's current default
+ * (soxr_hq) is an un-vendored C library and stays unpinned.
+ * in: device f32 [n_signals, n_in]; out: device f32 [n_signals, avs_resample_out_len(plan, n_in)] = ceil(n_in * target / orig). */
+typedef struct avs_resample_plan avs_resample_plan;
+AVS_API int avs_resample_plan_create(int orig_sr, int target_sr, avs_resample_plan** out);
+AVS_API void avs_resample_plan_destroy(avs_resample_plan* plan);
+AVS_API long long avs_resample_out_len(const avs_resample_plan* plan, long long n_in);
+AVS_API int avs_resample(const avs_resample_plan* plan, const float* in, long long n_in, int n_signals, float* out,
+                 void* stream);
+
 /* Optional per-kernel timing: when enabled, every launch of a profiled kernel is bracketed by CUDA
  * events on its own stream.  slot: 0 pack, 1 conv1, 2 conv2, 3 conv3, 4 vstats, 5 mfcc log-mel,
  * 6 mfcc stats, 7 score GEMM, 8 score, 9 GRU operand pack, 10 GRU input GEMM, 11 GRU recurrence,

@@ -529,6 +529,58 @@ def test_feature_extractor_and_dataset_vs_oracle(A, lipnet_sd, det_sd):
     np.testing.assert_allclose(scores[0].cpu().numpy(), per_shift, rtol=1e-3, atol=2e-5)
 
 
+def test_resample_vs_oracle(A):
+    """GPU resampler (librosa.resample's place, misalignment_detection_train.py:202-204) against oracle/resample_ref.py,
+    itself pinned to torchaudio's Kaiser-sinc interpolator: float32 taps and accumulation against float64, 5e-6 on
+    signals of amplitude ~0.4 (measured: see the report lines)."""
+    from oracle import resample_ref as R
+    rng = np.random.default_rng(2)
+    x = rng.normal(0, 0.1, (3, 40003)).astype(np.float32)
+    for orig, new in ((44100, 16000), (48000, 16000), (22050, 16000), (8000, 16000), (16000, 8000)):
+        got = A.resample_audio(x, orig, new).cpu().numpy()
+        want = np.stack([R.resample(x[i], orig, new) for i in range(3)])
+        assert got.shape == want.shape, (orig, new)
+        report(f"resample {orig}->{new}", got, want)
+        np.testing.assert_allclose(got, want, rtol=0, atol=5e-6)
+    one = A.resample_audio(x[0], 44100, 16000)
+    assert one.dim() == 1 and torch.equal(one, A.resample_audio(x, 44100, 16000)[0])
+    assert torch.equal(A.resample_audio(x[0], 16000, 16000).cpu(), torch.from_numpy(x[0]))
+    assert A.resample_audio(np.zeros(0, np.float32), 44100, 16000).shape == (0,)
+
+
+def test_feature_extractor_reference_signature_on_44k_audio(A, lipnet_sd, tmp_path):
+    """The reference call `FeatureExtractor(grid, lipnet, device, cfg).build_feature(path, k)` on a 44.1 kHz clip:
+    audio is loaded by the default loader, resampled to 16 kHz on the GPU, shifted and turned into MFCC statistics.
+    Against the oracle chain (resample_ref -> shift_audio -> compute_audio_stats); the precomputed-sweep dataset path
+    must give the same features."""
+    from scipy.io import wavfile
+    from oracle import resample_ref as R
+    rng = np.random.default_rng(4)
+    t = np.arange(3 * 44100) / 44100.0
+    env = np.interp(t, np.linspace(0, 3, 13), rng.uniform(0, 1, 13)) ** 2
+    x = (rng.normal(0, 0.1, t.size) * env).clip(-1, 1)
+    wav = str(tmp_path / "clip_31_.wav")
+    wavfile.write(wav, 44100, (x * 32767).astype(np.int16))
+    x = (x * 32767).astype(np.int16).astype(np.float32) / 32768.0
+    net = make_lipnet(A, lipnet_sd, "bf16x3")
+    cfg = A.DetectorConfig(max_shift_frames=20)
+    fx = A.FeatureExtractor(_Grid(), net, torch.device("cuda"), cfg)
+    want_audio = R.resample(x, 44100, 16000)
+    assert want_audio.shape == (48000,)
+    with torch.no_grad():
+        v = sweep_ref.visual_stats(lipnet_ref.stcnn(lipnet_sd, sweep_ref.synth_frames(1, seed=31))[0])
+    for k in (0, 5, -20):
+        feat, meta = fx.build_feature(wav, k)
+        assert feat.shape == (13864,) and meta["fps"] == 25.0
+        want = torch.cat([v, sweep_ref.compute_audio_stats(sweep_ref.shift_audio(want_audio, k, 25.0, 16000), 16000, 20)])
+        report(f"feature 44.1k k={k}", feat.numpy()[13824:], want.numpy()[13824:])
+        np.testing.assert_allclose(feat.numpy(), want.numpy(), rtol=1e-3, atol=2e-3)
+    table = fx.build_features_sweep(wav, 20)
+    assert torch.equal(table[20 + 5], fx.build_feature(wav, 5)[0])
+    ds = A.MisalignmentDataset([wav], fx, cfg, seed=3, precompute=True)
+    assert torch.equal(ds[0][0], fx.build_feature(wav, 0)[0])
+
+
 def test_evaluate_model_drop_in(A, lipnet_sd, capsys):
     net = make_lipnet(A, lipnet_sd, "bf16x3")
     frames = sweep_ref.synth_frames(4, seed=5)

@@ -236,3 +236,27 @@ def test_conv_work_partition_covers_every_item_once_and_is_balanced():
             assert max(costs) - min(costs) <= 2 * nt, (n_tiles, nt, n_clips, steps, ctas, max(costs), min(costs))
     f, l = ctypes.c_int(), ctypes.c_int()
     assert L.avs_conv_item_span(1, 75, 5, 2, 4, 4, ctypes.byref(f), ctypes.byref(l)) != 0      # cta out of range
+
+
+def test_feature_extractor_keeps_the_reference_constructor_and_audio_loading(tmp_path):
+    """FeatureExtractor(grid, lipnet, device, cfg) — the reference's four arguments (:148) — must construct and load
+    audio by itself: librosa -> moviepy like the reference, scipy for .wav when neither is installed; failures raise
+    the reference's RuntimeError (:191)."""
+    from scipy.io import wavfile
+
+    class Grid:
+        def process_video(self, path):
+            return torch.zeros((1, 75, 50, 100))
+    fx = A.FeatureExtractor(Grid(), A.LipNet(39).eval(), torch.device("cpu"), A.DetectorConfig())
+    assert fx.audio_loader is A.default_audio_loader and fx.visual_cache == {} and fx.audio_cache == {} and fx.fps_cache == {}
+    rng = np.random.default_rng(1)
+    pcm = (rng.normal(0, 0.1, (4410, 2)).clip(-1, 1) * 32767).astype(np.int16)
+    wav = str(tmp_path / "clip.wav")
+    wavfile.write(wav, 44100, pcm)
+    audio, sr = fx._load_audio(wav)
+    assert sr == 44100 and audio.dtype == np.float32 and audio.shape == (4410,)
+    np.testing.assert_allclose(audio, pcm.astype(np.float32).mean(axis=1) / 32768.0, atol=1e-6)
+    assert fx._load_audio(wav)[0] is audio                                   # cached per path
+    with pytest.raises(RuntimeError, match="Failed to load audio from"):
+        fx._load_audio(str(tmp_path / "missing.mpg"))
+    assert A.get_video_fps("clip.npy", 30.0) == 30.0 and A.get_video_fps(str(tmp_path / "missing.mpg")) == 25.0

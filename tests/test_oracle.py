@@ -168,3 +168,32 @@ def test_metrics_restatement_known_answers():
     assert abs(M.cer("bin blu", "bin blue") - 1 / 8) < 1e-12
     assert M.wer("bin  blue at", "bin blue at f") == 0.25 and M.wer("a b", "") == 1.0 and M.wer("   ", "") == 0.0
     assert M.char_accuracy("abcd", "abxd") == 75.0 and M.char_accuracy("", "abc") == 0.0
+
+
+# ------------------------------------------------------------------------------------------ resampling (librosa.resample)
+def test_resample_oracle_vs_torchaudio_and_scipy():
+    """oracle/resample_ref.py restates torchaudio.functional.resample's Kaiser-sinc interpolator (resampy kaiser_best
+    parameters).  Pinned against torchaudio itself (float64: 1e-7; its float32 path: 5e-5) for several rate pairs, and —
+    as an independent design — against scipy.signal.resample_poly and the analytic samples of a band-limited signal."""
+    import scipy.signal
+    torchaudio = pytest.importorskip("torchaudio")
+    from oracle import resample_ref as R
+    rng = np.random.default_rng(0)
+    x = rng.normal(0, 0.1, 30011).astype(np.float32)
+    for orig, new in ((44100, 16000), (48000, 16000), (22050, 16000), (8000, 16000), (11025, 16000), (16000, 8000)):
+        y = R.resample(x, orig, new)
+        kw = dict(lowpass_filter_width=R.ZEROS, rolloff=R.ROLLOFF, resampling_method="sinc_interp_kaiser", beta=R.BETA)
+        t64 = torchaudio.functional.resample(torch.from_numpy(x).double(), orig, new, **kw).numpy()
+        t32 = torchaudio.functional.resample(torch.from_numpy(x), orig, new, **kw).numpy()
+        assert y.shape == t64.shape == (-(-len(x) * new // orig),), (orig, new)
+        assert np.abs(y - t64).max() < 1e-7, (orig, new)
+        assert np.abs(y - t32).max() < 5e-5, (orig, new)     # torchaudio's float32 path builds its taps in float32
+    assert np.array_equal(R.resample(x, 16000, 16000), x)
+    tt = np.arange(44100) / 44100.0
+    parts = ((220.0, 0.1), (1000.0, 1.0), (3333.0, 2.0), (5900.0, 0.5))
+    z = sum(0.1 * np.sin(2 * np.pi * f * tt + ph) for f, ph in parts)
+    exact = sum(0.1 * np.sin(2 * np.pi * f * np.arange(16000) / 16000.0 + ph) for f, ph in parts)
+    y = R.resample(z, 44100, 16000)
+    assert np.abs(y[300:-300] - exact[300:-300]).max() < 1e-6                 # interior: band-limited reconstruction
+    sp = scipy.signal.resample_poly(z, 160, 441)
+    assert np.abs(y[300:-300] - sp[300:-300]).max() < 1e-3                    # scipy's shorter Kaiser(5.0) FIR: 2e-4 off
