@@ -291,10 +291,16 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
 
   using K = LayerKind<KIND>;
   constexpr int NT = K::NT;
+  // conv1 (one 32-column block per tile, the shortest MMAs, epilogue-paced): 16-column units with the next unit's TMEM
+  // loads in flight; the other kinds: 32-column units
+  constexpr bool kEpi16 = KIND == KIND_L1;
+  // Accumulator hand-over in halves (barriers [buffer * 2 + half]) only where the buffer cannot be doubled — conv3, whose
+  // two tiles fill TMEM; the double-buffered kinds hand whole buffers over through the barriers of half 0.
+  constexpr bool kHalves = KIND == KIND_L3;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.ring; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 2);   // both issuers commit
+    for (int i = 0; i < p.ring; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 1);
     for (int i = 0; i < p.wstages; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
-    for (int i = 0; i < 2 * p.NBUF; ++i) mbar_init(&acc_full[i], 2), mbar_init(&acc_empty[i], 8);
+    for (int i = 0; i < 2 * p.NBUF; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 8);
     for (int i = 0; i < 4; ++i) mbar_init(&turn[i], 1);
     mbar_fence_init();
   }
@@ -388,8 +394,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     // ============================================================ MMA issuers
     // Both warps walk the whole schedule converged (slot and phase counters stay identical); issuer x owns every
     // other weight stage (global stage counter g, g & 1 == x).  For an owned stage: wait for its operands, then issue
-    // it in two halves under the token protocol below.  Barriers that cover MMAs of both issuers (a_empty, acc_full)
-    // take a commit from each.
+    // it in two halves under the token protocol below.
     const uint32_t x = warp >> 1;
     const uint32_t idesc_n = umma_idesc_bf16(128, K::N), idesc_w = umma_idesc_bf16(128, 2 * K::N);
     const uint32_t units_lo = (smem_u32(s_units) & 0x3FFFFu) >> 4, w_lo = (smem_u32(s_w) & 0x3FFFFu) >> 4;
@@ -401,10 +406,6 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     const uint32_t lbo_a = (K::first ? Wt : (K::split ? 4u : 2u) * arr16) << 16;
     constexpr uint32_t lbo_b = static_cast<uint32_t>(K::split ? 2 * K::N : K::NROW * K::N) << 16;
     const int n_stages = p.n_stages, n_tiles = p.n_tiles, dbg = AVS_DBG(p);
-    // Accumulator hand-over in halves only where the buffer cannot be doubled (conv3: its two tiles fill TMEM).  With two
-    // buffers the epilogue is never waiting for TMEM space, and letting the other issuer's next item overtake the second
-    // half of this one only delays the tiles the in-order epilogue needs next (conv1 measured 4.9 -> 9.7 ms per 1024 clips).
-    constexpr bool kHalves = KIND == KIND_L3;
     uint32_t a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0, acc_buf = 0, acc_phase = 0;
     uint32_t a_loaded = 0, w_loaded = 0;  // only used by the dbg switches
     uint32_t g = 0, turn_phase = 0;
@@ -432,10 +433,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
           if (!acc_ready0) {
             mbar_wait(&acc_empty[acc_buf * 2], acc_phase ^ 1);
             acc_ready0 = true;
-            if (!kHalves) {  // double-buffered kinds take the buffer back whole
-              mbar_wait(&acc_empty[acc_buf * 2 + 1], acc_phase ^ 1);
-              acc_ready1 = true;
-            }
+            if (!kHalves) acc_ready1 = true;  // double-buffered kinds take the buffer back whole
           }
           uint32_t ab[3];
           if (K::reuse) {
@@ -497,10 +495,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
                 tc_commit(&a_empty[a_slot]);
               }
             }
-            if (st == n_stages - 1) {
-              if (!kHalves) tc_commit(&acc_full[acc_buf * 2]);
-              tc_commit(&acc_full[acc_buf * 2 + 1]);
-            }
+            if (st == n_stages - 1) tc_commit(&acc_full[acc_buf * 2 + (kHalves ? 1 : 0)]);
             tc_commit(&turn[2 + (x ^ 1)]);
           }
           __syncwarp();
@@ -510,23 +505,12 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
             const long long tk3 = clock64();
             tk_prep += tk1 - tk0; tk_turn += tk2 - tk1; tk_issue += tk3 - tk2;
           }
-        } else if ((last_of_unit || st == n_stages - 1) && elect_one()) {
-          // barriers over MMAs of both issuers (A slots, accumulator): the issuer that does not own the boundary stage
-          // commits its share as it walks by
-          if (last_of_unit && !(dbg & 2)) {
-            if (K::reuse) {
-              if (K::first) {
-                tc_commit(&a_empty[w.t % K::RING]);
-                if (!cont_next) tc_commit(&a_empty[(w.t + 1) % K::RING]), tc_commit(&a_empty[(w.t + 2) % K::RING]);
-              } else if (unit == 0 || !cont_next) {
-                tc_commit(&a_empty[slot0]);
-              }
-            } else {
-              tc_commit(&a_empty[a_slot]);
-            }
-          }
-          if (st == n_stages - 1) tc_commit(&acc_full[acc_buf * 2]), tc_commit(&acc_full[acc_buf * 2 + 1]);
         }
+        // (Barriers that cover MMAs of both issuers — A slots, accumulators — take ONE commit, from the issuer that owns the
+        // boundary stage: its second half is issued after the other issuer's previous stage has completed (final token),
+        // so when that commit fires every earlier MMA of either issuer is done.  A second commit from the issuer walking
+        // by is not free: tcgen05.commit queues behind the MMAs in flight — conv1, whose items are one stage, lost
+        // ~1700 cycles per extra commit.)
         __syncwarp();
         ++w_loaded;
         if (++w_slot == wstages) w_slot = 0, w_phase ^= 1;
@@ -549,6 +533,178 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     }
   } else if (warp >= 4) {
     // ============================================================ epilogue
+    // Two flavours, chosen per layer kind by measurement (profiles/r02_epilogue_variants.txt).
+    if constexpr (kEpi16) {
+    // Two groups of four warps (warps 4-7 and 8-11); warp w may read TMEM lanes 32*(w%4)..+31.  The work unit is a
+    // 16-column block of one tile (both row accumulators): group 0 takes the even blocks of every tile, group 1 the odd
+    // ones, so both groups drain the same tile and a tile (and with it an accumulator half) is free after
+    // N/32 units per warp.  TMEM reads run at 64 B/cycle per SM — 512 cycles for a conv1 tile, about what its MMAs
+    // take — so the loads of unit k+1 are issued before the arithmetic of unit k (two register buffers), which keeps the
+    // TMEM pipe busy instead of alternating between loading and computing.
+    const int q = warp & 3, grp = (warp - 4) >> 2;
+    using KN = LayerKind<K::NEXT>;             // the layer that reads our output (conv3: unused)
+    constexpr bool kToEmb = K::N == 96;        // conv3 writes the f32 embedding
+    constexpr int kHo = K::H / 2, kWo = K::W / 2, kPlane = kHo * kWo;
+    constexpr int UPT = K::N / 32;             // units per tile for one group
+    constexpr int UMAX = NT * UPT;             // units per item for one warp
+    constexpr bool kPipe = !K::split;          // the split kinds need four loads per unit: no room for a second buffer
+    const int half = lane & 1;                 // even lane keeps channels 0..7 of a 16-column block, odd lane 8..15
+    uint32_t buf = 0, phase = 0;
+    ItemWalk w;
+    w.init(p);
+    for (; w.valid(); w.next(), buf = (buf + 1 == static_cast<uint32_t>(p.NBUF)) ? 0 : buf + 1, phase ^= (buf == 0)) {
+      const int b = w.b, t = w.t, ts = w.ts;
+      const int nt = min(NT, p.n_tiles - ts * NT);
+      const int n_units = (AVS_DBG(p) & 4) ? 0 : nt * UPT;
+      // tiles [0, h0) are the first half of the accumulator buffer; the single-tile split kinds halve it by row
+      // accumulator instead, and need both halves for the first unit already
+      const int h0 = (nt + 1) >> 1;
+      mbar_wait(&acc_full[buf * 2], phase);
+      bool full1 = false;
+      if (K::split && nt == 1) {
+        mbar_wait(&acc_full[buf * 2 + 1], phase);
+        full1 = true;
+      }
+      __syncwarp();  // tcgen05.ld below is .aligned
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + buf * (NT * 2 * K::ACC) + (static_cast<uint32_t>(q * 32) << 16);
+      // does tile i hold any position of this warp's 32 lanes?  (positions grow with the lane and with i)
+      auto tile_has_work = [&](int i) {
+        if (K::tcat) return ((t * NT + i) * 128 + q * 32) / K::PITCH < p.T_out;
+        return ((ts * NT + i) * 128 + q * 32) / K::WT < kHo;
+      };
+      // tiles from h0 on belong to the second accumulator half, which completes a little later than the first
+      auto need_half1 = [&](int i) {
+        if (kHalves && i >= h0 && !full1) {
+          mbar_wait(&acc_full[buf * 2 + 1], phase);
+          __syncwarp();
+          tc_fence_after();
+          full1 = true;
+        }
+      };
+      uint32_t va[2][16], vb[2][16];
+      auto issue_loads = [&](int k, uint32_t (&x0)[16], uint32_t (&x1)[16]) {
+        const int i = k / UPT, cb = (2 * (k % UPT) + grp) * 16;
+        tmem_ld16(d_base + (i * 2 + 0) * K::ACC + cb, x0);
+        tmem_ld16(d_base + (i * 2 + 1) * K::ACC + cb, x1);
+      };
+      if (kPipe && n_units > 0 && tile_has_work(0)) issue_loads(0, va[0], vb[0]);
+      bool released0 = false, released1 = false;
+#pragma unroll
+      for (int k = 0; k < UMAX; ++k) {
+        if (k >= n_units) break;
+        const int i = k / UPT, cb = (2 * (k % UPT) + grp) * 16;
+        const bool work = tile_has_work(i);
+        uint32_t (&v0)[16] = va[kPipe ? (k & 1) : 0];
+        uint32_t (&v1)[16] = vb[kPipe ? (k & 1) : 0];
+        if (!kPipe && work) {
+          need_half1(i);
+          issue_loads(k, v0, v1);
+          tmem_ld_wait();
+          if (K::split) {  // second column block: A_hi * B_lo, the small term, added last
+            uint32_t u0[16], u1[16];
+            tmem_ld16(d_base + (i * 2 + 0) * K::ACC + K::N + cb, u0);
+            tmem_ld16(d_base + (i * 2 + 1) * K::ACC + K::N + cb, u1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              v0[c] = __float_as_uint(__uint_as_float(v0[c]) + __uint_as_float(u0[c]));
+              v1[c] = __float_as_uint(__uint_as_float(v1[c]) + __uint_as_float(u1[c]));
+            }
+          }
+        }
+        const int ch0 = cb + half * 8;
+        float bias[8];  // fetched while the TMEM loads are in flight
+        {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + 1);
+          bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w; bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+        }
+        if (kPipe) tmem_ld_wait();  // unit k's loads (nothing else is outstanding)
+        // hand the accumulator halves back as soon as their last loads have landed in registers
+        if (kHalves && k == h0 * UPT - 1 && !(K::split && nt == 1)) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf * 2]);
+          released0 = true;
+        }
+        if (k == n_units - 1) {
+          need_half1(NT);  // (an item without second-half tiles: do not hand the half back before the issuers are done with it)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (!released0) mbar_arrive(&acc_empty[buf * 2]);
+            if (kHalves) mbar_arrive(&acc_empty[buf * 2 + 1]);
+          }
+          released0 = released1 = true;
+        }
+        if (kPipe && k + 1 < n_units) {  // loads of the next unit, under the arithmetic of this one
+          const int i1 = (k + 1) / UPT;
+          need_half1(i1);
+          if (tile_has_work(i1)) issue_loads(k + 1, va[(k + 1) & 1], vb[(k + 1) & 1]);
+        }
+        if (!work) continue;
+        if ((AVS_DBG(p) & 32) && v0[0] != 0x7fc12345u) continue;  // experiment: TMEM reads only
+        int Q = (ts * NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
+        int t_out = t;
+        if (K::tcat) {  // time-concatenated position space: item index -> (time step, position in its plane)
+          const int S = (t * NT + i) * 128 + q * 32 + lane;
+          t_out = S / K::PITCH;
+          Q = S - t_out * K::PITCH;
+        }
+        const int r = Q / K::WT, wc = Q % K::WT;            // pooled row, conv column
+        const int wo = wc >> 1;
+        const bool valid = (r < kHo) && (wo < kWo) && (t_out < p.T_out);
+        float o[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          // rows 2r, 2r+1: max of the two accumulators; columns 2wo, 2wo+1: exchange with the
+          // neighbouring lane — each lane keeps 8 of the 16 channels and ships the other 8
+          const float lo = fmaxf(__uint_as_float(v0[c]), __uint_as_float(v1[c]));
+          const float hi = fmaxf(__uint_as_float(v0[c + 8]), __uint_as_float(v1[c + 8]));
+          const float got = __shfl_xor_sync(0xffffffffu, half ? lo : hi, 1);
+          o[c] = fmaxf(fmaxf(half ? hi : lo, got) + bias[c], 0.f);
+        }
+        if ((AVS_DBG(p) & 64) && o[0] != 12345.678f) continue;  // experiment: no stores
+        if (valid && !kToEmb) {
+          // the NEXT layer's parity-plane layout (its geometry is a compile-time property of the kind)
+          const int hp = r + KN::KH / 2;
+          const int pos = KN::KW / 2 + (hp >> 1) * KN::WT + wo;
+          // element offset of array `a` (= chunk array * 2 + parity), position `pos` of time plane t + 1
+          auto out_ptr = [&](int a) {
+            if (KN::tcat)
+              return p.eo.act + ((static_cast<long long>(b) * (KN::N_CHUNKS * 2) + a) * KN::TCAT_LEN + (t + 1) * KN::PITCH + pos) * 8;
+            return p.eo.act + ((((static_cast<long long>(b) * (p.T_out + 2) + t + 1) * KN::N_CHUNKS) * 2 + a) * KN::PP + pos) * 8;
+          };
+          const int chunk = ch0 >> 3;
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x0 = o[2 * e], x1 = o[2 * e + 1];
+            const __nv_bfloat16 h0b = __float2bfloat16_rn(x0), h1b = __float2bfloat16_rn(x1);
+            hi[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
+            if (K::split) lo[e] = pack_bf16x2(x0 - __bfloat162float(h0b), x1 - __bfloat162float(h1b));
+          }
+          const int idx = K::split ? 2 * chunk : chunk;
+          *reinterpret_cast<uint4*>(out_ptr(idx * 2 + (hp & 1))) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (K::split) *reinterpret_cast<uint4*>(out_ptr((idx + 1) * 2 + (hp & 1))) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        } else if (valid) {
+          float* dst = p.eo.emb + (static_cast<long long>(b) * p.T_out + t_out) * (K::N * kPlane) + ch0 * kPlane + r * kWo + wo;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) dst[c * kPlane] = o[c];
+        }
+      }
+      if (!released1) {  // experiment switch 4 (no units): still hand the buffer back
+        need_half1(NT);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (!released0) mbar_arrive(&acc_empty[buf * 2]);
+          if (kHalves) mbar_arrive(&acc_empty[buf * 2 + 1]);
+        }
+      }
+    }
+  
+    } else {
     // Two groups of four warps (warps 4-7 and 8-11); warp w may read TMEM lanes 32*(w%4)..+31.  The work unit is a
     // 32-column block of one tile (both row accumulators); the units of an item, in (tile, block) order, alternate between
     // the groups.  An accumulator half goes back to the issuers as soon as this warp's last unit of the half has been
@@ -581,7 +737,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       mbar_wait(&acc_full[buf * 2], phase);
       bool full1 = false;
       auto need_half1 = [&]() {  // the second accumulator half completes a little later than the first
-        if (!full1) {
+        if (kHalves && !full1) {
           mbar_wait(&acc_full[buf * 2 + 1], phase);
           __syncwarp();
           tc_fence_after();
@@ -589,9 +745,10 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         }
       };
       auto release = [&](int h) {
+        if (!kHalves && h == 0) return;  // whole-buffer kinds: one arrival, when the warp's last unit has been read
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf * 2 + h]);
+        if (lane == 0) mbar_arrive(&acc_empty[buf * 2 + (kHalves ? h : 0)]);
       };
       __syncwarp();  // tcgen05.ld below is .aligned
       tc_fence_after();
@@ -707,6 +864,8 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         if (!released0) release(0);
         release(1);
       }
+    }
+  
     }
   }
   tc_fence_before();

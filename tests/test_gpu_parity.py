@@ -491,11 +491,13 @@ class _Grid:
     idx_to_char = lipnet_ref.make_vocab()
 
     def process_video(self, path):
-        return sweep_ref.synth_frames(1, seed=int(path.split("_")[1]))[0]
+        import os
+        return sweep_ref.synth_frames(1, seed=int(os.path.basename(path).split("_")[1]))[0]
 
 
 def _audio_loader(path):
-    return sweep_ref.synth_audio(1, seed=int(path.split("_")[1]), kind="speechlike")[0], 16000
+    import os
+    return sweep_ref.synth_audio(1, seed=int(os.path.basename(path).split("_")[1]), kind="speechlike")[0], 16000
 
 
 def test_feature_extractor_and_dataset_vs_oracle(A, lipnet_sd, det_sd):
