@@ -293,10 +293,16 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   constexpr int NT = K::NT;
   // conv1 (one 32-column block per tile, the shortest MMAs, epilogue-paced): 16-column units with the next unit's TMEM
   // loads in flight; the other kinds: 32-column units
-  constexpr bool kEpi16 = KIND == KIND_L1;
+#ifndef AVS_VAR_EPI16
+#define AVS_VAR_EPI16 0   // measured choice (profiles/r02_variants_ab.txt); tools can rebuild with the other value
+#endif
+#ifndef AVS_VAR_HALVES
+#define AVS_VAR_HALVES 1
+#endif
+  constexpr bool kEpi16 = AVS_VAR_EPI16 && KIND == KIND_L1;
   // Accumulator hand-over in halves (barriers [buffer * 2 + half]) only where the buffer cannot be doubled — conv3, whose
   // two tiles fill TMEM; the double-buffered kinds hand whole buffers over through the barriers of half 0.
-  constexpr bool kHalves = KIND == KIND_L3;
+  constexpr bool kHalves = AVS_VAR_HALVES && KIND == KIND_L3;
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.ring; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 1);
     for (int i = 0; i < p.wstages; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);

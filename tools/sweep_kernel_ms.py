@@ -10,11 +10,22 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import avsync_b200 as A
 import bench
 
-A._native.use_experiments_build()
+# --lib NAME: load libavsync_b200_var_NAME.so (make -C csrc VARIANT=NAME VARIANT_FLAGS=...), or "product"; default: the
+# experiments build (AVS_* environment knobs)
+args = [a for a in sys.argv[1:]]
+LIB = "exp"
+if "--lib" in args:
+    i = args.index("--lib")
+    LIB = args[i + 1]
+    del args[i:i + 2]
+if LIB == "exp":
+    A._native.use_experiments_build()
+elif LIB != "product":
+    A._native.LIB_PATH = os.path.join(os.path.dirname(A._native.LIB_PATH), f"libavsync_b200_var_{LIB}.so")
 L = A._native.lib()
-C = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-PREC = sys.argv[3] if len(sys.argv) > 3 else "bf16"
+C = int(args[0]) if len(args) > 0 else 1024
+STEPS = int(args[1]) if len(args) > 1 else 10
+PREC = args[2] if len(args) > 2 else "bf16"
 torch.manual_seed(0)
 net = A.LipNet(39, precision=PREC).cuda().eval()
 torch.manual_seed(1)
@@ -42,4 +53,4 @@ for i, n in enumerate(names):
     L.avs_prof_read(i, ctypes.byref(t), ctypes.byref(c))
     out.append(f"{n} {t.value / STEPS:.2f}")
 knobs = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("AVS_"))
-print(f"[{knobs or 'defaults'}] {PREC} {C} clips: {ms:.2f} ms/step = {C / ms * 1e3:.0f} clips/s | " + " | ".join(out), flush=True)
+print(f"[lib={LIB} {knobs or 'defaults'}] {PREC} {C} clips: {ms:.2f} ms/step = {C / ms * 1e3:.0f} clips/s | " + " | ".join(out), flush=True)
