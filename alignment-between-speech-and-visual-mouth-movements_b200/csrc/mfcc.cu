@@ -433,14 +433,12 @@ using namespace avs;
 // variant is slower, 39.8 against 38.1 ms per 1024 clips (conv2 -1.1 ms, conv3 +3.1 ms): with four-warp CTAs only one
 // CTA (two working warps) fits beside a conv CTA instead of three one-warp CTAs, the audio branch stretches past conv2
 // and lands on conv3, whose epilogue sits on its critical path.
-static bool fft_sched_mode() {
 #ifdef AVS_EXPERIMENTS
+static bool fft_sched_mode() {
   static const int mode = getenv("AVS_K1_SCHED") ? atoi(getenv("AVS_K1_SCHED")) : 0;
   return mode != 0;
-#else
-  return false;
-#endif
 }
+#endif
 
 extern "C" int avs_mfcc_plan_describe(int n_samples, int sample_rate, const int32_t* shift_samples, int n_shifts,
                                       int* n_frames_out, int* n_unique_out, int32_t* frames_out, int32_t* map_out) {
@@ -570,11 +568,14 @@ extern "C" int avs_mfcc_sweep_debug(const avs_mfcc_plan* p, const float* audio, 
     {
       ProfScope ps(PROF_LOGMEL, st);
 #define AVS_LOGMEL_ARGS au, p->n_samples, p->d_frames, p->n_unique, p->d_window, p->d_tw, p->d_tw2, p->d_mel_tab, p->d_mel_w, p->d_dct, lm, fmf, frg
+#ifdef AVS_EXPERIMENTS
       if (fft_sched_mode()) {
         const dim3 g1(cdiv(p->n_unique, kFftCtaFrames), nc);
         if (p->n_mfcc <= 20) mfcc_logmel_warp_kernel<true, 20><<<g1, 32 * kFftCtaWarps, 0, st>>>(AVS_LOGMEL_ARGS);
         else mfcc_logmel_warp_kernel<true, kMaxQ><<<g1, 32 * kFftCtaWarps, 0, st>>>(AVS_LOGMEL_ARGS);
-      } else {
+      } else
+#endif
+      {
         const dim3 g1(cdiv(p->n_unique, kWarpFftWarps), nc);
         if (p->n_mfcc <= 20) mfcc_logmel_warp_kernel<false, 20><<<g1, 32 * kWarpFftWarps, 0, st>>>(AVS_LOGMEL_ARGS);
         else mfcc_logmel_warp_kernel<false, kMaxQ><<<g1, 32 * kWarpFftWarps, 0, st>>>(AVS_LOGMEL_ARGS);
