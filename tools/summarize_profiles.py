@@ -25,7 +25,7 @@ for r in rows[1:]:
 tot = sum(a[1] for a in agg.values())
 with open(f"profiles/{tag}_launches.txt", "w") as f:
     f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
-    f.write(f"# source: {launches}; command: python bench.py --steps 2 --warmup 3 --clips-per-gpu 256 --cpu-clips 0 --no-e2e\n")
+    f.write(f"# source: {launches}; command: python bench.py --steps 2 --warmup 3 --clips-per-gpu 256 --cpu-clips 0 --no-e2e --no-configs (tools/ncu_round.sh)\n")
     f.write(f"{'kernel':72s} {'n':>5s} {'total ms':>10s} {'share':>7s} {'avg us':>10s}  grid / block\n")
     for k, (n, t, g, b) in sorted(agg.items(), key=lambda x: -x[1][1]):
         f.write(f"{k:72s} {n:5d} {t / 1e3:10.3f} {t / tot:7.1%} {t / n:10.1f}  {g} / {b}\n")
