@@ -38,6 +38,7 @@
 // this is what overlaps the TMEM read-out (64 B/cycle per SM: 1536 cycles per conv3 tile) with tensor work for the
 // layer whose two tiles fill TMEM and cannot be double-buffered.
 #include <stdlib.h>
+#include <algorithm>
 #include <vector>
 #include "stcnn.cuh"
 
@@ -932,57 +933,75 @@ static void kind_traits_for(int kind, int* NT, int* acc, int* spu, int* pairs, i
 // for frames that came from 8-bit pixels.
 template <typename TIn>
 __global__ void __launch_bounds__(256)
-pack_frames_kernel(const TIn* __restrict__ frames, __nv_bfloat16* __restrict__ act, LayerGeom g, int split, int T) {
-  extern __shared__ uint16_t s_val[];           // [2][PP + 8]: hi, lo
-  __shared__ uint32_t s_lut[256];               // u8 variant: bf16 hi | bf16 lo << 16 of float32(v / 255.0)
+pack_frames_kernel(const TIn* __restrict__ frames, __nv_bfloat16* __restrict__ act, int PP, int split, int T, int n_items) {
+  extern __shared__ __align__(16) uint16_t s_val[];  // [2][NV]: hi, lo (NV = PP + 8 rounded up to 8 values)
+  __shared__ uint32_t s_lut[256];                    // u8 variant: bf16 hi | bf16 lo << 16 of float32(v / 255.0)
   constexpr bool kU8 = sizeof(TIn) == 1;
-  const int n = g.PP + 8;
+  // LipNet's frame geometry (the layer-1 kind's constants): 50 x 100 pixels, padding 2, row pitch 102, 27 rows per parity
+  using K1 = LayerKind<KIND_L1>;
+  constexpr int H = K1::H, W = K1::W, PH = K1::KH / 2, PW = K1::KW / 2, WT = K1::WT, HH = H / 2 + PH, QW = W / 4;
+  const int nv = (PP + 8 + 7) & ~7;
   uint16_t* s_hi = s_val;
-  uint16_t* s_lo = s_val + n;
-  const int par = blockIdx.x & 1, tp = (blockIdx.x >> 1) % (T + 2);
-  const long long b = (blockIdx.x >> 1) / (T + 2);
-  for (int i = threadIdx.x; i < 2 * n; i += 256) s_val[i] = 0;
-  if (kU8) {
+  uint16_t* s_lo = s_val + nv;
+  if (kU8) {  // once per CTA: the CTA then walks many (clip, plane, parity) items
     const float v = static_cast<float>(static_cast<double>(threadIdx.x) / 255.0);
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     s_lut[threadIdx.x] = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) |
                          (static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hi)))) << 16);
   }
-  __syncthreads();
-  if (tp >= 1 && tp <= T) {
-    const TIn* f = frames + (b * T + (tp - 1)) * static_cast<long long>(g.H) * g.W;
-    for (int i = threadIdx.x; i < g.Hh * g.W; i += 256) {
-      const int row = i / g.W, wq = i - row * g.W;
-      const int h = 2 * row + par - g.ph;
-      if (h >= 0 && h < g.H) {
-        const int pos = g.pw + row * g.Wt + wq;
+  const int nch = split ? 2 : 1;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int par = item & 1, tp = (item >> 1) % (T + 2);
+    const long long b = (item >> 1) / (T + 2);
+    __syncthreads();  // the previous item's reads of s_val are done (and the table is in place)
+    for (int i = threadIdx.x; i < 2 * nv / 8; i += 256) reinterpret_cast<uint4*>(s_val)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (tp >= 1 && tp <= T) {
+      // a work unit is four consecutive pixels of one row (the row pitch, the padding and 4-pixel groups are all even,
+      // so a group is two aligned 32-bit stores of bf16 pairs)
+      const TIn* f = frames + (b * T + (tp - 1)) * static_cast<long long>(H * W);
+      for (int i = threadIdx.x; i < HH * QW; i += 256) {
+        const int row = i / QW, wq = (i - row * QW) * 4;
+        const int h = 2 * row + par - PH;
+        if (h < 0 || h >= H) continue;
+        uint32_t e[4];
         if constexpr (kU8) {
-          const uint32_t e = s_lut[f[h * g.W + wq]];
-          s_hi[pos] = static_cast<uint16_t>(e);
-          s_lo[pos] = static_cast<uint16_t>(e >> 16);
+          const uint32_t px = *reinterpret_cast<const uint32_t*>(f + h * W + wq);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) e[j] = s_lut[(px >> (8 * j)) & 0xFFu];
         } else {
-          const float v = f[h * g.W + wq];
-          const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-          s_hi[pos] = __bfloat16_as_ushort(hi);
-          s_lo[pos] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hi)));
+          const float4 v4 = *reinterpret_cast<const float4*>(f + h * W + wq);
+          const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
+            e[j] = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) |
+                   (static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(v[j] - __bfloat162float(hi)))) << 16);
+          }
         }
+        const int pos = PW + row * WT + wq;
+        uint32_t* dh = reinterpret_cast<uint32_t*>(s_hi + pos);
+        uint32_t* dl = reinterpret_cast<uint32_t*>(s_lo + pos);
+        dh[0] = (e[0] & 0xFFFFu) | (e[1] << 16);
+        dh[1] = (e[2] & 0xFFFFu) | (e[3] << 16);
+        dl[0] = (e[0] >> 16) | (e[1] & 0xFFFF0000u);
+        dl[1] = (e[2] >> 16) | (e[3] & 0xFFFF0000u);
       }
     }
-  }
-  __syncthreads();
-  const int nch = split ? 2 : 1;
-  __nv_bfloat16* base = act + ((b * (T + 2) + tp) * nch) * 2 * static_cast<long long>(g.PP) * 8;
-  uint4* out_hi = reinterpret_cast<uint4*>(base + static_cast<long long>(par) * g.PP * 8);
-  uint4* out_lo = reinterpret_cast<uint4*>(base + (2LL + par) * g.PP * 8);
-  for (int p = threadIdx.x; p < g.PP; p += 256) {
-    uint32_t w[4];
+    __syncthreads();
+    __nv_bfloat16* base = act + ((b * (T + 2) + tp) * nch) * 2 * static_cast<long long>(PP) * 8;
+    uint4* out_hi = reinterpret_cast<uint4*>(base + static_cast<long long>(par) * PP * 8);
+    uint4* out_lo = reinterpret_cast<uint4*>(base + (2LL + par) * PP * 8);
+    for (int p = threadIdx.x; p < PP; p += 256) {
+      uint32_t w[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) w[e] = static_cast<uint32_t>(s_hi[p + 2 * e]) | (static_cast<uint32_t>(s_hi[p + 2 * e + 1]) << 16);
-    out_hi[p] = make_uint4(w[0], w[1], w[2], w[3]);
-    if (split) {
+      for (int e = 0; e < 4; ++e) w[e] = static_cast<uint32_t>(s_hi[p + 2 * e]) | (static_cast<uint32_t>(s_hi[p + 2 * e + 1]) << 16);
+      out_hi[p] = make_uint4(w[0], w[1], w[2], w[3]);
+      if (split) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) w[e] = static_cast<uint32_t>(s_lo[p + 2 * e]) | (static_cast<uint32_t>(s_lo[p + 2 * e + 1]) << 16);
-      out_lo[p] = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int e = 0; e < 4; ++e) w[e] = static_cast<uint32_t>(s_lo[p + 2 * e]) | (static_cast<uint32_t>(s_lo[p + 2 * e + 1]) << 16);
+        out_lo[p] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
     }
   }
 }
@@ -1246,12 +1265,15 @@ void umma_layer_free(UmmaLayer* L) {
   L->d_w = nullptr; L->d_bias = nullptr;
 }
 
-int umma_pack_frames(const void* frames, bool frames_u8, __nv_bfloat16* act, const LayerGeom& g, int split, int B, cudaStream_t st) {
+int umma_pack_frames(const void* frames, bool frames_u8, __nv_bfloat16* act, const LayerGeom& g, int split, int B, int n_sms, cudaStream_t st) {
   ProfScope ps(PROF_PACK, st);
-  const size_t sm = static_cast<size_t>(2) * (g.PP + 8) * sizeof(uint16_t);
-  const unsigned grid = static_cast<unsigned>(B) * (AVS_T + 2) * 2;
-  if (frames_u8) pack_frames_kernel<uint8_t><<<grid, 256, sm, st>>>(static_cast<const uint8_t*>(frames), act, g, split, AVS_T);
-  else pack_frames_kernel<float><<<grid, 256, sm, st>>>(static_cast<const float*>(frames), act, g, split, AVS_T);
+  AVS_REQUIRE(g.H == AVS_H && g.W == AVS_W && g.KH == 5 && g.KW == 5 && g.Cin == 1, "pack_frames: LipNet layer-1 geometry only");
+  const size_t sm = static_cast<size_t>(2) * ((g.PP + 8 + 7) & ~7) * sizeof(uint16_t);
+  // grid-stride over the (clip, plane, parity) items: 8 CTAs per SM keep the stores of one item under the loads of others
+  const int n_items = B * (AVS_T + 2) * 2;
+  const unsigned grid = static_cast<unsigned>(std::min(n_items, n_sms * 8));
+  if (frames_u8) pack_frames_kernel<uint8_t><<<grid, 256, sm, st>>>(static_cast<const uint8_t*>(frames), act, g.PP, split, AVS_T, n_items);
+  else pack_frames_kernel<float><<<grid, 256, sm, st>>>(static_cast<const float*>(frames), act, g.PP, split, AVS_T, n_items);
   AVS_LAUNCHED();
   return AVS_OK;
 }

@@ -186,26 +186,36 @@ mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const in
 #pragma unroll
   for (int i = 0; i < 32; ++i) z[lane + 32 * bitrev5(i)] = v[i];  // natural order, flat [1024]
   __syncwarp();
-  // split post-pass for the real transform: bins k = lane + 32 i, i = 0..32 (k <= 1024)
-  float pw[33];
+  // split post-pass for the real transform.  With E = (Z[k] + conj Z[N/2-k]) / 2 and O = (Z[k] - conj Z[N/2-k]) / 2i,
+  // X[k] = E + W^k O and X[N/2-k] = conj(E - W^k O): bins k and 1024 - k come from the same pair of loads and the same
+  // complex product, so a lane takes k = lane + 32 i for i = 0..15 (k < 512) together with its mirror; k = 512 is its
+  // own mirror (lane 0).
+  float pa[16], pb[16], pmid = 0.f;
 #pragma unroll
-  for (int i = 0; i < 33; ++i) {
+  for (int i = 0; i < 16; ++i) {
     const int k = lane + 32 * i;
-    pw[i] = 0.f;
-    if (k <= kHalf) {
-      const float2 zk = z[k & (kHalf - 1)], zn = z[(kHalf - k) & (kHalf - 1)];
-      const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-      const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
-      const float2 wo = cmul(__ldg(tw2 + k), o);
-      const float xr = e.x + wo.x, xi = e.y + wo.y;
-      pw[i] = xr * xr + xi * xi;
-    }
+    const float2 zk = z[k], zn = z[(kHalf - k) & (kHalf - 1)];
+    const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+    const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+    const float2 wo = cmul(__ldg(tw2 + k), o);
+    const float ar = e.x + wo.x, ai = e.y + wo.y, br = e.x - wo.x, bi = e.y - wo.y;
+    pa[i] = ar * ar + ai * ai;
+    pb[i] = br * br + bi * bi;
+  }
+  if (lane == 0) {  // k = 512: Z[512] with itself, W^512 = -i
+    const float2 zk = z[kHalf / 2];
+    const float2 wo = cmul(__ldg(tw2 + kHalf / 2), make_float2(zk.y, 0.f));
+    const float xr = zk.x + wo.x, xi = wo.y;
+    pmid = xr * xr + xi * xi;
   }
   __syncwarp();
   float* s_pow = reinterpret_cast<float*>(z);
 #pragma unroll
-  for (int i = 0; i < 33; ++i)
-    if (lane + 32 * i <= kHalf) s_pow[lane + 32 * i] = pw[i];
+  for (int i = 0; i < 16; ++i) {
+    s_pow[lane + 32 * i] = pa[i];
+    s_pow[kHalf - lane - 32 * i] = pb[i];
+  }
+  if (lane == 0) s_pow[kHalf / 2] = pmid;
   __syncwarp();
   // sparse mel: lane takes one band of each quartile (bands lane, lane+32, lane+64, lane+96)
   float* out = logmel + (static_cast<size_t>(clip) * n_unique + u) * kMels;

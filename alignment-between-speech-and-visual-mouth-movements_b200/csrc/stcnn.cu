@@ -177,7 +177,7 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
       AVS_CUDA(cudaMemsetAsync(w.act[1], 0, umma_act_bytes(net->L[1].g, split, B), st));
       AVS_CUDA(cudaMemsetAsync(w.act[2], 0, umma_act_bytes(net->L[2].g, split, B), st));
     }
-    if ((rc = umma_pack_frames(frames_any, frames_u8, w.act[0], net->L[0].g, split, B, st))) return rc;
+    if ((rc = umma_pack_frames(frames_any, frames_u8, w.act[0], net->L[0].g, split, B, net->n_sms, st))) return rc;
     for (int l = 0; l < 3; ++l) {
       EpiOut eo{};
       if (l < 2) {

@@ -57,7 +57,7 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
 void umma_layer_free(UmmaLayer* L);
 void conv_item_span(int n_clips, int T, int n_tiles, int NT, int grid, int cta, int* first, int* last);
 size_t umma_act_bytes(const LayerGeom& g, int split, int B);   // bytes of the input activation buffer of a layer
-int umma_pack_frames(const void* frames, bool frames_u8, __nv_bfloat16* act, const LayerGeom& g1, int split, int B, cudaStream_t st);
+int umma_pack_frames(const void* frames, bool frames_u8, __nv_bfloat16* act, const LayerGeom& g1, int split, int B, int n_sms, cudaStream_t st);
 int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const EpiOut& eo, int B, int n_sms, cudaStream_t st);
 int umma_unpack_act(const __nv_bfloat16* act, float* out_ncdhw, const LayerGeom& g_next, int split, int C, int B, cudaStream_t st);
 
