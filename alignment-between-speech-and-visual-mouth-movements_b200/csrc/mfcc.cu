@@ -160,13 +160,25 @@ mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const in
   const int4 fr = frames[u];
   float2 v[32];
   // z[n] = w[2n] x[p+2n] + i w[2n+1] x[p+2n+1] (zero outside [lo, hi)), n = 32*n1 + lane: lane = n2
+  // interior frames (the window lies inside the valid range and starts on an 8-byte boundary: every frame of the
+  // 640-sample shift grid that does not touch the signal's ends) load sample pairs unconditionally; the rest checks every sample
+  if (fr.x >= fr.y && fr.x + kNfft <= fr.z && (reinterpret_cast<uintptr_t>(x + fr.x) & 7) == 0) {
+    const float2* xp = reinterpret_cast<const float2*>(x + fr.x);
 #pragma unroll
-  for (int n1 = 0; n1 < 32; ++n1) {
-    const int n = 32 * n1 + lane;
-    const int i0 = fr.x + 2 * n, i1 = i0 + 1;
-    const float2 w = __ldg(reinterpret_cast<const float2*>(window) + n);
-    v[n1] = make_float2((i0 >= fr.y && i0 < fr.z) ? __ldg(x + i0) * w.x : 0.f,
-                        (i1 >= fr.y && i1 < fr.z) ? __ldg(x + i1) * w.y : 0.f);
+    for (int n1 = 0; n1 < 32; ++n1) {
+      const int n = 32 * n1 + lane;
+      const float2 w = __ldg(reinterpret_cast<const float2*>(window) + n), a = __ldg(xp + n);
+      v[n1] = make_float2(a.x * w.x, a.y * w.y);
+    }
+  } else {
+#pragma unroll
+    for (int n1 = 0; n1 < 32; ++n1) {
+      const int n = 32 * n1 + lane;
+      const int i0 = fr.x + 2 * n, i1 = i0 + 1;
+      const float2 w = __ldg(reinterpret_cast<const float2*>(window) + n);
+      v[n1] = make_float2((i0 >= fr.y && i0 < fr.z) ? __ldg(x + i0) * w.x : 0.f,
+                          (i1 >= fr.y && i1 < fr.z) ? __ldg(x + i1) * w.y : 0.f);
+    }
   }
   fft32(v);  // over n1: v[i] = Y[n2 = lane][k1 = bitrev5(i)]
 #pragma unroll
