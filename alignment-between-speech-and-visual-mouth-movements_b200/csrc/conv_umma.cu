@@ -75,7 +75,7 @@ struct ConvKernelParams {
   int T, n_items, split;        // T: steps per (clip, tile set) of the item walk (time steps; conv3 bf16: items per clip)
   int T_out;                    // time steps of the clip (75)
   // experiment switches (avs_debug_set): 1 = weights loaded once, 2 = A planes loaded once, 4 = epilogue off, 8 = every
-  // MMA issued twice, 16 = clock64 split of the issuer warps (printf), 32 = epilogue reads TMEM only, 64 = epilogue without stores
+  // MMA issued twice, 16 = clock64 split of the issuer warps (printf), 32 = epilogue reads TMEM only, 64 = epilogue without stores, 128 = clock64 split of the epilogue
   int dbg;                      // only read when built with -DAVS_EXPERIMENTS (tools/); the product build folds it to 0
   long long clip_stride, plane_stride;  // elements (bf16) between clips / time planes of `act`
 };
@@ -727,6 +727,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     constexpr int UPT = K::N / 32;             // units per tile
     const int half = lane & 1;                 // even lane: channels 0..15 of a 32-column block, odd: 16..31
     uint32_t buf = 0, phase = 0;
+    long long ek_full = 0, ek_tmem = 0, ek_work = 0, ek_total = clock64();  // dbg 128: epilogue time split (warps 4 and 8 of block 0)
     ItemWalk w;
     w.init(p);
     for (; w.valid(); w.next(), buf = (buf + 1 == static_cast<uint32_t>(p.NBUF)) ? 0 : buf + 1, phase ^= (buf == 0)) {
@@ -741,11 +742,15 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       const int own_last = ((n_units - 1) & 1) == grp ? n_units - 1 : n_units - 2;
       const int n_units0 = by_rows ? 0 : h0 * UPT;
       const int own_last0 = ((n_units0 - 1) & 1) == grp ? n_units0 - 1 : n_units0 - 2;
+      const long long ek0 = (AVS_DBG(p) & 128) ? clock64() : 0;
       mbar_wait(&acc_full[buf * 2], phase);
+      if (AVS_DBG(p) & 128) ek_full += clock64() - ek0;
       bool full1 = false;
       auto need_half1 = [&]() {  // the second accumulator half completes a little later than the first
         if (kHalves && !full1) {
+          const long long e0 = (AVS_DBG(p) & 128) ? clock64() : 0;
           mbar_wait(&acc_full[buf * 2 + 1], phase);
+          if (AVS_DBG(p) & 128) ek_full += clock64() - e0;
           __syncwarp();
           tc_fence_after();
           full1 = true;
@@ -791,6 +796,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         uint32_t v0[32], v1[32];
         const int ch0 = cb + half * 16;
         float bias[16];
+        const long long ek1 = (AVS_DBG(p) & 128) ? clock64() : 0;
         if (warp_has_work) {
           tmem_ld32(d_base + (i * 2 + 0) * K::ACC + cb, v0);
           tmem_ld32(d_base + (i * 2 + 1) * K::ACC + cb, v1);
@@ -812,6 +818,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
             }
           }
         }
+        const long long ek2 = (AVS_DBG(p) & 128) ? clock64() : 0;
         // hand the accumulator halves back: this warp's TMEM reads of them are in registers
         if (u == own_last0) {
           release(0);
@@ -825,6 +832,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         }
         if (!warp_has_work) continue;
         if ((AVS_DBG(p) & 32) && v0[0] != 0x7fc12345u) continue;  // experiment: TMEM reads only
+        const long long ek3 = (AVS_DBG(p) & 128) ? clock64() : 0;
         float o[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
@@ -867,12 +875,18 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
           for (int c = 0; c < 16; ++c) dst[c * kPlane] = o[c];
         }
         __syncwarp();
+        if (AVS_DBG(p) & 128) ek_tmem += ek2 - ek1, ek_work += clock64() - ek3;
       }
       if (own_last < 0) {  // no unit of this item was ours (or the experiment switches skipped them all)
         need_half1();
         if (!released0) release(0);
         release(1);
       }
+    }
+    if ((AVS_DBG(p) & 128) && lane == 0 && blockIdx.x == 0 && q == 0) {
+      ek_total = clock64() - ek_total;
+      printf("conv epilogue group %d block 0 (N=%d): total %lld cycles | wait acc_full %lld | tmem loads %lld | math+stores %lld | rest %lld\n",
+             grp, p.N, ek_total, ek_full, ek_tmem, ek_work, ek_total - ek_full - ek_tmem - ek_work);
     }
   
     }
