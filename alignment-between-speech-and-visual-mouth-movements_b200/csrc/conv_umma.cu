@@ -52,7 +52,12 @@ namespace avs {
 #define AVS_DBG(p) 0
 #endif
 
-constexpr int kConvThreads = 384;  // 4 control warps + 2 epilogue groups of 4 warps
+#ifndef AVS_VAR_L1_GROUPS
+#define AVS_VAR_L1_GROUPS 3
+#endif
+// 4 control warps + 2 (conv1: 3) epilogue groups of 4 warps
+__host__ __device__ constexpr int epi_groups(int kind) { return kind == 0 /* KIND_L1 */ ? AVS_VAR_L1_GROUPS : 2; }
+__host__ __device__ constexpr int conv_threads(int kind) { return (4 + 4 * epi_groups(kind)) * 32; }
 constexpr int kMaxUnits = 6;
 constexpr int kMaxRing = 4;
 constexpr int kMaxWStages = 8;
@@ -292,22 +297,21 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
 
   using K = LayerKind<KIND>;
   constexpr int NT = K::NT;
-  // conv1 (one 32-column block per tile, the shortest MMAs, epilogue-paced): 16-column units with the next unit's TMEM
-  // loads in flight; the other kinds: 32-column units
-#ifndef AVS_VAR_EPI16
-#define AVS_VAR_EPI16 0   // measured choice (profiles/r02_variants_ab.txt); tools can rebuild with the other value
-#endif
 #ifndef AVS_VAR_HALVES
 #define AVS_VAR_HALVES 1
 #endif
-  constexpr bool kEpi16 = AVS_VAR_EPI16 && KIND == KIND_L1;
+  // Epilogue groups of four warps.  conv1 is paced by its epilogue, and the epilogue by instruction latency, not by the
+  // TMEM read-out (clock64 split, profiles/r02_epilogue_split.txt: 134 cycles of TMEM loads against ~900 of arithmetic +
+  // stores and ~770 of index work per 32-column unit and warp): it gets a third group (512 threads x 128 registers = the
+  // whole register file; the audio branch never runs beside conv1).
+  constexpr int kGroups = epi_groups(KIND);
   // Accumulator hand-over in halves (barriers [buffer * 2 + half]) only where the buffer cannot be doubled — conv3, whose
   // two tiles fill TMEM; the double-buffered kinds hand whole buffers over through the barriers of half 0.
   constexpr bool kHalves = AVS_VAR_HALVES && KIND == KIND_L3;
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.ring; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 1);
     for (int i = 0; i < p.wstages; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
-    for (int i = 0; i < 2 * p.NBUF; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 8);
+    for (int i = 0; i < 2 * p.NBUF; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 4 * kGroups);
     for (int i = 0; i < 4; ++i) mbar_init(&turn[i], 1);
     mbar_fence_init();
   }
@@ -540,181 +544,10 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     }
   } else if (warp >= 4) {
     // ============================================================ epilogue
-    // Two flavours, chosen per layer kind by measurement (profiles/r02_epilogue_variants.txt).
-    if constexpr (kEpi16) {
-    // Two groups of four warps (warps 4-7 and 8-11); warp w may read TMEM lanes 32*(w%4)..+31.  The work unit is a
-    // 16-column block of one tile (both row accumulators): group 0 takes the even blocks of every tile, group 1 the odd
-    // ones, so both groups drain the same tile and a tile (and with it an accumulator half) is free after
-    // N/32 units per warp.  TMEM reads run at 64 B/cycle per SM — 512 cycles for a conv1 tile, about what its MMAs
-    // take — so the loads of unit k+1 are issued before the arithmetic of unit k (two register buffers), which keeps the
-    // TMEM pipe busy instead of alternating between loading and computing.
-    const int q = warp & 3, grp = (warp - 4) >> 2;
-    using KN = LayerKind<K::NEXT>;             // the layer that reads our output (conv3: unused)
-    constexpr bool kToEmb = K::N == 96;        // conv3 writes the f32 embedding
-    constexpr int kHo = K::H / 2, kWo = K::W / 2, kPlane = kHo * kWo;
-    constexpr int UPT = K::N / 32;             // units per tile for one group
-    constexpr int UMAX = NT * UPT;             // units per item for one warp
-    constexpr bool kPipe = !K::split;          // the split kinds need four loads per unit: no room for a second buffer
-    const int half = lane & 1;                 // even lane keeps channels 0..7 of a 16-column block, odd lane 8..15
-    uint32_t buf = 0, phase = 0;
-    ItemWalk w;
-    w.init(p);
-    for (; w.valid(); w.next(), buf = (buf + 1 == static_cast<uint32_t>(p.NBUF)) ? 0 : buf + 1, phase ^= (buf == 0)) {
-      const int b = w.b, t = w.t, ts = w.ts;
-      const int nt = min(NT, p.n_tiles - ts * NT);
-      const int n_units = (AVS_DBG(p) & 4) ? 0 : nt * UPT;
-      // tiles [0, h0) are the first half of the accumulator buffer; the single-tile split kinds halve it by row
-      // accumulator instead, and need both halves for the first unit already
-      const int h0 = (nt + 1) >> 1;
-      mbar_wait(&acc_full[buf * 2], phase);
-      bool full1 = false;
-      if (K::split && nt == 1) {
-        mbar_wait(&acc_full[buf * 2 + 1], phase);
-        full1 = true;
-      }
-      __syncwarp();  // tcgen05.ld below is .aligned
-      tc_fence_after();
-      const uint32_t d_base = tmem_base + buf * (NT * 2 * K::ACC) + (static_cast<uint32_t>(q * 32) << 16);
-      // does tile i hold any position of this warp's 32 lanes?  (positions grow with the lane and with i)
-      auto tile_has_work = [&](int i) {
-        if (K::tcat) return ((t * NT + i) * 128 + q * 32) / K::PITCH < p.T_out;
-        return ((ts * NT + i) * 128 + q * 32) / K::WT < kHo;
-      };
-      // tiles from h0 on belong to the second accumulator half, which completes a little later than the first
-      auto need_half1 = [&](int i) {
-        if (kHalves && i >= h0 && !full1) {
-          mbar_wait(&acc_full[buf * 2 + 1], phase);
-          __syncwarp();
-          tc_fence_after();
-          full1 = true;
-        }
-      };
-      uint32_t va[2][16], vb[2][16];
-      auto issue_loads = [&](int k, uint32_t (&x0)[16], uint32_t (&x1)[16]) {
-        const int i = k / UPT, cb = (2 * (k % UPT) + grp) * 16;
-        tmem_ld16(d_base + (i * 2 + 0) * K::ACC + cb, x0);
-        tmem_ld16(d_base + (i * 2 + 1) * K::ACC + cb, x1);
-      };
-      if (kPipe && n_units > 0 && tile_has_work(0)) issue_loads(0, va[0], vb[0]);
-      bool released0 = false, released1 = false;
-#pragma unroll
-      for (int k = 0; k < UMAX; ++k) {
-        if (k >= n_units) break;
-        const int i = k / UPT, cb = (2 * (k % UPT) + grp) * 16;
-        const bool work = tile_has_work(i);
-        uint32_t (&v0)[16] = va[kPipe ? (k & 1) : 0];
-        uint32_t (&v1)[16] = vb[kPipe ? (k & 1) : 0];
-        if (!kPipe && work) {
-          need_half1(i);
-          issue_loads(k, v0, v1);
-          tmem_ld_wait();
-          if (K::split) {  // second column block: A_hi * B_lo, the small term, added last
-            uint32_t u0[16], u1[16];
-            tmem_ld16(d_base + (i * 2 + 0) * K::ACC + K::N + cb, u0);
-            tmem_ld16(d_base + (i * 2 + 1) * K::ACC + K::N + cb, u1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              v0[c] = __float_as_uint(__uint_as_float(v0[c]) + __uint_as_float(u0[c]));
-              v1[c] = __float_as_uint(__uint_as_float(v1[c]) + __uint_as_float(u1[c]));
-            }
-          }
-        }
-        const int ch0 = cb + half * 8;
-        float bias[8];  // fetched while the TMEM loads are in flight
-        {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + 1);
-          bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w; bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
-        }
-        if (kPipe) tmem_ld_wait();  // unit k's loads (nothing else is outstanding)
-        // hand the accumulator halves back as soon as their last loads have landed in registers
-        if (kHalves && k == h0 * UPT - 1 && !(K::split && nt == 1)) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf * 2]);
-          released0 = true;
-        }
-        if (k == n_units - 1) {
-          need_half1(NT);  // (an item without second-half tiles: do not hand the half back before the issuers are done with it)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (!released0) mbar_arrive(&acc_empty[buf * 2]);
-            if (kHalves) mbar_arrive(&acc_empty[buf * 2 + 1]);
-          }
-          released0 = released1 = true;
-        }
-        if (kPipe && k + 1 < n_units) {  // loads of the next unit, under the arithmetic of this one
-          const int i1 = (k + 1) / UPT;
-          need_half1(i1);
-          if (tile_has_work(i1)) issue_loads(k + 1, va[(k + 1) & 1], vb[(k + 1) & 1]);
-        }
-        if (!work) continue;
-        if ((AVS_DBG(p) & 32) && v0[0] != 0x7fc12345u) continue;  // experiment: TMEM reads only
-        int Q = (ts * NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
-        int t_out = t;
-        if (K::tcat) {  // time-concatenated position space: item index -> (time step, position in its plane)
-          const int S = (t * NT + i) * 128 + q * 32 + lane;
-          t_out = S / K::PITCH;
-          Q = S - t_out * K::PITCH;
-        }
-        const int r = Q / K::WT, wc = Q % K::WT;            // pooled row, conv column
-        const int wo = wc >> 1;
-        const bool valid = (r < kHo) && (wo < kWo) && (t_out < p.T_out);
-        float o[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          // rows 2r, 2r+1: max of the two accumulators; columns 2wo, 2wo+1: exchange with the
-          // neighbouring lane — each lane keeps 8 of the 16 channels and ships the other 8
-          const float lo = fmaxf(__uint_as_float(v0[c]), __uint_as_float(v1[c]));
-          const float hi = fmaxf(__uint_as_float(v0[c + 8]), __uint_as_float(v1[c + 8]));
-          const float got = __shfl_xor_sync(0xffffffffu, half ? lo : hi, 1);
-          o[c] = fmaxf(fmaxf(half ? hi : lo, got) + bias[c], 0.f);
-        }
-        if ((AVS_DBG(p) & 64) && o[0] != 12345.678f) continue;  // experiment: no stores
-        if (valid && !kToEmb) {
-          // the NEXT layer's parity-plane layout (its geometry is a compile-time property of the kind)
-          const int hp = r + KN::KH / 2;
-          const int pos = KN::KW / 2 + (hp >> 1) * KN::WT + wo;
-          // element offset of array `a` (= chunk array * 2 + parity), position `pos` of time plane t + 1
-          auto out_ptr = [&](int a) {
-            if (KN::tcat)
-              return p.eo.act + ((static_cast<long long>(b) * (KN::N_CHUNKS * 2) + a) * KN::TCAT_LEN + (t + 1) * KN::PITCH + pos) * 8;
-            return p.eo.act + ((((static_cast<long long>(b) * (p.T_out + 2) + t + 1) * KN::N_CHUNKS) * 2 + a) * KN::PP + pos) * 8;
-          };
-          const int chunk = ch0 >> 3;
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float x0 = o[2 * e], x1 = o[2 * e + 1];
-            const __nv_bfloat16 h0b = __float2bfloat16_rn(x0), h1b = __float2bfloat16_rn(x1);
-            hi[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
-            if (K::split) lo[e] = pack_bf16x2(x0 - __bfloat162float(h0b), x1 - __bfloat162float(h1b));
-          }
-          const int idx = K::split ? 2 * chunk : chunk;
-          *reinterpret_cast<uint4*>(out_ptr(idx * 2 + (hp & 1))) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (K::split) *reinterpret_cast<uint4*>(out_ptr((idx + 1) * 2 + (hp & 1))) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        } else if (valid) {
-          float* dst = p.eo.emb + (static_cast<long long>(b) * p.T_out + t_out) * (K::N * kPlane) + ch0 * kPlane + r * kWo + wo;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) dst[c * kPlane] = o[c];
-        }
-      }
-      if (!released1) {  // experiment switch 4 (no units): still hand the buffer back
-        need_half1(NT);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (!released0) mbar_arrive(&acc_empty[buf * 2]);
-          if (kHalves) mbar_arrive(&acc_empty[buf * 2 + 1]);
-        }
-      }
-    }
-  
-    } else {
-    // Two groups of four warps (warps 4-7 and 8-11); warp w may read TMEM lanes 32*(w%4)..+31.  The work unit is a
-    // 32-column block of one tile (both row accumulators); the units of an item, in (tile, block) order, alternate between
-    // the groups.  An accumulator half goes back to the issuers as soon as this warp's last unit of the half has been
+    {
+    // kGroups groups of four warps (warps 4-7, 8-11, ...); warp w may read TMEM lanes 32*(w%4)..+31.  The work unit is a
+    // 32-column block of one tile (both row accumulators); the units of an item, in (tile, block) order, go round the
+    // groups.  An accumulator half goes back to the issuers as soon as this warp's last unit of the half has been
     // loaded into registers — before the arithmetic and the stores.
     // (Measured and dropped, profiles/r02_bench_d_epilogue16_pipelined.json: 16-column units with the next unit's TMEM
     // loads in flight under the arithmetic of the current one.  conv3 7.45 -> 7.2 ms per 1024 clips, but conv1 4.9 -> 6.6:
@@ -738,10 +571,11 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       // accumulator instead, and need both halves from the first unit on
       const bool by_rows = K::split && nt == 1;
       const int h0 = (nt + 1) >> 1;
-      // this warp's last unit (units u with (u & 1) == grp are ours) overall and inside the first half; -1: none
-      const int own_last = ((n_units - 1) & 1) == grp ? n_units - 1 : n_units - 2;
+      // this warp's last unit (units u with u % kGroups == grp are ours) overall and inside the first half; negative: none
+      auto last_own = [&](int n) { return n - 1 - grp < 0 ? -1 : n - 1 - (n - 1 - grp) % kGroups; };
+      const int own_last = last_own(n_units);
       const int n_units0 = by_rows ? 0 : h0 * UPT;
-      const int own_last0 = ((n_units0 - 1) & 1) == grp ? n_units0 - 1 : n_units0 - 2;
+      const int own_last0 = last_own(n_units0);
       const long long ek0 = (AVS_DBG(p) & 128) ? clock64() : 0;
       mbar_wait(&acc_full[buf * 2], phase);
       if (AVS_DBG(p) & 128) ek_full += clock64() - ek0;
@@ -771,40 +605,45 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         released0 = true;
       }
       const uint32_t d_base = tmem_base + buf * (NT * 2 * K::ACC) + (static_cast<uint32_t>(q * 32) << 16);
+      // where this item's outputs start in the next layer's input (element pointer; per-unit offsets fit 32 bits)
+      __nv_bfloat16* out_item = nullptr;
+      if (!kToEmb)
+        out_item = KN::tcat ? p.eo.act + (static_cast<long long>(b) * (KN::N_CHUNKS * 2) * KN::TCAT_LEN + (t + 1) * KN::PITCH) * 8
+                            : p.eo.act + (static_cast<long long>(b) * (p.T_out + 2) + t + 1) * (KN::N_CHUNKS * 2) * KN::PP * 8;
       // runtime loop over the tiles, unrolled over the column blocks of a tile only: a fully unrolled item is NT copies of
       // the unit body, and conv1 (NT = 4) ran 30 % slower with it — instruction fetch, not arithmetic
       for (int i = 0; i < nt && n_units > 0; ++i)
 #pragma unroll
       for (int cbi = 0; cbi < UPT; ++cbi) {
         const int u = i * UPT + cbi, cb = cbi * 32;
-        if ((u & 1) != grp) continue;  // warp-uniform
-        int Q = (ts * NT + i) * 128 + q * 32 + lane;  // output position in pooled-row space
-        int t_out = t;
-        bool warp_has_work = true;  // positions grow with the lane: if the warp's first lane is past the end, nobody has work
-        if (K::tcat) {  // time-concatenated position space: item index -> (time step, position in its plane)
-          const int S = (t * NT + i) * 128 + q * 32 + lane;
-          t_out = S / K::PITCH;
-          Q = S - t_out * K::PITCH;
-          warp_has_work = ((t * NT + i) * 128 + q * 32) / K::PITCH < p.T_out;
-        } else {
-          warp_has_work = ((ts * NT + i) * 128 + q * 32) / K::WT < kHo;
-        }
-        const int r = Q / K::WT, wc = Q % K::WT;            // pooled row, conv column
-        const int wo = wc >> 1;
-        const bool valid = (r < kHo) && (wo < kWo) && (t_out < p.T_out);
+        if ((u % kGroups) != grp) continue;  // warp-uniform
+        // positions grow with the lane and with the tile: if the warp's first lane is past the end, nobody has work
+        const int S0 = ((K::tcat ? t : ts) * NT + i) * 128 + q * 32;
+        const bool warp_has_work = K::tcat ? (S0 / K::PITCH < p.T_out) : (S0 / K::WT < kHo);
         if (i >= h0) need_half1();
         uint32_t v0[32], v1[32];
         const int ch0 = cb + half * 16;
         float bias[16];
         const long long ek1 = (AVS_DBG(p) & 128) ? clock64() : 0;
-        if (warp_has_work) {
+        if (warp_has_work) {  // TMEM loads first: the bias fetch and the index arithmetic below run under them
           tmem_ld32(d_base + (i * 2 + 0) * K::ACC + cb, v0);
           tmem_ld32(d_base + (i * 2 + 1) * K::ACC + cb, v1);
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {  // fetched while the TMEM loads are in flight
+          for (int c4 = 0; c4 < 4; ++c4) {
             const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + c4);
             bias[c4 * 4 + 0] = bv.x; bias[c4 * 4 + 1] = bv.y; bias[c4 * 4 + 2] = bv.z; bias[c4 * 4 + 3] = bv.w;
           }
+        }
+        int Q = S0 + lane;  // output position in pooled-row space
+        int t_out = t;
+        if (K::tcat) {  // time-concatenated position space: item index -> (time step, position in its plane)
+          t_out = Q / K::PITCH;
+          Q -= t_out * K::PITCH;
+        }
+        const int r = Q / K::WT, wc = Q - r * K::WT;        // pooled row, conv column
+        const int wo = wc >> 1;
+        const bool valid = (r < kHo) && (wo < kWo) && (t_out < p.T_out);
+        if (warp_has_work) {
           tmem_ld_wait();
           if (K::split) {  // second column block: A_hi * B_lo, the small term, added last
             uint32_t u0[32], u1[32];
@@ -848,11 +687,9 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
           // the NEXT layer's parity-plane layout (its geometry is a compile-time property of the kind)
           const int hp = r + KN::KH / 2;
           const int pos = KN::KW / 2 + (hp >> 1) * KN::WT + wo;
-          // element offset of array `a` (= chunk array * 2 + parity), position `pos` of time plane t + 1
+          // array `a` (= chunk array * 2 + parity), position `pos` of time plane t + 1: 32-bit offsets from the item's base
           auto out_ptr = [&](int a) {
-            if (KN::tcat)
-              return p.eo.act + ((static_cast<long long>(b) * (KN::N_CHUNKS * 2) + a) * KN::TCAT_LEN + (t + 1) * KN::PITCH + pos) * 8;
-            return p.eo.act + ((((static_cast<long long>(b) * (p.T_out + 2) + t + 1) * KN::N_CHUNKS) * 2 + a) * KN::PP + pos) * 8;
+            return out_item + (a * (KN::tcat ? KN::TCAT_LEN : KN::PP) + pos) * 8;
           };
 #pragma unroll
           for (int c8 = 0; c8 < 2; ++c8) {
@@ -861,9 +698,9 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float x0 = o[c8 * 8 + 2 * e], x1 = o[c8 * 8 + 2 * e + 1];
-              const __nv_bfloat16 h0b = __float2bfloat16_rn(x0), h1b = __float2bfloat16_rn(x1);
-              hi[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
-              if (K::split) lo[e] = pack_bf16x2(x0 - __bfloat162float(h0b), x1 - __bfloat162float(h1b));
+              hi[e] = pack_bf16x2(x0, x1);  // one cvt.rn.bf16x2.f32
+              if (K::split)
+                lo[e] = pack_bf16x2(x0 - __uint_as_float(hi[e] << 16), x1 - __uint_as_float(hi[e] & 0xFFFF0000u));
             }
             const int idx = K::split ? 2 * chunk : chunk;
             *reinterpret_cast<uint4*>(out_ptr(idx * 2 + (hp & 1))) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -1334,7 +1171,7 @@ int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const Epi
   p.clip_stride = g.tcat_len > 0 ? static_cast<long long>(g.n_chunks) * 2 * g.tcat_len * 8 : p.plane_stride * (AVS_T + 2);
   const int grid = static_cast<int>(std::min<long long>(items, n_sms));
   ProfScope ps(L.g.Cin == 1 ? PROF_CONV1 : (L.g.Cout == 64 ? PROF_CONV2 : PROF_CONV3), st);
-  conv_kernel_for(L.kind)<<<grid, kConvThreads, L.smem_bytes, st>>>(p);
+  conv_kernel_for(L.kind)<<<grid, conv_threads(L.kind), L.smem_bytes, st>>>(p);
   AVS_LAUNCHED();
   return AVS_OK;
 }
