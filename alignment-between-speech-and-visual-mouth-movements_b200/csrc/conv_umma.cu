@@ -53,7 +53,7 @@ namespace avs {
 #endif
 
 #ifndef AVS_VAR_L1_GROUPS
-#define AVS_VAR_L1_GROUPS 3
+#define AVS_VAR_L1_GROUPS 2   // a third group was measured (profiles/r02_variants_ab_3.txt): conv1 5.0 against 4.8 ms per 1024 clips
 #endif
 // 4 control warps + 2 (conv1: 3) epilogue groups of 4 warps
 __host__ __device__ constexpr int epi_groups(int kind) { return kind == 0 /* KIND_L1 */ ? AVS_VAR_L1_GROUPS : 2; }
@@ -301,9 +301,9 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
 #define AVS_VAR_HALVES 1
 #endif
   // Epilogue groups of four warps.  conv1 is paced by its epilogue, and the epilogue by instruction latency, not by the
-  // TMEM read-out (clock64 split, profiles/r02_epilogue_split.txt: 134 cycles of TMEM loads against ~900 of arithmetic +
-  // stores and ~770 of index work per 32-column unit and warp): it gets a third group (512 threads x 128 registers = the
-  // whole register file; the audio branch never runs beside conv1).
+  // TMEM read-out (clock64 split, profiles/r02_epilogue_split.txt: ~150-250 cycles of TMEM loads against ~900 of
+  // arithmetic + stores and as much index / hand-over work per 32-column unit and warp).  A third group does not help:
+  // conv1's four tiles do not divide by three, and its warps take issue slots from the MMA issuers.
   constexpr int kGroups = epi_groups(KIND);
   // Accumulator hand-over in halves (barriers [buffer * 2 + half]) only where the buffer cannot be doubled — conv3, whose
   // two tiles fill TMEM; the double-buffered kinds hand whole buffers over through the barriers of half 0.
