@@ -125,11 +125,24 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug must surface as a launch failure, never as a hung GPU.
+#ifndef AVS_VAR_POLL_LIGHT
+#define AVS_VAR_POLL_LIGHT 1
+#endif
+// Bounded spin: a protocol bug must surface as a launch failure, never as a hung GPU.  The watchdog clock is read once per
+// 32 polls: a waiting warp then issues two or three instructions per poll instead of nine — in the conv kernels the poll
+// loops were 16 % (conv1) to 45 % (conv2) of all executed instructions, and every one of them competes with the
+// MMA-issuing and epilogue warps of its scheduler for an issue slot.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  for (;;) {
+#if AVS_VAR_POLL_LIGHT
+#pragma unroll 1
+    for (int i = 0; i < 32; ++i)
+      if (mbar_try_wait(bar, parity)) return;
+#else
+    if (mbar_try_wait(bar, parity)) return;
+#endif
     if (clock64() - t0 > 40000000000LL) {  // ~20 s at 2 GHz: far beyond any legitimate wait, even when time-sliced
       printf("avsync: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
              smem_u32(bar), parity);
@@ -143,7 +156,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
   if (mbar_test_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_test_wait(bar, parity)) {
+  for (;;) {
+#if AVS_VAR_POLL_LIGHT
+#pragma unroll 1
+    for (int i = 0; i < 32; ++i)
+      if (mbar_test_wait(bar, parity)) return;
+#else
+    if (mbar_test_wait(bar, parity)) return;
+#endif
     if (clock64() - t0 > 40000000000LL) {
       printf("avsync: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
              smem_u32(bar), parity);
@@ -234,6 +254,13 @@ __device__ __host__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
          | (1u << 10)                           // b_format = BF16
          | (static_cast<uint32_t>(N >> 3) << 17)  // n_dim
          | (static_cast<uint32_t>(M >> 4) << 24); // m_dim
+}
+
+// three-input maximum (one FMNMX3 on sm_100)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

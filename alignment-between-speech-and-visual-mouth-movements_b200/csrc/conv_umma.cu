@@ -297,6 +297,9 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
 
   using K = LayerKind<KIND>;
   constexpr int NT = K::NT;
+#ifndef AVS_VAR_MAX3
+#define AVS_VAR_MAX3 1
+#endif
 #ifndef AVS_VAR_HALVES
 #define AVS_VAR_HALVES 1
 #endif
@@ -680,7 +683,12 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
           const float lo = fmaxf(__uint_as_float(v0[c]), __uint_as_float(v1[c]));
           const float hi = fmaxf(__uint_as_float(v0[c + 16]), __uint_as_float(v1[c + 16]));
           const float got = __shfl_xor_sync(0xffffffffu, half ? lo : hi, 1);
+#if AVS_VAR_MAX3
+          // relu(max(keep, got) + b) == max(keep, got, -b) + b exactly (below -b both give +0; above, the same sum)
+          o[c] = fmax3(half ? hi : lo, got, -bias[c]) + bias[c];
+#else
           o[c] = fmaxf(fmaxf(half ? hi : lo, got) + bias[c], 0.f);
+#endif
         }
         if ((AVS_DBG(p) & 64) && o[0] != 12345.678f) continue;  // experiment: no stores
         if (valid && !kToEmb) {
