@@ -275,4 +275,25 @@ int gru_recurrence_umma(const float* xp, const __nv_bfloat16* w_packed, const fl
   return AVS_OK;
 }
 
+#ifdef AVS_EXPERIMENTS
+// tools: how many 8-CTA clusters of the recurrence kernel the device can hold at once
+int gru_max_active_clusters() {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kClu * 64, 2, 1);
+  cfg.blockDim = dim3(kGruThreads, 1, 1);
+  cfg.dynamicSmemBytes = kGruSmem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kClu; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaFuncSetAttribute(gru_cluster_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGruSmem));
+  int n = -1;
+  if (cudaOccupancyMaxActiveClusters(&n, gru_cluster_umma_kernel, &cfg) != cudaSuccess) n = -1;
+  return n;
+}
+#endif
+
 }  // namespace avs
+#ifdef AVS_EXPERIMENTS
+extern "C" __attribute__((visibility("default"))) int avs_gru_max_active_clusters(void) { return avs::gru_max_active_clusters(); }
+#endif
