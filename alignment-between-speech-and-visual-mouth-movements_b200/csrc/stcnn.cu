@@ -24,7 +24,6 @@ struct StcnnWs {  // workspace carve, shared by size query and forward
   float* f32frames;                                  // fp32 path fed with u8 pixels: the f32 frames it convolves
   float* p1; float* p2; float* emb;                  // fp32 path: pooled NCDHW activations; emb when caller passes none
   __nv_bfloat16* act[3];                             // tensor-core path: parity-plane inputs of the three layers
-  __nv_bfloat16* act0_alt;                           // second layer-1 input: the next chunk is packed while this one convolves
   size_t act_bytes[3];
   size_t total;
 };
@@ -45,7 +44,6 @@ static StcnnWs carve(const avs_stcnn* net, int B, void* ws, bool need_emb) {
       r.act_bytes[l] = umma_act_bytes(net->L[l].g, split, B);
       r.act[l] = reinterpret_cast<__nv_bfloat16*>(c.take<uint8_t>(r.act_bytes[l]));
     }
-    r.act0_alt = reinterpret_cast<__nv_bfloat16*>(c.take<uint8_t>(r.act_bytes[0]));
   }
   if (need_emb) r.emb = c.take<float>(static_cast<size_t>(B) * AVS_T * AVS_EMB);
   r.total = align_up(c.off, 256);
@@ -111,8 +109,6 @@ int avs::stcnn_fill(avs_stcnn* net, const float* w1, const float* b1, const floa
   return AVS_OK;
 }
 
-int avs::stcnn_tensor_path(const avs_stcnn* net) { return net && net->precision != AVS_PREC_FP32; }
-
 extern "C" void avs_stcnn_destroy(avs_stcnn* net) {
   if (!net) return;
   for (int l = 0; l < 3; ++l) {
@@ -131,28 +127,10 @@ extern "C" size_t avs_stcnn_workspace_bytes(const avs_stcnn* net, int n_clips) {
 // cap_clips: the workspace is carved for this many clips (>= B), so that repeated calls with different
 // B see the same buffer placement; pads_clean: the caller guarantees that the padding positions of the
 // parity-plane buffers are still zero (zeroed once, and kernels only ever write data positions).
-// Layer-1 input of a chunk (X8 parity planes) into slot 0 / 1 of the workspace, on its own: the sweep packs chunk i+1 on
-// another stream while chunk i convolves (the pack is HBM-bound, the conv kernels are tensor-bound).
-int avs::stcnn_pack_impl(const avs_stcnn* net, const void* frames_any, bool frames_u8, int B, int cap_clips, int slot,
-                         void* workspace, size_t workspace_bytes, void* stream) {
-  AVS_REQUIRE(net && frames_any && workspace && net->precision != AVS_PREC_FP32 && (slot == 0 || slot == 1), "bad argument");
-  AVS_REQUIRE(cap_clips >= B, "workspace capacity below batch");
-  if (B <= 0) return AVS_OK;
-  StcnnWs w = carve(net, cap_clips, workspace, false);
-  if (workspace_bytes < w.total) {
-    set_error("stcnn workspace too small: %zu < %zu", workspace_bytes, w.total);
-    return AVS_EWORKSPACE;
-  }
-  return umma_pack_frames(frames_any, frames_u8, slot ? w.act0_alt : w.act[0], net->L[0].g, net->precision == AVS_PREC_BF16X3, B,
-                          net->n_sms, static_cast<cudaStream_t>(stream));
-}
-
-// packed_slot >= 0: the layer-1 input has been packed into that slot by stcnn_pack_impl (frames_any is not read).
-int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool frames_u8, int packed_slot, int B, int cap_clips, bool pads_clean,
+int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool frames_u8, int B, int cap_clips, bool pads_clean,
                             cudaEvent_t after_layer1, float* out_emb, float* out_vstats, float* out_pool1, float* out_pool2, void* workspace,
                             size_t workspace_bytes, void* stream) {
-  AVS_REQUIRE(net && (frames_any || packed_slot >= 0) && workspace, "null argument");
-  AVS_REQUIRE(packed_slot < 0 || (net->precision != AVS_PREC_FP32 && packed_slot <= 1), "bad packed slot");
+  AVS_REQUIRE(net && frames_any && workspace, "null argument");
   AVS_REQUIRE(out_emb || out_vstats, "nothing to compute");
   AVS_REQUIRE(cap_clips >= B, "workspace capacity below batch");
   if (B <= 0) return AVS_OK;
@@ -199,7 +177,7 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
       AVS_CUDA(cudaMemsetAsync(w.act[1], 0, umma_act_bytes(net->L[1].g, split, B), st));
       AVS_CUDA(cudaMemsetAsync(w.act[2], 0, umma_act_bytes(net->L[2].g, split, B), st));
     }
-    if (packed_slot < 0 && (rc = umma_pack_frames(frames_any, frames_u8, w.act[0], net->L[0].g, split, B, net->n_sms, st))) return rc;
+    if ((rc = umma_pack_frames(frames_any, frames_u8, w.act[0], net->L[0].g, split, B, net->n_sms, st))) return rc;
     for (int l = 0; l < 3; ++l) {
       EpiOut eo{};
       if (l < 2) {
@@ -212,7 +190,7 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
         eo.mode = 1;
         eo.emb = emb;
       }
-      if ((rc = umma_conv_forward(net->L[l], (l == 0 && packed_slot == 1) ? w.act0_alt : w.act[l], eo, B, net->n_sms, st))) return rc;
+      if ((rc = umma_conv_forward(net->L[l], w.act[l], eo, B, net->n_sms, st))) return rc;
       if (l == 0 && after_layer1) AVS_CUDA(cudaEventRecord(after_layer1, st));
     }
     if (out_pool1 && (rc = umma_unpack_act(w.act[1], out_pool1, net->L[1].g, split, 32, B, st))) return rc;
@@ -225,13 +203,13 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
 extern "C" int avs_stcnn_forward_debug(const avs_stcnn* net, const float* frames, int B, float* out_emb,
                                        float* out_vstats, float* out_pool1, float* out_pool2, void* workspace,
                                        size_t workspace_bytes, void* stream) {
-  return stcnn_forward_impl(net, frames, false, -1, B, B, false, nullptr, out_emb, out_vstats, out_pool1, out_pool2, workspace,
+  return stcnn_forward_impl(net, frames, false, B, B, false, nullptr, out_emb, out_vstats, out_pool1, out_pool2, workspace,
                             workspace_bytes, stream);
 }
 
 extern "C" int avs_stcnn_forward_u8(const avs_stcnn* net, const uint8_t* frames, int n_clips, float* out_emb, float* out_vstats,
                                     void* workspace, size_t workspace_bytes, void* stream) {
-  return stcnn_forward_impl(net, frames, true, -1, n_clips, n_clips, false, nullptr, out_emb, out_vstats, nullptr, nullptr, workspace,
+  return stcnn_forward_impl(net, frames, true, n_clips, n_clips, false, nullptr, out_emb, out_vstats, nullptr, nullptr, workspace,
                             workspace_bytes, stream);
 }
 

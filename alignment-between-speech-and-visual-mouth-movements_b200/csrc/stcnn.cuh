@@ -62,11 +62,7 @@ int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const Epi
 int umma_unpack_act(const __nv_bfloat16* act, float* out_ncdhw, const LayerGeom& g_next, int split, int C, int B, cudaStream_t st);
 
 // after_layer1 (nullable) is recorded on the stream right after layer 1 has been enqueued
-int stcnn_pack_impl(const avs_stcnn* net, const void* frames, bool frames_u8, int B, int cap_clips, int slot, void* workspace,
-                    size_t workspace_bytes, void* stream);
-int stcnn_tensor_path(const avs_stcnn* net);  // 1 when the handle runs the tcgen05 kernels (bf16 / bf16x3)
-// packed_slot: -1 = pack `frames` here; 0 / 1 = the layer-1 input already sits in that slot (stcnn_pack_impl)
-int stcnn_forward_impl(const avs_stcnn* net, const void* frames, bool frames_u8, int packed_slot, int B, int cap_clips, bool pads_clean,
+int stcnn_forward_impl(const avs_stcnn* net, const void* frames, bool frames_u8, int B, int cap_clips, bool pads_clean,
                        cudaEvent_t after_layer1, float* out_emb,
                        float* out_vstats, float* out_pool1, float* out_pool2, void* workspace, size_t workspace_bytes,
                        void* stream);

@@ -27,12 +27,8 @@ struct avs_sweep {
   float* astats = nullptr;  // [cap, K, 2*n_mfcc]
   float* d_scores_all = nullptr; int32_t* d_best_all = nullptr;  // host entry point results
   int cap = 0;
-  cudaStream_t side = nullptr, copy = nullptr, pre = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_last = nullptr, ev_start = nullptr;
-  // tensor-core handles pack the layer-1 input of chunk i+1 (HBM-bound) on `pre` / the copy stream while chunk i convolves
-  // (tensor-bound): two input slots in the STCNN workspace, ev_pack[slot] = packed, ev_l1[slot] = conv1 has consumed it
-  cudaEvent_t ev_pack[2] = {nullptr, nullptr}, ev_l1[2] = {nullptr, nullptr};
-  bool tensor = false;
+  cudaStream_t side = nullptr, copy = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_last = nullptr;
   bool has_last = false;
   // host entry points: double-buffered device inputs + pinned staging (frames slots hold f32 or u8)
   void* d_frames[2] = {nullptr, nullptr};
@@ -72,14 +68,7 @@ extern "C" int avs_sweep_create(const avs_stcnn* net, const avs_mfcc_plan* plan,
   ck(cudaMalloc(&s->ws_stcnn, s->ws_stcnn_bytes));
   if (rc == AVS_OK) ck(cudaMemset(s->ws_stcnn, 0, s->ws_stcnn_bytes));  // parity-plane pads stay zero from here on
   ck(cudaMalloc(&s->ws_mfcc, s->ws_mfcc_bytes));
-  s->tensor = stcnn_tensor_path(net) != 0;
   ck(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
-  ck(cudaStreamCreateWithFlags(&s->pre, cudaStreamNonBlocking));
-  ck(cudaEventCreateWithFlags(&s->ev_start, cudaEventDisableTiming));
-  for (int i = 0; i < 2; ++i) {
-    ck(cudaEventCreateWithFlags(&s->ev_pack[i], cudaEventDisableTiming));
-    ck(cudaEventCreateWithFlags(&s->ev_l1[i], cudaEventDisableTiming));
-  }
   ck(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
   ck(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
   ck(cudaEventCreateWithFlags(&s->ev_last, cudaEventDisableTiming));
@@ -102,12 +91,6 @@ extern "C" void avs_sweep_destroy(avs_sweep* s) {
     if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]);
     if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]);
   }
-  for (int i = 0; i < 2; ++i) {
-    if (s->ev_pack[i]) cudaEventDestroy(s->ev_pack[i]);
-    if (s->ev_l1[i]) cudaEventDestroy(s->ev_l1[i]);
-  }
-  if (s->ev_start) cudaEventDestroy(s->ev_start);
-  if (s->pre) cudaStreamDestroy(s->pre);
   if (s->side) cudaStreamDestroy(s->side);
   if (s->copy) cudaStreamDestroy(s->copy);
   if (s->main) cudaStreamDestroy(s->main);
@@ -151,8 +134,7 @@ static int ensure_capacity(avs_sweep* s, int n_clips, cudaStream_t st) {
 
 // statistics of one chunk (n <= s->chunk clips starting at clip c0); audio branch on the side stream, joined back
 // into `st` before returning.
-// packed_slot >= 0: the chunk's layer-1 input is already packed in that workspace slot (and `st` has been made to wait for it).
-static int run_chunk(avs_sweep* s, const void* frames, bool frames_u8, int packed_slot, const float* audio, int c0, int n, cudaStream_t st) {
+static int run_chunk(avs_sweep* s, const void* frames, bool frames_u8, const float* audio, int c0, int n, cudaStream_t st) {
   int rc;
   float* vst = s->vstats + static_cast<size_t>(c0) * AVS_VSTATS;
   float* ast = s->astats + static_cast<size_t>(c0) * s->K * 2 * s->n_mfcc;
@@ -161,22 +143,19 @@ static int run_chunk(avs_sweep* s, const void* frames, bool frames_u8, int packe
 #ifdef AVS_EXPERIMENTS
   static const int audio_mode = env_knob("AVS_AUDIO_MODE", 0);  // 1 serial, 2 fork at chunk start
   if (audio_mode == 1) {
-    if ((rc = stcnn_forward_impl(s->net, frames, frames_u8, packed_slot, n, s->chunk, true, packed_slot >= 0 ? s->ev_l1[packed_slot] : nullptr,
-                                 nullptr, vst, nullptr, nullptr, s->ws_stcnn, s->ws_stcnn_bytes, st)))
+    if ((rc = stcnn_forward_impl(s->net, frames, frames_u8, n, s->chunk, true, nullptr, nullptr, vst, nullptr, nullptr, s->ws_stcnn, s->ws_stcnn_bytes, st)))
       return rc;
     return avs_mfcc_stats_sweep(s->plan, audio, n, ast, s->ws_mfcc, s->ws_mfcc_bytes, st);
   }
   if (audio_mode == 2) AVS_CUDA(cudaEventRecord(s->ev_fork, st));
-  const bool fork_early = audio_mode == 2;
+  cudaEvent_t fork_after_l1 = audio_mode == 2 ? nullptr : s->ev_fork;
 #else
-  constexpr bool fork_early = false;
+  cudaEvent_t fork_after_l1 = s->ev_fork;
 #endif
-  // the event recorded after conv1 is both the audio branch's fork point and "this chunk's packed input has been consumed"
-  cudaEvent_t after_l1 = packed_slot >= 0 ? s->ev_l1[packed_slot] : s->ev_fork;
-  if ((rc = stcnn_forward_impl(s->net, frames, frames_u8, packed_slot, n, s->chunk, true, after_l1, nullptr, vst, nullptr, nullptr,
+  if ((rc = stcnn_forward_impl(s->net, frames, frames_u8, n, s->chunk, true, fork_after_l1, nullptr, vst, nullptr, nullptr,
                                s->ws_stcnn, s->ws_stcnn_bytes, st)))
     return rc;
-  AVS_CUDA(cudaStreamWaitEvent(s->side, fork_early ? s->ev_fork : after_l1, 0));
+  AVS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
   if ((rc = avs_mfcc_stats_sweep(s->plan, audio, n, ast, s->ws_mfcc, s->ws_mfcc_bytes, s->side))) return rc;
   AVS_CUDA(cudaEventRecord(s->ev_join, s->side));
   AVS_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
@@ -197,29 +176,11 @@ static int sweep_run_device(avs_sweep* s, const void* frames, bool frames_u8, co
   int rc;
   if ((rc = begin_call(s, st)) || (rc = ensure_capacity(s, n_clips, st))) return rc;
   const size_t fstride = kFrameElems * (frames_u8 ? 1 : sizeof(float));
-  auto pack_chunk = [&](int i) -> int {  // layer-1 input of chunk i into slot i & 1, on the `pre` stream
-    const int c0 = i * s->chunk, n = std::min(s->chunk, n_clips - c0), sl = i & 1;
-    if (i >= 2) AVS_CUDA(cudaStreamWaitEvent(s->pre, s->ev_l1[sl], 0));  // conv1 of chunk i-2 has read the slot
-    const int r = stcnn_pack_impl(s->net, static_cast<const uint8_t*>(frames) + c0 * fstride, frames_u8, n, s->chunk, sl, s->ws_stcnn,
-                                  s->ws_stcnn_bytes, s->pre);
-    if (r) return r;
-    AVS_CUDA(cudaEventRecord(s->ev_pack[sl], s->pre));
-    return AVS_OK;
-  };
-  const int n_chunks = (n_clips + s->chunk - 1) / s->chunk;
-  if (s->tensor) {  // the inputs were produced on `st` (and the previous call on this handle has been waited for there)
-    AVS_CUDA(cudaEventRecord(s->ev_start, st));
-    AVS_CUDA(cudaStreamWaitEvent(s->pre, s->ev_start, 0));
-    rc = pack_chunk(0);
-  }
-  for (int i = 0; i < n_chunks && !rc; ++i) {
-    const int c0 = i * s->chunk, n = std::min(s->chunk, n_clips - c0);
-    if (s->tensor) {
-      if (i + 1 < n_chunks && (rc = pack_chunk(i + 1))) break;  // under this chunk's conv kernels
-      AVS_CUDA(cudaStreamWaitEvent(st, s->ev_pack[i & 1], 0));
-    }
-    rc = run_chunk(s, static_cast<const uint8_t*>(frames) + c0 * fstride, frames_u8, s->tensor ? (i & 1) : -1,
-                   audio + static_cast<size_t>(c0) * s->n_samples, c0, n, st);
+  for (int c0 = 0; c0 < n_clips; c0 += s->chunk) {
+    const int n = std::min(s->chunk, n_clips - c0);
+    if ((rc = run_chunk(s, static_cast<const uint8_t*>(frames) + c0 * fstride, frames_u8, audio + static_cast<size_t>(c0) * s->n_samples,
+                        c0, n, st)))
+      break;
   }
   if (!rc) rc = score_all(s, n_clips, out_scores, out_best, st);
   const int rc2 = end_call(s, st);  // recorded even after a failure: whatever was enqueued still uses the buffers
@@ -300,13 +261,9 @@ static int sweep_run_host(avs_sweep* s, const void* frames_host, bool frames_u8,
     }
     AVS_CUDA(cudaMemcpyAsync(s->d_frames[sl], fsrc, n * fstride, cudaMemcpyHostToDevice, s->copy));
     AVS_CUDA(cudaMemcpyAsync(s->d_audio[sl], asrc, static_cast<size_t>(n) * s->n_samples * sizeof(float), cudaMemcpyHostToDevice, s->copy));
-    if (s->tensor) {  // the layer-1 input is packed right behind the copy, off the compute stream
-      if (i >= 2) AVS_CUDA(cudaStreamWaitEvent(s->copy, s->ev_l1[sl], 0));  // conv1 of chunk i-2 has read the slot
-      if ((rc = stcnn_pack_impl(s->net, s->d_frames[sl], frames_u8, n, s->chunk, sl, s->ws_stcnn, s->ws_stcnn_bytes, s->copy))) break;
-    }
     AVS_CUDA(cudaEventRecord(s->ev_in[sl], s->copy));
     AVS_CUDA(cudaStreamWaitEvent(s->main, s->ev_in[sl], 0));
-    rc = run_chunk(s, s->d_frames[sl], frames_u8, s->tensor ? sl : -1, s->d_audio[sl], c0, n, s->main);
+    rc = run_chunk(s, s->d_frames[sl], frames_u8, s->d_audio[sl], c0, n, s->main);
     AVS_CUDA(cudaEventRecord(s->ev_done[sl], s->main));
     c0 += n;
   }
