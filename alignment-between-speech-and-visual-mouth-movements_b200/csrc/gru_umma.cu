@@ -28,8 +28,12 @@ constexpr int kGrpClips = 16, kGroups = 2;                // clips per group, gr
 constexpr int kBBytes = kChunks * 2 * kGrpClips * 16;     // one h buffer (hi + lo) of one group: 16 KB
 constexpr int kXsPitch = kGrpClips + 1;
 constexpr int kStageBytes = 4 * 2 * kGrpClips * 16;       // this CTA's 32 units (4 chunks) of h, hi + lo: 2 KB
-constexpr int kCpt = kGrpClips / 8;                       // clips per thread and group (thread = (unit, warp's clips))
-constexpr int kGruThreads = 288;                          // 8 worker warps + the MMA-issuing warp
+#ifndef AVS_VAR_GRU_WORKERS
+#define AVS_VAR_GRU_WORKERS 16
+#endif
+constexpr int kWorkers = AVS_VAR_GRU_WORKERS;             // worker warps: 16 = one clip of the group per warp (8: two)
+constexpr int kCpt = kGrpClips / kWorkers;                // clips per thread and group (thread = (unit, warp's clips))
+constexpr int kGruThreads = (kWorkers + 1) * 32;          // worker warps + the MMA-issuing warp
 constexpr size_t kGruSmem = 2ull * kABytes + kGroups * 2ull * kBBytes + kGroups * kRows * kXsPitch * 4 +
                             kGroups * 2 * kStageBytes + 128;
 
@@ -50,7 +54,7 @@ __device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster_addr, const void* 
                "r"(smem_u32(src_smem)), "r"(bytes), "r"(mbar_cluster_addr)
                : "memory");
 }
-__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the eight worker warps
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkers * 32) : "memory"); }  // the worker warps
 
 // wp: packed W_hh [2 dirs][8 ranks][2 kinds][32 chunks][128 rows][8] bf16 (gru_pack_whh)
 //
@@ -106,7 +110,7 @@ gru_cluster_umma_kernel(const float* __restrict__ xp, const __nv_bfloat16* __res
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 
-  if (warp == 8) {
+  if (warp == kWorkers) {
     // ============================================================ MMA issuer
     // In a cluster launch the shared-window address of a CTA carries its cluster rank above bit 24 (rank 1: 0x01000400).
     // The descriptor's start-address field is 14 bits of (address >> 4): mask, or the rank lands in the LBO field.
@@ -205,7 +209,7 @@ gru_cluster_umma_kernel(const float* __restrict__ xp, const __nv_bfloat16* __res
           fence_proxy_async();  // staged with generic stores, read by the bulk-copy engine
           workers_sync();
           // ... and pushed to chunks [4 rank, 4 rank + 4) of every CTA's next buffer of this group: one bulk copy per CTA
-          if (tid < kClu) {
+          if (tid < kClu) {  // (lanes 0..7 of worker warp 0)
             const uint32_t dst_off = static_cast<uint32_t>((g * 2 + (cur ^ 1)) * kBBytes + rank * kStageBytes);
             bulk_s2c(map_to_rank(smem_u32(s_b) + dst_off, tid), stage, kStageBytes, map_to_rank(smem_u32(&bar_h[g * 2 + (cur ^ 1)]), tid));
           }

@@ -8,6 +8,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import avsync_b200 as A
 
+if os.environ.get("K3_LIB"):   # a variant build: make -C csrc VARIANT=name VARIANT_FLAGS=...
+    A._native.LIB_PATH = os.path.join(os.path.dirname(A._native.LIB_PATH), f"libavsync_b200_var_{os.environ['K3_LIB']}.so")
 B = int(os.environ.get("K3_CLIPS", "256"))
 prec = os.environ.get("K3_PRECISION", "bf16x3")
 torch.manual_seed(0)
