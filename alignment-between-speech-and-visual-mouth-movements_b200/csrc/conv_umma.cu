@@ -55,11 +55,14 @@ namespace avs {
 #ifndef AVS_VAR_L1_GROUPS
 #define AVS_VAR_L1_GROUPS 2   // a third group was measured (profiles/r02_variants_ab_3.txt): conv1 5.0 against 4.8 ms per 1024 clips
 #endif
+#ifndef AVS_VAR_L1_RING
+#define AVS_VAR_L1_RING 4     // plane slots of conv1's ring
+#endif
 // 4 control warps + 2 (conv1: 3) epilogue groups of 4 warps
 __host__ __device__ constexpr int epi_groups(int kind) { return kind == 0 /* KIND_L1 */ ? AVS_VAR_L1_GROUPS : 2; }
 __host__ __device__ constexpr int conv_threads(int kind) { return (4 + 4 * epi_groups(kind)) * 32; }
 constexpr int kMaxUnits = 6;
-constexpr int kMaxRing = 4;
+constexpr int kMaxRing = 8;
 constexpr int kMaxWStages = 8;
 
 struct UnitDesc {
@@ -148,8 +151,16 @@ struct LayerKind {
   static constexpr int KW = KH;
   static constexpr int NROW = first ? 3 : KH;       // bf16: row taps R[0..NROW-1] of one filter column (conv1: row pairs)
   static constexpr int PAIRS = first ? 1 : (split ? 2 : (N == 64 ? 2 : 4));  // K = 16 steps (channel pairs) per tap in a unit
-  static constexpr int ACC = split ? (N == 96 ? 256 : 2 * N) : N;            // TMEM columns between even/odd-row accumulators
-  static constexpr int NT = KIND == KIND_L1 ? 4 : (KIND <= KIND_L1_SPLIT ? 2 : 1);  // tiles per work item
+  // conv1, bf16: COLUMN-parity stacking on top of the row-parity stacking.  The layer-1 input holds one X8 entry per
+  // POOLED column wo — the 8 padded-row values 2wo .. 2wo+7 — so the taps of the even conv column 2wo are K slots 0..4 and
+  // those of the odd column 2wo+1 are slots 1..5 of the SAME entry: B = [W(slots 0..4) | W(slots 1..5)] (2 x 32 rows)
+  // computes both columns from one fetch of A.  A tile is then 128 POOLED positions whose four pool candidates sit in
+  // four 32-column blocks of the same TMEM lane: half the MMAs (N = 128 / 64 instead of 64 / 32), no lane exchange in
+  // the epilogue, and a layer-1 input of half the size.
+  static constexpr bool colstack = KIND == KIND_L1;
+  static constexpr int NB = colstack ? 2 * N : N;                             // B rows (accumulator columns) per conv-row accumulator
+  static constexpr int ACC = split ? (N == 96 ? 256 : 2 * N) : NB;           // TMEM columns between even/odd-row accumulators
+  static constexpr int NT = KIND <= KIND_L1_SPLIT ? 2 : 1;                    // tiles per work item
   // stages per A unit: bf16 = one filter column per stage, bf16x3 = one filter row per stage; conv1: the unit is one stage
   static constexpr int SPU = first ? 1 : KW;
   // bf16 kinds keep the three input planes of an item in a ring of three plane slots (slot = padded plane index % 3)
@@ -162,12 +173,12 @@ struct LayerKind {
   static constexpr bool reuse = !split && !tcat;
   // conv1's items are a single stage, so a plane is only released when the whole item is done: a fourth slot lets the
   // next item's new plane load meanwhile (multi-stage kinds release an item's first plane after its first unit)
-  static constexpr int RING = first ? 4 : 3;
+  static constexpr int RING = first ? AVS_VAR_L1_RING : 3;
   // Geometry of LipNet's layer (50 x 100 frames, halved by every pool), mirrored from geom_finalize()/umma_layer_build()
   // — which refuse anything else — so that the two strides of the activation layout are COMPILE-time constants
   // and every descriptor of the schedule is "uniform base + immediate".
   static constexpr int H = first ? 50 : (N == 64 ? 25 : 12), W = first ? 100 : (N == 64 ? 50 : 25);
-  static constexpr int WT = W + KW / 2;                                  // row pitch (positions)
+  static constexpr int WT = colstack ? W / 2 : W + KW / 2;               // row pitch (positions); colstack: entries are self-contained, no gap
   static constexpr int HALO = first ? (KH / 2 + 1) * WT + 8 : (KH / 2) * WT + KW - 1;
   static constexpr int REGION_FULL = NT * 128 + HALO;
   static constexpr int NTILES = ((H / 2) * WT + 127) / 128, NTS = (NTILES + NT - 1) / NT;
@@ -202,8 +213,8 @@ __device__ __forceinline__ void issue_stage_bf16(const uint32_t (&a_base)[3], ui
         const int q = e < K::NROW - 1 ? e + 1 : (e == K::NROW - 1 ? 0 : K::NROW);
         const bool wide = q >= 1 && q <= K::NROW - 1;
         const uint32_t a = a_base[kd] + (pr * 4 + (q & 1)) * arr16 + (q >> 1) * Wt;  // conv1: one plane slot per kd
-        const uint32_t b = b_base + (kd * K::PAIRS + pr) * (2 * K::NROW * K::N) + (K::NROW - 1 - (q == K::NROW ? K::NROW - 1 : q)) * K::N;
-        const uint32_t d = d_base + (q == K::NROW ? K::N : 0);
+        const uint32_t b = b_base + (kd * K::PAIRS + pr) * (2 * K::NROW * K::NB) + (K::NROW - 1 - (q == K::NROW ? K::NROW - 1 : q)) * K::NB;
+        const uint32_t d = d_base + (q == K::NROW ? K::NB : 0);
         const uint32_t acc = (kd == 0 && pr == 0 && e == 0) ? (overwrite ? 0u : 1u) : 1u;
 #pragma unroll
         for (int i = LO; i < HI; ++i) umma_f16(d + i * 2 * K::ACC, kDescHi | (a + i * 128), kDescHi | b, wide ? idesc_w : idesc_n, acc);
@@ -410,7 +421,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     // other weight stage (global stage counter g, g & 1 == x).  For an owned stage: wait for its operands, then issue
     // it in two halves under the token protocol below.
     const uint32_t x = warp >> 1;
-    const uint32_t idesc_n = umma_idesc_bf16(128, K::N), idesc_w = umma_idesc_bf16(128, 2 * K::N);
+    const uint32_t idesc_n = umma_idesc_bf16(128, K::NB), idesc_w = umma_idesc_bf16(128, 2 * K::NB);
     const uint32_t units_lo = (smem_u32(s_units) & 0x3FFFFu) >> 4, w_lo = (smem_u32(s_w) & 0x3FFFFu) >> 4;
     const uint32_t unit_step = static_cast<uint32_t>(p.unit_slot_bytes) >> 4, stage_step = static_cast<uint32_t>(p.stage_bytes) >> 4;
     const uint32_t ring = p.ring, wstages = p.wstages, nbuf = p.NBUF;
@@ -418,7 +429,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     // LBO fields (16-byte units, bits 16..29): A = next 8-channel chunk of the same parity (conv1: next row of the same
     // parity, the second kh of the pair); B = the other K half of the tile
     const uint32_t lbo_a = (K::first ? Wt : (K::split ? 4u : 2u) * arr16) << 16;
-    constexpr uint32_t lbo_b = static_cast<uint32_t>(K::split ? 2 * K::N : K::NROW * K::N) << 16;
+    constexpr uint32_t lbo_b = static_cast<uint32_t>(K::split ? 2 * K::N : K::NROW * K::NB) << 16;
     const int n_stages = p.n_stages, n_tiles = p.n_tiles, dbg = AVS_DBG(p);
     uint32_t a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0, acc_buf = 0, acc_phase = 0;
     uint32_t a_loaded = 0, w_loaded = 0;  // only used by the dbg switches
@@ -560,8 +571,10 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     using KN = LayerKind<K::NEXT>;             // the layer that reads our output (conv3: unused)
     constexpr bool kToEmb = K::N == 96;        // conv3 writes the f32 embedding
     constexpr int kHo = K::H / 2, kWo = K::W / 2, kPlane = kHo * kWo;
-    constexpr int UPT = K::N / 32;             // units per tile
-    const int half = lane & 1;                 // even lane: channels 0..15 of a 32-column block, odd: 16..31
+    // units per tile: 32-column blocks of both row accumulators; colstack (conv1): 16 output channels, i.e. 16 columns
+    // of each of the tile's four 32-column blocks (even/odd conv row x even/odd conv column) — the four pool candidates
+    constexpr int UPT = K::colstack ? 2 : K::N / 32;
+    const int half = K::colstack ? 0 : (lane & 1);  // even lane: channels 0..15 of a 32-column block, odd: 16..31
     uint32_t buf = 0, phase = 0;
     long long ek_full = 0, ek_tmem = 0, ek_work = 0, ek_total = clock64();  // dbg 128: epilogue time split (warps 4 and 8 of block 0)
     ItemWalk w;
@@ -618,7 +631,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       for (int i = 0; i < nt && n_units > 0; ++i)
 #pragma unroll
       for (int cbi = 0; cbi < UPT; ++cbi) {
-        const int u = i * UPT + cbi, cb = cbi * 32;
+        const int u = i * UPT + cbi, cb = cbi * (K::colstack ? 16 : 32);
         if ((u % kGroups) != grp) continue;  // warp-uniform
         // positions grow with the lane and with the tile: if the warp's first lane is past the end, nobody has work
         const int S0 = ((K::tcat ? t : ts) * NT + i) * 128 + q * 32;
@@ -629,8 +642,15 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         float bias[16];
         const long long ek1 = (AVS_DBG(p) & 128) ? clock64() : 0;
         if (warp_has_work) {  // TMEM loads first: the bias fetch and the index arithmetic below run under them
-          tmem_ld32(d_base + (i * 2 + 0) * K::ACC + cb, v0);
-          tmem_ld32(d_base + (i * 2 + 1) * K::ACC + cb, v1);
+          if (K::colstack) {  // v0 = even conv row (even | odd column), v1 = odd conv row (even | odd column)
+            tmem_ld16(d_base + (i * 2 + 0) * K::ACC + cb, *reinterpret_cast<uint32_t(*)[16]>(&v0[0]));
+            tmem_ld16(d_base + (i * 2 + 0) * K::ACC + K::N + cb, *reinterpret_cast<uint32_t(*)[16]>(&v0[16]));
+            tmem_ld16(d_base + (i * 2 + 1) * K::ACC + cb, *reinterpret_cast<uint32_t(*)[16]>(&v1[0]));
+            tmem_ld16(d_base + (i * 2 + 1) * K::ACC + K::N + cb, *reinterpret_cast<uint32_t(*)[16]>(&v1[16]));
+          } else {
+            tmem_ld32(d_base + (i * 2 + 0) * K::ACC + cb, v0);
+            tmem_ld32(d_base + (i * 2 + 1) * K::ACC + cb, v1);
+          }
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + c4);
@@ -644,7 +664,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
           Q -= t_out * K::PITCH;
         }
         const int r = Q / K::WT, wc = Q - r * K::WT;        // pooled row, conv column
-        const int wo = wc >> 1;
+        const int wo = K::colstack ? wc : wc >> 1;  // colstack: positions ARE pooled columns
         const bool valid = (r < kHo) && (wo < kWo) && (t_out < p.T_out);
         if (warp_has_work) {
           tmem_ld_wait();
@@ -676,6 +696,13 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         if ((AVS_DBG(p) & 32) && v0[0] != 0x7fc12345u) continue;  // experiment: TMEM reads only
         const long long ek3 = (AVS_DBG(p) & 128) ? clock64() : 0;
         float o[16];
+        if (K::colstack) {
+          // all four pool candidates of a (pooled position, channel) are in this lane: relu(max4 + b) == max(max3, v, -b) + b
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            o[c] = fmax3(fmax3(__uint_as_float(v0[c]), __uint_as_float(v0[c + 16]), __uint_as_float(v1[c])),
+                         __uint_as_float(v1[c + 16]), -bias[c]) + bias[c];
+        } else {
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           // rows 2r, 2r+1: max of the two accumulators; columns 2wo, 2wo+1: exchange with the
@@ -689,6 +716,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
 #else
           o[c] = fmaxf(fmaxf(half ? hi : lo, got) + bias[c], 0.f);
 #endif
+        }
         }
         if ((AVS_DBG(p) & 64) && o[0] != 12345.678f) continue;  // experiment: no stores
         if (valid && !kToEmb) {
@@ -797,7 +825,7 @@ pack_frames_kernel(const TIn* __restrict__ frames, __nv_bfloat16* __restrict__ a
   __shared__ uint32_t s_lut[256];                    // u8 variant: bf16 hi | bf16 lo << 16 of float32(v / 255.0)
   constexpr bool kU8 = sizeof(TIn) == 1;
   // LipNet's frame geometry (the layer-1 kind's constants): 50 x 100 pixels, padding 2, row pitch 102, 27 rows per parity
-  using K1 = LayerKind<KIND_L1>;
+  using K1 = LayerKind<KIND_L1_SPLIT>;  // (the bf16 kind has its own layout: pack_frames_pooled_kernel)
   constexpr int H = K1::H, W = K1::W, PH = K1::KH / 2, PW = K1::KW / 2, WT = K1::WT, HH = H / 2 + PH, QW = W / 4;
   const int nv = (PP + 8 + 7) & ~7;
   uint16_t* s_hi = s_val;
@@ -865,6 +893,62 @@ pack_frames_kernel(const TIn* __restrict__ frames, __nv_bfloat16* __restrict__ a
   }
 }
 
+// Layer-1 input of the bf16 kind (LayerKind::colstack): one X8 entry per POOLED column — entry (row, wo) of a parity array
+// holds the padded-row values 2wo .. 2wo+7 (padded column = column + 2), rows back to back with pitch W/2 and no gaps
+// (an entry carries all its horizontal taps, for the even and for the odd conv column).  Same staging as above: the
+// padded parity rows go to shared memory as bf16, then every thread emits 16-byte entries.
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+pack_frames_pooled_kernel(const TIn* __restrict__ frames, __nv_bfloat16* __restrict__ act, int PP, int T, int n_items) {
+  constexpr bool kU8 = sizeof(TIn) == 1;
+  using K1 = LayerKind<KIND_L1>;
+  constexpr int H = K1::H, W = K1::W, PH = K1::KH / 2, PW = K1::KW / 2, HH = H / 2 + PH, QW = W / 4, WO = W / 2;
+  constexpr int SP = 112;                              // staging row pitch (values): >= 2 * (WO - 1) + 8, multiple of 8
+  static_assert(K1::WT == WO && SP >= 2 * (WO - 1) + 8 && SP >= W + 2 * PW, "pooled X8 layout");
+  __shared__ __align__(16) uint16_t s_hi[HH * SP];
+  __shared__ uint32_t s_lut[256];                      // u8 variant: bf16 of float32(v / 255.0)
+  if (kU8) s_lut[threadIdx.x] = __bfloat16_as_ushort(__float2bfloat16_rn(static_cast<float>(static_cast<double>(threadIdx.x) / 255.0)));
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int par = item & 1, tp = (item >> 1) % (T + 2);
+    const long long b = (item >> 1) / (T + 2);
+    __syncthreads();  // the previous item's reads of s_hi are done (and the table is in place)
+    for (int i = threadIdx.x; i < HH * SP / 8; i += 256) reinterpret_cast<uint4*>(s_hi)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (tp >= 1 && tp <= T) {
+      const TIn* f = frames + (b * T + (tp - 1)) * static_cast<long long>(H * W);
+      for (int i = threadIdx.x; i < HH * QW; i += 256) {  // four consecutive pixels of one row per step
+        const int row = i / QW, wq = (i - row * QW) * 4;
+        const int h = 2 * row + par - PH;
+        if (h < 0 || h >= H) continue;
+        uint32_t e[4];
+        if constexpr (kU8) {
+          const uint32_t px = *reinterpret_cast<const uint32_t*>(f + h * W + wq);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) e[j] = s_lut[(px >> (8 * j)) & 0xFFu];
+        } else {
+          const float4 v4 = *reinterpret_cast<const float4*>(f + h * W + wq);
+          e[0] = __bfloat16_as_ushort(__float2bfloat16_rn(v4.x)); e[1] = __bfloat16_as_ushort(__float2bfloat16_rn(v4.y));
+          e[2] = __bfloat16_as_ushort(__float2bfloat16_rn(v4.z)); e[3] = __bfloat16_as_ushort(__float2bfloat16_rn(v4.w));
+        }
+        uint32_t* d = reinterpret_cast<uint32_t*>(s_hi + row * SP + PW + wq);
+        d[0] = e[0] | (e[1] << 16);
+        d[1] = e[2] | (e[3] << 16);
+      }
+    }
+    __syncthreads();
+    uint4* out = reinterpret_cast<uint4*>(act + ((b * (T + 2) + tp) * 2 + par) * static_cast<long long>(PP) * 8);
+    for (int p = threadIdx.x; p < PP; p += 256) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (p < HH * WO) {
+        const int row = p / WO, wo = p - row * WO;
+        const uint32_t* sv = reinterpret_cast<const uint32_t*>(s_hi + row * SP + 2 * wo);
+        v = make_uint4(sv[0], sv[1], sv[2], sv[3]);
+      }
+      out[p] = v;
+    }
+  }
+}
+
 // debug: parity-plane input of a layer (C channels, geometry g) -> f32 NCDHW [B, C, T, H, W]
 __global__ void __launch_bounds__(256)
 unpack_act_kernel(const __nv_bfloat16* __restrict__ act, float* __restrict__ out, LayerGeom g, int split, int C, int T,
@@ -918,7 +1002,7 @@ static LayerCfg pick_cfg(const LayerGeom& g, int split) {
   // ~330 cycles) over more MMAs: conv2 bf16 uses one kernel row (5 taps, 40 MMAs) per stage.
   // split mode doubles the accumulator width (hi*hi+lo*hi | hi*lo column blocks), so fewer tiles fit in TMEM
   // bf16 kinds: ring = LayerKind::RING plane slots (the plane ring of the kernel), not tunable
-  if (g.Cin == 1) c = split ? LayerCfg{2, 2, 3, 4} : LayerCfg{4, 2, 4, 2};
+  if (g.Cin == 1) c = split ? LayerCfg{2, 2, 3, 4} : LayerCfg{2, 2, AVS_VAR_L1_RING, 2};
   else if (g.Cout == 64) c = split ? LayerCfg{1, 2, 2, 2} : LayerCfg{2, 2, 3, 3};
   else c = split ? LayerCfg{1, 1, 3, 2} : LayerCfg{2, 1, 2, 2};  // bf16: two unit slots of NT*128 + halo positions (time-concatenated tiling)  // Cout = 96 (TMEM: 2 tiles x 2 accs x 96 columns, or 1 x 2 x 256 split)
 #ifdef AVS_EXPERIMENTS
@@ -949,7 +1033,7 @@ void geom_finalize(LayerGeom& g, int split) {
   g.pw = g.KW / 2;
   g.Ho = g.H / 2;
   g.Wo = g.W / 2;
-  g.Wt = g.W + g.pw;
+  g.Wt = (g.Cin == 1 && !split) ? g.W / 2 : g.W + g.pw;  // conv1 bf16: one self-contained X8 entry per pooled column (LayerKind::colstack)
   g.Hh = g.Ho + g.KH / 2;
   g.n_q = g.Ho * g.Wt;
   g.n_tiles = cdiv(g.n_q, 128);
@@ -1016,8 +1100,10 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
     // q = 0 and q = n touch one accumulator only (width Cout).
     //   conv2/conv3: R[j] = W[kd][kh = j][kw], K = 16 input channels, A(q) = parity plane q&1 shifted q>>1 rows;
     //                one weight stage per (kd, kw): [channel pair][K half][R[n-1] .. R[0]][Cout rows][8].
-    //   conv1 (X8 input, K = 2 rows x 8 kw'): A(q) = rows (2r+q, 2r+q+2) as the two K halves;
-    //          R[0] = (kh0, kh2), R[1] = (kh1, kh3), R[2] = (0, kh4); ONE stage: [kd][K half][R2 R1 R0][32 rows][8].
+    //   conv1 (X8 input, K = 2 rows x 8 slots): A(q) = rows (2r+q, 2r+q+2) as the two K halves;
+    //          R[0] = (kh0, kh2), R[1] = (kh1, kh3), R[2] = (0, kh4); ONE stage: [kd][K half][R2 R1 R0][64 rows][8], where the
+    //          64 rows of a tap are [even conv column: kw = slot | odd conv column: kw = slot - 1] x 32 channels (the entry of
+    //          pooled column wo holds padded-row values 2wo .. 2wo+7: LayerKind::colstack).
     const int n = first ? 3 : g.KH;
     const int pairs = first ? 1 : g.Cin / 16;
     const int cols = first ? 1 : g.KW;
@@ -1026,12 +1112,13 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
         for (int pr = 0; pr < pairs; ++pr)
           for (int half = 0; half < 2; ++half)
             for (int j = n - 1; j >= 0; --j)
-              for (int row = 0; row < N; ++row)
+              for (int row = 0; row < (first ? 2 * N : N); ++row)
                 for (int k = 0; k < 8; ++k) {
                   float x;
                   if (first) {
                     const int kh = half == 0 ? (j < 2 ? j : -1) : j + 2;
-                    x = (kh >= 0 && k < g.KW) ? wat(row, 0, kd, kh, k) : 0.f;
+                    const int kw = k - (row >= N ? 1 : 0);  // rows N..2N-1: the odd conv column reads one slot further
+                    x = (kh >= 0 && kw >= 0 && kw < g.KW) ? wat(row % N, 0, kd, kh, kw) : 0.f;
                   } else {
                     x = wat(row, pr * 16 + half * 8 + k, kd, j, kw);
                   }
@@ -1043,7 +1130,7 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
     }
     if (first) n_stages = 1;
     L->unit_planes = 1;
-    if (pairs != kPAIRS || L->ring != (first ? 4 : (kTLEN ? 2 : 3))) return AVS_EINVAL;
+    if (pairs != kPAIRS || L->ring != (first ? AVS_VAR_L1_RING : (kTLEN ? 2 : 3))) return AVS_EINVAL;
   } else {
     // ---- bf16x3: operands split hi/lo.  One B tile = [2 K-halves][N hi rows | N lo rows][8]: ONE MMA of width 2N
     // computes A_hi*B_hi and A_hi*B_lo with a single fetch of A (adjacent accumulator column blocks, added in
@@ -1131,7 +1218,10 @@ int umma_pack_frames(const void* frames, bool frames_u8, __nv_bfloat16* act, con
   // grid-stride over the (clip, plane, parity) items: 8 CTAs per SM keep the stores of one item under the loads of others
   const int n_items = B * (AVS_T + 2) * 2;
   const unsigned grid = static_cast<unsigned>(std::min(n_items, n_sms * 8));
-  if (frames_u8) pack_frames_kernel<uint8_t><<<grid, 256, sm, st>>>(static_cast<const uint8_t*>(frames), act, g.PP, split, AVS_T, n_items);
+  if (!split) {  // bf16 kind: one X8 entry per pooled column
+    if (frames_u8) pack_frames_pooled_kernel<uint8_t><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(frames), act, g.PP, AVS_T, n_items);
+    else pack_frames_pooled_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(frames), act, g.PP, AVS_T, n_items);
+  } else if (frames_u8) pack_frames_kernel<uint8_t><<<grid, 256, sm, st>>>(static_cast<const uint8_t*>(frames), act, g.PP, split, AVS_T, n_items);
   else pack_frames_kernel<float><<<grid, 256, sm, st>>>(static_cast<const float*>(frames), act, g.PP, split, AVS_T, n_items);
   AVS_LAUNCHED();
   return AVS_OK;

@@ -34,8 +34,10 @@ sw = A.SyncSweeper(net, det, 20, 48000, chunk_clips=min(128, C))
 fr, au = bench.synth_inputs(C, seed=1000)
 fr, au = fr.cuda(), au.cuda()
 for _ in range(3):
-    sw.run(fr, au)
+    res = sw.run(fr, au)
 torch.cuda.synchronize()
+# checksum of the results, so that variants can be compared for bit identity inside one session
+CHK = f"scores {res[0].double().sum().item():.12f} best {int(res[1].long().sum().item())}"
 L.avs_prof_reset()
 L.avs_prof_enable(1)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -53,4 +55,4 @@ for i, n in enumerate(names):
     L.avs_prof_read(i, ctypes.byref(t), ctypes.byref(c))
     out.append(f"{n} {t.value / STEPS:.2f}")
 knobs = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("AVS_"))
-print(f"[lib={LIB} {knobs or 'defaults'}] {PREC} {C} clips: {ms:.2f} ms/step = {C / ms * 1e3:.0f} clips/s | " + " | ".join(out), flush=True)
+print(f"[lib={LIB} {knobs or 'defaults'}] {PREC} {C} clips: {ms:.2f} ms/step = {C / ms * 1e3:.0f} clips/s | " + " | ".join(out) + " | " + CHK, flush=True)
