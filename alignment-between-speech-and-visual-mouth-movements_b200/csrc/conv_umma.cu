@@ -287,7 +287,7 @@ __device__ __forceinline__ void issue_half(int nt, const uint32_t (&ab)[3], uint
 
 template <int KIND>
 // 128 registers per thread so that one FFT CTA (256 x 64 registers) of the audio branch fits beside it on the SM
-__global__ void __maxnreg__(128)
+__global__ void __maxnreg__(KIND == KIND_L1 && AVS_VAR_L1_GROUPS >= 4 ? 96 : 128)
 conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // carve: [unit slots][weight stages][barriers][tmem ptr]
@@ -558,7 +558,86 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     }
   } else if (warp >= 4) {
     // ============================================================ epilogue
-    {
+    if constexpr (K::colstack) {
+      // conv1 (column-parity stacking): a lane owns one POOLED position of the tile and finds its four pool candidates in
+      // the tile's four 32-column blocks (even / odd conv row x even / odd conv column), so the unit of work — 16 output
+      // channels of one tile — is 4 TMEM loads, 2 three-input maxima and an add per channel, one bf16 pack per channel
+      // pair and two 16-byte stores: no lane exchange, no selects.  Warp groups split the item's (tile, channel half)
+      // units: 2 groups = one channel half of both tiles each, 4 groups = one unit each.  Everything that does not depend
+      // on the time step (position decode, validity, the offset inside the next layer's plane) is computed when the CTA's
+      // span moves to another tile set — once per 75 items — and the bias of the warp's channel half lives in registers.
+      static_assert(kGroups == 2 || kGroups == 4, "conv1 epilogue: 2 or 4 warp groups");
+      static_assert(K::NTILES % NT == 0 && NT == 2 && !K::tcat, "conv1 items are full pairs of tiles");
+      using KN = LayerKind<K::NEXT>;
+      static_assert(!KN::tcat && KN::N_CHUNKS == K::N / 8, "layer 2 reads parity planes of 32 channels");
+      const int q = warp & 3, grp = (warp - 4) >> 2;
+      const int ch0 = (grp & 1) * 16;                        // this warp's channel half
+      float bias[16];
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + c4);
+        bias[c4 * 4 + 0] = bv.x; bias[c4 * 4 + 1] = bv.y; bias[c4 * 4 + 2] = bv.z; bias[c4 * 4 + 3] = bv.w;
+      }
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ch0;
+      constexpr long long kPlaneElems = static_cast<long long>(KN::N_CHUNKS) * 2 * KN::PP * 8;  // one time plane of layer 2's input
+      int ts_cached = -1;
+      int off[NT];     // element offset of this lane's pooled position inside a (chunk 0) parity array pair of the plane
+      bool val[NT];
+      uint32_t buf = 0, phase = 0;
+      ItemWalk w;
+      w.init(p);
+      for (; w.valid(); w.next(), buf ^= 1u, phase ^= (buf == 0)) {
+        if (w.ts != ts_cached) {
+          ts_cached = w.ts;
+#pragma unroll
+          for (int i = 0; i < NT; ++i) {
+            const int Q = (w.ts * NT + i) * 128 + q * 32 + lane;  // pooled position of the plane, row-major 25 x 50
+            const int r = Q / K::WT, wo = Q - r * K::WT;
+            const int hp = r + KN::KH / 2;                          // padded row of layer 2's input
+            off[i] = (((ch0 >> 3) * 2 + (hp & 1)) * KN::PP + KN::KW / 2 + (hp >> 1) * KN::WT + wo) * 8;
+            val[i] = r < K::H / 2;
+          }
+        }
+        __nv_bfloat16* out_item = p.eo.act + (static_cast<long long>(w.b) * (p.T_out + 2) + w.t + 1) * kPlaneElems;
+        mbar_wait(&acc_full[buf * 2], phase);
+        __syncwarp();  // tcgen05.ld is .aligned
+        tc_fence_after();
+        const uint32_t d = lane_addr + buf * (NT * 2 * K::ACC);
+        const bool skip = (AVS_DBG(p) & 4) != 0;  // experiment: no epilogue work
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+          if (kGroups == 4 && i != (grp >> 1)) continue;
+          const bool last = kGroups == 4 || i == NT - 1;
+          uint32_t v[4][16];
+          if (!skip) {
+#pragma unroll
+            for (int blk = 0; blk < 4; ++blk) tmem_ld16(d + i * 2 * K::ACC + blk * K::N, v[blk]);
+            tmem_ld_wait();
+          }
+          if (last) {  // this warp's reads of the buffer are in registers: hand it back before the arithmetic
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf * 2]);
+          }
+          if (skip) continue;
+          uint32_t pk[8];
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            // relu(max4 + b) == max(max3(v0, v1, v2), v3, -b) + b exactly
+            const float o0 = fmax3(fmax3(__uint_as_float(v[0][c]), __uint_as_float(v[1][c]), __uint_as_float(v[2][c])),
+                                   __uint_as_float(v[3][c]), -bias[c]) + bias[c];
+            const float o1 = fmax3(fmax3(__uint_as_float(v[0][c + 1]), __uint_as_float(v[1][c + 1]), __uint_as_float(v[2][c + 1])),
+                                   __uint_as_float(v[3][c + 1]), -bias[c + 1]) + bias[c + 1];
+            pk[c >> 1] = pack_bf16x2(o0, o1);
+          }
+          if (val[i]) {
+            uint4* dst = reinterpret_cast<uint4*>(out_item + off[i]);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);                       // channels ch0 .. ch0+7: chunk ch0/8
+            dst[2 * KN::PP] = make_uint4(pk[4], pk[5], pk[6], pk[7]);              // next chunk: two parity arrays further
+          }
+        }
+      }
+    } else {
     // kGroups groups of four warps (warps 4-7, 8-11, ...); warp w may read TMEM lanes 32*(w%4)..+31.  The work unit is a
     // 32-column block of one tile (both row accumulators); the units of an item, in (tile, block) order, go round the
     // groups.  An accumulator half goes back to the issuers as soon as this warp's last unit of the half has been
@@ -571,10 +650,8 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     using KN = LayerKind<K::NEXT>;             // the layer that reads our output (conv3: unused)
     constexpr bool kToEmb = K::N == 96;        // conv3 writes the f32 embedding
     constexpr int kHo = K::H / 2, kWo = K::W / 2, kPlane = kHo * kWo;
-    // units per tile: 32-column blocks of both row accumulators; colstack (conv1): 16 output channels, i.e. 16 columns
-    // of each of the tile's four 32-column blocks (even/odd conv row x even/odd conv column) — the four pool candidates
-    constexpr int UPT = K::colstack ? 2 : K::N / 32;
-    const int half = K::colstack ? 0 : (lane & 1);  // even lane: channels 0..15 of a 32-column block, odd: 16..31
+    constexpr int UPT = K::N / 32;             // units per tile
+    const int half = lane & 1;                 // even lane: channels 0..15 of a 32-column block, odd: 16..31
     uint32_t buf = 0, phase = 0;
     long long ek_full = 0, ek_tmem = 0, ek_work = 0, ek_total = clock64();  // dbg 128: epilogue time split (warps 4 and 8 of block 0)
     ItemWalk w;
@@ -631,7 +708,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       for (int i = 0; i < nt && n_units > 0; ++i)
 #pragma unroll
       for (int cbi = 0; cbi < UPT; ++cbi) {
-        const int u = i * UPT + cbi, cb = cbi * (K::colstack ? 16 : 32);
+        const int u = i * UPT + cbi, cb = cbi * 32;
         if ((u % kGroups) != grp) continue;  // warp-uniform
         // positions grow with the lane and with the tile: if the warp's first lane is past the end, nobody has work
         const int S0 = ((K::tcat ? t : ts) * NT + i) * 128 + q * 32;
@@ -642,15 +719,8 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         float bias[16];
         const long long ek1 = (AVS_DBG(p) & 128) ? clock64() : 0;
         if (warp_has_work) {  // TMEM loads first: the bias fetch and the index arithmetic below run under them
-          if (K::colstack) {  // v0 = even conv row (even | odd column), v1 = odd conv row (even | odd column)
-            tmem_ld16(d_base + (i * 2 + 0) * K::ACC + cb, *reinterpret_cast<uint32_t(*)[16]>(&v0[0]));
-            tmem_ld16(d_base + (i * 2 + 0) * K::ACC + K::N + cb, *reinterpret_cast<uint32_t(*)[16]>(&v0[16]));
-            tmem_ld16(d_base + (i * 2 + 1) * K::ACC + cb, *reinterpret_cast<uint32_t(*)[16]>(&v1[0]));
-            tmem_ld16(d_base + (i * 2 + 1) * K::ACC + K::N + cb, *reinterpret_cast<uint32_t(*)[16]>(&v1[16]));
-          } else {
-            tmem_ld32(d_base + (i * 2 + 0) * K::ACC + cb, v0);
-            tmem_ld32(d_base + (i * 2 + 1) * K::ACC + cb, v1);
-          }
+          tmem_ld32(d_base + (i * 2 + 0) * K::ACC + cb, v0);
+          tmem_ld32(d_base + (i * 2 + 1) * K::ACC + cb, v1);
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + c4);
@@ -664,7 +734,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
           Q -= t_out * K::PITCH;
         }
         const int r = Q / K::WT, wc = Q - r * K::WT;        // pooled row, conv column
-        const int wo = K::colstack ? wc : wc >> 1;  // colstack: positions ARE pooled columns
+        const int wo = wc >> 1;
         const bool valid = (r < kHo) && (wo < kWo) && (t_out < p.T_out);
         if (warp_has_work) {
           tmem_ld_wait();
@@ -696,13 +766,6 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         if ((AVS_DBG(p) & 32) && v0[0] != 0x7fc12345u) continue;  // experiment: TMEM reads only
         const long long ek3 = (AVS_DBG(p) & 128) ? clock64() : 0;
         float o[16];
-        if (K::colstack) {
-          // all four pool candidates of a (pooled position, channel) are in this lane: relu(max4 + b) == max(max3, v, -b) + b
-#pragma unroll
-          for (int c = 0; c < 16; ++c)
-            o[c] = fmax3(fmax3(__uint_as_float(v0[c]), __uint_as_float(v0[c + 16]), __uint_as_float(v1[c])),
-                         __uint_as_float(v1[c + 16]), -bias[c]) + bias[c];
-        } else {
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           // rows 2r, 2r+1: max of the two accumulators; columns 2wo, 2wo+1: exchange with the
@@ -716,7 +779,6 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
 #else
           o[c] = fmaxf(fmaxf(half ? hi : lo, got) + bias[c], 0.f);
 #endif
-        }
         }
         if ((AVS_DBG(p) & 64) && o[0] != 12345.678f) continue;  // experiment: no stores
         if (valid && !kToEmb) {
@@ -761,7 +823,6 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       printf("conv epilogue group %d block 0 (N=%d): total %lld cycles | wait acc_full %lld | tmem loads %lld | math+stores %lld | rest %lld\n",
              grp, p.N, ek_total, ek_full, ek_tmem, ek_work, ek_total - ek_full - ek_tmem - ek_work);
     }
-  
     }
   }
   tc_fence_before();
