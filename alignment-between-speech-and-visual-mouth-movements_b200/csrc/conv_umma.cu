@@ -56,11 +56,25 @@ namespace avs {
 #define AVS_VAR_L1_GROUPS 2   // a third group was measured (profiles/r02_variants_ab_3.txt): conv1 5.0 against 4.8 ms per 1024 clips
 #endif
 #ifndef AVS_VAR_L1_RING
-#define AVS_VAR_L1_RING 4     // plane slots of conv1's ring
+#define AVS_VAR_L1_RING 6     // plane slots of conv1's ring: the new plane of an item is requested three items ahead (4 slots = one item ahead: 4.05 -> 3.66 ms per 1024 clips)
 #endif
 // 4 control warps + 2 (conv1: 3) epilogue groups of 4 warps
 __host__ __device__ constexpr int epi_groups(int kind) { return kind == 0 /* KIND_L1 */ ? AVS_VAR_L1_GROUPS : 2; }
-__host__ __device__ constexpr int conv_threads(int kind) { return (4 + 4 * epi_groups(kind)) * 32; }
+// MMA-issuing warps per kind (the stages of the schedule go round them): warps 1 and 3, a third one sits behind the
+// epilogue warps
+#ifndef AVS_VAR_ISS_L1
+#define AVS_VAR_ISS_L1 3
+#endif
+#ifndef AVS_VAR_ISS_L2
+#define AVS_VAR_ISS_L2 2
+#endif
+#ifndef AVS_VAR_ISS_L3
+#define AVS_VAR_ISS_L3 2
+#endif
+__host__ __device__ constexpr int conv_issuers(int kind) {
+  return kind == 0 ? AVS_VAR_ISS_L1 : (kind == 1 ? AVS_VAR_ISS_L2 : (kind == 2 ? AVS_VAR_ISS_L3 : 2));
+}
+__host__ __device__ constexpr int conv_threads(int kind) { return (4 + 4 * epi_groups(kind) + (conv_issuers(kind) - 2)) * 32; }
 constexpr int kMaxUnits = 6;
 constexpr int kMaxRing = 8;
 constexpr int kMaxWStages = 8;
@@ -302,7 +316,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   uint64_t* acc_full = w_empty + kMaxWStages;   // [buffer * 2 + half]
   uint64_t* acc_empty = acc_full + 4;
   uint64_t* turn = acc_empty + 4;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(turn + 4);  // turn[x]: early token for issuer x, turn[2 + x]: final token
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(turn + 6);  // turn[x]: early token for issuer x, turn[kIss + x]: final token
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -319,6 +333,8 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   // arithmetic + stores and as much index / hand-over work per 32-column unit and warp).  A third group does not help:
   // conv1's four tiles do not divide by three, and its warps take issue slots from the MMA issuers.
   constexpr int kGroups = epi_groups(KIND);
+  constexpr int kIss = conv_issuers(KIND);
+  constexpr int kExtraIssuerWarp = 4 + 4 * kGroups;  // third issuer (kIss == 3)
   // Accumulator hand-over in halves (barriers [buffer * 2 + half]) only where the buffer cannot be doubled — conv3, whose
   // two tiles fill TMEM; the double-buffered kinds hand whole buffers over through the barriers of half 0.
   constexpr bool kHalves = AVS_VAR_HALVES && KIND == KIND_L3;
@@ -326,7 +342,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     for (int i = 0; i < p.ring; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 1);
     for (int i = 0; i < p.wstages; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
     for (int i = 0; i < 2 * p.NBUF; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 4 * kGroups);
-    for (int i = 0; i < 4; ++i) mbar_init(&turn[i], 1);
+    for (int i = 0; i < 6; ++i) mbar_init(&turn[i], 1);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<512>(s_tmem);
@@ -415,12 +431,13 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
                  &w_full[slot]);
       }
     }
-  } else if (warp == 1 || warp == 3) {
+  } else if (warp == 1 || warp == 3 || (kIss == 3 && warp == kExtraIssuerWarp)) {
     // ============================================================ MMA issuers
     // Both warps walk the whole schedule converged (slot and phase counters stay identical); issuer x owns every
     // other weight stage (global stage counter g, g & 1 == x).  For an owned stage: wait for its operands, then issue
     // it in two halves under the token protocol below.
-    const uint32_t x = warp >> 1;
+    const uint32_t x = warp == kExtraIssuerWarp ? 2u : static_cast<uint32_t>(warp >> 1);
+    const uint32_t nx = (x + 1 == kIss) ? 0u : x + 1;  // the issuer of the next stage
     const uint32_t idesc_n = umma_idesc_bf16(128, K::NB), idesc_w = umma_idesc_bf16(128, 2 * K::NB);
     const uint32_t units_lo = (smem_u32(s_units) & 0x3FFFFu) >> 4, w_lo = (smem_u32(s_w) & 0x3FFFFu) >> 4;
     const uint32_t unit_step = static_cast<uint32_t>(p.unit_slot_bytes) >> 4, stage_step = static_cast<uint32_t>(p.stage_bytes) >> 4;
@@ -453,7 +470,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         // plane ring: which of this unit's planes go back to the producer when the unit is done (conv1's single
         // stage spans all three planes); sequential ring: the unit's slot, always
         const uint32_t slot0 = K::reuse ? static_cast<uint32_t>((w.t + unit) % K::RING) : a_slot;
-        if ((g & 1) == x) {
+        if ((kIss == 2 ? (g & 1u) : g % 3u) == x) {
           const long long tk0 = (dbg & 16) ? clock64() : 0;
           if (!acc_ready0) {
             mbar_wait(&acc_empty[acc_buf * 2], acc_phase ^ 1);
@@ -497,12 +514,12 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
             for (int rep = 0; rep < ((dbg & 8) ? 2 : 1); ++rep)  // dbg 8: issue every MMA twice (tensor-vs-issue bound test)
               issue_half<KIND, 0>(nt, ab, bb, d_base, st == 0 && rep == 0, s_in_unit, idesc_n, idesc_w);
             if (kHalves && st == n_stages - 1) tc_commit(&acc_full[acc_buf * 2]);  // the item's first tiles are complete: the epilogue may start on them
-            tc_commit(&turn[x ^ 1]);
+            tc_commit(&turn[nx]);
             if (!acc_ready1) {  // the second half of the accumulator buffer is drained later than the first
               mbar_wait(&acc_empty[acc_buf * 2 + 1], acc_phase ^ 1);
               tc_fence_after();
             }
-            if (g != 0) mbar_wait_poll(&turn[2 + x], turn_phase);  // "final" token: its second half has completed
+            if (g != 0) mbar_wait_poll(&turn[kIss + x], turn_phase);  // "final" token: its second half has completed
             for (int rep = 0; rep < ((dbg & 8) ? 2 : 1); ++rep)
               issue_half<KIND, 1>(nt, ab, bb, d_base, st == 0 && rep == 0, s_in_unit, idesc_n, idesc_w);
             // commits before the final token: when the other issuer may pass this point of the schedule, every
@@ -521,7 +538,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
               }
             }
             if (st == n_stages - 1) tc_commit(&acc_full[acc_buf * 2 + (kHalves ? 1 : 0)]);
-            tc_commit(&turn[2 + (x ^ 1)]);
+            tc_commit(&turn[kIss + nx]);
           }
           __syncwarp();
           acc_ready1 = true;
@@ -556,7 +573,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       printf("conv issuer %u (hw warp slot %u) block %d (N=%d): total %lld cycles | operand waits %lld | turn wait %lld | issue+commit %lld | rest %lld\n",
              x, hw_warp, blockIdx.x, p.N, tk_total, tk_prep, tk_turn, tk_issue, tk_total - tk_prep - tk_turn - tk_issue);
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < kExtraIssuerWarp) {
     // ============================================================ epilogue
     if constexpr (K::colstack) {
       // conv1 (column-parity stacking): a lane owns one POOLED position of the tile and finds its four pool candidates in
@@ -1243,7 +1260,7 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
   L->chunks_per_unit = g.n_chunks / (n_units * L->unit_planes / 3);
   L->plane_slot_bytes = L->unit_planes * L->chunks_per_unit * 2 * static_cast<int>(arr_bytes);
   L->smem_bytes = static_cast<size_t>(L->ring) * L->plane_slot_bytes + static_cast<size_t>(region_full - L->region_pos) * 16 +
-                  static_cast<size_t>(L->wstages) * L->stage_bytes + (2 * kMaxRing + 2 * kMaxWStages + 12) * 8 + 16;
+                  static_cast<size_t>(L->wstages) * L->stage_bytes + (2 * kMaxRing + 2 * kMaxWStages + 14) * 8 + 16;
   if (L->smem_bytes > 232448 || L->ring > kMaxRing || L->wstages > kMaxWStages || n_units > kMaxUnits || L->NT != kNT ||
       n_stages != (first && !split ? 1 : n_units * kSPU) || wp.size() * 2 != static_cast<size_t>(L->n_stages) * L->stage_bytes || L->stage_bytes % 16 != 0) {
     set_error("umma layer config invalid: smem %zu stage_bytes %d n_stages %d units %d packed %zu", L->smem_bytes, L->stage_bytes,

@@ -18,7 +18,7 @@
 #include <map>
 #include <tuple>
 #include <vector>
-#include "common.cuh"
+#include "stcnn.cuh"
 
 namespace avs {
 
@@ -125,7 +125,9 @@ mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const in
                         const float* __restrict__ window, const float2* __restrict__ tw, const float2* __restrict__ tw2,
                         const int4* __restrict__ mel_tab, const float* __restrict__ mel_w, const float* __restrict__ dct_t,
                         float* __restrict__ logmel, float* __restrict__ frame_mfcc, float2* __restrict__ frame_range) {
-  __shared__ float2 s_z[SCHED ? kFftCtaFrames : kWarpFftWarps][32 * 33];
+  // one 32 x 33 float plane per warp (4.2 KB): the transposes move the real and the imaginary parts one after the other,
+  // so that twice as many of these one-warp CTAs fit into the shared memory the persistent conv kernels leave free
+  __shared__ float s_z[SCHED ? kFftCtaFrames : kWarpFftWarps][32 * 33];
   __shared__ int s_take;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int clip = blockIdx.y;
@@ -154,8 +156,11 @@ mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const in
     zslot = warp;
     u = blockIdx.x * kWarpFftWarps + warp;
   }
+  // (One CTA per frame on purpose.  A fixed grid of long-lived one-warp CTAs walking the frames with a grid stride was
+  // measured, profiles/r02_k1_grid.txt: the loop costs 168 registers instead of 95, alone it is slower — 5.75 against
+  // 4.78 us/clip at 20 CTAs per SM — and beside a conv CTA 4 CTAs per SM need 38 ms per 1024 clips against 21.5.)
   if (u >= n_unique) return;  // warp-uniform; no block barriers below
-  float2* z = s_z[zslot];
+  float* z = s_z[zslot];
   const float* x = audio + static_cast<size_t>(clip) * n_samples;
   const int4 fr = frames[u];
   float2 v[32];
@@ -183,30 +188,55 @@ mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const in
   fft32(v);  // over n1: v[i] = Y[n2 = lane][k1 = bitrev5(i)]
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
-    constexpr int dummy = 0;
-    (void)dummy;
     const int k1 = bitrev5(i);
-    float2 y = v[i];
-    if (k1 != 0) y = cmul(y, __ldg(tw + ((lane * k1) & (kHalf - 1))));  // W_1024^(n2 k1)
-    z[lane * 33 + k1] = y;
+    if (k1 != 0) v[i] = cmul(v[i], __ldg(tw + ((lane * k1) & (kHalf - 1))));  // W_1024^(n2 k1)
   }
+  // transpose (n2 = lane, k1) -> (k1 = lane, n2), real parts then imaginary parts through the same plane
+#pragma unroll
+  for (int i = 0; i < 32; ++i) z[lane * 33 + bitrev5(i)] = v[i].x;
   __syncwarp();
 #pragma unroll
-  for (int n2 = 0; n2 < 32; ++n2) v[n2] = z[n2 * 33 + lane];  // lane = k1
+  for (int n2 = 0; n2 < 32; ++n2) v[n2].x = z[n2 * 33 + lane];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) z[lane * 33 + bitrev5(i)] = v[i].y;
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) v[n2].y = z[n2 * 33 + lane];
   fft32(v);  // over n2: v[i] = Z[k1 + 32 * bitrev5(i)]
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 32; ++i) z[lane + 32 * bitrev5(i)] = v[i];  // natural order, flat [1024]
   __syncwarp();
   // split post-pass for the real transform.  With E = (Z[k] + conj Z[N/2-k]) / 2 and O = (Z[k] - conj Z[N/2-k]) / 2i,
   // X[k] = E + W^k O and X[N/2-k] = conj(E - W^k O): bins k and 1024 - k come from the same pair of loads and the same
   // complex product, so a lane takes k = lane + 32 i for i = 0..15 (k < 512) together with its mirror; k = 512 is its
   // own mirror (lane 0).
+  // (natural order, flat [1024]: again the real parts first, then the imaginary parts)
+  float zkx[16], znx[16], zky[16], zny[16], zmid_x = 0.f, zmid_y = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) z[lane + 32 * bitrev5(i)] = v[i].x;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int k = lane + 32 * i;
+    zkx[i] = z[k];
+    znx[i] = z[(kHalf - k) & (kHalf - 1)];
+  }
+  zmid_x = z[kHalf / 2];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) z[lane + 32 * bitrev5(i)] = v[i].y;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int k = lane + 32 * i;
+    zky[i] = z[k];
+    zny[i] = z[(kHalf - k) & (kHalf - 1)];
+  }
+  zmid_y = z[kHalf / 2];
   float pa[16], pb[16], pmid = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int k = lane + 32 * i;
-    const float2 zk = z[k], zn = z[(kHalf - k) & (kHalf - 1)];
+    const float2 zk = make_float2(zkx[i], zky[i]), zn = make_float2(znx[i], zny[i]);
     const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
     const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
     const float2 wo = cmul(__ldg(tw2 + k), o);
@@ -215,13 +245,13 @@ mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const in
     pb[i] = br * br + bi * bi;
   }
   if (lane == 0) {  // k = 512: Z[512] with itself, W^512 = -i
-    const float2 zk = z[kHalf / 2];
+    const float2 zk = make_float2(zmid_x, zmid_y);
     const float2 wo = cmul(__ldg(tw2 + kHalf / 2), make_float2(zk.y, 0.f));
     const float xr = zk.x + wo.x, xi = wo.y;
     pmid = xr * xr + xi * xi;
   }
   __syncwarp();
-  float* s_pow = reinterpret_cast<float*>(z);
+  float* s_pow = z;  // 1025 of the plane's 1056 floats
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     s_pow[lane + 32 * i] = pa[i];
@@ -566,8 +596,9 @@ extern "C" size_t avs_mfcc_workspace_bytes(const avs_mfcc_plan* p, int n_clips) 
          align_up(frames * sizeof(float2), 256);
 }
 
-extern "C" int avs_mfcc_sweep_debug(const avs_mfcc_plan* p, const float* audio, int n_clips, float* out_stats,
-                                    float* out_mfcc, void* workspace, size_t workspace_bytes, void* stream) {
+// after_logmel (nullable) is recorded on the stream between the log-mel kernel and the statistics kernel
+int avs::mfcc_sweep_impl(const avs_mfcc_plan* p, const float* audio, int n_clips, float* out_stats, float* out_mfcc,
+                         void* workspace, size_t workspace_bytes, void* stream, cudaEvent_t after_logmel) {
   AVS_REQUIRE(p && audio && out_stats && workspace, "null argument");
   if (n_clips <= 0) return AVS_OK;
   if (workspace_bytes < avs_mfcc_workspace_bytes(p, n_clips)) {
@@ -599,12 +630,16 @@ extern "C" int avs_mfcc_sweep_debug(const avs_mfcc_plan* p, const float* audio, 
 #endif
       {
         const dim3 g1(cdiv(p->n_unique, kWarpFftWarps), nc);
+#ifdef AVS_VAR_K1_CARVE  // experiment: K1 alone with the L1 the conv kernels leave it (shared-memory carve-out at its maximum)
+        cudaFuncSetAttribute(mfcc_logmel_warp_kernel<false, 20>, cudaFuncAttributePreferredSharedMemoryCarveout, AVS_VAR_K1_CARVE);
+#endif
         if (p->n_mfcc <= 20) mfcc_logmel_warp_kernel<false, 20><<<g1, 32 * kWarpFftWarps, 0, st>>>(AVS_LOGMEL_ARGS);
         else mfcc_logmel_warp_kernel<false, kMaxQ><<<g1, 32 * kWarpFftWarps, 0, st>>>(AVS_LOGMEL_ARGS);
       }
 #undef AVS_LOGMEL_ARGS
     }
     AVS_LAUNCHED();
+    if (after_logmel) AVS_CUDA(cudaEventRecord(after_logmel, st));
     dim3 g2(p->n_shifts, nc);
     ProfScope ps2(PROF_MFCC_STATS, st);
     if (p->n_mfcc <= 20) {
@@ -623,9 +658,14 @@ extern "C" int avs_mfcc_sweep_debug(const avs_mfcc_plan* p, const float* audio, 
   return AVS_OK;
 }
 
+extern "C" int avs_mfcc_sweep_debug(const avs_mfcc_plan* p, const float* audio, int n_clips, float* out_stats,
+                                    float* out_mfcc, void* workspace, size_t workspace_bytes, void* stream) {
+  return avs::mfcc_sweep_impl(p, audio, n_clips, out_stats, out_mfcc, workspace, workspace_bytes, stream, nullptr);
+}
+
 extern "C" int avs_mfcc_stats_sweep(const avs_mfcc_plan* p, const float* audio, int n_clips, float* out_stats,
                                     void* workspace, size_t workspace_bytes, void* stream) {
-  return avs_mfcc_sweep_debug(p, audio, n_clips, out_stats, nullptr, workspace, workspace_bytes, stream);
+  return avs::mfcc_sweep_impl(p, audio, n_clips, out_stats, nullptr, workspace, workspace_bytes, stream, nullptr);
 }
 
 extern "C" __attribute__((visibility("hidden"))) int avs_mfcc_plan_nshifts_internal(const avs_mfcc_plan* p, int* K, int* n_mfcc, int* n_samples) {

@@ -128,7 +128,7 @@ extern "C" size_t avs_stcnn_workspace_bytes(const avs_stcnn* net, int n_clips) {
 // B see the same buffer placement; pads_clean: the caller guarantees that the padding positions of the
 // parity-plane buffers are still zero (zeroed once, and kernels only ever write data positions).
 int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool frames_u8, int B, int cap_clips, bool pads_clean,
-                            cudaEvent_t after_layer1, float* out_emb, float* out_vstats, float* out_pool1, float* out_pool2, void* workspace,
+                            const StcnnHooks& hooks, float* out_emb, float* out_vstats, float* out_pool1, float* out_pool2, void* workspace,
                             size_t workspace_bytes, void* stream) {
   AVS_REQUIRE(net && frames_any && workspace, "null argument");
   AVS_REQUIRE(out_emb || out_vstats, "nothing to compute");
@@ -142,6 +142,13 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
   }
   float* emb = out_emb ? out_emb : w.emb;
   int rc;
+  auto after_l1 = [&]() -> int {
+    if (hooks.after_layer1) AVS_CUDA(cudaEventRecord(hooks.after_layer1, st));
+    return AVS_OK;
+  };
+  // (the host hook runs once layer 2 has been ENQUEUED: grids are dispatched in submission order, and the side stream's
+  // FFT grid of 95 000 CTAs submitted ahead of conv2 keeps conv2's CTAs off the SMs until it has been dispatched whole)
+  auto after_l2 = [&]() -> int { return hooks.on_layer1 ? hooks.on_layer1(hooks.on_layer1_arg) : AVS_OK; };
   if (net->precision == AVS_PREC_FP32) {
     const float* frames = static_cast<const float*>(frames_any);
     if (frames_u8) {
@@ -159,10 +166,12 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
       if ((rc = conv_pool_ffma(f, net->w[0], net->b[0], p1, nb, 1, 32, AVS_T, 50, 100, 5, 5, 32LL * AVS_T * 1250,
                                AVS_T * 1250LL, 1250, st)))
         return rc;
-      if (b0 == 0 && after_layer1) AVS_CUDA(cudaEventRecord(after_layer1, st));
+      if (b0 == 0 && (rc = after_l1())) return rc;
       if ((rc = conv_pool_ffma(p1, net->w[1], net->b[1], p2, nb, 32, 64, AVS_T, 25, 50, 5, 5, 64LL * AVS_T * 300,
                                AVS_T * 300LL, 300, st)))
         return rc;
+      if (b0 == 0 && (rc = after_l2())) return rc;
+      if (b0 == 0 && hooks.before_layer3) AVS_CUDA(cudaStreamWaitEvent(st, hooks.before_layer3, 0));
       // layer 3 writes the permuted (B, T, C*72) embedding directly (model.py:81-82)
       if ((rc = conv_pool_ffma(p2, net->w[2], net->b[2], emb + static_cast<size_t>(b0) * AVS_T * AVS_EMB, nb, 64, 96,
                                AVS_T, 12, 25, 3, 3, static_cast<long long>(AVS_T) * AVS_EMB, 72, AVS_EMB, st)))
@@ -190,8 +199,10 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
         eo.mode = 1;
         eo.emb = emb;
       }
+      if (l == 2 && hooks.before_layer3) AVS_CUDA(cudaStreamWaitEvent(st, hooks.before_layer3, 0));
       if ((rc = umma_conv_forward(net->L[l], w.act[l], eo, B, net->n_sms, st))) return rc;
-      if (l == 0 && after_layer1) AVS_CUDA(cudaEventRecord(after_layer1, st));
+      if (l == 0 && (rc = after_l1())) return rc;
+      if (l == 1 && (rc = after_l2())) return rc;
     }
     if (out_pool1 && (rc = umma_unpack_act(w.act[1], out_pool1, net->L[1].g, split, 32, B, st))) return rc;
     if (out_pool2 && (rc = umma_unpack_act(w.act[2], out_pool2, net->L[2].g, split, 64, B, st))) return rc;
@@ -203,13 +214,13 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
 extern "C" int avs_stcnn_forward_debug(const avs_stcnn* net, const float* frames, int B, float* out_emb,
                                        float* out_vstats, float* out_pool1, float* out_pool2, void* workspace,
                                        size_t workspace_bytes, void* stream) {
-  return stcnn_forward_impl(net, frames, false, B, B, false, nullptr, out_emb, out_vstats, out_pool1, out_pool2, workspace,
+  return stcnn_forward_impl(net, frames, false, B, B, false, StcnnHooks{}, out_emb, out_vstats, out_pool1, out_pool2, workspace,
                             workspace_bytes, stream);
 }
 
 extern "C" int avs_stcnn_forward_u8(const avs_stcnn* net, const uint8_t* frames, int n_clips, float* out_emb, float* out_vstats,
                                     void* workspace, size_t workspace_bytes, void* stream) {
-  return stcnn_forward_impl(net, frames, true, n_clips, n_clips, false, nullptr, out_emb, out_vstats, nullptr, nullptr, workspace,
+  return stcnn_forward_impl(net, frames, true, n_clips, n_clips, false, StcnnHooks{}, out_emb, out_vstats, nullptr, nullptr, workspace,
                             workspace_bytes, stream);
 }
 

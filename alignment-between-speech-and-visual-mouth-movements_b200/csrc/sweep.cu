@@ -28,7 +28,7 @@ struct avs_sweep {
   float* d_scores_all = nullptr; int32_t* d_best_all = nullptr;  // host entry point results
   int cap = 0;
   cudaStream_t side = nullptr, copy = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_last = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_logmel = nullptr, ev_join = nullptr, ev_last = nullptr;
   bool has_last = false;
   // host entry points: double-buffered device inputs + pinned staging (frames slots hold f32 or u8)
   void* d_frames[2] = {nullptr, nullptr};
@@ -71,6 +71,7 @@ extern "C" int avs_sweep_create(const avs_stcnn* net, const avs_mfcc_plan* plan,
   ck(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
   ck(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
   ck(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+  ck(cudaEventCreateWithFlags(&s->ev_logmel, cudaEventDisableTiming));
   ck(cudaEventCreateWithFlags(&s->ev_last, cudaEventDisableTiming));
   if (rc) {
     avs_sweep_destroy(s);
@@ -96,6 +97,7 @@ extern "C" void avs_sweep_destroy(avs_sweep* s) {
   if (s->main) cudaStreamDestroy(s->main);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
   if (s->ev_join) cudaEventDestroy(s->ev_join);
+  if (s->ev_logmel) cudaEventDestroy(s->ev_logmel);
   if (s->ev_last) cudaEventDestroy(s->ev_last);
   delete s;
 }
@@ -134,30 +136,45 @@ static int ensure_capacity(avs_sweep* s, int n_clips, cudaStream_t st) {
 
 // statistics of one chunk (n <= s->chunk clips starting at clip c0); audio branch on the side stream, joined back
 // into `st` before returning.
+struct AudioBranch {
+  avs_sweep* s; const float* audio; float* ast; int n;
+};
+// host hook of the STCNN, called when layer 1 has been enqueued (and ev_fork recorded behind it): enqueue K1 on the side stream
+static int enqueue_audio_branch(void* arg) {
+  const AudioBranch* a = static_cast<const AudioBranch*>(arg);
+  avs_sweep* s = a->s;
+  AVS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
+  const int rc = mfcc_sweep_impl(s->plan, a->audio, a->n, a->ast, nullptr, s->ws_mfcc, s->ws_mfcc_bytes, s->side, s->ev_logmel);
+  AVS_CUDA(cudaEventRecord(s->ev_join, s->side));
+  return rc;
+}
+
 static int run_chunk(avs_sweep* s, const void* frames, bool frames_u8, const float* audio, int c0, int n, cudaStream_t st) {
   int rc;
   float* vst = s->vstats + static_cast<size_t>(c0) * AVS_VSTATS;
   float* ast = s->astats + static_cast<size_t>(c0) * s->K * 2 * s->n_mfcc;
-  // The audio branch forks AFTER layer 1: conv1 is the one layer that is CUDA-core sensitive (thin MMAs,
-  // heavy epilogue), while conv2/conv3 are tensor/smem bound and leave the ALUs to the FFT kernels.
+  // The audio branch forks AFTER layer 1 — conv1 is the one layer that is CUDA-core sensitive (thin MMAs, heavy
+  // epilogue) — and its FFT kernel shares the SMs with conv2 only: conv3 waits for it (ev_logmel) and runs beside the
+  // light statistics kernel.  Once conv2 is done the FFT kernel has the whole GPU and finishes its last frames at four
+  // times the speed, while beside conv3 it would halve conv3 (profiles/r02_k1_grid.txt).
+  AudioBranch ab{s, audio, ast, n};
+  StcnnHooks hooks;
+  hooks.after_layer1 = s->ev_fork;
+  hooks.on_layer1 = enqueue_audio_branch;
+  hooks.on_layer1_arg = &ab;
+  hooks.before_layer3 = s->ev_logmel;
 #ifdef AVS_EXPERIMENTS
-  static const int audio_mode = env_knob("AVS_AUDIO_MODE", 0);  // 1 serial, 2 fork at chunk start
+  static const int audio_mode = env_knob("AVS_AUDIO_MODE", 0);  // 1 serial, 2 conv3 does not wait for the FFT kernel
   if (audio_mode == 1) {
-    if ((rc = stcnn_forward_impl(s->net, frames, frames_u8, n, s->chunk, true, nullptr, nullptr, vst, nullptr, nullptr, s->ws_stcnn, s->ws_stcnn_bytes, st)))
+    if ((rc = stcnn_forward_impl(s->net, frames, frames_u8, n, s->chunk, true, StcnnHooks{}, nullptr, vst, nullptr, nullptr, s->ws_stcnn, s->ws_stcnn_bytes, st)))
       return rc;
     return avs_mfcc_stats_sweep(s->plan, audio, n, ast, s->ws_mfcc, s->ws_mfcc_bytes, st);
   }
-  if (audio_mode == 2) AVS_CUDA(cudaEventRecord(s->ev_fork, st));
-  cudaEvent_t fork_after_l1 = audio_mode == 2 ? nullptr : s->ev_fork;
-#else
-  cudaEvent_t fork_after_l1 = s->ev_fork;
+  if (audio_mode == 2) hooks.before_layer3 = nullptr;
 #endif
-  if ((rc = stcnn_forward_impl(s->net, frames, frames_u8, n, s->chunk, true, fork_after_l1, nullptr, vst, nullptr, nullptr,
+  if ((rc = stcnn_forward_impl(s->net, frames, frames_u8, n, s->chunk, true, hooks, nullptr, vst, nullptr, nullptr,
                                s->ws_stcnn, s->ws_stcnn_bytes, st)))
     return rc;
-  AVS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
-  if ((rc = avs_mfcc_stats_sweep(s->plan, audio, n, ast, s->ws_mfcc, s->ws_mfcc_bytes, s->side))) return rc;
-  AVS_CUDA(cudaEventRecord(s->ev_join, s->side));
   AVS_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
   return AVS_OK;
 }
