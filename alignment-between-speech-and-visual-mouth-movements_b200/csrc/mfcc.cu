@@ -203,35 +203,29 @@ mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const in
   __syncwarp();
 #pragma unroll
   for (int n2 = 0; n2 < 32; ++n2) v[n2].y = z[n2 * 33 + lane];
-  fft32(v);  // over n2: v[i] = Z[k1 + 32 * bitrev5(i)]
-  __syncwarp();
+  fft32(v);  // over n2: v[i] = Z[k1 + 32 * bitrev5(i)], k1 = lane
   // split post-pass for the real transform.  With E = (Z[k] + conj Z[N/2-k]) / 2 and O = (Z[k] - conj Z[N/2-k]) / 2i,
-  // X[k] = E + W^k O and X[N/2-k] = conj(E - W^k O): bins k and 1024 - k come from the same pair of loads and the same
+  // X[k] = E + W^k O and X[N/2-k] = conj(E - W^k O): bins k and 1024 - k come from the same pair of values and the same
   // complex product, so a lane takes k = lane + 32 i for i = 0..15 (k < 512) together with its mirror; k = 512 is its
-  // own mirror (lane 0).
-  // (natural order, flat [1024]: again the real parts first, then the imaginary parts)
-  float zkx[16], znx[16], zky[16], zny[16], zmid_x = 0.f, zmid_y = 0.f;
+  // own mirror (lane 0).  Z[k] is this lane's register bitrev5(i); the mirror Z[1024 - k] = Z[(32 - lane) + 32 (31 - i)]
+  // is register bitrev5(31 - i) of lane 32 - lane — one shuffle per component — except in lane 0, whose mirrors
+  // Z[32 (32 - i)] are its own registers: no second pass through shared memory (whose pipe the tensor core of a
+  // co-resident conv CTA keeps 80 % busy).
+  float zkx[16], znx[16], zky[16], zny[16];
+  {
+    const int src = (32 - lane) & 31;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) z[lane + 32 * bitrev5(i)] = v[i].x;
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int k = lane + 32 * i;
-    zkx[i] = z[k];
-    znx[i] = z[(kHalf - k) & (kHalf - 1)];
+    for (int i = 0; i < 16; ++i) {
+      const float2 own = v[bitrev5(i)];
+      const float2 far = v[bitrev5(31 - i)];                 // what lane 32 - lane needs from this lane for the same i
+      const float2 self = v[bitrev5((32 - i) & 31)];         // lane 0: Z[32 (32 - i)]
+      const float sx = __shfl_sync(0xffffffffu, far.x, src), sy = __shfl_sync(0xffffffffu, far.y, src);
+      zkx[i] = own.x; zky[i] = own.y;
+      znx[i] = lane == 0 ? self.x : sx;
+      zny[i] = lane == 0 ? self.y : sy;
+    }
   }
-  zmid_x = z[kHalf / 2];
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 32; ++i) z[lane + 32 * bitrev5(i)] = v[i].y;
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int k = lane + 32 * i;
-    zky[i] = z[k];
-    zny[i] = z[(kHalf - k) & (kHalf - 1)];
-  }
-  zmid_y = z[kHalf / 2];
+  const float zmid_x = v[bitrev5(16)].x, zmid_y = v[bitrev5(16)].y;  // Z[512] (lane 0)
   float pa[16], pb[16], pmid = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {

@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call: the round's ncu evidence.  Every profiled command first runs plain and must exit 0.
 #   launches.csv          every launch of a short bench run with its device time
-#   conv2_full.ncu-rep    ncu --set full of the layer-2 conv kernel, 64 clips
+#   conv_full.ncu-rep     ncu --set full (with source) of the three conv kernels of one forward, 64 clips
 #   all_kernels.ncu-rep   ncu --set full of one launch of every kernel of the path, 16 clips
 set -u
 mkdir -p gpurun_out
@@ -11,8 +11,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 echo "launch list rc=$?"
 export PROF_CLIPS=64
 python tools/prof_conv.py > gpurun_out/plain_conv.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 4 -c 1 -f -o gpurun_out/conv2_full python tools/prof_conv.py > gpurun_out/ncu_conv2.log 2>&1
-echo "conv2 full rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 3 -c 3 -f -o gpurun_out/conv_full python tools/prof_conv.py > gpurun_out/ncu_conv2.log 2>&1
+echo "conv1/conv2/conv3 full rc=$?"
 export PROF_CLIPS=16
 python tools/prof_sweep.py > gpurun_out/plain_sweep.log 2>&1
 rc=$?
