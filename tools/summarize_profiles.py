@@ -4,6 +4,7 @@
 """
 import collections
 import csv
+import re
 import subprocess
 import sys
 
@@ -33,7 +34,7 @@ print(open(f"profiles/{tag}_launches.txt").read())
 
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 r = list(csv.reader(out.splitlines()))
-hdr, units, vals = r[0], r[1], r[2]
+hdr, units = r[0], r[1]
 keep = ["Kernel Name", "gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__grid_size", "launch__block_size",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
@@ -44,18 +45,23 @@ keep = ["Kernel Name", "gpu__time_duration.sum", "sm__cycles_elapsed.max", "laun
         "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_tensor.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum"]
+GFLOP = {"0": 1.8, "1": 28.8, "2": 7.46}  # algorithmic GFLOP per clip of the three layers
 with open(f"profiles/{tag}_conv2_ncu_full.txt", "w") as f:
-    f.write(f"# ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 4 -c 1 python tools/prof_conv.py\n")
-    f.write(f"# layer-2 conv_umma_kernel, {clips} clips in the launch (PROF_CLIPS), bf16\n")
-    d = {}
-    for h, u, v in zip(hdr, units, vals):
-        if h in keep:
-            f.write(f"{h:95s} {v} {u}\n")
-            d[h] = (v, u)
-    try:
-        rd, wr = float(d["dram__bytes_read.sum"][0].replace(",", "")), float(d["dram__bytes_write.sum"][0].replace(",", ""))
-        f.write(f"# derived: DRAM traffic per launch = {rd + wr:.1f} {d['dram__bytes_read.sum'][1]} = {(rd + wr) / clips:.2f} per clip; "
-                f"algorithmic 28.8 GFLOP/clip\n")
-    except Exception as e:
-        f.write(f"# derived: n/a ({e})\n")
+    f.write(f"# ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 3 -c 3 python tools/prof_conv.py\n")
+    f.write(f"# the three conv_umma_kernel launches of one STCNN forward (layer 1, 2, 3), {clips} clips per launch (PROF_CLIPS), bf16; "
+            f"layer 2 is the roofline kernel of bench.py\n")
+    for vals in r[2:]:
+        d = {}
+        f.write("\n")
+        for h, u, v in zip(hdr, units, vals):
+            if h in keep:
+                f.write(f"{h:95s} {v} {u}\n")
+                d[h] = (v, u)
+        try:
+            rd, wr = float(d["dram__bytes_read.sum"][0].replace(",", "")), float(d["dram__bytes_write.sum"][0].replace(",", ""))
+            kind = re.search(r"<(?:\(int\))?(\d)>", d["Kernel Name"][0]).group(1)
+            f.write(f"# derived: DRAM traffic per launch = {rd + wr:.1f} {d['dram__bytes_read.sum'][1]} = {(rd + wr) / clips:.2f} per clip; "
+                    f"algorithmic {GFLOP[kind]} GFLOP/clip\n")
+        except Exception as e:
+            f.write(f"# derived: n/a ({e})\n")
 print(open(f"profiles/{tag}_conv2_ncu_full.txt").read())
