@@ -20,19 +20,19 @@
 //     are plain sub-ranges of it) — KH+1 fetches of A per filter column instead of 2*KH;
 //   * a tile's halo'd input is one contiguous run per (chunk, parity): plain cp.async.bulk.
 //
-// Kernel structure: persistent CTAs (one per SM, each walking one contiguous span of work items), 12 warps:
+// Kernel structure: persistent CTAs (one per SM, each walking one contiguous span of work items), 12 warps (conv1: 13):
 //   warp 0  lane 0 : A producer   — bulk-copies input planes into a ring of plane slots (bf16 kinds: only the plane the
 //                                   previous item did not have; split kinds: the item's three units)
 //   warp 2  lane 0 : B producer   — bulk-copies weight stages (bf16: one filter column, split: one filter row)
-//   warps 1 and 3  : MMA issuers  — take the weight stages of the schedule in turn (one elected lane each issues
+//   warps 1 and 3  : MMA issuers  — (conv1: and warp 12) take the weight stages of the schedule in turn (one elected lane each issues
 //                                   tcgen05.mma into TMEM): the tensor pipe accepts an MMA only about one
 //                                   instruction ahead of the one executing (tools/umma_rate.cu), so everything an
 //                                   issuer does between two stages — barrier waits, address set-up, commits —
 //                                   would idle it; with two issuers one prepares while the other issues
 //   warp 2         : TMEM allocator
 //   warps 4..11    : epilogue     — two groups of four warps: tcgen05.ld, pool, bias, ReLU, bf16 (hi/lo) pack, store
-// mbarrier rings: a_full/a_empty[RING], w_full/w_empty[WSTAGES], acc_full/acc_empty[NBUF][2 halves]; turn[4] are the early
-// and final hand-over tokens between the two issuer warps.  An accumulator buffer is handed over in the two HALVES the
+// mbarrier rings: a_full/a_empty[RING], w_full/w_empty[WSTAGES], acc_full/acc_empty[NBUF][2 halves]; turn[2 * issuers] are the
+// early and final hand-over tokens between the issuer warps (a stage's tokens come from the stage before it).  An accumulator buffer is handed over in the two HALVES the
 // issuers write separately (first / second half of the item's tiles): the epilogue starts on the first tiles while the
 // last stage still runs on the others, and the issuers restart on the first tiles while the epilogue drains the rest —
 // this is what overlaps the TMEM read-out (64 B/cycle per SM: 1536 cycles per conv3 tile) with tensor work for the

@@ -146,8 +146,8 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
     if (hooks.after_layer1) AVS_CUDA(cudaEventRecord(hooks.after_layer1, st));
     return AVS_OK;
   };
-  // (the host hook runs once layer 2 has been ENQUEUED: grids are dispatched in submission order, and the side stream's
-  // FFT grid of 95 000 CTAs submitted ahead of conv2 keeps conv2's CTAs off the SMs until it has been dispatched whole)
+  // (the host hook runs once layer 2 has been enqueued, so that conv2's grid is submitted ahead of the side stream's FFT
+  // grid of 95 000 one-warp CTAs — the order the two have always been measured in)
   auto after_l2 = [&]() -> int { return hooks.on_layer1 ? hooks.on_layer1(hooks.on_layer1_arg) : AVS_OK; };
   if (net->precision == AVS_PREC_FP32) {
     const float* frames = static_cast<const float*>(frames_any);
