@@ -58,6 +58,8 @@ sweep_score_kernel(const float* __restrict__ hv, const float* __restrict__ astat
 // each CTA stages W1a^T once, then loops over clips; the 8 warps of a CTA take different shifts of the clip
 // (lane l owns hidden units l, l+32, ...: conflict-free shared-memory reads, a_k values broadcast), so there
 // is no block-wide reduction per shift and small batches no longer serialise 41 reductions per clip.
+// HPL > 0: hidden == 32 * HPL and n_shifts <= 8 * SPW, register-blocked inner loops; HPL == 0: any shape
+template <int HPL, int SPW>
 __global__ void __launch_bounds__(256)
 sweep_score_persistent_kernel(const float* __restrict__ hv, const float* __restrict__ astats, int n_clips, int n_shifts,
                               int a_dim, const float* __restrict__ w1a, int ldw, const float* __restrict__ w2,
@@ -80,6 +82,49 @@ sweep_score_persistent_kernel(const float* __restrict__ hv, const float* __restr
     for (int i = tid; i < n_shifts * a_dim; i += 256) s_a[i] = a[i];
     __syncthreads();
     const float* hrow = hv + static_cast<size_t>(clip) * hidden;
+    if (HPL > 0) {
+      // register-blocked: the warp's SPW shifts (warp, warp + 8, ...) at once, lane l owning hidden units l + 32 j —
+      // per input i one read of each a_k[i] (broadcast) and of each W1a[i][h], SPW x HPL FMAs.  Every (shift, hidden)
+      // accumulator still sees hv + the a_dim products in ascending i, and the reductions over the lane's hidden units
+      // and over the lanes run in the order of the plain loop below: the same bits, an eighth of the shared-memory reads.
+      float acc[SPW][HPL > 0 ? HPL : 1];
+#pragma unroll
+      for (int j = 0; j < HPL; ++j) {
+        const float h0 = __ldg(hrow + lane + 32 * j);
+#pragma unroll
+        for (int s = 0; s < SPW; ++s) acc[s][j] = h0;
+      }
+      int kk[SPW];
+#pragma unroll
+      for (int s = 0; s < SPW; ++s) kk[s] = min(warp + 8 * s, n_shifts - 1);  // surplus slots repeat the last shift (not stored)
+      for (int i = 0; i < a_dim; ++i) {
+        float av[SPW];
+#pragma unroll
+        for (int s = 0; s < SPW; ++s) av[s] = s_a[kk[s] * a_dim + i];
+#pragma unroll
+        for (int j = 0; j < HPL; ++j) {
+          const float w = s_w[i * pitch + lane + 32 * j];
+#pragma unroll
+          for (int s = 0; s < SPW; ++s) acc[s][j] = fmaf(w, av[s], acc[s][j]);
+        }
+      }
+      float w2v[HPL > 0 ? HPL : 1];
+#pragma unroll
+      for (int j = 0; j < HPL; ++j) w2v[j] = __ldg(w2 + lane + 32 * j);
+#pragma unroll
+      for (int s = 0; s < SPW; ++s) {
+        float part = 0.f;
+#pragma unroll
+        for (int j = 0; j < HPL; ++j) part = fmaf(fmaxf(acc[s][j], 0.f), w2v[j], part);
+        part = warp_sum(part);
+        const int k = warp + 8 * s;
+        if (lane == 0 && k < n_shifts) {
+          const float sc = 1.0f / (1.0f + expf(-(part + bias2)));
+          s_sc[k] = sc;
+          out_scores[static_cast<size_t>(clip) * n_shifts + k] = sc;
+        }
+      }
+    } else
     for (int k = warp; k < n_shifts; k += 8) {
       float part = 0.f;
       for (int h = lane; h < hidden; h += 32) {
@@ -199,10 +244,11 @@ extern "C" int avs_sweep_score(const float* vstats, const float* astats, int n_c
     int dev = 0, n_sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
-    AVS_CUDA(cudaFuncSetAttribute(sweep_score_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_p)));
     const int grid = std::min(n_clips, n_sms * (sm_p <= 100 * 1024 ? 2 : 1));
-    sweep_score_persistent_kernel<<<grid, 256, sm_p, st>>>(hv, astats, n_clips, n_shifts, a_dim, w1 + v_dim, ld, w2, b2,
-                                                           hidden, out_scores, out_best);
+    // the detector of the reference (hidden 512) with up to 48 shifts takes the register-blocked instantiation
+    auto kern = (hidden == 512 && n_shifts <= 48) ? sweep_score_persistent_kernel<16, 6> : sweep_score_persistent_kernel<0, 1>;
+    AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_p)));
+    kern<<<grid, 256, sm_p, st>>>(hv, astats, n_clips, n_shifts, a_dim, w1 + v_dim, ld, w2, b2, hidden, out_scores, out_best);
   } else {
     sweep_score_kernel<<<n_clips, 128, sm, st>>>(hv, astats, n_shifts, a_dim, w1 + v_dim, ld, w2, b2, hidden,
                                                  out_scores, out_best);

@@ -18,12 +18,14 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
   A += static_cast<size_t>(blockIdx.z) * K;
   B += static_cast<size_t>(blockIdx.z) * K;
   C += static_cast<size_t>(blockIdx.z) * M * ldc;
-  __shared__ float As[2][BK][BM + 4];
-  __shared__ float Bs[2][BK][BN + 4];
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int lr = tid >> 1, lk = (tid & 1) * 4;  // each thread stages one float4 of A and one of B per k-tile
-  const int tx = tid & 15, ty = tid >> 4;       // 16 x 16 threads, 8 x 8 outputs each (strided by 16)
+  // 16 x 16 threads, 8 x 8 outputs each: rows ty*4 .. +3 and 64 + ty*4 .. +3, columns likewise — two 128-bit shared-memory
+  // loads per operand and k instead of eight scalar ones (the kernel was LDS-issue bound: 16 LDS per 64 FMA)
+  const int tx = tid & 15, ty = tid >> 4;
   float acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -47,11 +49,10 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
     }
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      float a[8], b[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = As[buf][k][ty + 16 * i];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) b[j] = Bs[buf][k][tx + 16 * j];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]), a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]), b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -67,11 +68,11 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int m = m0 + ty + 16 * i;
+    const int m = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
     if (m >= M) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int n = n0 + tx + 16 * j;
+      const int n = n0 + (j >> 2) * 64 + tx * 4 + (j & 3);
       if (n < N) C[static_cast<size_t>(m) * ldc + n] = acc[i][j] + (bias ? bias[n] : 0.f);
     }
   }
