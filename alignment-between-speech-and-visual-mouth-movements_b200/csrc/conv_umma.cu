@@ -104,16 +104,26 @@ struct ConvKernelParams {
 
 // Work items in (clip, tile set, t) order: a CTA takes ONE contiguous span, so that consecutive items are consecutive
 // time steps of the same tile region and two of an item's three input planes are already in shared memory.  Spans are
-// balanced by cost (tiles per item: the last tile set of a plane may be partial), all roles of a CTA walk the same span.
-// first item (in (clip, tile set, t) order) whose cost prefix is >= x; cost of an item = its tile count
+// balanced by cost, all roles of a CTA walk the same span.  Cost of an item: 5 per tile, 7 per tile for the partial last
+// tile set of a plane — measured (clock64 per item, conv2: 22 270 cycles per two-tile item, 15 620 per single-tile item):
+// with one tile the two halves of a stage cannot overlap, the tensor pipe drains at every hand-over between the issuers.
+// Balancing by tile count alone left the CTAs whose span holds the single-tile items 13 % behind the others.
+__host__ __device__ inline int item_cost(int nt, int NT) { return nt * (nt == NT ? 5 : 7); }
+__host__ __device__ inline long long clip_cost(int T, int n_tiles, int n_tilesets, int NT) {
+  long long c = 0;
+  for (int ts = 0; ts < n_tilesets; ++ts) c += static_cast<long long>(T) * item_cost((NT < n_tiles - ts * NT) ? NT : n_tiles - ts * NT, NT);
+  return c;
+}
+// first item (in (clip, tile set, t) order) whose cost prefix is >= x
 __host__ __device__ inline int span_item_at_cost(int T, int n_tiles, int n_tilesets, int NT, long long x) {
-  const int per_clip = T * n_tiles;
+  const long long per_clip = clip_cost(T, n_tiles, n_tilesets, NT);
   const int b = static_cast<int>(x / per_clip);
-  int rem = static_cast<int>(x % per_clip);
+  long long rem = x % per_clip;
   const int base = b * n_tilesets * T;
   for (int ts = 0; ts < n_tilesets; ++ts) {
-    const int nt = (NT < n_tiles - ts * NT) ? NT : n_tiles - ts * NT, row = T * nt;
-    if (rem < row) return base + ts * T + (rem + nt - 1) / nt;
+    const int c = item_cost((NT < n_tiles - ts * NT) ? NT : n_tiles - ts * NT, NT);
+    const long long row = static_cast<long long>(T) * c;
+    if (rem < row) return base + ts * T + static_cast<int>((rem + c - 1) / c);
     rem -= row;
   }
   return base + n_tilesets * T;
@@ -125,7 +135,7 @@ struct ItemWalk {
     return span_item_at_cost(p.T, p.n_tiles, p.n_tilesets, p.NT, x);
   }
   __device__ __forceinline__ void init(const ConvKernelParams& p) {
-    const long long total = static_cast<long long>(p.n_items / p.n_tilesets) * p.n_tiles;  // clips * T * tiles per plane
+    const long long total = static_cast<long long>(p.n_items / p.n_tilesets / p.T) * clip_cost(p.T, p.n_tiles, p.n_tilesets, p.NT);
     first = item_at_cost(p, total * blockIdx.x / gridDim.x);
     last = item_at_cost(p, total * (blockIdx.x + 1) / gridDim.x);
     item = first;
@@ -455,8 +465,16 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     long long tk_prep = 0, tk_turn = 0, tk_issue = 0, tk_total = clock64();  // dbg 16: issuer time split
     ItemWalk w;
     w.init(p);
+    long long tk_item = tk_total, tk_by_nt[2] = {0, 0};  // dbg 16: time between item starts, by the item's tile count (1 / more)
+    int n_by_nt[2] = {0, 0}, nt_prev = 0;
     for (; w.valid(); w.next()) {
       const int nt = min(NT, n_tiles - w.ts * NT);
+      if (dbg & 16) {
+        const long long now = clock64();
+        if (nt_prev) tk_by_nt[nt_prev > 1] += now - tk_item, n_by_nt[nt_prev > 1] += 1;
+        tk_item = now;
+        nt_prev = nt;
+      }
       bool acc_ready0 = false, acc_ready1 = false;  // this issuer has seen the accumulator halves released by the epilogue
       const uint32_t d_base = tmem_base + acc_buf * (NT * 2 * K::ACC);
       const bool cont_next = w.continues_next();
@@ -566,12 +584,14 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       }
       if (++acc_buf == nbuf) acc_buf = 0, acc_phase ^= 1;
     }
-    if ((dbg & 16) && lane == 0 && blockIdx.x == 0) {
+    if ((dbg & 16) && lane == 0 && blockIdx.x <= 2) {
       tk_total = clock64() - tk_total;
       uint32_t hw_warp;
       asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw_warp));
-      printf("conv issuer %u (hw warp slot %u) block %d (N=%d): total %lld cycles | operand waits %lld | turn wait %lld | issue+commit %lld | rest %lld\n",
-             x, hw_warp, blockIdx.x, p.N, tk_total, tk_prep, tk_turn, tk_issue, tk_total - tk_prep - tk_turn - tk_issue);
+      printf("conv issuer %u (hw warp slot %u) block %d (N=%d): total %lld cycles | operand waits %lld | turn wait %lld | issue+commit %lld | rest %lld"
+             " | single-tile items %d: %lld cycles each | full items %d: %lld cycles each\n",
+             x, hw_warp, blockIdx.x, p.N, tk_total, tk_prep, tk_turn, tk_issue, tk_total - tk_prep - tk_turn - tk_issue,
+             n_by_nt[0], n_by_nt[0] ? tk_by_nt[0] / n_by_nt[0] : 0LL, n_by_nt[1], n_by_nt[1] ? tk_by_nt[1] / n_by_nt[1] : 0LL);
     }
   } else if (warp >= 4 && warp < kExtraIssuerWarp) {
     // ============================================================ epilogue
@@ -1278,7 +1298,7 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
 // host mirror of ItemWalk::init, for the CPU test of the partition (tests/test_host.py)
 void conv_item_span(int n_clips, int T, int n_tiles, int NT, int grid, int cta, int* first, int* last) {
   const int n_tilesets = cdiv(n_tiles, NT);
-  const long long total = static_cast<long long>(n_clips) * T * n_tiles;
+  const long long total = static_cast<long long>(n_clips) * clip_cost(T, n_tiles, n_tilesets, NT);
   *first = span_item_at_cost(T, n_tiles, n_tilesets, NT, total * cta / grid);
   *last = span_item_at_cost(T, n_tiles, n_tilesets, NT, total * (cta + 1) / grid);
 }

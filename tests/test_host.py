@@ -222,7 +222,8 @@ def test_conv_work_partition_covers_every_item_once_and_is_balanced():
         for n_clips, steps, ctas in ((1, 75, 148), (3, 75, 148), (64, 75, 148), (5, 75, 7), (2, 4, 148), (1, 1, 1)):
             n_items = n_clips * steps * n_ts
             grid = min(n_items, ctas)
-            cost = lambda it: min(nt, n_tiles - ((it // steps) % n_ts) * nt)
+            tiles = lambda it: min(nt, n_tiles - ((it // steps) % n_ts) * nt)
+            cost = lambda it: tiles(it) * (5 if tiles(it) == nt else 7)   # a partial tile set costs 1.4x per tile (measured)
             prev_last, costs = 0, []
             for c in range(grid):
                 f, l = ctypes.c_int(), ctypes.c_int()
@@ -231,9 +232,8 @@ def test_conv_work_partition_covers_every_item_once_and_is_balanced():
                 prev_last = l.value
                 costs.append(sum(cost(i) for i in range(f.value, l.value)))
             assert prev_last == n_items
-            total = n_clips * steps * n_tiles
-            assert sum(costs) == total
-            assert max(costs) - min(costs) <= 2 * nt, (n_tiles, nt, n_clips, steps, ctas, max(costs), min(costs))
+            assert sum(costs) == sum(cost(i) for i in range(n_items))
+            assert max(costs) - min(costs) <= 2 * 5 * nt, (n_tiles, nt, n_clips, steps, ctas, max(costs), min(costs))
     f, l = ctypes.c_int(), ctypes.c_int()
     assert L.avs_conv_item_span(1, 75, 5, 2, 4, 4, ctypes.byref(f), ctypes.byref(l)) != 0      # cta out of range
 
