@@ -100,6 +100,7 @@ struct ConvKernelParams {
   // MMA issued twice, 16 = clock64 split of the issuer warps (printf), 32 = epilogue reads TMEM only, 64 = epilogue without stores, 128 = clock64 split of the epilogue
   int dbg;                      // only read when built with -DAVS_EXPERIMENTS (tools/); the product build folds it to 0
   long long clip_stride, plane_stride;  // elements (bf16) between clips / time planes of `act`
+  int cta0, n_cta;              // this kind's CTAs are blocks [cta0, cta0 + n_cta) of the launch (conv2: main and tail kind share one)
 };
 
 // Work items in (clip, tile set, t) order: a CTA takes ONE contiguous span, so that consecutive items are consecutive
@@ -136,8 +137,9 @@ struct ItemWalk {
   }
   __device__ __forceinline__ void init(const ConvKernelParams& p) {
     const long long total = static_cast<long long>(p.n_items / p.n_tilesets / p.T) * clip_cost(p.T, p.n_tiles, p.n_tilesets, p.NT);
-    first = item_at_cost(p, total * blockIdx.x / gridDim.x);
-    last = item_at_cost(p, total * (blockIdx.x + 1) / gridDim.x);
+    const long long cta = static_cast<long long>(blockIdx.x) - p.cta0;
+    first = item_at_cost(p, total * cta / p.n_cta);
+    last = item_at_cost(p, total * (cta + 1) / p.n_cta);
     item = first;
     T = p.T; n_tilesets = p.n_tilesets;
     b = item / (n_tilesets * T);
@@ -165,12 +167,19 @@ struct ItemWalk {
 // adds per tcgen05.mma and nothing else.  Measured (tools/umma_rate.cu): descriptors fetched from a shared-memory
 // table cost 10-14 cycles per MMA that no amount of unrolling hides (LDS -> IADD -> R2UR feeding UTCHMMA);
 // compile-time offsets issue at the hardware rate, max((4 KB + 32 N) / 128 B, N / 2) cycles per 128 x N x 16 MMA.
-enum : int { KIND_L1 = 0, KIND_L2 = 1, KIND_L3 = 2, KIND_L1_SPLIT = 3, KIND_L2_SPLIT = 4, KIND_L3_SPLIT = 5 };
+// KIND_L2_TAIL: the fifth (last, lone) tile of conv2's planes.  A plane has 5 tiles and an item holds 2, so the last tile
+// set of a plane would be a single-tile item — and with one tile the two halves of a stage cannot overlap: the tensor pipe
+// drains at every hand-over between the issuers (measured: 15 620 cycles per single-tile item against 22 270 for two
+// tiles, 1.4x per tile, a fifth of conv2's tiles).  The tail kind runs as a second launch over the same input and
+// weights: an item is the fifth tile of TWO consecutive time steps (tile i = time step 2 tp + i), its planes live in a
+// ring of FOUR slots of the single-tile region (pair tp needs padded planes 2tp .. 2tp+3 and brings two new ones).
+enum : int { KIND_L1 = 0, KIND_L2 = 1, KIND_L3 = 2, KIND_L1_SPLIT = 3, KIND_L2_SPLIT = 4, KIND_L3_SPLIT = 5, KIND_L2_TAIL = 6 };
 template <int KIND>
 struct LayerKind {
-  static constexpr bool split = KIND >= KIND_L1_SPLIT;
+  static constexpr bool split = KIND >= KIND_L1_SPLIT && KIND <= KIND_L3_SPLIT;
   static constexpr bool first = KIND == KIND_L1 || KIND == KIND_L1_SPLIT;               // Cin = 1, X8 input
-  static constexpr int N = first ? 32 : ((KIND == KIND_L2 || KIND == KIND_L2_SPLIT) ? 64 : 96);  // Cout
+  static constexpr bool tail = KIND == KIND_L2_TAIL;
+  static constexpr int N = first ? 32 : ((KIND == KIND_L2 || KIND == KIND_L2_SPLIT || tail) ? 64 : 96);  // Cout
   static constexpr int KH = first ? 5 : (N == 64 ? 5 : 3);
   static constexpr int KW = KH;
   static constexpr int NROW = first ? 3 : KH;       // bf16: row taps R[0..NROW-1] of one filter column (conv1: row pairs)
@@ -184,7 +193,7 @@ struct LayerKind {
   static constexpr bool colstack = KIND == KIND_L1;
   static constexpr int NB = colstack ? 2 * N : N;                             // B rows (accumulator columns) per conv-row accumulator
   static constexpr int ACC = split ? (N == 96 ? 256 : 2 * N) : NB;           // TMEM columns between even/odd-row accumulators
-  static constexpr int NT = KIND <= KIND_L1_SPLIT ? 2 : 1;                    // tiles per work item
+  static constexpr int NT = (KIND <= KIND_L1_SPLIT || tail) ? 2 : 1;          // tiles per work item
   // stages per A unit: bf16 = one filter column per stage, bf16x3 = one filter row per stage; conv1: the unit is one stage
   static constexpr int SPU = first ? 1 : KW;
   // bf16 kinds keep the three input planes of an item in a ring of three plane slots (slot = padded plane index % 3)
@@ -197,23 +206,25 @@ struct LayerKind {
   static constexpr bool reuse = !split && !tcat;
   // conv1's items are a single stage, so a plane is only released when the whole item is done: a fourth slot lets the
   // next item's new plane load meanwhile (multi-stage kinds release an item's first plane after its first unit)
-  static constexpr int RING = first ? AVS_VAR_L1_RING : 3;
+  static constexpr int RING = first ? AVS_VAR_L1_RING : (tail ? 4 : 3);
   // Geometry of LipNet's layer (50 x 100 frames, halved by every pool), mirrored from geom_finalize()/umma_layer_build()
   // — which refuse anything else — so that the two strides of the activation layout are COMPILE-time constants
   // and every descriptor of the schedule is "uniform base + immediate".
   static constexpr int H = first ? 50 : (N == 64 ? 25 : 12), W = first ? 100 : (N == 64 ? 50 : 25);
   static constexpr int WT = colstack ? W / 2 : W + KW / 2;               // row pitch (positions); colstack: entries are self-contained, no gap
   static constexpr int HALO = first ? (KH / 2 + 1) * WT + 8 : (KH / 2) * WT + KW - 1;
-  static constexpr int REGION_FULL = NT * 128 + HALO;
+  static constexpr int REGION_MAIN = NT * 128 + HALO;                     // positions a full item reads per (chunk, parity)
+  static constexpr int REGION_FULL = tail ? 128 + HALO : REGION_MAIN;      // tail: the two tiles are the same tile of two time steps
   static constexpr int NTILES = ((H / 2) * WT + 127) / 128, NTS = (NTILES + NT - 1) / NT;
+  static constexpr int TAIL_TILE = NTILES - 1;                              // tail: the tile of the plane this kind computes
   static constexpr int EXTENT = ((KW / 2 + (H / 2 + KH / 2) * WT + (first ? 8 : 0)) + 7) / 8 * 8;
   static constexpr int ARR16 = (NTS == 1 && !tcat) ? (REGION_FULL < EXTENT ? REGION_FULL : EXTENT) : REGION_FULL;  // positions per (chunk, parity) run in a slot
   static constexpr int PITCH = EXTENT;                                       // tcat: positions per time plane
   static constexpr int TCAT_ITEMS = (AVS_T * PITCH + NT * 128 - 1) / (NT * 128);                       // items per clip
   static constexpr int TCAT_LEN = ((TCAT_ITEMS - 1) * NT * 128 + 2 * PITCH + REGION_FULL + 7) / 8 * 8;  // positions per (clip, chunk, parity) array
-  static constexpr int PP = tcat ? PITCH : NTS == 1 ? ARR16 : (NTS - 1) * NT * 128 + REGION_FULL;                      // positions per (plane, chunk, parity) array in HBM
+  static constexpr int PP = tcat ? PITCH : NTS == 1 ? ARR16 : (NTS - 1) * NT * 128 + REGION_MAIN;                      // positions per (plane, chunk, parity) array in HBM
   static constexpr int N_CHUNKS = (first ? 1 : (N == 64 ? 32 : 64) / 8) * (split ? 2 : 1);              // chunk arrays of this layer's INPUT
-  static constexpr int NEXT = (N == 96) ? KIND : KIND + 1;                                              // kind of the layer that reads our output
+  static constexpr int NEXT = (N == 96) ? KIND : (tail ? KIND_L3 : KIND + 1);                           // kind of the layer that reads our output
 };
 
 constexpr uint64_t kDescHi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, descriptor version 1
@@ -236,12 +247,14 @@ __device__ __forceinline__ void issue_stage_bf16(const uint32_t (&a_base)[3], ui
         // padded input row 2r+q; the wide entries go first so that an item's very first MMA covers both accumulators
         const int q = e < K::NROW - 1 ? e + 1 : (e == K::NROW - 1 ? 0 : K::NROW);
         const bool wide = q >= 1 && q <= K::NROW - 1;
-        const uint32_t a = a_base[kd] + (pr * 4 + (q & 1)) * arr16 + (q >> 1) * Wt;  // conv1: one plane slot per kd
+        const uint32_t a_off = (pr * 4 + (q & 1)) * arr16 + (q >> 1) * Wt;
+        const uint32_t a = a_base[kd] + a_off;  // conv1: one plane slot per kd
         const uint32_t b = b_base + (kd * K::PAIRS + pr) * (2 * K::NROW * K::NB) + (K::NROW - 1 - (q == K::NROW ? K::NROW - 1 : q)) * K::NB;
         const uint32_t d = d_base + (q == K::NROW ? K::NB : 0);
         const uint32_t acc = (kd == 0 && pr == 0 && e == 0) ? (overwrite ? 0u : 1u) : 1u;
 #pragma unroll
-        for (int i = LO; i < HI; ++i) umma_f16(d + i * 2 * K::ACC, kDescHi | (a + i * 128), kDescHi | b, wide ? idesc_w : idesc_n, acc);
+        for (int i = LO; i < HI; ++i)  // tail kind: a_base[i] is the plane slot of tile i (time step 2 tp + i), same positions
+          umma_f16(d + i * 2 * K::ACC, kDescHi | (K::tail ? a_base[i] + a_off : a + i * 128), kDescHi | b, wide ? idesc_w : idesc_n, acc);
       }
 }
 
@@ -292,7 +305,7 @@ __device__ __forceinline__ void issue_stage(const uint32_t (&a_base)[3], uint32_
   if (K::split) {
     issue_stage_split<KIND, LO, HI, AMASK>(a_base[0], b_base, d_base, overwrite, s_in_unit, idesc_n, idesc_w);
   } else {
-    const uint32_t ab[3] = {a_base[0] + (K::first ? 0 : s_in_unit), a_base[1], a_base[2]};  // generic layers: + kw
+    const uint32_t ab[3] = {a_base[0] + (K::first ? 0 : s_in_unit), a_base[1] + (K::tail ? s_in_unit : 0), a_base[2]};  // generic layers: + kw
     issue_stage_bf16<KIND, LO, HI>(ab, b_base, d_base, overwrite, idesc_n, idesc_w);
   }
 }
@@ -310,9 +323,7 @@ __device__ __forceinline__ void issue_half(int nt, const uint32_t (&ab)[3], uint
 }
 
 template <int KIND>
-// 128 registers per thread so that one FFT CTA (256 x 64 registers) of the audio branch fits beside it on the SM
-__global__ void __maxnreg__(KIND == KIND_L1 && AVS_VAR_L1_GROUPS >= 4 ? 96 : 128)
-conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
+__device__ __forceinline__ void conv_body(const ConvKernelParams& p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // carve: [unit slots][weight stages][barriers][tmem ptr]
   uint8_t* s_units = smem;
@@ -391,10 +402,14 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       const uint32_t n_arrays = static_cast<uint32_t>(p.n_chunks) * 2u;
       for (; w.valid(); w.next()) {
         if ((AVS_DBG(p) & 2) && w.item > w.first) continue;
-        const int q0 = w.ts * p.NT * 128;
+        const int q0 = K::tail ? K::TAIL_TILE * 128 : w.ts * p.NT * 128;
         const uint32_t bytes = static_cast<uint32_t>(min(p.region_pos, p.PP - q0)) * 16u;
-        for (int kd = w.continues_prev() ? 2 : 0; kd < 3; ++kd) {
-          const int tp = w.t + kd;
+        // tail kind: item tp is the tile of time steps 2tp and 2tp+1 (the last item of a clip: 2tp only) and needs padded
+        // planes 2tp .. 2tp+3 (.. 2tp+2), two of which the previous item of the span already brought
+        const int t0 = K::tail ? 2 * w.t : w.t;
+        const int n_planes = K::tail ? ((t0 + 1 < p.T_out) ? 4 : 3) : 3;
+        for (int kd = w.continues_prev() ? 2 : 0; kd < n_planes; ++kd) {
+          const int tp = t0 + kd;
           const uint32_t slot = static_cast<uint32_t>(tp % K::RING);
           mbar_wait(&a_empty[slot], ((fill_parity >> slot) & 1u) ^ 1u);  // the slot's previous tenant has been released
           fill_parity ^= 1u << slot;
@@ -468,7 +483,8 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     long long tk_item = tk_total, tk_by_nt[2] = {0, 0};  // dbg 16: time between item starts, by the item's tile count (1 / more)
     int n_by_nt[2] = {0, 0}, nt_prev = 0;
     for (; w.valid(); w.next()) {
-      const int nt = min(NT, n_tiles - w.ts * NT);
+      const int t0 = K::tail ? 2 * w.t : w.t;  // tail kind: tile i of the item is time step t0 + i
+      const int nt = K::tail ? ((t0 + 1 < p.T_out) ? 2 : 1) : min(NT, n_tiles - w.ts * NT);
       if (dbg & 16) {
         const long long now = clock64();
         if (nt_prev) tk_by_nt[nt_prev > 1] += now - tk_item, n_by_nt[nt_prev > 1] += 1;
@@ -478,8 +494,8 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       bool acc_ready0 = false, acc_ready1 = false;  // this issuer has seen the accumulator halves released by the epilogue
       const uint32_t d_base = tmem_base + acc_buf * (NT * 2 * K::ACC);
       const bool cont_next = w.continues_next();
-      if (K::reuse) {  // the fills this item brings: all three planes, or only the last one
-        for (int kd = w.continues_prev() ? 2 : 0; kd < 3; ++kd) fill_parity ^= 1u << ((w.t + kd) % K::RING);
+      if (K::reuse) {  // the fills this item brings: all its planes, or only the new one(s)
+        for (int kd = w.continues_prev() ? 2 : 0; kd < (K::tail ? nt + 2 : 3); ++kd) fill_parity ^= 1u << ((t0 + kd) % K::RING);
       }
       int s_in_unit = 0;  // stage inside the current A unit: the filter column (bf16) / filter row (bf16x3) of the stage
       int unit = 0;       // K::reuse: the unit is time plane kd = unit
@@ -487,7 +503,8 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         const bool last_of_unit = s_in_unit == K::SPU - 1;
         // plane ring: which of this unit's planes go back to the producer when the unit is done (conv1's single
         // stage spans all three planes); sequential ring: the unit's slot, always
-        const uint32_t slot0 = K::reuse ? static_cast<uint32_t>((w.t + unit) % K::RING) : a_slot;
+        const uint32_t slot0 = K::reuse ? static_cast<uint32_t>((t0 + unit) % K::RING) : a_slot;
+        const uint32_t slot1 = static_cast<uint32_t>((t0 + 1 + unit) % K::RING);  // tail kind: the plane of the item's second tile
         if ((kIss == 2 ? (g & 1u) : g % 3u) == x) {
           const long long tk0 = (dbg & 16) ? clock64() : 0;
           if (!acc_ready0) {
@@ -509,6 +526,10 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
             } else {
               if (wait_a) mbar_wait(&a_full[slot0], ((fill_parity >> slot0) & 1u) ^ 1u);
               ab[0] = ab[1] = ab[2] = (units_lo + slot0 * unit_step) | lbo_a;
+              if (K::tail && nt == 2) {
+                if (wait_a) mbar_wait(&a_full[slot1], ((fill_parity >> slot1) & 1u) ^ 1u);
+                ab[1] = (units_lo + slot1 * unit_step) | lbo_a;
+              }
             }
           } else {
             if (!(dbg & 2) || a_loaded < ring) mbar_wait(&a_full[a_slot], a_phase);
@@ -548,6 +569,11 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
                 if (K::first) {
                   tc_commit(&a_empty[w.t % K::RING]);
                   if (!cont_next) tc_commit(&a_empty[(w.t + 1) % K::RING]), tc_commit(&a_empty[(w.t + 2) % K::RING]);
+                } else if (K::tail) {
+                  // plane t0 is done after unit 0, plane t0 + 1 (tile 0's unit 1, tile 1's unit 0) after unit 1; planes
+                  // t0 + 2 and t0 + 3 are the next item's first two
+                  if (unit <= 1 || !cont_next) tc_commit(&a_empty[slot0]);
+                  if (unit == 2 && !cont_next && nt == 2) tc_commit(&a_empty[slot1]);
                 } else if (unit == 0 || !cont_next) {
                   tc_commit(&a_empty[slot0]);  // planes kd = 1, 2 stay for the next time step
                 }
@@ -695,7 +721,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
     w.init(p);
     for (; w.valid(); w.next(), buf = (buf + 1 == static_cast<uint32_t>(p.NBUF)) ? 0 : buf + 1, phase ^= (buf == 0)) {
       const int b = w.b, t = w.t, ts = w.ts;
-      const int nt = min(NT, p.n_tiles - ts * NT);
+      const int nt = K::tail ? ((2 * t + 1 < p.T_out) ? 2 : 1) : min(NT, p.n_tiles - ts * NT);
       const int n_units = (AVS_DBG(p) & 4) ? 0 : nt * UPT;
       // tiles [0, h0) are the first half of the accumulator buffer; the single-tile split kinds halve it by row
       // accumulator instead, and need both halves from the first unit on
@@ -736,10 +762,12 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
       }
       const uint32_t d_base = tmem_base + buf * (NT * 2 * K::ACC) + (static_cast<uint32_t>(q * 32) << 16);
       // where this item's outputs start in the next layer's input (element pointer; per-unit offsets fit 32 bits)
+      // (tail kind: tile i of the item is time step 2t + i — the base of time step 2t, tile 1 adds one plane pitch)
       __nv_bfloat16* out_item = nullptr;
+      const int t_first = K::tail ? 2 * t : t;
       if (!kToEmb)
-        out_item = KN::tcat ? p.eo.act + (static_cast<long long>(b) * (KN::N_CHUNKS * 2) * KN::TCAT_LEN + (t + 1) * KN::PITCH) * 8
-                            : p.eo.act + (static_cast<long long>(b) * (p.T_out + 2) + t + 1) * (KN::N_CHUNKS * 2) * KN::PP * 8;
+        out_item = KN::tcat ? p.eo.act + (static_cast<long long>(b) * (KN::N_CHUNKS * 2) * KN::TCAT_LEN + (t_first + 1) * KN::PITCH) * 8
+                            : p.eo.act + (static_cast<long long>(b) * (p.T_out + 2) + t_first + 1) * (KN::N_CHUNKS * 2) * KN::PP * 8;
       // runtime loop over the tiles, unrolled over the column blocks of a tile only: a fully unrolled item is NT copies of
       // the unit body, and conv1 (NT = 4) ran 30 % slower with it — instruction fetch, not arithmetic
       for (int i = 0; i < nt && n_units > 0; ++i)
@@ -748,7 +776,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
         const int u = i * UPT + cbi, cb = cbi * 32;
         if ((u % kGroups) != grp) continue;  // warp-uniform
         // positions grow with the lane and with the tile: if the warp's first lane is past the end, nobody has work
-        const int S0 = ((K::tcat ? t : ts) * NT + i) * 128 + q * 32;
+        const int S0 = K::tail ? K::TAIL_TILE * 128 + q * 32 : ((K::tcat ? t : ts) * NT + i) * 128 + q * 32;
         const bool warp_has_work = K::tcat ? (S0 / K::PITCH < p.T_out) : (S0 / K::WT < kHo);
         if (i >= h0) need_half1();
         uint32_t v0[32], v1[32];
@@ -765,7 +793,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
           }
         }
         int Q = S0 + lane;  // output position in pooled-row space
-        int t_out = t;
+        int t_out = K::tail ? 2 * t + i : t;
         if (K::tcat) {  // time-concatenated position space: item index -> (time step, position in its plane)
           t_out = Q / K::PITCH;
           Q -= t_out * K::PITCH;
@@ -824,7 +852,7 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
           const int pos = KN::KW / 2 + (hp >> 1) * KN::WT + wo;
           // array `a` (= chunk array * 2 + parity), position `pos` of time plane t + 1: 32-bit offsets from the item's base
           auto out_ptr = [&](int a) {
-            return out_item + (a * (KN::tcat ? KN::TCAT_LEN : KN::PP) + pos) * 8;
+            return out_item + (a * (KN::tcat ? KN::TCAT_LEN : KN::PP) + pos + (K::tail ? i * KN::PITCH : 0)) * 8;
           };
 #pragma unroll
           for (int c8 = 0; c8 < 2; ++c8) {
@@ -871,6 +899,22 @@ conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
   }
 }
 
+// 128 registers per thread so that FFT CTAs of the audio branch fit beside a conv CTA on the SM
+template <int KIND>
+__global__ void __maxnreg__(KIND == KIND_L1 && AVS_VAR_L1_GROUPS >= 4 ? 96 : 128)
+conv_umma_kernel(const __grid_constant__ ConvKernelParams p) {
+  conv_body<KIND>(p);
+}
+// conv2 (bf16): ONE launch for both of its kinds — the first pm.n_cta CTAs walk the two full tile sets of every plane, the
+// others the planes' lone fifth tile in pairs of time steps (KIND_L2_TAIL).  Two launches were measured first: at the
+// boundary between them the audio branch's one-warp CTAs flood the idle SMs and the second launch pays for it
+// (conv2 20.9 -> 22.3 ms per 1024 clips in the step although the two kernels alone take 17.1 against 17.8 us/clip).
+__global__ void __maxnreg__(128)
+conv_l2_fused_kernel(const __grid_constant__ ConvKernelParams pm, const __grid_constant__ ConvKernelParams pt) {
+  if (static_cast<int>(blockIdx.x) < pm.n_cta) conv_body<KIND_L2>(pm);
+  else conv_body<KIND_L2_TAIL>(pt);
+}
+
 #ifdef AVS_EXPERIMENTS
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -888,6 +932,7 @@ static ConvKernel conv_kernel_for(int kind) {
     case KIND_L1_SPLIT: return conv_umma_kernel<KIND_L1_SPLIT>;
     case KIND_L2_SPLIT: return conv_umma_kernel<KIND_L2_SPLIT>;
     case KIND_L3_SPLIT: return conv_umma_kernel<KIND_L3_SPLIT>;
+    case KIND_L2_TAIL: return conv_umma_kernel<KIND_L2_TAIL>;
   }
   return nullptr;
 }
@@ -1292,6 +1337,18 @@ int umma_layer_build(UmmaLayer* L, const LayerGeom& g, int split, const float* w
   AVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&L->d_bias), N * sizeof(float)));
   AVS_CUDA(cudaMemcpy(L->d_bias, bias, N * sizeof(float), cudaMemcpyHostToDevice));
   AVS_CUDA(cudaFuncSetAttribute(conv_kernel_for(L->kind), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  L->tail_smem_bytes = 0;
+  if (L->kind == KIND_L2) {  // the planes' fifth tile runs as a second launch (KIND_L2_TAIL): four slots of the single-tile region
+    using KT = LayerKind<KIND_L2_TAIL>;
+    static_assert(KT::NTILES == 2 * LayerKind<KIND_L2>::NT + 1 && KT::PP == LayerKind<KIND_L2>::PP && KT::N_CHUNKS == LayerKind<KIND_L2>::N_CHUNKS,
+                  "conv2: two full tile sets and one lone tile per plane");
+    L->tail_region_pos = KT::ARR16;
+    L->tail_slot_bytes = g.n_chunks * 2 * KT::ARR16 * 16;
+    L->tail_smem_bytes = static_cast<size_t>(KT::RING) * L->tail_slot_bytes + static_cast<size_t>(L->wstages) * L->stage_bytes +
+                         (2 * kMaxRing + 2 * kMaxWStages + 14) * 8 + 16;
+    if (L->tail_smem_bytes > 232448) return AVS_EINVAL;
+    AVS_CUDA(cudaFuncSetAttribute(conv_l2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  }
   return AVS_OK;
 }
 
@@ -1365,8 +1422,33 @@ int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const Epi
   p.n_items = static_cast<int>(items);
   p.plane_stride = static_cast<long long>(g.n_chunks) * 2 * g.PP * 8;
   p.clip_stride = g.tcat_len > 0 ? static_cast<long long>(g.n_chunks) * 2 * g.tcat_len * 8 : p.plane_stride * (AVS_T + 2);
-  const int grid = static_cast<int>(std::min<long long>(items, n_sms));
   ProfScope ps(L.g.Cin == 1 ? PROF_CONV1 : (L.g.Cout == 64 ? PROF_CONV2 : PROF_CONV3), st);
+  if (L.tail_smem_bytes) {
+    // conv2: the two full tile sets of every plane (main kind) and the lone fifth tile (tail kind) share one launch;
+    // the CTAs are divided by cost: 2 x 75 full items against 38 per clip
+    p.n_tiles = 2 * L.NT;
+    p.n_tilesets = 2;
+    p.n_items = B * p.T * p.n_tilesets;
+    ConvKernelParams q = p;
+    q.ring = LayerKind<KIND_L2_TAIL>::RING;
+    q.unit_slot_bytes = L.tail_slot_bytes;
+    q.region_pos = q.region_full = L.tail_region_pos;
+    q.T = (AVS_T + 1) / 2;  // items per clip: pairs of time steps
+    q.n_tiles = L.NT;
+    q.n_tilesets = 1;
+    q.n_items = B * q.T;
+    const int grid = static_cast<int>(std::min<long long>(p.n_items + q.n_items, n_sms));
+    int n_tail = static_cast<int>((static_cast<long long>(grid) * q.T + (p.T * p.n_tilesets + q.T) / 2) / (p.T * p.n_tilesets + q.T));
+    n_tail = std::max(1, std::min(n_tail, std::min(grid - 1, q.n_items)));
+    p.cta0 = 0; p.n_cta = grid - n_tail;
+    q.cta0 = p.n_cta; q.n_cta = n_tail;
+    AVS_REQUIRE(p.n_cta >= 1, "conv2 needs at least two SMs");
+    conv_l2_fused_kernel<<<grid, conv_threads(KIND_L2), std::max(L.tail_smem_bytes, L.smem_bytes), st>>>(p, q);
+    AVS_LAUNCHED();
+    return AVS_OK;
+  }
+  const int grid = static_cast<int>(std::min<long long>(p.n_items, n_sms));
+  p.cta0 = 0; p.n_cta = grid;
   conv_kernel_for(L.kind)<<<grid, conv_threads(L.kind), L.smem_bytes, st>>>(p);
   AVS_LAUNCHED();
   return AVS_OK;

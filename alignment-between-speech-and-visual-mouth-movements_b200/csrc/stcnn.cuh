@@ -47,6 +47,9 @@ struct UmmaLayer {                // device-resident, built once by stcnn_create
   __nv_bfloat16* d_w = nullptr;   // packed B tiles, n_stages * stage_bytes
   float* d_bias = nullptr;
   size_t smem_bytes;
+  // conv2 (bf16): second launch for the planes' lone fifth tile (conv_umma.cu: KIND_L2_TAIL); 0 = none
+  int tail_slot_bytes = 0, tail_region_pos = 0;
+  size_t tail_smem_bytes = 0;
 };
 
 struct EpiOut {                   // where the fused bias+ReLU+pool epilogue writes
