@@ -62,12 +62,12 @@ def peaks():
 
 def conv2_traffic(clips_per_launch: int, precision: str):
     """DRAM bytes per launch of the layer-2 conv kernel: a CONSTANT taken from the committed `ncu --set full` capture
-    (profiles/r01_conv2_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum = 864.9 MB for a 64-clip bf16
-    launch = 13.51 MB per clip; algorithmic: 8.6 MB padded input + 2.9 MB pooled output), scaled to the clips one
+    (profiles/r02_conv2_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum = 746.1 MB for a 64-clip bf16
+    launch = 11.66 MB per clip; algorithmic: 8.6 MB padded input + 2.9 MB pooled output), scaled to the clips one
     bench launch processes — not measured by this run."""
     if precision != "bf16":
         return None
-    return 13.51e6 * clips_per_launch
+    return 11.66e6 * clips_per_launch
 
 
 class ClockSampler:
@@ -536,11 +536,11 @@ def main():
         mult = 3 if args.precision == "bf16x3" else 1
         achieved = (CONV_FLOP[2] * clips_per_launch / (avg_ms / 1e3) / 1e12) if avg_ms > 0 else 0.0
         tensor_peak = pk["bf16_tflops_sustained"]
-        roof = {"kernel": "conv_umma_kernel[layer 2: Conv3d 32->64, 3x5x5 + bias + ReLU + pool]" if args.precision != "fp32"
+        roof = {"kernel": "conv_l2_fused_kernel[layer 2: Conv3d 32->64, 3x5x5 + bias + ReLU + pool]" if args.precision != "fp32"
                 else "conv_pool_ffma_kernel[layer 2]",
                 "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": achieved / tensor_peak, "traffic": conv2_traffic(clips_per_launch, args.precision),
-                "traffic_source": "constant from the committed ncu --set full capture (13.51 MB per clip) x clips per launch; "
+                "traffic_source": "constant from the committed ncu --set full capture (11.66 MB per clip) x clips per launch; "
                                   "not measured by this run",
                 "peak_source": f"{pk_src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "algorithmic_flop_per_launch": CONV_FLOP[2] * clips_per_launch,

@@ -1,5 +1,5 @@
-"""Tiny driver for ncu: two STCNN forwards (bf16) on a few clips, so `-k regex:conv_umma -s 4 -c 1`
-captures layer 2 of the second forward.  GPU box only."""
+"""Tiny driver for ncu: two STCNN forwards (bf16) on a few clips, so `-k 'regex:conv_umma|conv_l2_fused' -s 3 -c 3`
+captures the three conv launches of the second forward.  GPU box only."""
 import os
 import sys
 

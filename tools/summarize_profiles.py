@@ -47,8 +47,8 @@ keep = ["Kernel Name", "gpu__time_duration.sum", "sm__cycles_elapsed.max", "laun
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum"]
 GFLOP = {"0": 1.8, "1": 28.8, "2": 7.46}  # algorithmic GFLOP per clip of the three layers
 with open(f"profiles/{tag}_conv2_ncu_full.txt", "w") as f:
-    f.write(f"# ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 3 -c 3 python tools/prof_conv.py\n")
-    f.write(f"# the three conv_umma_kernel launches of one STCNN forward (layer 1, 2, 3), {clips} clips per launch (PROF_CLIPS), bf16; "
+    f.write(f"# ncu --set full --clock-control none --import-source on -k 'regex:conv_umma|conv_l2_fused' -s 3 -c 3 python tools/prof_conv.py\n")
+    f.write(f"# the three conv launches of one STCNN forward (conv_umma_kernel<0> = layer 1, conv_l2_fused_kernel = layer 2, conv_umma_kernel<2> = layer 3), {clips} clips per launch (PROF_CLIPS), bf16; "
             f"layer 2 is the roofline kernel of bench.py\n")
     for vals in r[2:]:
         d = {}
@@ -59,7 +59,7 @@ with open(f"profiles/{tag}_conv2_ncu_full.txt", "w") as f:
                 d[h] = (v, u)
         try:
             rd, wr = float(d["dram__bytes_read.sum"][0].replace(",", "")), float(d["dram__bytes_write.sum"][0].replace(",", ""))
-            kind = re.search(r"<(?:\(int\))?(\d)>", d["Kernel Name"][0]).group(1)
+            kind = "1" if "fused" in d["Kernel Name"][0] else re.search(r"<(?:\(int\))?(\d)>", d["Kernel Name"][0]).group(1)
             f.write(f"# derived: DRAM traffic per launch = {rd + wr:.1f} {d['dram__bytes_read.sum'][1]} = {(rd + wr) / clips:.2f} per clip; "
                     f"algorithmic {GFLOP[kind]} GFLOP/clip\n")
         except Exception as e:
