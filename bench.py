@@ -85,7 +85,15 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def count(self):
+        """Samples written so far."""
+        try:
+            return sum(1 for r in open(self.f.name) if r.count(",") >= 8)
+        except Exception:
+            return 0
+
+    def stop(self, first: int = 0):
+        """Stops nvidia-smi and summarises the samples from index `first` on."""
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -95,7 +103,7 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8][first:]
         os.unlink(self.f.name)
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
@@ -359,7 +367,7 @@ def ddp_config5(A, dev, world: int, rank: int, steps: int = 20):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp32"])
@@ -415,21 +423,38 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput
+    # nvidia-smi is started before the warm-up (it needs a few hundred ms to deliver its first sample); only samples
+    # taken from the start of the timed region on are used
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         step_device()
     barrier()
     L.avs_prof_reset()
     L.avs_prof_enable(1)
     launches0 = L.avs_launch_count()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    first_sample = sampler.count() if sampler else 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         scores, best = step_device()
     ev1.record()
     barrier()
-    clocks = sampler.stop() if sampler else None
     L.avs_prof_enable(0)
+    # a timed region shorter than ~0.4 s may see fewer than three 100 ms samples: keep the GPU under the identical load
+    # (untimed steps, all ranks) until three have been taken
+    extra = torch.zeros(1, device=dev, dtype=torch.int32)
+    t_extra = time.perf_counter()
+    while True:
+        extra[0] = 1 if (sampler is not None and sampler.count() - first_sample < 3 and time.perf_counter() - t_extra < 3.0) else 0
+        if world > 1:
+            dist.broadcast(extra, src=0)
+        if int(extra.item()) == 0:
+            break
+        step_device()
+        torch.cuda.synchronize()
+    clocks = sampler.stop(first_sample) if sampler else None
+    if clocks is not None:
+        clocks["window"] = "samples every 100 ms from the start of the timed region; if it ends before three were taken, identical untimed steps keep the load up until they are"
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     launches = torch.tensor([L.avs_launch_count() - launches0], device=dev, dtype=torch.int64)
     if world > 1:
