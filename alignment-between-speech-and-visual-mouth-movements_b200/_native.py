@@ -76,6 +76,7 @@ SIGNATURES = {
 # tools build only (make EXPERIMENTS=1 -> libavsync_b200_exp.so, loaded by tools/ through use_experiments_build())
 EXPERIMENT_SIGNATURES = {
     "avs_debug_set": (None, [c_int]),
+    "avs_prof_read_span": (c_int, [c_int, c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double)]),
 }
 
 _lib = None

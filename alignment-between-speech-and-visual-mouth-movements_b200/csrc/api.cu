@@ -62,6 +62,20 @@ extern "C" int avs_prof_read(int slot, double* total_ms, int* count) {
 #ifdef AVS_EXPERIMENTS
 namespace avs { extern int g_conv_dbg; }
 extern "C" void avs_debug_set(int flags) { avs::g_conv_dbg = flags; }
+// begin / end of the idx-th profiled launch of a slot, in ms since the first profiled pack launch (tools/sweep_timeline.py)
+extern "C" int avs_prof_read_span(int slot, int idx, double* begin_ms, double* end_ms) {
+  if (slot < 0 || slot >= avs::PROF_NSLOTS || !begin_ms || !end_ms) return AVS_EINVAL;
+  auto& p = avs::g_prof[slot];
+  auto& base = avs::g_prof[0];
+  if (idx < 0 || idx >= p.used || base.used < 1) return AVS_EINVAL;
+  AVS_CUDA(cudaEventSynchronize(p.ev[idx][1]));
+  float b = 0, e = 0;
+  AVS_CUDA(cudaEventElapsedTime(&b, base.ev[0][0], p.ev[idx][0]));
+  AVS_CUDA(cudaEventElapsedTime(&e, base.ev[0][0], p.ev[idx][1]));
+  *begin_ms = b;
+  *end_ms = e;
+  return AVS_OK;
+}
 #endif
 
 extern "C" int avs_conv_item_span(int n_clips, int n_steps, int n_tiles, int tiles_per_item, int n_ctas, int cta, int* first,

@@ -35,11 +35,12 @@ struct avs_mfcc_plan {
   int4* d_frames = nullptr;     // [U] (p, a, b, 0): window start, valid range in original-signal coordinates
   int* d_map = nullptr;         // [K][F] -> unique frame id
   float* d_window = nullptr;    // [2048] periodic Hann
-  float2* d_tw = nullptr;       // [1024] exp(-2 pi i e / 1024)
+  float2* d_tw = nullptr;       // [32 k1][32 lanes] exp(-2 pi i (lane * k1) / 1024): lane-major, one 256-byte run per k1
   float2* d_tw2 = nullptr;      // [1025] exp(-2 pi i k / 2048)
-  int4* d_mel_tab = nullptr;    // [128] (first bin, count, offset into d_mel_w, 0)
-  float* d_mel_w = nullptr;     // concatenated non-zero filter weights
-  float* d_dct = nullptr;       // [128][kMaxQ] DCT-II ortho basis, transposed, zero padded
+  int4* d_mel_tab = nullptr;    // [128] (first bin, longest band of the band's quartile, offset of the quartile in d_mel_w, count)
+  float* d_mel_w = nullptr;     // non-zero filter weights, lane-major per quartile of bands: [quartile][i][32 bands], zero padded
+  float* d_dct = nullptr;       // [128][kMaxQ] DCT-II ortho basis, transposed, zero padded (statistics kernel)
+  float4* d_dct_lane = nullptr; // the same basis lane-major for the log-mel kernel: [4 quartiles][kMaxQ / 4][32 bands] float4
 };
 
 namespace avs {
@@ -123,7 +124,7 @@ template <bool SCHED, int NQ>
 __global__ void __launch_bounds__(SCHED ? 32 * kFftCtaWarps : 32 * kWarpFftWarps)
 mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const int4* __restrict__ frames, int n_unique,
                         const float* __restrict__ window, const float2* __restrict__ tw, const float2* __restrict__ tw2,
-                        const int4* __restrict__ mel_tab, const float* __restrict__ mel_w, const float* __restrict__ dct_t,
+                        const int4* __restrict__ mel_tab, const float* __restrict__ mel_w, const float4* __restrict__ dct_lane,
                         float* __restrict__ logmel, float* __restrict__ frame_mfcc, float2* __restrict__ frame_range) {
   // one 32 x 33 float plane per warp (4.2 KB): the transposes move the real and the imaginary parts one after the other,
   // so that twice as many of these one-warp CTAs fit into the shared memory the persistent conv kernels leave free
@@ -189,7 +190,7 @@ mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const in
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     const int k1 = bitrev5(i);
-    if (k1 != 0) v[i] = cmul(v[i], __ldg(tw + ((lane * k1) & (kHalf - 1))));  // W_1024^(n2 k1)
+    if (k1 != 0) v[i] = cmul(v[i], __ldg(tw + 32 * k1 + lane));  // W_1024^(n2 k1), n2 = lane
   }
   // transpose (n2 = lane, k1) -> (k1 = lane, n2), real parts then imaginary parts through the same plane
 #pragma unroll
@@ -253,21 +254,24 @@ mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const in
   }
   if (lane == 0) s_pow[kHalf / 2] = pmid;
   __syncwarp();
-  // sparse mel: lane takes one band of each quartile (bands lane, lane+32, lane+64, lane+96)
+  // sparse mel: lane takes one band of each quartile (bands lane, lane+32, lane+64, lane+96).  The weights are stored
+  // lane-major ([i][32 bands] per quartile, zero padded to the quartile's longest band): every load of the warp is one
+  // 128-byte line instead of up to 32 lines (ncu of the band-major layout: 16.7 sectors and 12 L1 tag look-ups per
+  // load request — the kernel sat at 68 % of the L1 throughput alone, and beside a conv CTA, whose operand fetch owns
+  // that pipe, it ran four times slower).  Zero weights leave the sums bit-identical; the padded reads stay inside the
+  // plane (index clamped to the last bin).
   float* out = logmel + (static_cast<size_t>(clip) * n_unique + u) * kMels;
   float lm[kMels / 32];
 #pragma unroll
   for (int r = 0; r < kMels / 32; ++r) {
     const int m = lane + 32 * r;
     const int4 rg = __ldg(mel_tab + m);
-    const float* w = mel_w + rg.z;
+    const float* w = mel_w + rg.z + lane;
     float acc0 = 0.f, acc1 = 0.f;
-    int i = 0;
-    for (; i + 1 < rg.y; i += 2) {
-      acc0 = fmaf(__ldg(w + i), s_pow[rg.x + i], acc0);
-      acc1 = fmaf(__ldg(w + i + 1), s_pow[rg.x + i + 1], acc1);
+    for (int i = 0; i < rg.y; i += 2) {  // rg.y: the quartile's longest band, rounded up to even (warp-uniform)
+      acc0 = fmaf(__ldg(w + 32 * i), s_pow[min(rg.x + i, kHalf)], acc0);
+      acc1 = fmaf(__ldg(w + 32 * i + 32), s_pow[min(rg.x + i + 1, kHalf)], acc1);
     }
-    if (i < rg.y) acc0 = fmaf(__ldg(w + i), s_pow[rg.x + i], acc0);
     lm[r] = 10.0f * log10f(fmaxf(acc0 + acc1, 1e-10f));
     out[m] = lm[r];
   }
@@ -290,10 +294,10 @@ mfcc_logmel_warp_kernel(const float* __restrict__ audio, int n_samples, const in
   for (int q = 0; q < NP; ++q) part[q] = 0.f;
 #pragma unroll
   for (int r = 0; r < kMels / 32; ++r) {
-    const float4* d = reinterpret_cast<const float4*>(dct_t + (lane + 32 * r) * kMaxQ);
+    const float4* d = dct_lane + r * (kMaxQ / 4) * 32 + lane;  // lane-major: 512 contiguous bytes per load
 #pragma unroll
     for (int q4 = 0; q4 < NQ / 4; ++q4) {
-      const float4 dd = __ldg(d + q4);
+      const float4 dd = __ldg(d + 32 * q4);
       part[q4 * 4 + 0] = fmaf(dd.x, lm[r], part[q4 * 4 + 0]);
       part[q4 * 4 + 1] = fmaf(dd.y, lm[r], part[q4 * 4 + 1]);
       part[q4 * 4 + 2] = fmaf(dd.z, lm[r], part[q4 * 4 + 2]);
@@ -527,9 +531,12 @@ extern "C" int avs_mfcc_plan_create(int n_samples, int sample_rate, int n_mfcc, 
   const double kPi = 3.14159265358979323846;
   std::vector<float> window(kNfft);
   for (int n = 0; n < kNfft; ++n) window[n] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * kPi * n / kNfft));
-  std::vector<float2> tw(kHalf), tw2(kBins);
-  for (int e = 0; e < kHalf; ++e)
-    tw[e] = make_float2(static_cast<float>(std::cos(2.0 * kPi * e / kHalf)), static_cast<float>(-std::sin(2.0 * kPi * e / kHalf)));
+  std::vector<float2> tw(32 * 32), tw2(kBins);
+  for (int k1 = 0; k1 < 32; ++k1)
+    for (int lane = 0; lane < 32; ++lane) {
+      const int e = (lane * k1) & (kHalf - 1);
+      tw[32 * k1 + lane] = make_float2(static_cast<float>(std::cos(2.0 * kPi * e / kHalf)), static_cast<float>(-std::sin(2.0 * kPi * e / kHalf)));
+    }
   for (int k = 0; k < kBins; ++k)
     tw2[k] = make_float2(static_cast<float>(std::cos(2.0 * kPi * k / kNfft)), static_cast<float>(-std::sin(2.0 * kPi * k / kNfft)));
   // librosa.filters.mel(sr, n_fft=2048, n_mels=128, fmin=0, fmax=sr/2, htk=False, norm='slaney')
@@ -537,7 +544,7 @@ extern "C" int avs_mfcc_plan_create(int n_samples, int sample_rate, int n_mfcc, 
   const double mmin = hz_to_mel(0.0), mmax = hz_to_mel(sample_rate / 2.0);
   for (int i = 0; i < kMels + 2; ++i) mel_f[i] = mel_to_hz(mmin + (mmax - mmin) * i / (kMels + 1));
   std::vector<int4> rng(kMels);
-  std::vector<float> mw;
+  std::vector<std::vector<float>> band(kMels);
   for (int m = 0; m < kMels; ++m) {
     const double enorm = 2.0 / (mel_f[m + 2] - mel_f[m]);
     int first = -1, last = -2;
@@ -554,8 +561,21 @@ extern "C" int avs_mfcc_plan_create(int n_samples, int sample_rate, int n_mfcc, 
       }
     }
     if (first < 0) first = 0, last = -1;
-    rng[m] = make_int4(first, last - first + 1, static_cast<int>(mw.size()), 0);
-    for (int k = first; k <= last; ++k) mw.push_back(row[k]);
+    rng[m] = make_int4(first, 0, 0, last - first + 1);
+    for (int k = first; k <= last; ++k) band[m].push_back(row[k]);
+  }
+  std::vector<float> mw;
+  for (int r = 0; r < kMels / 32; ++r) {  // lane-major weights of the quartile's 32 bands, zero padded to an even length
+    size_t longest = 0;
+    for (int l = 0; l < 32; ++l) longest = std::max(longest, band[32 * r + l].size());
+    longest = (longest + 1) & ~static_cast<size_t>(1);
+    const int off = static_cast<int>(mw.size());
+    mw.resize(mw.size() + longest * 32, 0.f);
+    for (int l = 0; l < 32; ++l) {
+      for (size_t i = 0; i < band[32 * r + l].size(); ++i) mw[off + i * 32 + l] = band[32 * r + l][i];
+      rng[32 * r + l].y = static_cast<int>(longest);
+      rng[32 * r + l].z = off;
+    }
   }
   std::vector<float> dct(static_cast<size_t>(kMels) * kMaxQ, 0.f);
   for (int q = 0; q < n_mfcc; ++q)
@@ -564,9 +584,16 @@ extern "C" int avs_mfcc_plan_create(int n_samples, int sample_rate, int n_mfcc, 
       if (q == 0) v *= std::sqrt(0.5);
       dct[static_cast<size_t>(m) * kMaxQ + q] = static_cast<float>(v);
     }
+  std::vector<float4> dct_lane(static_cast<size_t>(kMels / 32) * (kMaxQ / 4) * 32);
+  for (int m = 0; m < kMels; ++m)
+    for (int q4 = 0; q4 < kMaxQ / 4; ++q4) {
+      const float* d = &dct[static_cast<size_t>(m) * kMaxQ + 4 * q4];
+      dct_lane[(static_cast<size_t>(m / 32) * (kMaxQ / 4) + q4) * 32 + (m & 31)] = make_float4(d[0], d[1], d[2], d[3]);
+    }
   int rc;
   if ((rc = upload(&p->d_frames, frames)) || (rc = upload(&p->d_map, map)) || (rc = upload(&p->d_window, window)) ||
-      (rc = upload(&p->d_tw, tw)) || (rc = upload(&p->d_tw2, tw2)) || (rc = upload(&p->d_mel_tab, rng)) || (rc = upload(&p->d_mel_w, mw)) || (rc = upload(&p->d_dct, dct))) {
+      (rc = upload(&p->d_tw, tw)) || (rc = upload(&p->d_tw2, tw2)) || (rc = upload(&p->d_mel_tab, rng)) || (rc = upload(&p->d_mel_w, mw)) || (rc = upload(&p->d_dct, dct)) ||
+      (rc = upload(&p->d_dct_lane, dct_lane))) {
     avs_mfcc_plan_destroy(p);
     return rc;
   }
@@ -577,7 +604,7 @@ extern "C" int avs_mfcc_plan_create(int n_samples, int sample_rate, int n_mfcc, 
 extern "C" void avs_mfcc_plan_destroy(avs_mfcc_plan* p) {
   if (!p) return;
   cudaFree(p->d_frames); cudaFree(p->d_map); cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_tw2);
-  cudaFree(p->d_mel_tab); cudaFree(p->d_mel_w); cudaFree(p->d_dct);
+  cudaFree(p->d_mel_tab); cudaFree(p->d_mel_w); cudaFree(p->d_dct); cudaFree(p->d_dct_lane);
   delete p;
 }
 extern "C" int avs_mfcc_plan_unique_frames(const avs_mfcc_plan* p) { return p ? p->n_unique : AVS_EINVAL; }
@@ -590,50 +617,84 @@ extern "C" size_t avs_mfcc_workspace_bytes(const avs_mfcc_plan* p, int n_clips) 
          align_up(frames * sizeof(float2), 256);
 }
 
-// after_logmel (nullable) is recorded on the stream between the log-mel kernel and the statistics kernel
-int avs::mfcc_sweep_impl(const avs_mfcc_plan* p, const float* audio, int n_clips, float* out_stats, float* out_mfcc,
-                         void* workspace, size_t workspace_bytes, void* stream, cudaEvent_t after_logmel) {
-  AVS_REQUIRE(p && audio && out_stats && workspace, "null argument");
-  if (n_clips <= 0) return AVS_OK;
+namespace {
+struct MfccWs {
+  float* logmel; float* frame_mfcc; float2* frame_range;
+};
+// placement of the three per-frame tables in a workspace carved for n_clips clips
+MfccWs carve_mfcc_ws(const avs_mfcc_plan* p, int n_clips, void* workspace) {
+  const size_t n_fr = static_cast<size_t>(n_clips) * p->n_unique;
+  MfccWs w;
+  w.logmel = static_cast<float*>(workspace);
+  w.frame_mfcc = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align_up(n_fr * kMels * sizeof(float), 256));
+  w.frame_range = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(w.frame_mfcc) + align_up(n_fr * kMaxQ * sizeof(float), 256));
+  return w;
+}
+int check_mfcc_ws(const avs_mfcc_plan* p, int n_clips, size_t workspace_bytes) {
   if (workspace_bytes < avs_mfcc_workspace_bytes(p, n_clips)) {
     set_error("mfcc workspace too small: %zu < %zu", workspace_bytes, avs_mfcc_workspace_bytes(p, n_clips));
     return AVS_EWORKSPACE;
   }
+  return AVS_OK;
+}
+}  // namespace
+
+// The log-mel / per-frame DCT tables of clips [c_begin, c_end) of a batch of n_clips (the workspace is carved for
+// n_clips): the sweep runs the first clips of a chunk ahead of the others (sweep.cu, "head start").
+int avs::mfcc_logmel_part(const avs_mfcc_plan* p, const float* audio, int n_clips, int c_begin, int c_end, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  AVS_REQUIRE(p && audio && workspace, "null argument");
+  AVS_REQUIRE(0 <= c_begin && c_end <= n_clips, "clip range outside the batch");
+  if (c_begin >= c_end) return AVS_OK;
+  int rc;
+  if ((rc = check_mfcc_ws(p, n_clips, workspace_bytes))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t n_fr = static_cast<size_t>(n_clips) * p->n_unique;
-  float* logmel = static_cast<float*>(workspace);
-  float* frame_mfcc = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align_up(n_fr * kMels * sizeof(float), 256));
-  float2* frame_range = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(frame_mfcc) + align_up(n_fr * kMaxQ * sizeof(float), 256));
+  const MfccWs w = carve_mfcc_ws(p, n_clips, workspace);
+  for (int c0 = c_begin; c0 < c_end; c0 += 32768) {  // gridDim.y limit
+    const int nc = std::min(32768, c_end - c0);
+    float* lm = w.logmel + static_cast<size_t>(c0) * p->n_unique * kMels;
+    float* fmf = w.frame_mfcc + static_cast<size_t>(c0) * p->n_unique * kMaxQ;
+    float2* frg = w.frame_range + static_cast<size_t>(c0) * p->n_unique;
+    const float* au = audio + static_cast<size_t>(c0) * p->n_samples;
+    ProfScope ps(PROF_LOGMEL, st);
+#define AVS_LOGMEL_ARGS au, p->n_samples, p->d_frames, p->n_unique, p->d_window, p->d_tw, p->d_tw2, p->d_mel_tab, p->d_mel_w, p->d_dct_lane, lm, fmf, frg
+#ifdef AVS_EXPERIMENTS
+    if (fft_sched_mode()) {
+      const dim3 g1(cdiv(p->n_unique, kFftCtaFrames), nc);
+      if (p->n_mfcc <= 20) mfcc_logmel_warp_kernel<true, 20><<<g1, 32 * kFftCtaWarps, 0, st>>>(AVS_LOGMEL_ARGS);
+      else mfcc_logmel_warp_kernel<true, kMaxQ><<<g1, 32 * kFftCtaWarps, 0, st>>>(AVS_LOGMEL_ARGS);
+    } else
+#endif
+    {
+      const dim3 g1(cdiv(p->n_unique, kWarpFftWarps), nc);
+#ifdef AVS_VAR_K1_CARVE  // experiment: K1 alone with the L1 the conv kernels leave it (shared-memory carve-out at its maximum)
+      cudaFuncSetAttribute(mfcc_logmel_warp_kernel<false, 20>, cudaFuncAttributePreferredSharedMemoryCarveout, AVS_VAR_K1_CARVE);
+#endif
+      if (p->n_mfcc <= 20) mfcc_logmel_warp_kernel<false, 20><<<g1, 32 * kWarpFftWarps, 0, st>>>(AVS_LOGMEL_ARGS);
+      else mfcc_logmel_warp_kernel<false, kMaxQ><<<g1, 32 * kWarpFftWarps, 0, st>>>(AVS_LOGMEL_ARGS);
+    }
+#undef AVS_LOGMEL_ARGS
+    AVS_LAUNCHED();
+  }
+  return AVS_OK;
+}
+
+// Per-shift statistics of all n_clips clips from the tables mfcc_logmel_part left in the workspace.
+int avs::mfcc_stats_part(const avs_mfcc_plan* p, int n_clips, float* out_stats, float* out_mfcc, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  AVS_REQUIRE(p && out_stats && workspace, "null argument");
+  if (n_clips <= 0) return AVS_OK;
+  int rc;
+  if ((rc = check_mfcc_ws(p, n_clips, workspace_bytes))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const MfccWs w = carve_mfcc_ws(p, n_clips, workspace);
   for (int c0 = 0; c0 < n_clips; c0 += 32768) {  // gridDim.y limit
     const int nc = std::min(32768, n_clips - c0);
     float* os = out_stats + static_cast<size_t>(c0) * p->n_shifts * 2 * p->n_mfcc;
     float* om = out_mfcc ? out_mfcc + static_cast<size_t>(c0) * p->n_shifts * p->n_frames * p->n_mfcc : nullptr;
-    float* lm = logmel + static_cast<size_t>(c0) * p->n_unique * kMels;
-    float* fmf = frame_mfcc + static_cast<size_t>(c0) * p->n_unique * kMaxQ;
-    float2* frg = frame_range + static_cast<size_t>(c0) * p->n_unique;
-    const float* au = audio + static_cast<size_t>(c0) * p->n_samples;
-    {
-      ProfScope ps(PROF_LOGMEL, st);
-#define AVS_LOGMEL_ARGS au, p->n_samples, p->d_frames, p->n_unique, p->d_window, p->d_tw, p->d_tw2, p->d_mel_tab, p->d_mel_w, p->d_dct, lm, fmf, frg
-#ifdef AVS_EXPERIMENTS
-      if (fft_sched_mode()) {
-        const dim3 g1(cdiv(p->n_unique, kFftCtaFrames), nc);
-        if (p->n_mfcc <= 20) mfcc_logmel_warp_kernel<true, 20><<<g1, 32 * kFftCtaWarps, 0, st>>>(AVS_LOGMEL_ARGS);
-        else mfcc_logmel_warp_kernel<true, kMaxQ><<<g1, 32 * kFftCtaWarps, 0, st>>>(AVS_LOGMEL_ARGS);
-      } else
-#endif
-      {
-        const dim3 g1(cdiv(p->n_unique, kWarpFftWarps), nc);
-#ifdef AVS_VAR_K1_CARVE  // experiment: K1 alone with the L1 the conv kernels leave it (shared-memory carve-out at its maximum)
-        cudaFuncSetAttribute(mfcc_logmel_warp_kernel<false, 20>, cudaFuncAttributePreferredSharedMemoryCarveout, AVS_VAR_K1_CARVE);
-#endif
-        if (p->n_mfcc <= 20) mfcc_logmel_warp_kernel<false, 20><<<g1, 32 * kWarpFftWarps, 0, st>>>(AVS_LOGMEL_ARGS);
-        else mfcc_logmel_warp_kernel<false, kMaxQ><<<g1, 32 * kWarpFftWarps, 0, st>>>(AVS_LOGMEL_ARGS);
-      }
-#undef AVS_LOGMEL_ARGS
-    }
-    AVS_LAUNCHED();
-    if (after_logmel) AVS_CUDA(cudaEventRecord(after_logmel, st));
+    const float* lm = w.logmel + static_cast<size_t>(c0) * p->n_unique * kMels;
+    const float* fmf = w.frame_mfcc + static_cast<size_t>(c0) * p->n_unique * kMaxQ;
+    const float2* frg = w.frame_range + static_cast<size_t>(c0) * p->n_unique;
     dim3 g2(p->n_shifts, nc);
     ProfScope ps2(PROF_MFCC_STATS, st);
     if (p->n_mfcc <= 20) {
@@ -652,14 +713,23 @@ int avs::mfcc_sweep_impl(const avs_mfcc_plan* p, const float* audio, int n_clips
   return AVS_OK;
 }
 
+int avs::mfcc_sweep_impl(const avs_mfcc_plan* p, const float* audio, int n_clips, float* out_stats, float* out_mfcc,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  AVS_REQUIRE(p && audio && out_stats && workspace, "null argument");
+  if (n_clips <= 0) return AVS_OK;
+  int rc;
+  if ((rc = mfcc_logmel_part(p, audio, n_clips, 0, n_clips, workspace, workspace_bytes, stream))) return rc;
+  return mfcc_stats_part(p, n_clips, out_stats, out_mfcc, workspace, workspace_bytes, stream);
+}
+
 extern "C" int avs_mfcc_sweep_debug(const avs_mfcc_plan* p, const float* audio, int n_clips, float* out_stats,
                                     float* out_mfcc, void* workspace, size_t workspace_bytes, void* stream) {
-  return avs::mfcc_sweep_impl(p, audio, n_clips, out_stats, out_mfcc, workspace, workspace_bytes, stream, nullptr);
+  return avs::mfcc_sweep_impl(p, audio, n_clips, out_stats, out_mfcc, workspace, workspace_bytes, stream);
 }
 
 extern "C" int avs_mfcc_stats_sweep(const avs_mfcc_plan* p, const float* audio, int n_clips, float* out_stats,
                                     void* workspace, size_t workspace_bytes, void* stream) {
-  return avs::mfcc_sweep_impl(p, audio, n_clips, out_stats, nullptr, workspace, workspace_bytes, stream, nullptr);
+  return avs::mfcc_sweep_impl(p, audio, n_clips, out_stats, nullptr, workspace, workspace_bytes, stream);
 }
 
 extern "C" __attribute__((visibility("hidden"))) int avs_mfcc_plan_nshifts_internal(const avs_mfcc_plan* p, int* K, int* n_mfcc, int* n_samples) {

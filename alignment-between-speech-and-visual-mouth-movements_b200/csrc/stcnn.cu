@@ -163,6 +163,7 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
       const float* f = frames + static_cast<size_t>(b0) * AVS_T * AVS_H * AVS_W;
       float* p1 = w.p1 + static_cast<size_t>(b0) * 32 * AVS_T * 25 * 50;
       float* p2 = w.p2 + static_cast<size_t>(b0) * 64 * AVS_T * 12 * 25;
+      if (b0 == 0 && hooks.before_layer1) AVS_CUDA(cudaStreamWaitEvent(st, hooks.before_layer1, 0));
       if ((rc = conv_pool_ffma(f, net->w[0], net->b[0], p1, nb, 1, 32, AVS_T, 50, 100, 5, 5, 32LL * AVS_T * 1250,
                                AVS_T * 1250LL, 1250, st)))
         return rc;
@@ -199,6 +200,7 @@ int avs::stcnn_forward_impl(const avs_stcnn* net, const void* frames_any, bool f
         eo.mode = 1;
         eo.emb = emb;
       }
+      if (l == 0 && hooks.before_layer1) AVS_CUDA(cudaStreamWaitEvent(st, hooks.before_layer1, 0));
       if (l == 2 && hooks.before_layer3) AVS_CUDA(cudaStreamWaitEvent(st, hooks.before_layer3, 0));
       if ((rc = umma_conv_forward(net->L[l], w.act[l], eo, B, net->n_sms, st))) return rc;
       if (l == 0 && (rc = after_l1())) return rc;

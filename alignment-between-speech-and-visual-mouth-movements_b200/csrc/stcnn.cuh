@@ -6,9 +6,14 @@ struct avs_stcnn;
 struct avs_mfcc_plan;
 namespace avs {
 
-// K1 (mfcc.cu); after_logmel (nullable) is recorded on the stream between the log-mel kernel and the statistics kernel
+// K1 (mfcc.cu): the whole thing, or its two kernels separately (log-mel / per-frame DCT tables of a clip range of the
+// batch, then the per-shift statistics of all clips) for the sweep, which starts a chunk's first clips early
 int mfcc_sweep_impl(const avs_mfcc_plan* p, const float* audio, int n_clips, float* out_stats, float* out_mfcc,
-                    void* workspace, size_t workspace_bytes, void* stream, cudaEvent_t after_logmel);
+                    void* workspace, size_t workspace_bytes, void* stream);
+int mfcc_logmel_part(const avs_mfcc_plan* p, const float* audio, int n_clips, int c_begin, int c_end, void* workspace,
+                     size_t workspace_bytes, void* stream);
+int mfcc_stats_part(const avs_mfcc_plan* p, int n_clips, float* out_stats, float* out_mfcc, void* workspace,
+                    size_t workspace_bytes, void* stream);
 
 // fp32 CUDA-core layer: in NCDHW f32, w OIDHW f32, out addressed as b*o_sb + c*o_sc + t*o_st + ho*Wo + wo
 int conv_pool_ffma(const float* in, const float* w, const float* bias, float* out, int B, int Cin, int Cout, int T,
@@ -69,11 +74,13 @@ int umma_pack_frames(const void* frames, bool frames_u8, __nv_bfloat16* act, con
 int umma_conv_forward(const UmmaLayer& L, const __nv_bfloat16* act_in, const EpiOut& eo, int B, int n_sms, cudaStream_t st);
 int umma_unpack_act(const __nv_bfloat16* act, float* out_ncdhw, const LayerGeom& g_next, int split, int C, int B, cudaStream_t st);
 
-// Hooks of the sweep (all nullable): after_layer1 is recorded on the stream right after layer 1 has been enqueued;
+// Hooks of the sweep (all nullable): the stream waits for before_layer1 between the pack kernel and layer 1;
+// after_layer1 is recorded on the stream right after layer 1 has been enqueued;
 // on_layer1(on_layer1_arg) runs on the host once layer 2 has been enqueued (the sweep enqueues its audio branch on the side
 // stream there, behind after_layer1), and the stream waits for before_layer3 — as recorded by then — before layer 3.
 typedef int (*StcnnHook)(void*);
 struct StcnnHooks {
+  cudaEvent_t before_layer1 = nullptr;
   cudaEvent_t after_layer1 = nullptr;
   StcnnHook on_layer1 = nullptr;
   void* on_layer1_arg = nullptr;

@@ -28,7 +28,7 @@ struct avs_sweep {
   float* d_scores_all = nullptr; int32_t* d_best_all = nullptr;  // host entry point results
   int cap = 0;
   cudaStream_t side = nullptr, copy = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_logmel = nullptr, ev_join = nullptr, ev_last = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_logmel = nullptr, ev_join = nullptr, ev_last = nullptr, ev_pre = nullptr, ev_head = nullptr, ev_conv2 = nullptr;
   bool has_last = false;
   // host entry points: double-buffered device inputs + pinned staging (frames slots hold f32 or u8)
   void* d_frames[2] = {nullptr, nullptr};
@@ -45,6 +45,14 @@ extern "C" int avs_mfcc_plan_nshifts_internal(const avs_mfcc_plan* p, int* K, in
 using namespace avs;
 
 static const size_t kFrameElems = static_cast<size_t>(AVS_T) * AVS_H * AVS_W;
+// run_chunk, two schedule switches measured in round 2 (profiles/r02_k1_lane_major_tables.txt) and left OFF:
+//   kHeadDiv > 0: the FFT frames of the first n / kHeadDiv clips of a chunk run beside the pack kernel and conv1 waits for
+//     them.  With the band-major K1 tables the FFT kernel outlasted conv2 by 0.15 ms per chunk and conv3 waited for it; a
+//     head start of n / 8 removed that wait but not measurably the step time, and with the lane-major tables K1 ends
+//     before conv2 by itself (step 34.0 ms without, 34.3 with the head start, same box, three alternations).
+//   kStatsAfterConv2: the statistics kernel waits for conv2 (it then runs beside conv3 only): 34.4 ms against 34.0.
+constexpr int kStatsAfterConv2 = 0;
+constexpr int kHeadDiv = 0;
 
 #ifdef AVS_EXPERIMENTS
 static int env_knob(const char* name, int dflt) {
@@ -73,6 +81,9 @@ extern "C" int avs_sweep_create(const avs_stcnn* net, const avs_mfcc_plan* plan,
   ck(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
   ck(cudaEventCreateWithFlags(&s->ev_logmel, cudaEventDisableTiming));
   ck(cudaEventCreateWithFlags(&s->ev_last, cudaEventDisableTiming));
+  ck(cudaEventCreateWithFlags(&s->ev_pre, cudaEventDisableTiming));
+  ck(cudaEventCreateWithFlags(&s->ev_head, cudaEventDisableTiming));
+  ck(cudaEventCreateWithFlags(&s->ev_conv2, cudaEventDisableTiming));
   if (rc) {
     avs_sweep_destroy(s);
     return rc;
@@ -99,6 +110,9 @@ extern "C" void avs_sweep_destroy(avs_sweep* s) {
   if (s->ev_join) cudaEventDestroy(s->ev_join);
   if (s->ev_logmel) cudaEventDestroy(s->ev_logmel);
   if (s->ev_last) cudaEventDestroy(s->ev_last);
+  if (s->ev_pre) cudaEventDestroy(s->ev_pre);
+  if (s->ev_head) cudaEventDestroy(s->ev_head);
+  if (s->ev_conv2) cudaEventDestroy(s->ev_conv2);
   delete s;
 }
 
@@ -137,14 +151,23 @@ static int ensure_capacity(avs_sweep* s, int n_clips, cudaStream_t st) {
 // statistics of one chunk (n <= s->chunk clips starting at clip c0); audio branch on the side stream, joined back
 // into `st` before returning.
 struct AudioBranch {
-  avs_sweep* s; const float* audio; float* ast; int n;
+  avs_sweep* s; const float* audio; float* ast; int n, head;
+  cudaStream_t st; bool stats_after_conv2;
 };
-// host hook of the STCNN, called when layer 1 has been enqueued (and ev_fork recorded behind it): enqueue K1 on the side stream
+// host hook of the STCNN, called when layer 2 has been enqueued (ev_fork recorded behind layer 1): enqueue the rest of K1
+// on the side stream — the log-mel tables of the clips the head start did not take, then the statistics of all clips
 static int enqueue_audio_branch(void* arg) {
   const AudioBranch* a = static_cast<const AudioBranch*>(arg);
   avs_sweep* s = a->s;
+  int rc;
   AVS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
-  const int rc = mfcc_sweep_impl(s->plan, a->audio, a->n, a->ast, nullptr, s->ws_mfcc, s->ws_mfcc_bytes, s->side, s->ev_logmel);
+  if ((rc = mfcc_logmel_part(s->plan, a->audio, a->n, a->head, a->n, s->ws_mfcc, s->ws_mfcc_bytes, s->side))) return rc;
+  AVS_CUDA(cudaEventRecord(s->ev_logmel, s->side));
+  if (a->stats_after_conv2) {  // the statistics kernel runs beside conv3, not beside conv2's last items
+    AVS_CUDA(cudaEventRecord(s->ev_conv2, a->st));
+    AVS_CUDA(cudaStreamWaitEvent(s->side, s->ev_conv2, 0));
+  }
+  rc = mfcc_stats_part(s->plan, a->n, a->ast, nullptr, s->ws_mfcc, s->ws_mfcc_bytes, s->side);
   AVS_CUDA(cudaEventRecord(s->ev_join, s->side));
   return rc;
 }
@@ -157,7 +180,18 @@ static int run_chunk(avs_sweep* s, const void* frames, bool frames_u8, const flo
   // epilogue) — and its FFT kernel shares the SMs with conv2 only: conv3 waits for it (ev_logmel) and runs beside the
   // light statistics kernel.  Once conv2 is done the FFT kernel has the whole GPU and finishes its last frames at four
   // times the speed, while beside conv3 it would halve conv3 (profiles/r02_k1_grid.txt).
-  AudioBranch ab{s, audio, ast, n};
+  //   (Optional head start, see kHeadDiv: the FFT frames of the chunk's first clips beside the pack kernel.)
+#ifdef AVS_EXPERIMENTS
+  static const int head_div = env_knob("AVS_K1_HEAD_DIV", kHeadDiv);  // 0: no head start
+#else
+  constexpr int head_div = kHeadDiv;
+#endif
+#ifdef AVS_EXPERIMENTS
+  static const int stats_after_conv2 = env_knob("AVS_STATS_AFTER_CONV2", kStatsAfterConv2);
+#else
+  constexpr int stats_after_conv2 = kStatsAfterConv2;
+#endif
+  AudioBranch ab{s, audio, ast, n, head_div > 0 ? n / head_div : 0, st, stats_after_conv2 != 0};
   StcnnHooks hooks;
   hooks.after_layer1 = s->ev_fork;
   hooks.on_layer1 = enqueue_audio_branch;
@@ -172,6 +206,13 @@ static int run_chunk(avs_sweep* s, const void* frames, bool frames_u8, const flo
   }
   if (audio_mode == 2) hooks.before_layer3 = nullptr;
 #endif
+  if (ab.head > 0) {
+    AVS_CUDA(cudaEventRecord(s->ev_pre, st));          // behind the previous chunk's kernels (and this chunk's inputs)
+    AVS_CUDA(cudaStreamWaitEvent(s->side, s->ev_pre, 0));
+    if ((rc = mfcc_logmel_part(s->plan, audio, n, 0, ab.head, s->ws_mfcc, s->ws_mfcc_bytes, s->side))) return rc;
+    AVS_CUDA(cudaEventRecord(s->ev_head, s->side));
+    hooks.before_layer1 = s->ev_head;
+  }
   if ((rc = stcnn_forward_impl(s->net, frames, frames_u8, n, s->chunk, true, hooks, nullptr, vst, nullptr, nullptr,
                                s->ws_stcnn, s->ws_stcnn_bytes, st)))
     return rc;

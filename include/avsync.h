@@ -242,6 +242,8 @@ AVS_API int avs_prof_read(int slot, double* total_ms, int* count);
  * 32 = epilogue reads TMEM only, 64 = epilogue without stores.  0 = normal operation.  The same build reads the
  * environment knobs AVS_CONV{1,2,3}_WSTAGES / _RING, AVS_AUDIO_MODE, AVS_HOST_FIRST_CHUNK, AVS_GRU_FMA. */
 AVS_API void avs_debug_set(int flags);
+/* begin / end of the idx-th profiled launch of a slot, in ms since the first profiled pack launch */
+AVS_API int avs_prof_read_span(int slot, int idx, double* begin_ms, double* end_ms);
 #endif
 /* How the persistent conv kernels split their work (host mirror of the device code, no GPU needed): the items of a
  * launch, in (clip, tile set, time step) order, are cut into n_ctas contiguous spans of near-equal cost (cost of an item =
