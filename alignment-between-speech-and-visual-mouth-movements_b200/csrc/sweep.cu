@@ -11,6 +11,8 @@
 // handle's previous call (event `ev_last`), so run / run_host may be mixed freely and issued from different
 // streams; per-call buffers grow with stream-ordered allocations, never with a device synchronisation.
 #include <algorithm>
+#include <cstring>
+#include <thread>
 #include "stcnn.cuh"
 
 struct avs_sweep {
@@ -263,6 +265,26 @@ static bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
+// Staging copy of a pageable chunk into the pinned slot.  One thread moves ~10 GB/s; the sweep consumes 17.6 GB/s of u8
+// frames + audio per GPU at 30 k clips/s, so large copies are cut into up to four slices on short-lived threads.
+static void staging_copy(void* dst, const void* src, size_t bytes) {
+  constexpr size_t kSlice = 8u << 20;
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const int n = static_cast<int>(std::min<size_t>({static_cast<size_t>(4), static_cast<size_t>(hw), bytes / kSlice}));
+  if (n <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t per = (bytes / n + 63) & ~static_cast<size_t>(63);
+  std::thread th[3];
+  for (int i = 1; i < n; ++i) {
+    const size_t off = per * i, len = std::min(per, bytes - off);
+    th[i - 1] = std::thread([=] { memcpy(static_cast<uint8_t*>(dst) + off, static_cast<const uint8_t*>(src) + off, len); });
+  }
+  memcpy(dst, src, per);
+  for (int i = 1; i < n; ++i) th[i - 1].join();
+}
+
 static int host_init(avs_sweep* s) {
   if (s->host_ready) return AVS_OK;
   const size_t fb = static_cast<size_t>(s->chunk) * kFrameElems * sizeof(float);  // sized for f32 frames; u8 uses a quarter
@@ -312,8 +334,8 @@ static int sweep_run_host(avs_sweep* s, const void* frames_host, bool frames_u8,
       if (!direct) AVS_CUDA(cudaEventSynchronize(s->ev_in[sl]));    // pinned staging slot has been read by its H2D
     }
     if (!direct) {
-      memcpy(s->h_frames[sl], fsrc, n * fstride);
-      memcpy(s->h_audio[sl], asrc, static_cast<size_t>(n) * s->n_samples * sizeof(float));
+      staging_copy(s->h_frames[sl], fsrc, n * fstride);
+      staging_copy(s->h_audio[sl], asrc, static_cast<size_t>(n) * s->n_samples * sizeof(float));
       fsrc = s->h_frames[sl];
       asrc = s->h_audio[sl];
     }

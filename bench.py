@@ -526,6 +526,14 @@ def main():
                    "h2d_bytes_per_step": n_total * (FRAME_ELEMS + N_SAMPLES) * 4,
                    "d2h_bytes_per_step": n_total * (N_SHIFTS + 1) * 4, "frames": "float32 tensor (avs_sweep_run_host)",
                    "matches_device_path": same}
+        if world == 1:
+            # the same call from ordinary (pageable) numpy arrays: every chunk is staged through the handle's pinned slots
+            # by a host memcpy on the calling thread (csrc/sweep.cu, sweep_run_host: `direct == false`)
+            fp, ap = np.array(frames_h.numpy(), copy=True), np.array(audio_h.numpy(), copy=True)
+            v, same = time_host(fp, ap)
+            e2e["pageable_host_buffers"] = {"value": v, "unit": "clips/s", "matches_device_path": same,
+                                            "what": "uint8 frames + f32 audio in pageable memory, staged chunk by chunk"}
+            del fp, ap
     del f32_h
 
     # ---------------- parity of the headline dtype on this batch, and the other BASELINE configs (outside the timed region)

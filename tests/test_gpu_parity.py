@@ -514,7 +514,14 @@ def test_feature_extractor_and_dataset_vs_oracle(A, lipnet_sd, det_sd):
         assert feat.device.type == "cpu" and feat.shape == (13864,) and meta == {"video_path": path, "shift_frames": k, "fps": 25.0}
         want = torch.cat([v, sweep_ref.compute_audio_stats(sweep_ref.shift_audio(audio, k, 25.0, 16000), 16000, 20)])
         np.testing.assert_allclose(feat.numpy(), want.numpy(), rtol=1e-3, atol=2e-3)
-    assert list(fx.visual_cache) == [path] and list(fx.audio_cache) == [path]
+        # build_feature serves shifts within cfg.max_shift_frames from ONE all-shift K1 launch per clip: same bits as a
+        # launch for this shift alone
+        alone = A.audio_stats_sweep(torch.from_numpy(audio[None]).cuda(), [640 * k])[0, 0].cpu()
+        assert torch.equal(feat[13824:], alone)
+    assert list(fx.visual_cache) == [path] and list(fx.audio_cache) == [path] and list(fx._astats_table) == [path]
+    far, _ = fx.build_feature(path, 25)          # outside the configured range: a launch of its own
+    want = sweep_ref.compute_audio_stats(sweep_ref.shift_audio(audio, 25, 25.0, 16000), 16000, 20)
+    np.testing.assert_allclose(far[13824:].numpy(), want.numpy(), rtol=1e-3, atol=2e-3)
     table = fx.build_features_sweep(path, 20)
     assert table.shape == (41, 13864)
     assert torch.equal(table[20 + 7], fx.build_feature(path, 7)[0])
