@@ -11,6 +11,7 @@
 // TMEM accumulators, warp roles as in conv_umma.cu.
 #include "common.cuh"
 #include "gemm_umma.cuh"
+#include "sgemm.cuh"
 
 namespace avs {
 
@@ -26,6 +27,10 @@ struct GemmParams {
   const float* bias;
   float* c;
   int M, N, K8, Mp, Np, ldc, tiles_m, tiles_n;
+  // split K (the detector's hidden layer: 16 output tiles, K = 13824): slice ks of an output tile covers the k-blocks
+  // [ks * nk_split, (ks + 1) * nk_split) and writes its own dense [M, N] partial without bias; splits == 1: c + bias
+  int splits, nk_split;
+  float* partial;
 };
 
 __global__ void __launch_bounds__(kGThreads, 1)
@@ -48,15 +53,16 @@ gemm_umma_kernel(const __grid_constant__ GemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const int n_tiles = p.tiles_m * p.tiles_n, n_k = p.K8 / (kGK / 8);
+  const int n_out = p.tiles_m * p.tiles_n, n_tiles = n_out * p.splits, n_k = p.nk_split;
 
   if (warp == 0 && lane == 0) {
     // ---------------------------------------------------------------- producer
     uint32_t slot = 0, phase = 0;
     const size_t a_kind = static_cast<size_t>(p.K8) * p.Mp * 8, w_kind = static_cast<size_t>(p.K8) * p.Np * 8;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.tiles_n) * kGM, n0 = (tile % p.tiles_n) * kGN;
-      for (int kb = 0; kb < n_k; ++kb) {
+      const int ot = tile % n_out, kb0 = (tile / n_out) * n_k;
+      const int m0 = (ot / p.tiles_n) * kGM, n0 = (ot % p.tiles_n) * kGN;
+      for (int kb = kb0; kb < kb0 + n_k; ++kb) {
         mbar_wait(&empty[slot], phase ^ 1);
         mbar_expect_tx(&full[slot], kStageBytes);
         uint8_t* sa = smem + static_cast<size_t>(slot) * kStageBytes;
@@ -109,12 +115,14 @@ gemm_umma_kernel(const __grid_constant__ GemmParams p) {
     const int q = warp & 3;
     uint32_t buf = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.tiles_n) * kGM, n0 = (tile % p.tiles_n) * kGN;
+      const int ot = tile % n_out, ks = tile / n_out;
+      const int m0 = (ot / p.tiles_n) * kGM, n0 = (ot % p.tiles_n) * kGN;
       mbar_wait(&acc_full[buf], aphase);
       __syncwarp();  // tcgen05.ld below is .aligned
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
-      float* crow = p.c + static_cast<size_t>(row) * p.ldc + n0;
+      const bool split = p.partial != nullptr;
+      float* crow = split ? p.partial + (static_cast<size_t>(ks) * p.M + row) * p.N + n0 : p.c + static_cast<size_t>(row) * p.ldc + n0;
       const uint32_t d = tmem_base + buf * kGN + (static_cast<uint32_t>(q * 32) << 16);
       for (int cb = 0; cb < kGN; cb += 32) {
         uint32_t v[32];
@@ -125,13 +133,13 @@ gemm_umma_kernel(const __grid_constant__ GemmParams p) {
           for (int c4 = 0; c4 < 32; c4 += 4) {
             const int n = n0 + cb + c4;
             if (n + 3 < p.N) {
-              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n);
+              const float4 b4 = split ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(p.bias + n);
               *reinterpret_cast<float4*>(crow + cb + c4) =
                   make_float4(__uint_as_float(v[c4]) + b4.x, __uint_as_float(v[c4 + 1]) + b4.y,
                               __uint_as_float(v[c4 + 2]) + b4.z, __uint_as_float(v[c4 + 3]) + b4.w);
             } else {
               for (int e = 0; e < 4; ++e)
-                if (n + e < p.N) crow[cb + c4 + e] = __uint_as_float(v[c4 + e]) + p.bias[n + e];
+                if (n + e < p.N) crow[cb + c4 + e] = __uint_as_float(v[c4 + e]) + (split ? 0.f : p.bias[n + e]);
             }
           }
         }
@@ -195,7 +203,15 @@ int gemm_pack(const float* x, int ld, int rows, int K, int tile, __nv_bfloat16* 
 
 int gemm_umma_nt(const __nv_bfloat16* a_packed, const __nv_bfloat16* w_packed, const float* bias, float* c, int ldc, int M,
                  int N, int K, int n_sms, cudaStream_t st) {
+  return gemm_umma_nt_splitk(a_packed, w_packed, bias, c, ldc, M, N, K, 1, nullptr, n_sms, st);
+}
+
+// splits > 1: `partial` holds splits * M * N floats, c is dense (ldc == N); the slices are summed in slice order by
+// splitk_reduce_kernel (deterministic: a row's result does not depend on M or on the row's place in its tile)
+int gemm_umma_nt_splitk(const __nv_bfloat16* a_packed, const __nv_bfloat16* w_packed, const float* bias, float* c, int ldc, int M,
+                        int N, int K, int splits, float* partial, int n_sms, cudaStream_t st) {
   AVS_REQUIRE(K % kGK == 0 && ldc % 4 == 0 && N % 4 == 0, "gemm_umma_nt shape");
+  AVS_REQUIRE(splits >= 1 && (K / kGK) % splits == 0 && (splits == 1 || (partial && ldc == N)), "gemm_umma_nt split-K configuration");
   // per-device attribute: set on every call (cheap), a process may drive several GPUs
   AVS_CUDA(cudaFuncSetAttribute(gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem)));
   GemmParams p;
@@ -203,9 +219,11 @@ int gemm_umma_nt(const __nv_bfloat16* a_packed, const __nv_bfloat16* w_packed, c
   p.M = M; p.N = N; p.K8 = K / 8; p.ldc = ldc;
   p.tiles_m = cdiv(M, kGM); p.tiles_n = cdiv(N, kGN);
   p.Mp = p.tiles_m * kGM; p.Np = p.tiles_n * kGN;
-  const int grid = std::min(p.tiles_m * p.tiles_n, n_sms);
+  p.splits = splits; p.nk_split = K / kGK / splits; p.partial = splits > 1 ? partial : nullptr;
+  const int grid = std::min(p.tiles_m * p.tiles_n * splits, n_sms);
   gemm_umma_kernel<<<grid, kGThreads, kGemmSmem, st>>>(p);
   AVS_LAUNCHED();
+  if (splits > 1) return splitk_reduce(partial, bias, c, M, N, splits, st);
   return AVS_OK;
 }
 

@@ -7,7 +7,9 @@
 //   (2) per clip: for each shift  score = sigmoid(w2 . relu(hv + W1a . a_k) + b2), then arg-max.
 #include <algorithm>
 #include "common.cuh"
+#include "gemm_umma.cuh"
 #include "sgemm.cuh"
+#include "stcnn.cuh"
 
 namespace avs {
 
@@ -214,14 +216,46 @@ extern "C" size_t avs_sweep_score_workspace_bytes(int n_clips, int hidden) {
   return align_up(static_cast<size_t>(n_clips) * hidden * sizeof(float), 256) * 17;  // hv + up to 16 split-K partials
 }
 
+// K slices of the tensor-core form of the hidden-layer GEMM: fixed per K (bit-identical scores whatever the batch), the
+// largest divisor of the k-block count up to 16 — 9 for the detector's 13824 visual dims (432 blocks of 32), i.e. 144
+// CTAs at 1024 clips where the unsplit GEMM has 16 output tiles.
+static int tensor_gemm_splits(int v_dim) {
+  const int nk = v_dim / 32;
+  int s = 1;
+  for (int d = 2; d <= 16; ++d)
+    if (nk % d == 0) s = d;
+  return s;
+}
+bool avs::sweep_score_tensor_gemm_ok(int v_dim, int a_dim, int hidden) {
+  return v_dim % 32 == 0 && (v_dim + a_dim) % 4 == 0 && hidden % 4 == 0;
+}
+size_t avs::sweep_score_workspace_bytes_tensor(int n_clips, int hidden, int v_dim) {
+  if (n_clips <= 0 || hidden <= 0) return 0;
+  return avs_sweep_score_workspace_bytes(n_clips, hidden) + align_up(gemm_packed_bytes(n_clips, v_dim, 128), 256) +
+         align_up(gemm_packed_bytes(hidden, v_dim, 256), 256);
+}
+
 extern "C" int avs_sweep_score(const float* vstats, const float* astats, int n_clips, int n_shifts, int v_dim,
                                int a_dim, const float* w1, const float* b1, const float* w2, const float* b2,
                                int hidden, float* out_scores, int32_t* out_best, void* workspace,
                                size_t workspace_bytes, void* stream) {
+  return avs::sweep_score_impl(vstats, astats, n_clips, n_shifts, v_dim, a_dim, w1, b1, w2, b2, hidden, out_scores, out_best,
+                               workspace, workspace_bytes, false, stream);
+}
+
+// tensor_gemm: the shift-invariant part of the hidden layer as a hi/lo-split tcgen05 GEMM (three bf16 MMAs per product,
+// relative error ~2^-16) instead of the fp32 CUDA-core GEMM.  The sweep handle asks for it when the STCNN itself runs in
+// bf16 (the visual statistics then carry ~1e-3 of relative error already); the fp32-grade modes and the public
+// avs_sweep_score keep fp32 FFMA accumulation.  The operands are packed on every call: w1 aliases live parameters.
+int avs::sweep_score_impl(const float* vstats, const float* astats, int n_clips, int n_shifts, int v_dim, int a_dim,
+                          const float* w1, const float* b1, const float* w2, const float* b2, int hidden, float* out_scores,
+                          int32_t* out_best, void* workspace, size_t workspace_bytes, bool tensor_gemm, void* stream) {
   AVS_REQUIRE(vstats && astats && w1 && b1 && w2 && b2 && out_scores && workspace, "null argument");
   AVS_REQUIRE(n_shifts > 0 && v_dim > 0 && a_dim > 0 && hidden > 0, "bad shape");
   if (n_clips <= 0) return AVS_OK;
-  if (workspace_bytes < avs_sweep_score_workspace_bytes(n_clips, hidden)) {
+  tensor_gemm = tensor_gemm && sweep_score_tensor_gemm_ok(v_dim, a_dim, hidden);
+  if (workspace_bytes < (tensor_gemm ? sweep_score_workspace_bytes_tensor(n_clips, hidden, v_dim)
+                                     : avs_sweep_score_workspace_bytes(n_clips, hidden))) {
     set_error("sweep_score workspace too small");
     return AVS_EWORKSPACE;
   }
@@ -232,8 +266,20 @@ extern "C" int avs_sweep_score(const float* vstats, const float* astats, int n_c
   {
     ProfScope ps(PROF_SCORE_GEMM, st);
     float* partial = hv + align_up(static_cast<size_t>(n_clips) * hidden * sizeof(float), 256) / sizeof(float);
-    rc = sgemm_nt_splitk(vstats, v_dim, w1, ld, b1, hv, n_clips, hidden, v_dim, score_splits(n_clips, hidden, v_dim),
-                         partial, st);
+    if (tensor_gemm) {
+      uint8_t* base = static_cast<uint8_t*>(workspace) + avs_sweep_score_workspace_bytes(n_clips, hidden);
+      __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(base);
+      __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(base + align_up(gemm_packed_bytes(n_clips, v_dim, 128), 256));
+      int dev = 0, n_sms = 148;
+      AVS_CUDA(cudaGetDevice(&dev));
+      AVS_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+      if ((rc = gemm_pack(vstats, v_dim, n_clips, v_dim, 128, ap, st))) return rc;
+      if ((rc = gemm_pack(w1, ld, hidden, v_dim, 256, wp, st))) return rc;
+      rc = gemm_umma_nt_splitk(ap, wp, b1, hv, hidden, n_clips, hidden, v_dim, tensor_gemm_splits(v_dim), partial, n_sms, st);
+    } else {
+      rc = sgemm_nt_splitk(vstats, v_dim, w1, ld, b1, hv, n_clips, hidden, v_dim, score_splits(n_clips, hidden, v_dim),
+                           partial, st);
+    }
   }
   if (rc) return rc;
   ProfScope ps(PROF_SCORE, st);

@@ -100,6 +100,10 @@ int sgemm_nt_splitk(const float* A, int lda, const float* B, int ldb, const floa
   if (ldb % 4 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0) sgemm_nt_kernel<true><<<grid, 256, 0, st>>>(A, lda, B, ldb, nullptr, partial, N, M, N, K / splits);
   else sgemm_nt_kernel<false><<<grid, 256, 0, st>>>(A, lda, B, ldb, nullptr, partial, N, M, N, K / splits);
   AVS_LAUNCHED();
+  return splitk_reduce(partial, bias, C, M, N, splits, st);
+}
+
+int splitk_reduce(const float* partial, const float* bias, float* C, int M, int N, int splits, cudaStream_t st) {
   splitk_reduce_kernel<<<cdiv(M * N, 1024), 256, 0, st>>>(partial, bias, C, M, N, splits);
   AVS_LAUNCHED();
   return AVS_OK;

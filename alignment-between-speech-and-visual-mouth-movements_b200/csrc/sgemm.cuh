@@ -9,4 +9,6 @@ int sgemm_nt(const float* A, int lda, const float* B, int ldb, const float* bias
              int K, cudaStream_t st);
 int sgemm_nt_splitk(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int M, int N, int K,
                     int splits, float* partial, cudaStream_t st);
+// C[M, N] = sum over the `splits` dense [M, N] slices of `partial`, in slice order, + bias (nullable)
+int splitk_reduce(const float* partial, const float* bias, float* C, int M, int N, int splits, cudaStream_t st);
 }  // namespace avs

@@ -119,6 +119,8 @@ extern "C" void avs_stcnn_destroy(avs_stcnn* net) {
   delete net;
 }
 
+int avs::stcnn_precision(const avs_stcnn* net) { return net->precision; }
+
 extern "C" size_t avs_stcnn_workspace_bytes(const avs_stcnn* net, int n_clips) {
   if (!net || n_clips <= 0) return 0;
   return carve(net, n_clips, nullptr, true).total;

@@ -19,6 +19,14 @@ int mfcc_stats_part(const avs_mfcc_plan* p, int n_clips, float* out_stats, float
 int conv_pool_ffma(const float* in, const float* w, const float* bias, float* out, int B, int Cin, int Cout, int T,
                    int H, int W, int KH, int KW, long long o_sb, long long o_sc, long long o_st, cudaStream_t st);
 int vstats(const float* emb, float* out, int B, int F, cudaStream_t st);
+int stcnn_precision(const avs_stcnn* net);
+
+// K4 (score.cu): avs_sweep_score with the choice of the hidden-layer GEMM (tensor_gemm: hi/lo-split tcgen05 GEMM)
+bool sweep_score_tensor_gemm_ok(int v_dim, int a_dim, int hidden);
+size_t sweep_score_workspace_bytes_tensor(int n_clips, int hidden, int v_dim);
+int sweep_score_impl(const float* vstats, const float* astats, int n_clips, int n_shifts, int v_dim, int a_dim,
+                     const float* w1, const float* b1, const float* w2, const float* b2, int hidden, float* out_scores,
+                     int32_t* out_best, void* workspace, size_t workspace_bytes, bool tensor_gemm, void* stream);
 
 // ---- tcgen05 path ------------------------------------------------------------------------------
 // Geometry of one layer in the "parity-plane" activation layout.

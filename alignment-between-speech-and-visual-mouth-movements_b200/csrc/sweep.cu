@@ -20,6 +20,7 @@ struct avs_sweep {
   const avs_mfcc_plan* plan;
   const float *w1, *b1, *w2, *b2;
   int hidden, chunk, K, n_mfcc, n_samples;
+  bool tensor_k4 = false;   // K4's hidden-layer GEMM on the tensor cores (bf16 STCNN only; score.cu: sweep_score_impl)
   // device buffers (per chunk)
   void* ws_stcnn = nullptr; size_t ws_stcnn_bytes = 0;
   void* ws_mfcc = nullptr;  size_t ws_mfcc_bytes = 0;
@@ -71,6 +72,10 @@ extern "C" int avs_sweep_create(const avs_stcnn* net, const avs_mfcc_plan* plan,
   s->net = net; s->plan = plan; s->w1 = w1; s->b1 = b1; s->w2 = w2; s->b2 = b2;
   s->hidden = hidden; s->chunk = chunk_clips;
   avs_mfcc_plan_nshifts_internal(plan, &s->K, &s->n_mfcc, &s->n_samples);
+  s->tensor_k4 = stcnn_precision(net) == AVS_PREC_BF16 && sweep_score_tensor_gemm_ok(AVS_VSTATS, 2 * s->n_mfcc, hidden);
+#ifdef AVS_EXPERIMENTS
+  if (env_knob("AVS_K4_FFMA", 0)) s->tensor_k4 = false;
+#endif
   s->ws_stcnn_bytes = avs_stcnn_workspace_bytes(net, chunk_clips);
   s->ws_mfcc_bytes = avs_mfcc_workspace_bytes(plan, chunk_clips);
   int rc = AVS_OK;
@@ -140,7 +145,8 @@ static int ensure_capacity(avs_sweep* s, int n_clips, cudaStream_t st) {
     if (p) AVS_CUDA(cudaFreeAsync(p, st));
   s->vstats = s->astats = nullptr; s->ws_score = nullptr; s->d_scores_all = nullptr; s->d_best_all = nullptr;
   s->cap = 0;
-  s->ws_score_bytes = avs_sweep_score_workspace_bytes(cap, s->hidden);
+  s->ws_score_bytes = s->tensor_k4 ? sweep_score_workspace_bytes_tensor(cap, s->hidden, AVS_VSTATS)
+                                   : avs_sweep_score_workspace_bytes(cap, s->hidden);
   AVS_CUDA(cudaMallocAsync(&s->ws_score, s->ws_score_bytes, st));
   AVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&s->vstats), static_cast<size_t>(cap) * AVS_VSTATS * sizeof(float), st));
   AVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&s->astats), static_cast<size_t>(cap) * s->K * 2 * s->n_mfcc * sizeof(float), st));
@@ -224,8 +230,8 @@ static int run_chunk(avs_sweep* s, const void* frames, bool frames_u8, const flo
 
 // K4 over all clips of the call: one hidden-layer GEMM for the whole batch, then the per-shift scores
 static int score_all(avs_sweep* s, int n_clips, float* scores, int32_t* best, cudaStream_t st) {
-  return avs_sweep_score(s->vstats, s->astats, n_clips, s->K, AVS_VSTATS, 2 * s->n_mfcc, s->w1, s->b1, s->w2, s->b2,
-                         s->hidden, scores, best, s->ws_score, s->ws_score_bytes, st);
+  return sweep_score_impl(s->vstats, s->astats, n_clips, s->K, AVS_VSTATS, 2 * s->n_mfcc, s->w1, s->b1, s->w2, s->b2,
+                          s->hidden, scores, best, s->ws_score, s->ws_score_bytes, s->tensor_k4, st);
 }
 
 static int sweep_run_device(avs_sweep* s, const void* frames, bool frames_u8, const float* audio, int n_clips, float* out_scores,
