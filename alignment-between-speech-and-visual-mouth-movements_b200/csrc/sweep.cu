@@ -283,12 +283,19 @@ static void staging_copy(void* dst, const void* src, size_t bytes) {
   }
   const size_t per = (bytes / n + 63) & ~static_cast<size_t>(63);
   std::thread th[3];
+  int started = 0;
   for (int i = 1; i < n; ++i) {
     const size_t off = per * i, len = std::min(per, bytes - off);
-    th[i - 1] = std::thread([=] { memcpy(static_cast<uint8_t*>(dst) + off, static_cast<const uint8_t*>(src) + off, len); });
+    try {
+      th[i - 1] = std::thread([=] { memcpy(static_cast<uint8_t*>(dst) + off, static_cast<const uint8_t*>(src) + off, len); });
+      ++started;
+    } catch (...) {  // no thread to be had (resource limits): this thread copies the rest itself
+      memcpy(static_cast<uint8_t*>(dst) + off, static_cast<const uint8_t*>(src) + off, bytes - off);
+      break;
+    }
   }
   memcpy(dst, src, per);
-  for (int i = 1; i < n; ++i) th[i - 1].join();
+  for (int i = 0; i < started; ++i) th[i].join();
 }
 
 static int host_init(avs_sweep* s) {
