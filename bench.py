@@ -75,7 +75,7 @@ class ClockSampler:
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,power.draw.instant,enforced.power.limit")
 
     def __init__(self, gpu_index: int):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
@@ -110,8 +110,15 @@ class ClockSampler:
         sm = sorted(float(r[1]) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for j, n in enumerate(names) if any("Active" == r[5 + j].strip() for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "samples": len(rows),
-                "power_w_max": max(float(r[3]) for r in rows), "reasons": reasons}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "samples": len(rows),
+               "power_w_max": max(float(r[3]) for r in rows), "reasons": reasons}
+        try:   # power.draw is nvidia-smi's one-second average and lags a short timed region; the instantaneous reading and
+            # the enforced limit show how close to the cap the step runs (profiles/r02_power_trace.txt: 986 of 1000 W)
+            out["power_w_instant_max"] = max(float(r[9]) for r in rows)
+            out["power_limit_w"] = float(rows[0][10])
+        except (ValueError, IndexError):
+            pass
+        return out
 
 
 def synth_inputs(n: int, seed: int, pin: bool = True):
