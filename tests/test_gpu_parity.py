@@ -331,6 +331,32 @@ def test_sweep_score_kernel_vs_oracle(A, det_sd):
     assert (sc0 == 0.5).all() and (best0 == 0).all()
 
 
+def test_bf16_sweep_tensor_core_k4_vs_fp32_k4(A, lipnet_sd, det_sd):
+    """The bf16 sweep computes the detector's hidden layer with a split-K hi/lo tcgen05 GEMM (score.cu: sweep_score_impl);
+    the public avs_sweep_score keeps the fp32 FFMA GEMM.  Same visual / audio statistics through both: scores within 2e-6
+    (three bf16 MMAs per product, ~2^-16 relative), best offsets equal wherever the top-2 margin exceeds that, and a
+    clip's scores do not depend on the batch it is scored in (fixed K slices)."""
+    net = make_lipnet(A, lipnet_sd, "bf16")
+    det = make_detector(A, det_sd)
+    n = 96
+    frames = sweep_ref.synth_frames(n, seed=77).cuda()
+    audio = torch.from_numpy(sweep_ref.synth_audio(n, seed=200, kind="speechlike")).cuda()
+    sw = A.SyncSweeper(net, det, 20, audio.shape[1], chunk_clips=64)
+    sc_t, best_t = sw.run(frames, audio)
+    with torch.no_grad():
+        v = A.visual_stats(net, frames)
+    a = A.audio_stats_sweep(audio, [640 * k for k in range(-20, 21)])
+    sc_f, best_f = A.sweep_score(v, a, det)
+    d = (sc_t - sc_f).abs().max().item()
+    print(f"[parity] K4 tensor-core vs fp32 GEMM: max |dscore| {d:.3e}")
+    assert d <= 2e-6
+    top2 = torch.topk(sc_f, 2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 10 * max(d, 1e-7)
+    assert clear.any() and torch.equal((best_t + 20)[clear].long(), best_f[clear].long())
+    sc_1, _ = sw.run(frames[:5], audio[:5])          # another batch size, another chunking: same bits per clip
+    assert torch.equal(sc_1, sc_t[:5])
+
+
 # bf16: measured max |score - golden| = 7.5e-6 (the STCNN's bf16 error is common-mode across shifts and averaged over
 # 13 824 features); 5e-5 keeps the arg-max assertion live for both golden clips (top-2 margins 2.1e-3 and 4.6e-3)
 @pytest.mark.parametrize("precision,atol", [("fp32", 2e-5), ("bf16x3", 2e-5), ("bf16", 5e-5)])
