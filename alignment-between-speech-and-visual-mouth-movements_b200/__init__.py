@@ -9,7 +9,7 @@ error behaviour) over the C-ABI library ``libavsync_b200.so`` (``include/avsync.
         extract_visual_embeddings, FeatureExtractor, MisalignmentDataset, MisalignmentDetector, run_epoch,
         load_lipnet, save_detector}                  utils.evaluate_model
     misalignment_detection_train.{SyncSweeper, sync_sweep}, utils.ctc_greedy_decode   (new, batched)
-    distributed.{shard_range, sweep_sharded, gather_scores, ddp_detector_step}        (new, multi-GPU)
+    distributed.{shard_range, sweep_sharded, gather_scores, ddp_detector_step, GraphedDetectorStep}        (new, multi-GPU)
 
 Import as ``avsync_b200`` (the directory name is not a valid identifier; ``avsync_b200.py`` at the
 repo root aliases it).

@@ -365,10 +365,36 @@ def ddp_config5(A, dev, world: int, rank: int, steps: int = 20):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step, ms_ar = float(t[0]), float(t[1])
-    return {"value": ms_step, "unit": "ms/step", "global_batch": 64 * world, "grad_floats": n_grad,
-            "allreduce_ms": ms_ar, "allreduce_share": (ms_ar / ms_step) if ms_step else None,
-            "allreduce_busbw_gbs": (2 * (world - 1) / world * n_grad * 4 / (ms_ar / 1e3) / 1e9) if ms_ar else None,
-            "samples_per_s": 64 * world / (ms_step / 1e3)}
+    out = {"value": ms_step, "unit": "ms/step", "global_batch": 64 * world, "grad_floats": n_grad,
+           "allreduce_ms": ms_ar, "allreduce_share": (ms_ar / ms_step) if ms_step else None,
+           "allreduce_busbw_gbs": (2 * (world - 1) / world * n_grad * 4 / (ms_ar / 1e3) / 1e9) if ms_ar else None,
+           "samples_per_s": 64 * world / (ms_step / 1e3)}
+    # the same step captured in one CUDA graph (forward, loss, backward, all-reduce, Adam): the eager step is ~30
+    # launch-bound torch kernels.  Every rank must take the same branch, so a failure on any rank disables it on all.
+    if os.environ.get("AVS_BENCH_NO_GRAPH") != "1":
+        stepper, err = None, ""
+        try:
+            stepper = A.distributed.GraphedDetectorStep(det, opt, 64)
+        except Exception as e:                      # noqa: BLE001 - reported in the line
+            err = f"{type(e).__name__}: {e}"[:200]
+        ok = torch.tensor([1.0 if stepper is not None else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 1.0:
+            ms_g = torch.tensor([cuda_time(lambda: stepper.step(x, y), steps, warm=3)], device=dev)
+            flat_p = torch.cat([p.detach().reshape(-1) for p in det.parameters()])
+            spread = torch.stack([flat_p.max(), -flat_p.min(), flat_p.double().sum().float()])
+            lo = spread.clone()
+            if world > 1:
+                dist.all_reduce(ms_g, op=dist.ReduceOp.MAX)
+                dist.all_reduce(spread, op=dist.ReduceOp.MAX)
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            out["cuda_graph"] = {"value": float(ms_g), "unit": "ms/step", "samples_per_s": 64 * world / (float(ms_g) / 1e3),
+                                 "ranks_in_sync": bool(torch.equal(spread, lo)),
+                                 "what": "the same step as one CUDA graph replay (distributed.GraphedDetectorStep)"}
+        else:
+            out["cuda_graph"] = {"unavailable": err or "capture failed on another rank"}
+    return out
 
 
 def main():
