@@ -17,7 +17,8 @@ dev = torch.device("cuda", local)
 if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
-out = bench.ddp_config5(A, dev, world, rank)
+out, ctx = bench.ddp_config5(A, dev, world, rank)
+out["cuda_graph"] = bench.ddp_config5_graph(A, dev, world, rank, ctx)
 if rank == 0:
     print(json.dumps(out))
 if world > 1:
