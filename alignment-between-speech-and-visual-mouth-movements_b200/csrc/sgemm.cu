@@ -78,6 +78,45 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
   }
 }
 
+// Few outputs (one clip's hidden layer, the 39-class head of a clip or two): the 128 x 128 tiles above would be one to a
+// few CTAs walking K alone (config 1: 128 us for the detector's hidden layer of ONE clip, 75 us for the class head).  Here
+// every thread owns one output of one K slice and walks its rows of A and B with 128-bit loads — the SAME single fmaf
+// chain in ascending k as the tiled kernel, so a result does not depend on which kernel (i.e. which batch size) computed it.
+template <bool BVEC>
+__global__ void __launch_bounds__(128)
+sgemm_nt_skinny_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                       const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N, int K) {
+  A += static_cast<size_t>(blockIdx.z) * K;
+  B += static_cast<size_t>(blockIdx.z) * K;
+  C += static_cast<size_t>(blockIdx.z) * M * ldc;
+  const int idx = blockIdx.x * 128 + threadIdx.x;
+  if (idx >= M * N) return;
+  const int n = idx % N, m = idx / N;
+  const float* ap = A + static_cast<size_t>(m) * lda;
+  const float* bp = B + static_cast<size_t>(n) * ldb;
+  float acc = 0.f;
+  // 16 row segments of B in flight per thread (the kernel is a latency-bound stream of B: 28 MB for the detector's hidden
+  // layer, read by 8192 threads), then the fmaf chain over them in k order; A comes from L1 (its rows are shared)
+  constexpr int U = 16;
+  for (int k0 = 0; k0 < K; k0 += 4 * U) {
+    float4 b[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i)
+      if (k0 + 4 * i < K) b[i] = ld4(bp + k0 + 4 * i, BVEC);
+#pragma unroll
+    for (int i = 0; i < U; ++i)
+      if (k0 + 4 * i < K) {
+        const float4 a = *reinterpret_cast<const float4*>(ap + k0 + 4 * i);
+        acc = fmaf(a.x, b[i].x, acc);
+        acc = fmaf(a.y, b[i].y, acc);
+        acc = fmaf(a.z, b[i].z, acc);
+        acc = fmaf(a.w, b[i].w, acc);
+      }
+  }
+  C[static_cast<size_t>(m) * ldc + n] = acc + (bias ? bias[n] : 0.f);
+}
+constexpr int kSkinnyOutputs = 16384;  // outputs x K slices up to which the one-thread-per-output kernel is used
+
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias, float* __restrict__ C, int M, int N,
                      int splits) {
@@ -96,9 +135,16 @@ int sgemm_nt_splitk(const float* A, int lda, const float* B, int ldb, const floa
   AVS_REQUIRE(splits >= 1 && K % (splits * BK) == 0 && lda % 4 == 0, "bad split-K configuration");
   if (M <= 0 || N <= 0) return AVS_OK;
   if (splits == 1) return sgemm_nt(A, lda, B, ldb, bias, C, N, M, N, K, st);
-  dim3 grid(cdiv(N, BN), cdiv(M, BM), splits);
-  if (ldb % 4 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0) sgemm_nt_kernel<true><<<grid, 256, 0, st>>>(A, lda, B, ldb, nullptr, partial, N, M, N, K / splits);
-  else sgemm_nt_kernel<false><<<grid, 256, 0, st>>>(A, lda, B, ldb, nullptr, partial, N, M, N, K / splits);
+  const bool bvec = ldb % 4 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0;
+  if (static_cast<long long>(M) * N * splits <= kSkinnyOutputs) {
+    dim3 grid(cdiv(M * N, 128), 1, splits);
+    if (bvec) sgemm_nt_skinny_kernel<true><<<grid, 128, 0, st>>>(A, lda, B, ldb, nullptr, partial, N, M, N, K / splits);
+    else sgemm_nt_skinny_kernel<false><<<grid, 128, 0, st>>>(A, lda, B, ldb, nullptr, partial, N, M, N, K / splits);
+  } else {
+    dim3 grid(cdiv(N, BN), cdiv(M, BM), splits);
+    if (bvec) sgemm_nt_kernel<true><<<grid, 256, 0, st>>>(A, lda, B, ldb, nullptr, partial, N, M, N, K / splits);
+    else sgemm_nt_kernel<false><<<grid, 256, 0, st>>>(A, lda, B, ldb, nullptr, partial, N, M, N, K / splits);
+  }
   AVS_LAUNCHED();
   return splitk_reduce(partial, bias, C, M, N, splits, st);
 }
@@ -113,9 +159,15 @@ int sgemm_nt(const float* A, int lda, const float* B, int ldb, const float* bias
              int K, cudaStream_t st) {
   AVS_REQUIRE(K % BK == 0 && lda % 4 == 0, "sgemm_nt needs K % 8 == 0 and 16-byte aligned rows of A");
   if (M <= 0 || N <= 0) return AVS_OK;
-  dim3 grid(cdiv(N, BN), cdiv(M, BM));
-  if (ldb % 4 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0) sgemm_nt_kernel<true><<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
-  else sgemm_nt_kernel<false><<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+  const bool bvec = ldb % 4 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0;
+  if (static_cast<long long>(M) * N <= kSkinnyOutputs) {
+    if (bvec) sgemm_nt_skinny_kernel<true><<<cdiv(M * N, 128), 128, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+    else sgemm_nt_skinny_kernel<false><<<cdiv(M * N, 128), 128, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+  } else {
+    dim3 grid(cdiv(N, BN), cdiv(M, BM));
+    if (bvec) sgemm_nt_kernel<true><<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+    else sgemm_nt_kernel<false><<<grid, 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+  }
   AVS_LAUNCHED();
   return AVS_OK;
 }

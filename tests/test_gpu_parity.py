@@ -331,6 +331,26 @@ def test_sweep_score_kernel_vs_oracle(A, det_sd):
     assert (sc0 == 0.5).all() and (best0 == 0).all()
 
 
+def test_small_batches_take_the_skinny_gemm_with_identical_bits(A, lipnet_sd, det_sd):
+    """One or two clips run the fp32 GEMMs (detector hidden layer, class head) through the one-thread-per-output kernel
+    instead of 128 x 128 tiles (sgemm.cu: sgemm_nt_skinny_kernel, same fmaf chain per output): a clip's scores and
+    log-probabilities must not depend on the batch it came in."""
+    det = make_detector(A, det_sd)
+    g = torch.Generator().manual_seed(9)
+    v = torch.rand((40, 13824), generator=g).cuda()
+    a = (torch.randn((40, 31, 40), generator=g) * 20).cuda()
+    sc_all, best_all = A.sweep_score(v, a, det)                  # tiled kernel (40 x 512 x 16 slices)
+    for n in (1, 2):
+        sc_n, best_n = A.sweep_score(v[:n], a[:n], det)          # skinny kernel
+        assert torch.equal(sc_n, sc_all[:n]) and torch.equal(best_n, best_all[:n])
+    net = make_lipnet(A, lipnet_sd, "bf16x3")
+    frames = sweep_ref.synth_frames(8, seed=21).cuda()
+    with torch.no_grad():
+        lp8 = net(frames)                                        # class head: 600 x 39 outputs, tiled
+        lp1 = net(frames[:1])                                    # 75 x 39 outputs, skinny
+    assert torch.equal(lp1[0], lp8[0])
+
+
 def test_bf16_sweep_tensor_core_k4_vs_fp32_k4(A, lipnet_sd, det_sd):
     """The bf16 sweep computes the detector's hidden layer with a split-K hi/lo tcgen05 GEMM (score.cu: sweep_score_impl);
     the public avs_sweep_score keeps the fp32 FFMA GEMM.  Same visual / audio statistics through both: scores within 2e-6
