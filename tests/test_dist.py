@@ -72,3 +72,13 @@ def test_auc_acc_matches_sklearn_and_nan_on_single_class():
     assert 0 <= acc <= 1 and 0 <= auc <= 1
     _, auc1 = A.distributed.auc_acc(np.ones(10), rng.random(10))
     assert np.isnan(auc1)
+
+
+def test_graphed_detector_step_needs_cuda():
+    """The CUDA-graph form of the training step has no CPU fallback: a CPU model is refused, loudly."""
+    import pytest
+    import avsync_b200 as A
+    m = A.MisalignmentDetector(13864, 8)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        A.distributed.GraphedDetectorStep(m, opt, 4)
